@@ -1,0 +1,334 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the B200 hot path (contract: see DESIGN.md "Measurement").
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode tc|fp32]
+  N > 1: launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
+
+Headline workload = BASELINE.json config 3 per GPU: 65 536 lock-step Reacher-v2 envs, fused teacher MLP (2x64 tanh) in the
+loop, device-resident rollout buffer; one bench "step" = one 50-step chunk (one episode of every env) = 3 276 800 env-steps
+per GPU.  Weak scaling: every rank owns 65 536 envs (global env ids rank*65536 ..), no data-path collective.
+`value`   env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks.
+`e2e`     same metric through the host-buffer C-ABI call (rb_env_rollout_policy_host): H2D of the teacher parameters and D2H of
+          the whole rollout buffer (obs, pdflat, reward, done) inside the timed region.
+`distill` BASELINE.json config 4 shard (32 768 envs per GPU): DAgger iterations = env step + teacher label + student
+          forward/backward + KL + [NCCL all-reduce of the flat gradient] + Adam; samples/s == env-steps/s of that loop.
+`step_api` the gym-style single-step kernel (HBM-bound) at 4 194 304 envs.
+`cpu_baseline` / --impl reference: the float64 C restatement of the reference's CPU path (oracle/, OpenMP over host cores) on a
+          bounded sample of the same workload.  The reference itself (TF-1.10 + gym + MuJoCo-1.50) is not installable here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ENVS_PER_GPU = 65536
+CHUNK_T = 50
+DISTILL_ENVS_PER_GPU = 32768
+STEP_API_ENVS = 1 << 22
+ALG_BYTES_ROLLOUT = 68.0      # fused rollout writes one 17-float buffer row per env-step
+ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
+FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+FLOP_PER_ENV_STEP = 450.0 + 9856.0          # physics + teacher MLP
+FLOP_PER_SAMPLE = {"mlp": 144.4e3, "policy64": 30.3e3}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], bf16_burst=d["bf16_tflops"], bf16_sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, bf16_burst=1590.0, bf16_sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.lines, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append((time.time(), line.strip()))
+
+    def window(self, t0, t1):
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1] or [l for (_, l) in self.lines[-3:]]
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            f = [x.strip() for x in r.split(",")]
+            try:
+                sm.append(float(f[0])); mx = max(mx, float(f[1]))
+            except Exception:
+                continue
+            for nm, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx or None, reasons=sorted(reasons), samples=len(sm))
+
+    def stop(self):
+        if self.proc:
+            self.proc.kill()
+
+
+def cpu_reference_leg(seconds=12.0, nthreads=0):
+    """Time the C restatement of the reference's CPU rollout (teacher in the loop) on the host cores, bounded sample."""
+    import numpy as np
+    from oracle import reacher_c as RC
+    from reacherdistilation_b200.teacher import init_policy_params
+    p = init_policy_params(seed=0)
+    cores = RC.max_threads() if nthreads <= 0 else nthreads
+    cal = RC.ReacherOracleC(2048, seed=0, nthreads=nthreads); cal.reset()
+    t0 = time.perf_counter(); cal.rollout_policy(CHUNK_T, p, record=False); dt = time.perf_counter() - t0
+    rate = 2048 * CHUNK_T / dt
+    n = int(min(ENVS_PER_GPU, max(2048, rate * seconds / CHUNK_T)))
+    env = RC.ReacherOracleC(n, seed=0, nthreads=nthreads); env.reset()
+    obs, pd, rw, dn = (np.zeros((CHUNK_T, n, 11)), np.zeros((CHUNK_T, n, 4)), np.zeros((CHUNK_T, n)), np.zeros((CHUNK_T, n), np.uint8))
+    t0 = time.perf_counter()
+    env.rollout_policy(CHUNK_T, p, record=True)
+    dt = time.perf_counter() - t0
+    return dict(value=n * CHUNK_T / dt, unit="env-steps/s", cores=cores, kind="port",
+                sample="%d envs x %d steps teacher-in-the-loop rollout, float64 C restatement (oracle/reacher_oracle.c), %.1f s" % (n, CHUNK_T, dt)), n, dt
+
+
+def cpu_distill_leg(kind="mlp", seconds=6.0):
+    """numpy float64 restatement of one DAgger optimiser step (student fwd/bwd + KL + Adam) on a bounded batch."""
+    import numpy as np
+    from oracle import nn_np as NN
+    rng = np.random.default_rng(0)
+    B = 8192
+    if kind == "mlp":
+        P = (rng.standard_normal(NN.mlp_param_count()) * 0.1).astype(np.float32)
+        x = rng.standard_normal((B, 16))
+    else:
+        P = (rng.standard_normal(NN.policy_param_count(4)) * 0.1).astype(np.float32); P[:11] = 0; P[11:22] = 1
+        x = rng.standard_normal((B, 11))
+    t = rng.standard_normal((B, 4)) * 0.3
+    opt = NN.AdamTF(P.size)
+    theta = P.astype(np.float64)
+    n_it, t0 = 0, time.perf_counter()
+    while time.perf_counter() - t0 < seconds:
+        if kind == "mlp":
+            s, hs = NN.mlp_fwd(x, theta.astype(np.float32)); l, ds = NN.kl_loss(s, t); g = NN.mlp_bwd(hs, theta.astype(np.float32), ds)
+        else:
+            s = NN.policy_fwd(x, theta.astype(np.float32), nout=4); l, ds = NN.kl_loss(s, t); g = NN.policy_bwd(x, theta.astype(np.float32), ds)
+        theta = opt.update(theta, g)
+        n_it += 1
+    dt = time.perf_counter() - t0
+    return dict(value=B * n_it / dt, unit="samples/s", cores=os.cpu_count(), kind="port",
+                sample="%d optimiser steps of batch %d, numpy float64 restatement (oracle/nn_np.py), %.1f s" % (n_it, B, dt))
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path (restated; see module docstring)."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    steps, warm = max(1, args.steps), max(0, args.warmup)
+    import numpy as np
+    from oracle import reacher_c as RC
+    from reacherdistilation_b200.teacher import init_policy_params
+    p = init_policy_params(seed=0)
+    cores = RC.max_threads()
+    cal = RC.ReacherOracleC(2048, seed=0); cal.reset()
+    t0 = time.perf_counter(); cal.rollout_policy(CHUNK_T, p, record=False); rate = 2048 * CHUNK_T / (time.perf_counter() - t0)
+    budget = 120.0 / (steps + warm)                                  # whole run within a few minutes
+    n = int(min(ENVS_PER_GPU, max(1024, rate * min(budget, 10.0) / CHUNK_T)))
+    env = RC.ReacherOracleC(n, seed=0); env.reset()
+    for _ in range(warm):
+        env.rollout_policy(CHUNK_T, p, record=True)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        env.rollout_policy(CHUNK_T, p, record=True)
+    dt = time.perf_counter() - t0
+    val = n * CHUNK_T * steps / dt
+    sample = "%d of %d envs per step x %d steps/chunk, float64 C restatement of the MuJoCo+TF CPU path, OpenMP %d threads" % (n, ENVS_PER_GPU, CHUNK_T, cores)
+    line = dict(impl="reference", metric="reacher_env_steps_per_sec", value=val, unit="env-steps/s", n_gpus=args.gpus, steps=steps, warmup=warm,
+                ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
+                config=dict(workload="config3: fused teacher (11-64-64-2 tanh) rollout, 50-step chunks, rollout buffer recorded",
+                            envs_per_step=n, chunk_steps=CHUNK_T),
+                cpu_baseline=dict(value=val, unit="env-steps/s", cores=cores, kind="port", sample=sample),
+                e2e=dict(value=val, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=300)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default="auto", choices=["auto", "fp32", "tc"])
+    ap.add_argument("--student", default="mlp", choices=["mlp", "policy64"])
+    ap.add_argument("--quick", action="store_true", help="skip the secondary measurements (distill, step API, CPU legs)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import numpy as np
+    import torch
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC, STUDENT_MLP, STUDENT_POLICY64, _lib
+    from reacherdistilation_b200.dist import init_from_env, max_over_ranks
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.mlp_train import DaggerTrainer
+    from reacherdistilation_b200.teacher import init_policy_params
+
+    rank, world, local = init_from_env()
+    assert world == args.gpus or world == 1, "launch with torchrun --nproc-per-node == --gpus"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    K, W = max(1, args.steps), max(3, args.warmup)
+    L = _lib.lib()
+    mode = {"fp32": MODE_FP32, "tc": MODE_TC}.get(args.mode) if args.mode != "auto" else (MODE_TC if L.rb_mode_available(MODE_TC) else MODE_FP32)
+    mode_name = "tc(tcgen05 bf16x3)" if mode == MODE_TC else "fp32(cuda cores)"
+    pk = peaks()
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, iters):
+        """barrier+sync, CUDA events on the launching stream, barrier+sync; returns max-over-ranks seconds and host window."""
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0 = time.time()
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        barrier()
+        h1 = time.time()
+        return max_over_ranks(e0.elapsed_time(e1) / 1e3, dev), (h0, h1)
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    n = ENVS_PER_GPU
+    teacher = torch.from_numpy(init_policy_params(seed=0)).to(dev)
+    env = VecReacher(num_envs=n, seed=0, device=local, env_offset=rank * n)
+    env.reset()
+    buf = dict(obs=torch.empty((CHUNK_T, n, 11), device=dev), pdflat=torch.empty((CHUNK_T, n, 4), device=dev),
+               rew=torch.empty((CHUNK_T, n), device=dev), done=torch.empty((CHUNK_T, n), dtype=torch.uint8, device=dev))
+    step_fn = lambda: env.rollout_policy(teacher, CHUNK_T, nout=2, mode=mode, out=buf)
+    for _ in range(W):
+        step_fn()
+    sec, win = timed(step_fn, K)
+    env_steps = float(n) * CHUNK_T * K * world
+    value = env_steps / sec
+    kernel_s = sec / K                                                 # one kernel launch per step
+    clocks = sampler.window(*win) if sampler else None
+    mean_rew = float(buf["rew"].mean())
+
+    # ---- e2e: host-buffer C-ABI call, H2D params + D2H whole rollout buffer every step -----------------------
+    Ke = max(3, min(K, 20))
+    hbuf = dict(obs=torch.empty((CHUNK_T, n, 11)).pin_memory(), pdflat=torch.empty((CHUNK_T, n, 4)).pin_memory(),
+                rew=torch.empty((CHUNK_T, n)).pin_memory(), done=torch.empty((CHUNK_T, n), dtype=torch.uint8).pin_memory())
+    tparams_host = torch.from_numpy(init_policy_params(seed=0)).pin_memory()
+    e2e_fn = lambda: env.rollout_policy_host(tparams_host, CHUNK_T, nout=2, mode=mode, out=hbuf)
+    for _ in range(2):
+        e2e_fn()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(Ke):
+        e2e_fn()                                                       # synchronous call (copies + sync inside)
+    barrier()
+    e2e_sec = max_over_ranks(time.perf_counter() - t0, dev)
+    e2e = dict(value=float(n) * CHUNK_T * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
+               d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke,
+               api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host)")
+    env.close()
+    del buf, hbuf
+
+    line = dict(metric="reacher_env_steps_per_sec", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W, ms_per_step=1e3 * sec / K,
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload="config3: %d envs/GPU, fused teacher MLP (11-64-64-2 tanh) in the loop, 50-step chunk per step, "
+                                     "rollout buffer device-resident" % n, envs_per_gpu=n, chunk_steps=CHUNK_T, policy_mode=mode_name,
+                            l2="no flush: each step writes a fresh %.0f MB rollout buffer (> 126 MB L2); state 2.6 MB stays in registers"
+                               % (n * CHUNK_T * 68 / 1e6), seed=0, mean_teacher_reward=mean_rew),
+                e2e=e2e, gpu_launches=K, clocks=clocks)
+    line["roofline"] = dict(bound="hbm", achieved=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9, peak=pk["hbm"], unit="GB/s",
+                            frac=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9 / pk["hbm"], traffic=None, peak_source=pk["src"],
+                            kernel="k_rollout_policy_%s" % ("tc" if mode == MODE_TC else "fp32"),
+                            note="fused rollout is FP32/MUFU-pipe bound, not HBM bound (SURVEY 8(d)); see fp32_pipe")
+    line["fp32_pipe"] = dict(achieved_tflops=FLOP_PER_ENV_STEP * n * CHUNK_T / kernel_s / 1e12, peak_tflops=FP32_PEAK_TFLOPS,
+                             frac=FLOP_PER_ENV_STEP * n * CHUNK_T / kernel_s / 1e12 / FP32_PEAK_TFLOPS,
+                             flop_per_env_step=FLOP_PER_ENV_STEP, note="algorithmic FLOP (physics 450 + teacher 9856) vs 148 SM x 128 lanes x 2 x 1.965 GHz")
+
+    if not args.quick:
+        # ---- distill: DAgger iterations on the config-4 shard ---------------------------------------------------
+        kind = STUDENT_MLP if args.student == "mlp" else STUDENT_POLICY64
+        nd = DISTILL_ENVS_PER_GPU
+        tr = DaggerTrainer(num_envs=nd, seed=0, device=local, student_kind=kind, mode=mode, env_offset=rank * nd)
+        tr.sync_params()
+        Kd = max(20, min(K, 200))
+        for _ in range(W):
+            tr.step()
+        dsec, _ = timed(tr.step, Kd)
+        # student kernel alone (device time of the dominant kernel of this loop)
+        lg = lambda: tr.student.loss_grad(tr.x, tr.t_pd, s_out=tr.s_pd)
+        for _ in range(3):
+            lg()
+        ksec, _ = timed(lg, 20)
+        # e2e: the loss comes back to the host every iteration
+        loss_host = torch.empty(1).pin_memory()
+        def dstep_e2e():
+            tr.step()
+            loss_host.copy_(tr.last_loss().reshape(1), non_blocking=False)
+        barrier(); t0 = time.perf_counter()
+        for _ in range(Kd):
+            dstep_e2e()
+        barrier()
+        de2e = max_over_ranks(time.perf_counter() - t0, dev)
+        fl = FLOP_PER_SAMPLE[args.student]
+        line["distill"] = dict(metric="distill_samples_per_sec", value=float(nd) * Kd * world / dsec, unit="samples/s", steps=Kd,
+                               ms_per_step=1e3 * dsec / Kd, workload="config4 shard: %d envs/GPU, student %s, KL(s||t), TF-Adam, %s"
+                               % (nd, args.student, "NCCL all-reduce of flat grad" if world > 1 else "single GPU"),
+                               e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=4),
+                               gpu_launches_per_step=7, last_loss=float(tr.last_loss()),
+                               roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",
+                                             frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"], traffic=None, peak_source=pk["src"],
+                                             kernel="k_student(loss_grad) + k_reduce_partials", kernel_ms=1e3 * ksec / 20))
+        tr.close()
+        # ---- step API: HBM-bound single-step kernel at 4M envs ---------------------------------------------------
+        ns = STEP_API_ENVS
+        env2 = VecReacher(num_envs=ns, seed=0, device=local, env_offset=0)
+        env2.reset()
+        act = (torch.rand((ns, 2), device=dev) * 2 - 1)
+        sfn = lambda: env2.step(act)
+        for _ in range(W):
+            sfn()
+        ssec, _ = timed(sfn, 50)
+        line["step_api"] = dict(metric="reacher_env_steps_per_sec", value=float(ns) * 50 * world / ssec, unit="env-steps/s", envs_per_gpu=ns,
+                                roofline=dict(bound="hbm", achieved=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9, peak=pk["hbm"], unit="GB/s",
+                                              frac=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9 / pk["hbm"], traffic=None, peak_source=pk["src"], kernel="k_step",
+                                              note="working set %.0f MB > L2; actual bytes moved 137 B/env-step" % (ns * 137 / 1e6)))
+        env2.close()
+        if rank == 0 and world == 1:
+            cb, _, _ = cpu_reference_leg()
+            line["cpu_baseline"] = cb
+            line["distill"]["cpu_baseline"] = cpu_distill_leg(args.student)
+    if sampler:
+        sampler.stop()
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,166 @@
+/* reacher_b200.h -- C ABI of libreacher_b200.so: B200 (sm_100a) hot path of ReacherDistilation.
+ *
+ * The reference (winstonww/ReacherDistilation, paths below relative to its root) has no FFI layer: its seam is the
+ * gym env protocol plus the TF session calls inside the training loops.  Each entry point here replaces one of those
+ * call sites; the Python host layer (reacherdistilation_b200/) binds them with ctypes and exposes the reference's names.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative rb_status on failure; rb_last_error() gives the message
+ *     (thread-local).  Nothing here falls back to the CPU: without a CUDA device every call fails with RB_ERR_CUDA.
+ *   - pointers named *_dev are DEVICE pointers (the caller owns them, e.g. torch tensors); functions taking them are
+ *     ASYNCHRONOUS on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream), perform no hidden
+ *     synchronisation and no host round trip.  Functions suffixed _host take HOST pointers, copy in/out and synchronise.
+ *   - a handle is bound to one GPU and is not thread-safe; use one handle per rank.
+ *   - all floating-point data is IEEE fp32 unless stated; obs rows are 11 floats, pdflat rows 4 floats
+ *     (mean0, mean1, logstd0, logstd1), actions 2 floats; row-major, env index outermost ([N,11] ...),
+ *     rollout buffers time-major ([T,N,11] ...).
+ */
+#ifndef REACHER_B200_H
+#define REACHER_B200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    RB_OK = 0,
+    RB_ERR_INVALID = -1, /* bad argument */
+    RB_ERR_CUDA = -2,    /* CUDA runtime error / no device */
+    RB_ERR_ALLOC = -3,
+    RB_ERR_UNSUPPORTED = -4
+} rb_status;
+
+#define RB_OBS_DIM 11
+#define RB_ACT_DIM 2
+#define RB_PDFLAT_DIM 4
+#define RB_EPISODE_STEPS 50
+
+/* compute mode of the dense layers */
+#define RB_MODE_FP32 0 /* CUDA-core fp32 FMA (strict parity path)                         */
+#define RB_MODE_TC 1   /* tcgen05 tensor cores, bf16x3 split operands, fp32 accumulate in TMEM */
+
+/* student kinds */
+#define RB_STUDENT_POLICY64 0 /* backup/student_rollout.py:79-87  MlpPolicy 11-64-64-4, obfilter clip +-5      */
+#define RB_STUDENT_MLP 1      /* student_nn.py:51-57  16-24-128-128(lin)-32-4 on [dropout(ob), prev_pdflat, prev_rew] */
+
+/* loss kinds */
+#define RB_LOSS_KL_ST 0 /* loss.py:3-13  KL(student || teacher), summed                       */
+#define RB_LOSS_KL_TS 1 /* backup/student_rollout.py:639-640  KL(teacher || student), summed  */
+
+const char* rb_last_error(void);
+int rb_version(void);
+/* number of CUDA devices visible (<=0: none) and SM count of `device` */
+int rb_device_count(void);
+int rb_sm_count(int device);
+/* 1 if the given RB_MODE_* is compiled into this build (RB_MODE_TC needs the tcgen05 kernels) */
+int rb_mode_available(int mode);
+
+/* ------------------------------------------------------------------------------------------------ env ----
+ * rb_env = N lock-step Reacher-v2 environments resident in HBM.
+ * Replaces make_mujoco_env("Reacher-v2", 0)           src/distilation/mlp_train.py:21, lstm_train.py:21, teacher.py:29,40
+ * global_env_offset: first global env id of this shard -- Philox streams are keyed by GLOBAL env id so any
+ * partition of the envs over GPUs reproduces the same per-env trajectories.                                   */
+typedef struct rb_env rb_env;
+int rb_env_create(rb_env** out, int64_t num_envs, uint64_t seed, int device, uint32_t global_env_offset);
+int rb_env_destroy(rb_env* env);
+int64_t rb_env_num_envs(const rb_env* env);
+
+/* env.reset()  src/distilation/mlp_train.py:112 -- all envs to episode 0 of their Philox stream; obs_dev[N,11] */
+int rb_env_reset(rb_env* env, float* obs_dev, void* stream);
+/* env.step(a)  src/distilation/mlp_train.py:135,196 ; lstm_train.py:133,192
+ * act_dev[N,2] -> obs_dev[N,11], rew_dev[N], done_dev[N] (1 at the 50th step).  Finished envs are auto-reset and
+ * return their reset observation (the reference caller does `if new: ob = env.reset()`, mlp_train.py:137-139).   */
+int rb_env_step(rb_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream);
+/* same calls with HOST buffers (copies + synchronise inside) -- the gym-style surface for a host-resident caller */
+int rb_env_reset_host(rb_env* env, float* obs_host);
+int rb_env_step_host(rb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host);
+
+/* explicit state access (parity tests start device and oracle from identical states):
+ * qpos_dev[N,2], qvel_dev[N,2], target_dev[N,2], fingertip_dev[N,2] (MuJoCo's stale xpos), step_dev[N] int32,
+ * episode_dev[N] uint32.  Any pointer may be NULL.  set: fingertip NULL => recomputed by forward kinematics.      */
+int rb_env_get_state(rb_env* env, float* qpos_dev, float* qvel_dev, float* target_dev, float* fingertip_dev,
+                     int32_t* step_dev, uint32_t* episode_dev, void* stream);
+int rb_env_set_state(rb_env* env, const float* qpos_dev, const float* qvel_dev, const float* target_dev,
+                     const float* fingertip_dev, const int32_t* step_dev, const uint32_t* episode_dev, void* stream);
+/* current observation of every env (no stepping) */
+int rb_env_observe(rb_env* env, float* obs_dev, void* stream);
+
+/* Fused T-step rollout with Philox random actions a~U(-1,1)^2 keyed (seed, global env, step0+t)
+ * (BASELINE.json config 2).  State stays in registers for all T steps.  Buffers (any may be NULL):
+ * obs_buf_dev[T,N,11] = observation AFTER step t, act_buf_dev[T,N,2], rew_buf_dev[T,N], done_buf_dev[T,N].        */
+int rb_env_rollout_random(rb_env* env, int T, uint32_t step0, float* obs_buf_dev, float* act_buf_dev, float* rew_buf_dev,
+                          uint8_t* done_buf_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ policy -
+ * baselines MlpPolicy 11 -> 64 tanh -> 64 tanh -> nout, obfilter z = clip((ob-mean)/std, +-5).
+ * params (fp32, flat, rb_policy_param_count(nout) floats):
+ *   ob_mean[11] ob_std[11] W1[11][64] b1[64] W2[64][64] b2[64] W3[64][nout] b3[nout] logstd[2]
+ * nout = 2: teacher (teacher.py:12-16), pdflat = (mean, logstd).  nout = 4: student a5' (all four from the net). */
+int64_t rb_policy_param_count(int nout);
+/* sess.run((pi.pd.mean, pi.pd.flat))  src/distilation/mlp_train.py:123-125,165-167 ; obs_dev[n,11] -> pdflat_dev[n,4] */
+int rb_policy_fwd(const float* params_dev, int nout, const float* obs_dev, int64_t n, float* pdflat_dev, int mode,
+                  void* stream);
+int rb_policy_fwd_host(const float* params_host, int nout, const float* obs_host, int64_t n, float* pdflat_host, int mode,
+                       int device);
+
+/* Teacher warm-up / replay loop  src/distilation/mlp_train.py:120-139 (and teacher_replay, backup/student_rollout.py:93-120)
+ * fused on the device: for t in [0,T): record ob_t, pdflat_t = policy(ob_t); step with the pd mean; record reward, done.
+ * Rollout buffer (device resident, any pointer may be NULL):
+ *   obs_buf_dev[T,N,11]  observation the policy saw at step t      pd_buf_dev[T,N,4]  its pdflat
+ *   rew_buf_dev[T,N]     reward returned by that step              done_buf_dev[T,N]  1 when that step ended the episode */
+int rb_env_rollout_policy(rb_env* env, const float* params_dev, int nout, int T, float* obs_buf_dev, float* pd_buf_dev,
+                          float* rew_buf_dev, uint8_t* done_buf_dev, int mode, void* stream);
+/* host-buffer variant: params_host in, the four buffers out (pinned or pageable host memory), synchronises */
+int rb_env_rollout_policy_host(rb_env* env, const float* params_host, int nout, int T, float* obs_buf_host, float* pd_buf_host,
+                               float* rew_buf_host, uint8_t* done_buf_host, int mode);
+
+/* ------------------------------------------------------------------------------------------------ student -
+ * Flat parameter layout: POLICY64 = the nout=4 policy layout above; MLP = for each layer W[in][out] then b[out],
+ * layers 16-24-128-128-32-4.                                                                                 */
+int64_t rb_student_param_count(int kind);
+int rb_student_input_dim(int kind);
+int64_t rb_student_workspace_bytes(int kind, int64_t batch, int device);
+
+/* Student input assembly  src/distilation/mlp_train.py:50-52: x[B,16] = concat(dropout(ob, keep_prob), prev_pdflat, prev_rew)
+ * dropout mask = floor(keep_prob + u), u Philox keyed (seed, sample_id0 + row, iteration); keep_prob >= 1: no dropout. */
+int rb_student_mlp_input(const float* obs_dev, const float* prev_pdflat_dev, const float* prev_rew_dev, int64_t B,
+                         float keep_prob, uint64_t seed, uint32_t sample_id0, uint32_t iteration, float* x_dev, void* stream);
+
+/* sess.run(s_pdflat)  src/distilation/mlp_train.py:173-186 -- forward only.  x_dev[B,in] -> s_pdflat_dev[B,4] */
+int rb_student_fwd(int kind, const float* params_dev, const float* x_dev, int64_t B, float* s_pdflat_dev, int mode, void* stream);
+
+/* sess.run([loss, minimize_adam]) minus the Adam update  src/distilation/mlp_train.py:148-161 ;
+ * lossandgrad  backup/student_rollout.py:646,708.
+ * Forward + backward of the student with the loss (loss.py:3-13) and dL/dpdflat fused.
+ *   gradloss_dev[P+1]: flat gradient (same layout as params) followed by the summed loss -> ONE all-reduce carries both.
+ *   s_pdflat_dev[B,4] (may be NULL): student output (its mean half is the DAgger action).
+ *   workspace_dev: rb_student_workspace_bytes() bytes.  Deterministic: fixed reduction order, no atomics.          */
+int rb_student_loss_grad(int kind, const float* params_dev, const float* x_dev, const float* t_pdflat_dev, int64_t B,
+                         int loss_kind, float* s_pdflat_dev, float* gradloss_dev, void* workspace_dev, int mode, void* stream);
+
+/* adam.minimize  src/distilation/mlp_train.py:75-80 ; MpiAdam.update  backup/student_rollout.py:658,709
+ * TF1 form: lr_t = lr*sqrt(1-b2^t)/(1-b1^t); m,v EMA; p -= lr_t*m/(sqrt(v)+eps).  grad is multiplied by grad_scale first
+ * (1/world_size reproduces MpiAdam's averaged gradient).  step_t is 1-based.                                      */
+int rb_adam_step(float* params_dev, float* m_dev, float* v_dev, const float* grad_dev, int64_t P, int64_t step_t, float lr,
+                 float beta1, float beta2, float eps, float grad_scale, void* stream);
+
+/* ------------------------------------------------------------------------------------------------ DAgger --
+ * One lock-step DAgger iteration pieces (src/distilation/mlp_train.py:143-204 batched):
+ * rb_dagger_observe: for every env write ob[N,11], teacher label t_pdflat[N,4] and the student input x[N,in]
+ *   (POLICY64: x = ob; MLP: x = [dropout(ob), prev teacher pdflat, prev recorded reward], dataset.py:118-143 semantics,
+ *   zeros at the first step of an episode).
+ * rb_dagger_act: step every env with the mean half of s_pdflat[N,4]; records rew[N], done[N]; keeps prev-pdflat / prev-rew. */
+typedef struct rb_dagger rb_dagger;
+int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_prob);
+int rb_dagger_destroy(rb_dagger* d);
+int rb_dagger_observe(rb_dagger* d, const float* teacher_params_dev, uint32_t iteration, float* obs_dev, float* t_pdflat_dev,
+                      float* x_dev, int mode, void* stream);
+int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
+                  void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REACHER_B200_H */

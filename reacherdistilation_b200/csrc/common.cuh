@@ -1,0 +1,96 @@
+// Shared helpers: error handling, warp-staged row I/O (coalesced [N,11] / [N,4] rows), policy parameter layout.
+#pragma once
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+
+#include "../../include/reacher_b200.h"
+
+struct rb_env {
+    int64_t n = 0;
+    uint64_t seed = 0;
+    int device = 0;
+    uint32_t offset = 0;
+    float4* qv = nullptr;
+    float4* tp = nullptr;
+    uint2* ctr = nullptr;
+    // staging for the *_host entry points
+    float* d_act = nullptr; float* d_obs = nullptr; float* d_rew = nullptr; uint8_t* d_done = nullptr;
+    float* d_params = nullptr;
+    float* d_buf_obs = nullptr; float* d_buf_pd = nullptr; float* d_buf_rew = nullptr; uint8_t* d_buf_done = nullptr;
+    int64_t buf_T = 0;
+    cudaStream_t host_stream = nullptr;
+    int sm_count = 148;
+};
+
+namespace rb {
+
+void set_error(const char* fmt, ...);
+int cuda_fail(cudaError_t e, const char* what);
+
+#define RB_CUDA(call)                                             \
+    do {                                                          \
+        cudaError_t e__ = (call);                                 \
+        if (e__ != cudaSuccess) return rb::cuda_fail(e__, #call); \
+    } while (0)
+#define RB_REQUIRE(cond, msg)                        \
+    do {                                             \
+        if (!(cond)) {                               \
+            rb::set_error("%s: %s", __func__, msg);  \
+            return RB_ERR_INVALID;                   \
+        }                                            \
+    } while (0)
+
+constexpr int OBS = RB_OBS_DIM;
+constexpr int HID = 64;
+
+// Warp-staged store of W floats per lane to a row-major [rows, W] global array: lanes write their row into a
+// warp-private smem strip (stride W, conflict-free for odd W), then the warp streams the 32*W contiguous floats out
+// with 128-bit coalesced stores.  row0 = global row of lane 0; nvalid = rows of this warp that exist (<= 32).
+// Falls back to scalar stores when the destination strip is not 16-byte aligned.
+template <int W>
+__device__ __forceinline__ void warp_store_rows(float* __restrict__ g, int64_t row0, int nvalid, const float* vals,
+                                                float* strip, int lane) {
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) strip[lane * W + k] = vals[k];
+    __syncwarp();
+    float* dst = g + row0 * W;
+    const int total = nvalid * W;
+    const int n4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (total >> 2) : 0;
+    const float4* s4 = reinterpret_cast<const float4*>(strip);
+    float4* d4 = reinterpret_cast<float4*>(dst);
+    for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
+    for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = strip[i];
+}
+
+template <int W>
+__device__ __forceinline__ void warp_load_rows(const float* __restrict__ g, int64_t row0, int nvalid, float* vals, float* strip,
+                                               int lane) {
+    __syncwarp();
+    const float* src = g + row0 * W;
+    const int total = nvalid * W;
+    const int n4 = ((reinterpret_cast<uintptr_t>(src) & 15) == 0) ? (total >> 2) : 0;
+    float4* s4 = reinterpret_cast<float4*>(strip);
+    const float4* g4 = reinterpret_cast<const float4*>(src);
+    for (int i = lane; i < n4; i += 32) s4[i] = __ldg(g4 + i);
+    for (int i = (n4 << 2) + lane; i < total; i += 32) strip[i] = __ldg(src + i);
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < W; ++k) vals[k] = lane < nvalid ? strip[lane * W + k] : 0.f;
+}
+
+// ---- policy parameters (MlpPolicy 11-64-64-nout) ------------------------------------------------------------
+// global flat layout (include/reacher_b200.h): ob_mean[11] ob_std[11] W1[11][64] b1[64] W2[64][64] b2[64] W3[64][nout]
+// b3[nout] logstd[2]
+struct PolicyOffsets {
+    int mu, sd, W1, b1, W2, b2, W3, b3, logstd, total;
+};
+__host__ __device__ inline PolicyOffsets policy_offsets(int nout) {
+    PolicyOffsets o;
+    o.mu = 0; o.sd = 11; o.W1 = 22; o.b1 = o.W1 + 11 * HID; o.W2 = o.b1 + HID; o.b2 = o.W2 + HID * HID; o.W3 = o.b2 + HID;
+    o.b3 = o.W3 + HID * nout; o.logstd = o.b3 + nout; o.total = o.logstd + 2;
+    return o;
+}
+
+}  // namespace rb

@@ -1,0 +1,428 @@
+// Lock-step Reacher-v2 environments on the device: reset / step / observe / fused multi-step rollouts.
+// Replaces the gym env calls of the reference loops (/root/reference src/distilation/mlp_train.py:21,112,135,138,196,200;
+// lstm_train.py:21,111,133,136,192,196) -- see include/reacher_b200.h for the per-entry-point mapping.
+//
+// HBM layout (one env per thread, 128-bit coalesced state I/O):
+//   qv  float4[N] = (q0, q1, v0, v1)       tp  float4[N] = (tx, ty, px, py)      ctr uint2[N] = (step, episode)
+// Observation rows ([N,11] fp32, 44 B) are staged through a warp-private shared-memory strip so that the global
+// stores are 128-bit and contiguous.
+#include "common.cuh"
+#include "physics.cuh"
+#include "policy_simt.cuh"
+
+namespace rb {
+
+constexpr int ENV_BLOCK = 128;
+
+__device__ __forceinline__ EnvState<float> load_state(const float4* qv, const float4* tp, const uint2* ctr, int64_t i) {
+    const float4 a = qv[i], b = tp[i];
+    const uint2 c = ctr[i];
+    EnvState<float> e;
+    e.q0 = a.x; e.q1 = a.y; e.v0 = a.z; e.v1 = a.w; e.tx = b.x; e.ty = b.y; e.px = b.z; e.py = b.w;
+    e.step = (int)c.x; e.episode = c.y;
+    return e;
+}
+__device__ __forceinline__ void store_state(float4* qv, float4* tp, uint2* ctr, int64_t i, const EnvState<float>& e) {
+    qv[i] = make_float4(e.q0, e.q1, e.v0, e.v1);
+    tp[i] = make_float4(e.tx, e.ty, e.px, e.py);
+    ctr[i] = make_uint2((uint32_t)e.step, e.episode);
+}
+
+__global__ void __launch_bounds__(ENV_BLOCK) k_reset(int64_t n, float4* qv, float4* tp, uint2* ctr, float* obs, uint32_t k0,
+                                                     uint32_t k1, uint32_t offset) {
+    __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
+    const int64_t row0 = i - lane;
+    if (row0 >= n) return;
+    const int nvalid = (int)min((int64_t)32, n - row0);
+    float ob[OBS];
+    if (i < n) {
+        EnvState<float> e;
+        e.episode = 0u;
+        reset_env(e, k0, k1, offset + (uint32_t)i);
+        store_state(qv, tp, ctr, i, e);
+        observe(e, ob);
+    }
+    if (obs) warp_store_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
+}
+
+__global__ void __launch_bounds__(ENV_BLOCK) k_observe(int64_t n, const float4* qv, const float4* tp, const uint2* ctr, float* obs) {
+    __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
+    const int64_t row0 = i - lane;
+    if (row0 >= n) return;
+    const int nvalid = (int)min((int64_t)32, n - row0);
+    float ob[OBS];
+    if (i < n) { const EnvState<float> e = load_state(qv, tp, ctr, i); observe(e, ob); }
+    warp_store_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
+}
+
+// env.step: the single-step API kernel (HBM-bound: 113 algorithmic bytes per env-step)
+__global__ void __launch_bounds__(ENV_BLOCK) k_step(int64_t n, float4* __restrict__ qv, float4* __restrict__ tp, uint2* __restrict__ ctr,
+                                                    const float2* __restrict__ act, float* __restrict__ obs, float* __restrict__ rew,
+                                                    uint8_t* __restrict__ done, uint32_t k0, uint32_t k1, uint32_t offset) {
+    __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
+    const int64_t row0 = i - lane;
+    if (row0 >= n) return;
+    const int nvalid = (int)min((int64_t)32, n - row0);
+    float ob[OBS];
+    if (i < n) {
+        EnvState<float> e = load_state(qv, tp, ctr, i);
+        const float2 a = __ldg(act + i);
+        bool d;
+        const float r = step_env(e, a.x, a.y, k0, k1, offset + (uint32_t)i, d);
+        store_state(qv, tp, ctr, i, e);
+        if (rew) rew[i] = r;
+        if (done) done[i] = d ? 1 : 0;
+        observe(e, ob);
+    }
+    if (obs) warp_store_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
+}
+
+__global__ void k_get_state(int64_t n, const float4* qv, const float4* tp, const uint2* ctr, float2* qpos, float2* qvel,
+                            float2* target, float2* tip, int32_t* step, uint32_t* episode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 a = qv[i], b = tp[i];
+    const uint2 c = ctr[i];
+    if (qpos) qpos[i] = make_float2(a.x, a.y);
+    if (qvel) qvel[i] = make_float2(a.z, a.w);
+    if (target) target[i] = make_float2(b.x, b.y);
+    if (tip) tip[i] = make_float2(b.z, b.w);
+    if (step) step[i] = (int32_t)c.x;
+    if (episode) episode[i] = c.y;
+}
+__global__ void k_set_state(int64_t n, float4* qv, float4* tp, uint2* ctr, const float2* qpos, const float2* qvel,
+                            const float2* target, const float2* tip, const int32_t* step, const uint32_t* episode) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float4 a = qv[i], b = tp[i];
+    uint2 c = ctr[i];
+    if (qpos) { const float2 v = qpos[i]; a.x = v.x; a.y = v.y; }
+    if (qvel) { const float2 v = qvel[i]; a.z = v.x; a.w = v.y; }
+    if (target) { const float2 v = target[i]; b.x = v.x; b.y = v.y; }
+    if (tip) { const float2 v = tip[i]; b.z = v.x; b.w = v.y; }
+    else if (qpos) fk(a.x, a.y, b.z, b.w);
+    if (step) c.x = (uint32_t)step[i];
+    if (episode) c.y = episode[i];
+    qv[i] = a; tp[i] = b; ctr[i] = c;
+}
+
+// Fused T-step rollout with Philox random actions: state lives in registers for all T steps (FP32-pipe bound).
+__global__ void __launch_bounds__(ENV_BLOCK) k_rollout_random(int64_t n, float4* qv, float4* tp, uint2* ctr, int T, uint32_t step0,
+                                                              float* __restrict__ obs_buf, float2* __restrict__ act_buf,
+                                                              float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf,
+                                                              uint32_t k0, uint32_t k1, uint32_t offset) {
+    __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
+    const int64_t row0 = i - lane;
+    if (row0 >= n) return;
+    const int nvalid = (int)min((int64_t)32, n - row0);
+    const bool valid = i < n;
+    const uint32_t gid = offset + (uint32_t)i;
+    EnvState<float> e;
+    if (valid) e = load_state(qv, tp, ctr, i);
+    else { e.q0 = e.q1 = e.v0 = e.v1 = e.tx = e.ty = e.px = e.py = 0.f; e.step = 0; e.episode = 0; }
+    for (int t = 0; t < T; ++t) {
+        const uint4 r = philox4x32_10(gid, step0 + (uint32_t)t, 0u, STREAM_ACTION, k0, k1);
+        const float a0 = uniform_f32(r.x, -1.f, 1.f), a1 = uniform_f32(r.y, -1.f, 1.f);
+        bool d;
+        const float rw = step_env(e, a0, a1, k0, k1, gid, d);
+        const int64_t row = (int64_t)t * n + i;
+        if (valid) {
+            if (act_buf) act_buf[row] = make_float2(a0, a1);
+            if (rew_buf) rew_buf[row] = rw;
+            if (done_buf) done_buf[row] = d ? 1 : 0;
+        }
+        if (obs_buf) {
+            float ob[OBS];
+            observe(e, ob);
+            warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strips[warp], lane);
+        }
+    }
+    if (valid) store_state(qv, tp, ctr, i, e);
+}
+
+// Standalone policy forward (one thread per sample)
+template <int NOUT>
+__global__ void __launch_bounds__(ENV_BLOCK) k_policy_fwd_fp32(const float* __restrict__ params, const float* __restrict__ obs,
+                                                               int64_t n, float4* __restrict__ pd) {
+    __shared__ PolicySmem S;
+    __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
+    policy_load_smem(S, params, NOUT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int64_t base = (int64_t)blockIdx.x * ENV_BLOCK; base < n; base += (int64_t)gridDim.x * ENV_BLOCK) {
+        const int64_t i = base + threadIdx.x;
+        const int64_t row0 = i - lane;
+        if (row0 >= n) continue;
+        const int nvalid = (int)min((int64_t)32, n - row0);
+        float ob[OBS], o[4];
+        warp_load_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
+        policy_fwd_simt<NOUT>(S, ob, o);
+        if (i < n) pd[i] = make_float4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+// Fused policy-in-the-loop rollout (teacher warm-up loop, mlp_train.py:120-139), fp32 CUDA-core policy.
+template <int NOUT>
+__global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
+                                                                   int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
+                                                                   float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf,
+                                                                   uint32_t k0, uint32_t k1, uint32_t offset) {
+    __shared__ PolicySmem S;
+    __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
+    policy_load_smem(S, params, NOUT);
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
+    const int64_t row0 = i - lane;
+    if (row0 >= n) return;
+    const int nvalid = (int)min((int64_t)32, n - row0);
+    const bool valid = i < n;
+    const uint32_t gid = offset + (uint32_t)i;
+    EnvState<float> e;
+    if (valid) e = load_state(qv, tp, ctr, i);
+    else { e.q0 = e.q1 = e.v0 = e.v1 = e.tx = e.ty = e.px = e.py = 0.f; e.step = 0; e.episode = 0; }
+    for (int t = 0; t < T; ++t) {
+        float ob[OBS], pd[4];
+        observe(e, ob);
+        policy_fwd_simt<NOUT>(S, ob, pd);
+        bool d;
+        const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
+        const int64_t row = (int64_t)t * n + i;
+        if (valid) {
+            if (pd_buf) pd_buf[row] = make_float4(pd[0], pd[1], pd[2], pd[3]);
+            if (rew_buf) rew_buf[row] = rw;
+            if (done_buf) done_buf[row] = d ? 1 : 0;
+        }
+        if (obs_buf) warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strips[warp], lane);
+    }
+    if (valid) store_state(qv, tp, ctr, i, e);
+}
+
+inline unsigned env_grid(int64_t n) { return (unsigned)((n + ENV_BLOCK - 1) / ENV_BLOCK); }
+
+// implemented in policy_tc.cu
+int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, float* pd, cudaStream_t s);
+int rollout_policy_tc(rb_env* env, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf,
+                      uint8_t* done_buf, cudaStream_t s);
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" {
+
+int rb_env_create(rb_env** out, int64_t num_envs, uint64_t seed, int device, uint32_t global_env_offset) {
+    RB_REQUIRE(out != nullptr, "out is NULL");
+    RB_REQUIRE(num_envs > 0 && num_envs <= (int64_t)1 << 31, "num_envs out of range");
+    RB_REQUIRE((uint64_t)global_env_offset + (uint64_t)num_envs <= (uint64_t)1 << 32, "global env id overflows 32 bits");
+    RB_CUDA(cudaSetDevice(device));
+    rb_env* e = new rb_env();
+    e->n = num_envs; e->seed = seed; e->device = device; e->offset = global_env_offset;
+    cudaError_t err = cudaMalloc(&e->qv, sizeof(float4) * num_envs);
+    if (err == cudaSuccess) err = cudaMalloc(&e->tp, sizeof(float4) * num_envs);
+    if (err == cudaSuccess) err = cudaMalloc(&e->ctr, sizeof(uint2) * num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->qv, 0, sizeof(float4) * num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->tp, 0, sizeof(float4) * num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->ctr, 0, sizeof(uint2) * num_envs);
+    cudaDeviceProp prop;
+    if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, device);
+    if (err != cudaSuccess) { rb_env_destroy(e); return cuda_fail(err, "rb_env_create"); }
+    e->sm_count = prop.multiProcessorCount;
+    *out = e;
+    return RB_OK;
+}
+
+int rb_env_destroy(rb_env* e) {
+    if (!e) return RB_OK;
+    cudaSetDevice(e->device);
+    cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
+    cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
+    cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
+    if (e->host_stream) cudaStreamDestroy(e->host_stream);
+    delete e;
+    return RB_OK;
+}
+
+int64_t rb_env_num_envs(const rb_env* e) { return e ? e->n : 0; }
+
+int rb_env_reset(rb_env* e, float* obs_dev, void* stream) {
+    RB_REQUIRE(e != nullptr, "env is NULL");
+    k_reset<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, obs_dev, (uint32_t)e->seed,
+                                                                    (uint32_t)(e->seed >> 32), e->offset);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_env_observe(rb_env* e, float* obs_dev, void* stream) {
+    RB_REQUIRE(e != nullptr && obs_dev != nullptr, "NULL argument");
+    k_observe<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, obs_dev);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_env_step(rb_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream) {
+    RB_REQUIRE(e != nullptr && act_dev != nullptr, "NULL argument");
+    k_step<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float2*)act_dev, obs_dev, rew_dev,
+                                                                   done_dev, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+static int ensure_host_staging(rb_env* e) {
+    if (e->d_act) return RB_OK;
+    RB_CUDA(cudaSetDevice(e->device));
+    RB_CUDA(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+    RB_CUDA(cudaMalloc(&e->d_act, sizeof(float) * 2 * e->n));
+    RB_CUDA(cudaMalloc(&e->d_obs, sizeof(float) * OBS * e->n));
+    RB_CUDA(cudaMalloc(&e->d_rew, sizeof(float) * e->n));
+    RB_CUDA(cudaMalloc(&e->d_done, e->n));
+    RB_CUDA(cudaMalloc(&e->d_params, sizeof(float) * rb_policy_param_count(4)));
+    return RB_OK;
+}
+
+int rb_env_reset_host(rb_env* e, float* obs_host) {
+    RB_REQUIRE(e != nullptr && obs_host != nullptr, "NULL argument");
+    int rc = ensure_host_staging(e);
+    if (rc) return rc;
+    rc = rb_env_reset(e, e->d_obs, e->host_stream);
+    if (rc) return rc;
+    RB_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, sizeof(float) * OBS * e->n, cudaMemcpyDeviceToHost, e->host_stream));
+    RB_CUDA(cudaStreamSynchronize(e->host_stream));
+    return RB_OK;
+}
+
+int rb_env_step_host(rb_env* e, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host) {
+    RB_REQUIRE(e != nullptr && act_host != nullptr && obs_host != nullptr, "NULL argument");
+    int rc = ensure_host_staging(e);
+    if (rc) return rc;
+    cudaStream_t s = e->host_stream;
+    RB_CUDA(cudaMemcpyAsync(e->d_act, act_host, sizeof(float) * 2 * e->n, cudaMemcpyHostToDevice, s));
+    rc = rb_env_step(e, e->d_act, e->d_obs, e->d_rew, e->d_done, s);
+    if (rc) return rc;
+    RB_CUDA(cudaMemcpyAsync(obs_host, e->d_obs, sizeof(float) * OBS * e->n, cudaMemcpyDeviceToHost, s));
+    if (rew_host) RB_CUDA(cudaMemcpyAsync(rew_host, e->d_rew, sizeof(float) * e->n, cudaMemcpyDeviceToHost, s));
+    if (done_host) RB_CUDA(cudaMemcpyAsync(done_host, e->d_done, e->n, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(cudaStreamSynchronize(s));
+    return RB_OK;
+}
+
+int rb_env_get_state(rb_env* e, float* qpos, float* qvel, float* target, float* tip, int32_t* step, uint32_t* episode, void* stream) {
+    RB_REQUIRE(e != nullptr, "env is NULL");
+    k_get_state<<<(unsigned)((e->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (float2*)qpos, (float2*)qvel,
+                                                                                 (float2*)target, (float2*)tip, step, episode);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_env_set_state(rb_env* e, const float* qpos, const float* qvel, const float* target, const float* tip, const int32_t* step,
+                     const uint32_t* episode, void* stream) {
+    RB_REQUIRE(e != nullptr, "env is NULL");
+    k_set_state<<<(unsigned)((e->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float2*)qpos,
+                                                                                 (const float2*)qvel, (const float2*)target,
+                                                                                 (const float2*)tip, step, episode);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_env_rollout_random(rb_env* e, int T, uint32_t step0, float* obs_buf, float* act_buf, float* rew_buf, uint8_t* done_buf, void* stream) {
+    RB_REQUIRE(e != nullptr && T >= 0, "bad argument");
+    if (T == 0) return RB_OK;
+    k_rollout_random<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, T, step0, obs_buf, (float2*)act_buf,
+                                                                             rew_buf, done_buf, (uint32_t)e->seed,
+                                                                             (uint32_t)(e->seed >> 32), e->offset);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int64_t rb_policy_param_count(int nout) { return (nout == 2 || nout == 4) ? policy_offsets(nout).total : -1; }
+
+int rb_policy_fwd(const float* params, int nout, const float* obs, int64_t n, float* pd, int mode, void* stream) {
+    RB_REQUIRE(params && obs && pd, "NULL argument");
+    RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
+    RB_REQUIRE(n >= 0, "n < 0");
+    if (n == 0) return RB_OK;
+    if (mode == RB_MODE_TC) return policy_fwd_tc(params, nout, obs, n, pd, (cudaStream_t)stream);
+    RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
+    const unsigned grid = (unsigned)min((int64_t)148 * 8, (n + ENV_BLOCK - 1) / ENV_BLOCK);
+    if (nout == 2) k_policy_fwd_fp32<2><<<grid, ENV_BLOCK, 0, (cudaStream_t)stream>>>(params, obs, n, (float4*)pd);
+    else k_policy_fwd_fp32<4><<<grid, ENV_BLOCK, 0, (cudaStream_t)stream>>>(params, obs, n, (float4*)pd);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_policy_fwd_host(const float* params_host, int nout, const float* obs_host, int64_t n, float* pd_host, int mode, int device) {
+    RB_REQUIRE(params_host && obs_host && pd_host, "NULL argument");
+    RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
+    RB_CUDA(cudaSetDevice(device));
+    float *dp = nullptr, *dob = nullptr, *dpd = nullptr;
+    const int64_t P = rb_policy_param_count(nout);
+    RB_CUDA(cudaMalloc(&dp, sizeof(float) * P));
+    RB_CUDA(cudaMalloc(&dob, sizeof(float) * OBS * (n > 0 ? n : 1)));
+    RB_CUDA(cudaMalloc(&dpd, sizeof(float) * 4 * (n > 0 ? n : 1)));
+    int rc = RB_OK;
+    cudaError_t err = cudaMemcpy(dp, params_host, sizeof(float) * P, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) err = cudaMemcpy(dob, obs_host, sizeof(float) * OBS * n, cudaMemcpyHostToDevice);
+    if (err == cudaSuccess) rc = rb_policy_fwd(dp, nout, dob, n, dpd, mode, nullptr);
+    if (err == cudaSuccess && rc == RB_OK) err = cudaMemcpy(pd_host, dpd, sizeof(float) * 4 * n, cudaMemcpyDeviceToHost);
+    cudaFree(dp); cudaFree(dob); cudaFree(dpd);
+    if (err != cudaSuccess) return cuda_fail(err, "rb_policy_fwd_host");
+    return rc;
+}
+
+int rb_env_rollout_policy(rb_env* e, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf,
+                          uint8_t* done_buf, int mode, void* stream) {
+    RB_REQUIRE(e != nullptr && params != nullptr && T >= 0, "bad argument");
+    RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
+    if (T == 0) return RB_OK;
+    if (mode == RB_MODE_TC) return rollout_policy_tc(e, params, nout, T, obs_buf, pd_buf, rew_buf, done_buf, (cudaStream_t)stream);
+    RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
+    const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+    if (nout == 2)
+        k_rollout_policy_fp32<2><<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf,
+                                                                                         (float4*)pd_buf, rew_buf, done_buf, k0, k1, e->offset);
+    else
+        k_rollout_policy_fp32<4><<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf,
+                                                                                         (float4*)pd_buf, rew_buf, done_buf, k0, k1, e->offset);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
+                               uint8_t* done_host, int mode) {
+    RB_REQUIRE(e != nullptr && params_host != nullptr && T > 0, "bad argument");
+    RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
+    int rc = ensure_host_staging(e);
+    if (rc) return rc;
+    if (e->buf_T < T) {
+        cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
+        e->d_buf_obs = e->d_buf_pd = e->d_buf_rew = nullptr; e->d_buf_done = nullptr; e->buf_T = 0;
+        const int64_t rows = (int64_t)T * e->n;
+        RB_CUDA(cudaMalloc(&e->d_buf_obs, sizeof(float) * OBS * rows));
+        RB_CUDA(cudaMalloc(&e->d_buf_pd, sizeof(float) * 4 * rows));
+        RB_CUDA(cudaMalloc(&e->d_buf_rew, sizeof(float) * rows));
+        RB_CUDA(cudaMalloc(&e->d_buf_done, rows));
+        e->buf_T = T;
+    }
+    cudaStream_t s = e->host_stream;
+    const int64_t rows = (int64_t)T * e->n;
+    RB_CUDA(cudaMemcpyAsync(e->d_params, params_host, sizeof(float) * rb_policy_param_count(nout), cudaMemcpyHostToDevice, s));
+    rc = rb_env_rollout_policy(e, e->d_params, nout, T, obs_host ? e->d_buf_obs : nullptr, pd_host ? e->d_buf_pd : nullptr,
+                               rew_host ? e->d_buf_rew : nullptr, done_host ? e->d_buf_done : nullptr, mode, s);
+    if (rc) return rc;
+    if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host, e->d_buf_obs, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, s));
+    if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host, e->d_buf_pd, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, s));
+    if (rew_host) RB_CUDA(cudaMemcpyAsync(rew_host, e->d_buf_rew, sizeof(float) * rows, cudaMemcpyDeviceToHost, s));
+    if (done_host) RB_CUDA(cudaMemcpyAsync(done_host, e->d_buf_done, rows, cudaMemcpyDeviceToHost, s));
+    RB_CUDA(cudaStreamSynchronize(s));
+    return RB_OK;
+}
+
+}  // extern "C"

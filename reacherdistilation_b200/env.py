@@ -1,0 +1,147 @@
+"""Gym-style surface over the device-resident lock-step Reacher-v2 environments.
+
+Mirrors what the reference uses of its env object (/root/reference src/distilation/mlp_train.py:21,33,112,135; teacher.py:15,37):
+reset() -> ob, step(a) -> (ob, reward, done, info), observation_space.shape == (11,), action_space a 2-d Box in [-1,1], close().
+Batched generalisation: leading dim N on every tensor, done[N], finished envs auto-reset and return their reset observation.
+Returned tensors are views of buffers owned by the env, valid until the next step()/reset().
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, lib, ptr, stream_ptr
+
+
+class Box:
+    def __init__(self, low, high, shape):
+        self.low = np.full(shape, low, dtype=np.float32)
+        self.high = np.full(shape, high, dtype=np.float32)
+        self.shape = tuple(shape)
+        self.dtype = np.float32
+
+
+class VecReacher:
+    """N Reacher-v2 environments on one B200.  host=True gives the numpy-in / numpy-out surface (copies inside the call)."""
+
+    def __init__(self, num_envs=1, seed=0, device=0, env_offset=0, host=False, squeeze=False):
+        import ctypes as C
+        if not torch.cuda.is_available():
+            raise _lib.ReacherB200Error("reacherdistilation_b200 needs a CUDA device (there is no CPU path)")
+        self.num_envs, self.seed, self.env_offset = int(num_envs), int(seed), int(env_offset)
+        self.device = torch.device("cuda", device if isinstance(device, int) else torch.device(device).index or 0)
+        self.host, self.squeeze = host, squeeze and num_envs == 1
+        self.observation_space = Box(-np.inf, np.inf, (11,))
+        self.action_space = Box(-1.0, 1.0, (2,))
+        h = C.c_void_p()
+        check(lib().rb_env_create(C.byref(h), self.num_envs, self.seed, self.device.index, self.env_offset))
+        self._h = h
+        n = self.num_envs
+        if host:
+            self._obs = torch.empty((n, 11), dtype=torch.float32).pin_memory()
+            self._rew = torch.empty((n,), dtype=torch.float32).pin_memory()
+            self._done = torch.empty((n,), dtype=torch.uint8).pin_memory()
+            self._act = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+        else:
+            with torch.cuda.device(self.device):
+                self._obs = torch.empty((n, 11), dtype=torch.float32, device=self.device)
+                self._rew = torch.empty((n,), dtype=torch.float32, device=self.device)
+                self._done = torch.empty((n,), dtype=torch.uint8, device=self.device)
+
+    # ---- gym protocol --------------------------------------------------------------------------------------
+    def reset(self):
+        if self.host:
+            check(lib().rb_env_reset_host(self._h, ptr(self._obs)))
+            ob = self._obs.numpy()
+            return ob[0] if self.squeeze else ob
+        check(lib().rb_env_reset(self._h, ptr(self._obs), stream_ptr()))
+        return self._obs
+
+    def step(self, action):
+        n = self.num_envs
+        if self.host:
+            self._act.copy_(torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(n, 2)))
+            check(lib().rb_env_step_host(self._h, ptr(self._act), ptr(self._obs), ptr(self._rew), ptr(self._done)))
+            ob, rew, done = self._obs.numpy(), self._rew.numpy(), self._done.numpy().astype(bool)
+            if self.squeeze:
+                return ob[0], float(rew[0]), bool(done[0]), {}
+            return ob, rew, done, {}
+        a = action
+        assert a.is_cuda and a.dtype == torch.float32 and a.numel() == 2 * n, "action must be a float32 CUDA tensor [N,2]"
+        a = a.contiguous()
+        check(lib().rb_env_step(self._h, ptr(a), ptr(self._obs), ptr(self._rew), ptr(self._done), stream_ptr()))
+        return self._obs, self._rew, self._done, {}
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().rb_env_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def seed_(self, seed):
+        raise NotImplementedError("seed is fixed at construction (Philox key)")
+
+    # ---- device-side extras --------------------------------------------------------------------------------
+    def observe(self):
+        assert not self.host
+        check(lib().rb_env_observe(self._h, ptr(self._obs), stream_ptr()))
+        return self._obs
+
+    def get_state(self):
+        n, dev = self.num_envs, self.device
+        out = dict(qpos=torch.empty((n, 2), device=dev), qvel=torch.empty((n, 2), device=dev), target=torch.empty((n, 2), device=dev),
+                   fingertip=torch.empty((n, 2), device=dev), step=torch.empty((n,), dtype=torch.int32, device=dev),
+                   episode=torch.empty((n,), dtype=torch.int32, device=dev))
+        check(lib().rb_env_get_state(self._h, ptr(out["qpos"]), ptr(out["qvel"]), ptr(out["target"]), ptr(out["fingertip"]),
+                                     ptr(out["step"]), ptr(out["episode"]), stream_ptr()))
+        return out
+
+    def set_state(self, qpos=None, qvel=None, target=None, fingertip=None, step=None, episode=None):
+        def prep(t, dt):
+            return None if t is None else torch.as_tensor(t, dtype=dt).to(self.device).contiguous()
+        ts = [prep(qpos, torch.float32), prep(qvel, torch.float32), prep(target, torch.float32), prep(fingertip, torch.float32),
+              prep(step, torch.int32), prep(episode, torch.int32)]
+        check(lib().rb_env_set_state(self._h, *[ptr(t) for t in ts], stream_ptr()))
+        torch.cuda.current_stream().synchronize()   # keep the temporaries alive until the kernel has read them
+
+    def rollout_random(self, T, step0=0, record_obs=True, record_act=False):
+        """T fused steps with Philox U(-1,1) actions.  Returns dict of time-major device buffers."""
+        n, dev = self.num_envs, self.device
+        out = dict(obs=torch.empty((T, n, 11), device=dev) if record_obs else None,
+                   act=torch.empty((T, n, 2), device=dev) if record_act else None,
+                   rew=torch.empty((T, n), device=dev), done=torch.empty((T, n), dtype=torch.uint8, device=dev))
+        check(lib().rb_env_rollout_random(self._h, T, step0, ptr(out["obs"]), ptr(out["act"]), ptr(out["rew"]), ptr(out["done"]), stream_ptr()))
+        return out
+
+    def rollout_policy(self, params, T, nout=2, mode=_lib.MODE_FP32, out=None):
+        """Fused policy-in-the-loop rollout into a device-resident buffer (teacher warm-up, mlp_train.py:120-139)."""
+        n, dev = self.num_envs, self.device
+        if out is None:
+            out = dict(obs=torch.empty((T, n, 11), device=dev), pdflat=torch.empty((T, n, 4), device=dev),
+                       rew=torch.empty((T, n), device=dev), done=torch.empty((T, n), dtype=torch.uint8, device=dev))
+        check(lib().rb_env_rollout_policy(self._h, ptr(params), nout, T, ptr(out["obs"]), ptr(out["pdflat"]), ptr(out["rew"]),
+                                          ptr(out["done"]), mode, stream_ptr()))
+        return out
+
+    def rollout_policy_host(self, params_host, T, nout=2, mode=_lib.MODE_FP32, out=None):
+        """Same through HOST buffers (H2D of the parameters, D2H of the whole rollout buffer inside the call)."""
+        n = self.num_envs
+        if out is None:
+            out = dict(obs=torch.empty((T, n, 11)).pin_memory(), pdflat=torch.empty((T, n, 4)).pin_memory(),
+                       rew=torch.empty((T, n)).pin_memory(), done=torch.empty((T, n), dtype=torch.uint8).pin_memory())
+        check(lib().rb_env_rollout_policy_host(self._h, ptr(params_host), nout, T, ptr(out["obs"]), ptr(out["pdflat"]), ptr(out["rew"]),
+                                               ptr(out["done"]), mode))
+        return out
+
+
+def make_mujoco_env(env_id, seed, num_envs=1, device=0, rank=0, host=None):
+    """baselines.common.cmd_util.make_mujoco_env as the reference calls it (mlp_train.py:21): seed + 1000 * rank.
+    num_envs == 1 returns the host (numpy) surface of a single env, like gym; larger N returns device tensors."""
+    if env_id != "Reacher-v2":
+        raise ValueError("only Reacher-v2 is implemented (the reference uses nothing else)")
+    host = (num_envs == 1) if host is None else host
+    return VecReacher(num_envs=num_envs, seed=seed + 1000 * rank, device=device, host=host, squeeze=host)

@@ -1,0 +1,121 @@
+"""MLP distillation loop -- drop-in for /root/reference src/distilation/mlp_train.py:18-204 (`train(train, restore)`),
+and the batched variant backup/student_rollout.py:618-740 (`train_student`).
+
+The reference runs ONE env and one 200-sample optimiser step per env step, through three sess.run calls and Python list
+packing.  Here N lock-step envs live on the GPU; one DAgger iteration is
+    observe   ob_k, teacher label t_k = teacher(ob_k), student input x_k            (rb_dagger_observe)
+    loss/grad s_k = student(x_k); L = KL(s_k || t_k) summed; flat gradient          (rb_student_loss_grad)
+    exchange  one sum all-reduce of [grad, loss] across ranks (MpiAdam.update)      (NCCL, only if world_size > 1)
+    update    TF-form Adam                                                           (rb_adam_step)
+    act       env.step(mean(s_k)) -> reward, done; prev-pdflat / prev-reward shift   (rb_dagger_act)
+with no host round trip; the loss stays on the device until asked for.
+"""
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LOSS_KL_ST, MODE_FP32, STUDENT_MLP, check, lib, ptr, stream_ptr
+from .config import KEEP_PROB, MLP_BATCH_SIZE, NUM_ENVS, SEED, base_path
+from .env import VecReacher
+from .student_nn import StudentNet
+from .teacher import TeacherAgent
+
+
+class DaggerTrainer:
+    def __init__(self, num_envs=NUM_ENVS, seed=SEED, device=0, student_kind=STUDENT_MLP, keep_prob=KEEP_PROB, mode=MODE_FP32,
+                 teacher_params=None, teacher_seed=0, student_seed=1, env_offset=0, loss_kind=LOSS_KL_ST, lr=None, eps=None,
+                 process_group=None, average_grads=False, student_params=None):
+        import ctypes as C
+        self.env = VecReacher(num_envs=num_envs, seed=seed, device=device, env_offset=env_offset)
+        self.device = self.env.device
+        self.teacher = TeacherAgent(self.env, params=teacher_params, seed=teacher_seed, mode=mode)
+        self.student = StudentNet(kind=student_kind, seed=student_seed, device=self.device, mode=mode, lr=lr, eps=eps, params=student_params)
+        self.mode, self.loss_kind, self.n = mode, loss_kind, int(num_envs)
+        h = C.c_void_p()
+        check(lib().rb_dagger_create(C.byref(h), self.env._h, student_kind, float(keep_prob)))
+        self._h = h
+        n, dev = self.n, self.device
+        with torch.cuda.device(dev):
+            self.obs = torch.empty((n, 11), device=dev)
+            self.t_pd = torch.empty((n, 4), device=dev)
+            self.s_pd = torch.empty((n, 4), device=dev)
+            self.x = torch.empty((n, self.student.in_dim), device=dev)
+            self.rew = torch.empty((n,), device=dev)
+            self.done = torch.empty((n,), dtype=torch.uint8, device=dev)
+        self.pg = process_group
+        self.world = 1
+        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
+            self.world = torch.distributed.get_world_size(process_group)
+        self.grad_scale = (1.0 / self.world) if average_grads else 1.0   # MpiAdam averages (backup :709); KL sum = concatenated batch
+        self.iteration = 0
+        self.env.reset()
+
+    def sync_params(self):
+        """MpiAdam.sync() (backup/student_rollout.py:659): broadcast rank-0 student parameters."""
+        if self.world > 1:
+            torch.distributed.broadcast(self.student.params, src=0, group=self.pg)
+
+    def step(self):
+        """One DAgger iteration over all envs.  Asynchronous; returns nothing (loss: self.last_loss())."""
+        L, st = lib(), stream_ptr()
+        check(L.rb_dagger_observe(self._h, ptr(self.teacher.params), self.iteration, ptr(self.obs), ptr(self.t_pd), ptr(self.x), self.mode, st))
+        self.student.loss_grad(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd)
+        if self.world > 1:
+            torch.distributed.all_reduce(self.student.gradloss, group=self.pg)
+        self.student.adam_step(self.grad_scale)
+        check(L.rb_dagger_act(self._h, ptr(self.s_pd), ptr(self.t_pd), ptr(self.rew), ptr(self.done), st))
+        self.iteration += 1
+
+    def last_loss(self):
+        return self.student.gradloss[self.student.P]
+
+    def close(self):
+        if self._h:
+            lib().rb_dagger_destroy(self._h)
+            self._h = None
+        self.env.close()
+
+
+def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_episodes=5000, seed=SEED, device=0, student_kind=STUDENT_MLP,
+          keep_prob=KEEP_PROB, mode=MODE_FP32, warmup_episodes=2 * MLP_BATCH_SIZE + 1, log_every=50, checkpoint=None, verbose=True):
+    """Same entry point as the reference (`mlp_train.train(train, restore)`, main.py:26-27).
+
+    Phase A (mlp_train.py:120-139): every env plays `warmup_episodes / num_envs` (>= 1) teacher episodes into the device buffer.
+    Phase B (mlp_train.py:143-204): DAgger iterations until `total_episodes` episodes (5000 in the reference) or `iterations`.
+    Returns a dict with the loss curve (one summed KL per logged iteration) and mean per-step reward."""
+    rank, world = 0, 1
+    if torch.distributed.is_available() and torch.distributed.is_initialized():
+        rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    tr = DaggerTrainer(num_envs=num_envs, seed=seed, device=device, student_kind=student_kind, keep_prob=keep_prob, mode=mode,
+                       env_offset=rank * num_envs)
+    ckpt = checkpoint or os.path.join(base_path, "student_mlp_b200.pt")
+    if restore and os.path.exists(ckpt):
+        tr.student.load_state_dict(torch.load(ckpt))
+    tr.sync_params()
+    if not train:
+        return dict(trainer=tr)
+    if verbose and rank == 0:
+        print("Begin Training! First Accumulate observation with teacher")
+    eps_per_env = max(1, -(-warmup_episodes // (num_envs * world)))
+    warm = tr.env.rollout_policy(tr.teacher.params, 50 * eps_per_env, nout=2, mode=mode)
+    teacher_reward = float(warm["rew"].mean())
+    if verbose and rank == 0:
+        print("Accumulated sufficient data points from teacher. now train")
+    if iterations is None:
+        iterations = 50 * max(1, -(-total_episodes // (num_envs * world)))
+    losses, rewards = [], []
+    for it in range(iterations):
+        tr.step()
+        if (it + 1) % log_every == 0 or it == iterations - 1:
+            losses.append(float(tr.last_loss()))
+            rewards.append(float(tr.rew.mean()))
+            if verbose and rank == 0:
+                print("************** Episode %d ****************" % ((it + 1) // 50 * num_envs * world))
+                print("recent loss: %f " % losses[-1])
+    if rank == 0 and checkpoint is not None:
+        os.makedirs(os.path.dirname(ckpt) or ".", exist_ok=True)
+        torch.save(tr.student.state_dict(), ckpt)
+    out = dict(losses=losses, rewards=rewards, teacher_reward=teacher_reward, iterations=iterations, trainer=tr)
+    return out

@@ -1,0 +1,93 @@
+"""Student networks (/root/reference src/distilation/student_nn.py:51-57 and backup/student_rollout.py:79-87).
+
+StudentNet owns the flat fp32 parameter vector, Adam moments and the workspace on one GPU and drives the CUDA
+forward / loss+grad / Adam entry points.  `student_mlp_graph` keeps the reference's function name for the forward pass.
+"""
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LOSS_KL_ST, MODE_FP32, STUDENT_MLP, STUDENT_POLICY64, check, lib, ptr, stream_ptr
+from .teacher import init_policy_params
+
+MLP_DIMS = (16, 24, 128, 128, 32, 4)
+
+
+def init_mlp_params(seed=0, dims=MLP_DIMS):
+    """tf.layers.dense defaults: glorot-uniform kernels, zero biases; flat layout W[in][out], b[out] per layer."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    for i in range(len(dims) - 1):
+        lim = np.sqrt(6.0 / (dims[i] + dims[i + 1]))
+        parts.append(rng.uniform(-lim, lim, size=(dims[i], dims[i + 1])).astype(np.float32).ravel())
+        parts.append(np.zeros(dims[i + 1], np.float32))
+    return np.concatenate(parts)
+
+
+class StudentNet:
+    def __init__(self, kind=STUDENT_MLP, seed=0, device=0, lr=None, beta1=0.9, beta2=0.999, eps=None, mode=MODE_FP32, params=None):
+        self.kind, self.mode = kind, mode
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.P = lib().rb_student_param_count(kind)
+        self.in_dim = lib().rb_student_input_dim(kind)
+        if params is None:
+            params = init_mlp_params(seed) if kind == STUDENT_MLP else init_policy_params(seed, nout=4, logstd=(0.0, 0.0))
+        assert params.size == self.P
+        # reference optimiser settings: tf Adam lr 1e-4 eps 1e-8 (mlp_train.py:75-78); MpiAdam eps 1e-3 step 1e-3 (backup :658,709)
+        self.lr = lr if lr is not None else (1e-4 if kind == STUDENT_MLP else 1e-3)
+        self.eps = eps if eps is not None else (1e-8 if kind == STUDENT_MLP else 1e-3)
+        self.beta1, self.beta2 = beta1, beta2
+        with torch.cuda.device(self.device):
+            self.params = torch.from_numpy(np.ascontiguousarray(params, np.float32)).to(self.device)
+            self.m = torch.zeros_like(self.params)
+            self.v = torch.zeros_like(self.params)
+            self.gradloss = torch.zeros(self.P + 1, dtype=torch.float32, device=self.device)
+            ws = lib().rb_student_workspace_bytes(kind, 0, self.device.index)
+            self.workspace = torch.empty(ws // 4, dtype=torch.float32, device=self.device)
+        self.t = 0
+
+    def forward(self, x, out=None):
+        x = x.reshape(-1, self.in_dim).contiguous()
+        if out is None:
+            out = torch.empty((x.shape[0], 4), dtype=torch.float32, device=self.device)
+        check(lib().rb_student_fwd(self.kind, ptr(self.params), ptr(x), x.shape[0], ptr(out), self.mode, stream_ptr()))
+        return out
+
+    def loss_grad(self, x, t_pdflat, loss_kind=LOSS_KL_ST, s_out=None):
+        """Fills self.gradloss = [flat grad (P), summed loss]; returns the student pdflat [B,4]."""
+        x = x.reshape(-1, self.in_dim).contiguous()
+        t_pdflat = t_pdflat.reshape(-1, 4).contiguous()
+        B = x.shape[0]
+        if s_out is None:
+            s_out = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+        check(lib().rb_student_loss_grad(self.kind, ptr(self.params), ptr(x), ptr(t_pdflat), B, loss_kind, ptr(s_out), ptr(self.gradloss),
+                                         ptr(self.workspace), self.mode, stream_ptr()))
+        return s_out
+
+    def adam_step(self, grad_scale=1.0):
+        self.t += 1
+        check(lib().rb_adam_step(ptr(self.params), ptr(self.m), ptr(self.v), ptr(self.gradloss), self.P, self.t, self.lr, self.beta1, self.beta2,
+                                 self.eps, grad_scale, stream_ptr()))
+
+    def state_dict(self):
+        return dict(kind=self.kind, params=self.params.cpu(), m=self.m.cpu(), v=self.v.cpu(), t=self.t)
+
+    def load_state_dict(self, sd):
+        assert sd["kind"] == self.kind
+        self.params.copy_(sd["params"]); self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+
+
+def student_mlp_input(obs, prev_pdflat, prev_rew, keep_prob, seed, sample_id0=0, iteration=0, out=None):
+    """concat(dropout(ob, kp), prev_pdflat, prev_rew) -- mlp_train.py:50-52."""
+    B = obs.shape[0]
+    if out is None:
+        out = torch.empty((B, 16), dtype=torch.float32, device=obs.device)
+    check(lib().rb_student_mlp_input(ptr(obs.contiguous()), ptr(prev_pdflat), ptr(prev_rew), B, float(keep_prob), int(seed), int(sample_id0),
+                                     int(iteration), ptr(out), stream_ptr()))
+    return out
+
+
+def student_mlp_graph(training_input_batch, net):
+    """Reference name (student_nn.py:51): forward of the 16-24-128-128-32-4 student on [.., 16] inputs -> [.., 4]."""
+    shp = training_input_batch.shape[:-1]
+    return net.forward(training_input_batch).reshape(*shp, 4)

@@ -1,0 +1,74 @@
+"""DAgger loop (BASELINE config 4 semantics at test size): student loss curve vs the CPU restatement with identical teacher,
+student init, seeds and dropout masks (loss-curve parity is defined against the restatement)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_np as NN
+from oracle import reacher_np as RN
+
+pytestmark = pytest.mark.gpu
+
+
+def _oracle_loop(kind, n, iters, seed, teacher_p, student_p, keep_prob, lr, eps, offset=0):
+    from reacherdistilation_b200 import STUDENT_MLP
+    env = RN.ReacherOracle(n, seed=seed, env_offset=offset)
+    ob = env.reset()
+    theta = student_p.astype(np.float64)
+    opt = NN.AdamTF(theta.size, lr=lr, eps=eps)
+    prev_t, prev_rec_rew, last_rew = np.zeros((n, 4)), np.zeros(n), np.zeros(n)
+    losses, rews = [], []
+    for it in range(iters):
+        ob32 = ob.astype(np.float32)
+        t = NN.policy_fwd(ob32, teacher_p).astype(np.float32)
+        first = env.step_count == 0
+        th32 = theta.astype(np.float32)
+        if kind == STUDENT_MLP:
+            pp = np.where(first[:, None], 0.0, prev_t)
+            pr = np.where(first, 0.0, prev_rec_rew)
+            x = NN.student_input(ob32, pp, pr, keep_prob, seed, env.env_ids, it)
+            s, hs = NN.mlp_fwd(x, th32)
+            l, ds = NN.kl_loss(s, t)
+            g = NN.mlp_bwd(hs, th32, ds)
+        else:
+            s = NN.policy_fwd(ob32, th32, nout=4)
+            l, ds = NN.kl_loss(s, t)
+            g = NN.policy_bwd(ob32, th32, ds)
+        theta = opt.update(theta, g)
+        ob, r, d = env.step(s[:, :2].astype(np.float32).astype(np.float64))
+        prev_t, prev_rec_rew, last_rew = t.astype(np.float64), last_rew, r
+        losses.append(l); rews.append(r.mean())
+    return np.array(losses), np.array(rews), theta
+
+
+@pytest.mark.parametrize("kind_name,keep_prob", [("mlp", 0.5), ("mlp", 1.0), ("policy64", 1.0)])
+def test_loss_curve_matches_cpu_restatement(kind_name, keep_prob):
+    from reacherdistilation_b200 import STUDENT_MLP, STUDENT_POLICY64
+    from reacherdistilation_b200.mlp_train import DaggerTrainer
+    from reacherdistilation_b200.teacher import init_policy_params
+    kind = STUDENT_MLP if kind_name == "mlp" else STUDENT_POLICY64
+    n, iters, seed = 256, 70, 4
+    tp = init_policy_params(seed=0, final_std=0.3)
+    tr = DaggerTrainer(num_envs=n, seed=seed, student_kind=kind, keep_prob=keep_prob, teacher_params=tp, student_seed=1, lr=1e-3, eps=1e-8)
+    sp = tr.student.params.cpu().numpy().copy()
+    dev_losses, dev_rews = [], []
+    for it in range(iters):
+        tr.step()
+        dev_losses.append(float(tr.last_loss())); dev_rews.append(float(tr.rew.mean()))
+    ref_losses, ref_rews, theta = _oracle_loop(kind, n, iters, seed, tp, sp, keep_prob, 1e-3, 1e-8)
+    rel = np.abs(np.array(dev_losses) - ref_losses) / np.maximum(1.0, np.abs(ref_losses))
+    print("%s kp=%.1f loss curve: first %.4g last %.4g, max rel err %.3g; reward err %.3g" %
+          (kind_name, keep_prob, ref_losses[0], ref_losses[-1], rel.max(), np.abs(np.array(dev_rews) - ref_rews).max()))
+    assert ref_losses[-1] < ref_losses[0]                 # it learns
+    assert rel.max() <= 2e-3                              # stated loss-curve tolerance (fp32 device vs float64 restatement, closed loop)
+    assert np.abs(np.array(dev_rews) - ref_rews).max() <= 2e-3
+    assert np.abs(tr.student.params.cpu().numpy() - theta).max() <= 2e-3
+    tr.close()
+
+
+def test_train_entry_point_runs():
+    from reacherdistilation_b200 import mlp_train
+    out = mlp_train.train(True, False, num_envs=512, iterations=100, log_every=25, verbose=False)
+    assert len(out["losses"]) == 4 and out["losses"][-1] < out["losses"][0]
+    assert -1.0 < out["teacher_reward"] < 0.0
+    out["trainer"].close()

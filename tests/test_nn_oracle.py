@@ -1,0 +1,56 @@
+"""Host-side checks of the NN oracle: analytic gradients vs finite differences, TF-form Adam vs its closed form."""
+import numpy as np
+
+from oracle import nn_np as NN
+
+
+def test_mlp_gradient_matches_finite_differences():
+    rng = np.random.default_rng(0)
+    P = (rng.standard_normal(NN.mlp_param_count()) * 0.2).astype(np.float32)
+    x, t = rng.standard_normal((9, 16)), rng.standard_normal((9, 4)) * 0.3
+    s, hs = NN.mlp_fwd(x, P)
+    _, ds = NN.kl_loss(s, t)
+    g = NN.mlp_bwd(hs, P, ds)
+    for i in rng.integers(0, P.size, 25):
+        P1, P2 = P.copy(), P.copy()
+        P1[i] += 1e-3; P2[i] -= 1e-3
+        fd = (NN.kl_loss(NN.mlp_fwd(x, P1)[0], t)[0] - NN.kl_loss(NN.mlp_fwd(x, P2)[0], t)[0]) / (float(P1[i]) - float(P2[i]))
+        assert abs(fd - g[i]) <= 2e-4 * max(1.0, abs(g[i]))
+
+
+def test_policy_gradient_matches_finite_differences():
+    rng = np.random.default_rng(1)
+    P = (rng.standard_normal(NN.policy_param_count(4)) * 0.2).astype(np.float32)
+    P[:11] = 0; P[11:22] = 1
+    x, t = rng.standard_normal((7, 11)), rng.standard_normal((7, 4)) * 0.3
+    for loss in (NN.kl_loss, NN.kl_loss_rev):
+        s = NN.policy_fwd(x, P, nout=4)
+        _, ds = loss(s, t)
+        g = NN.policy_bwd(x, P, ds)
+        assert (g[:22] == 0).all() and (g[-2:] == 0).all()
+        for i in rng.integers(22, P.size - 2, 25):
+            P1, P2 = P.copy(), P.copy()
+            P1[i] += 1e-3; P2[i] -= 1e-3
+            fd = (loss(NN.policy_fwd(x, P1, nout=4), t)[0] - loss(NN.policy_fwd(x, P2, nout=4), t)[0]) / (float(P1[i]) - float(P2[i]))
+            assert abs(fd - g[i]) <= 2e-4 * max(1.0, abs(g[i]))
+
+
+def test_adam_tf_first_step_and_epsilon_placement():
+    opt = NN.AdamTF(3, lr=1e-3, eps=1e-8)
+    th = opt.update(np.zeros(3), np.array([1.0, -2.0, 0.5]))
+    assert np.allclose(th, [-1e-3, 1e-3, -1e-3], rtol=1e-6)       # first step = -lr * sign(g)
+    big = NN.AdamTF(1, lr=1e-3, eps=1e-3)                       # MpiAdam epsilon: visible effect on small gradients
+    th2 = big.update(np.zeros(1), np.array([1e-3]))
+    lr_t = 1e-3 * np.sqrt(1 - 0.999) / (1 - 0.9)
+    assert np.isclose(th2[0], -lr_t * 1e-4 / (np.sqrt(0.001 * 1e-6) + 1e-3))
+
+
+def test_dropout_mask_statistics_and_determinism():
+    ids = np.arange(20000, dtype=np.uint32)
+    k1 = NN.dropout_keep(5, ids, 3, 0.5)
+    k2 = NN.dropout_keep(5, ids, 3, 0.5)
+    assert np.array_equal(k1, k2) and set(np.unique(k1)) == {0.0, 1.0}
+    assert abs(k1.mean() - 0.5) < 0.01
+    assert not np.array_equal(k1, NN.dropout_keep(5, ids, 4, 0.5))
+    x = NN.student_input(np.ones((4, 11), np.float32), np.zeros((4, 4)), np.zeros(4), 0.5, 5, ids[:4], 3)
+    assert set(np.unique(x[:, :11])) <= {0.0, 2.0} and x.shape == (4, 16)

@@ -1,0 +1,89 @@
+"""Teacher policy kernels vs the oracle: standalone forward and the fused policy-in-the-loop rollout (BASELINE config 3)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import nn_np as NN
+from oracle import reacher_c as RC
+
+pytestmark = pytest.mark.gpu
+
+
+def _modes():
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC
+    from reacherdistilation_b200._lib import lib
+    out = [("fp32", MODE_FP32, 2e-6)]
+    if lib().rb_mode_available(MODE_TC):
+        out.append(("tc", MODE_TC, 5e-5))
+    return out
+
+
+@pytest.mark.parametrize("nout", [2, 4])
+@pytest.mark.parametrize("n", [1, 127, 128, 4097])
+def test_policy_forward_matches_oracle(n, nout):
+    from reacherdistilation_b200._lib import check, lib, ptr, stream_ptr
+    from reacherdistilation_b200.teacher import init_policy_params
+    rng = np.random.default_rng(n + nout)
+    p = init_policy_params(seed=3, nout=nout, final_std=0.5, ob_mean=rng.standard_normal(11) * 0.1, ob_std=1 + rng.random(11))
+    obs = (rng.standard_normal((n, 11)) * 3).astype(np.float32)     # exercises the +-5 clip
+    ref = NN.policy_fwd(obs, p, nout=nout)
+    for name, mode, tol in _modes():
+        out = torch.empty((n, 4), device="cuda")
+        check(lib().rb_policy_fwd(ptr(torch.from_numpy(p).cuda()), nout, ptr(torch.from_numpy(obs).cuda()), n, ptr(out), mode, stream_ptr()))
+        err = np.abs(out.cpu().numpy() - ref).max()
+        print("policy_fwd %s n=%d nout=%d max err %.3g" % (name, n, nout, err))
+        assert err <= tol, (name, err)
+
+
+def test_policy_forward_host_entry_point():
+    from reacherdistilation_b200._lib import MODE_FP32, check, lib
+    from reacherdistilation_b200.teacher import init_policy_params
+    p = init_policy_params(seed=1)
+    obs = np.random.default_rng(0).standard_normal((100, 11)).astype(np.float32)
+    out = np.zeros((100, 4), np.float32)
+    check(lib().rb_policy_fwd_host(p.ctypes.data, 2, obs.ctypes.data, 100, out.ctypes.data, MODE_FP32, 0))
+    assert np.abs(out - NN.policy_fwd(obs, p)).max() <= 2e-6
+    assert np.allclose(out[:, 2:], p[-2:])
+
+
+@pytest.mark.parametrize("mode_name", ["fp32", "tc"])
+def test_fused_teacher_rollout_vs_oracle(mode_name):
+    """Closed loop for 60 steps incl. an auto-reset: buffers (obs, pdflat, rew, done) vs the C oracle running the same policy.
+    The policy is in the loop, so differences in the action feed back; tolerance is the stated trajectory tolerance x 5."""
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.teacher import init_policy_params
+    sel = [m for m in _modes() if m[0] == mode_name]
+    if not sel:
+        pytest.skip("RB_MODE_TC not compiled into this build")
+    name, mode, ptol = sel[0]
+    n, T, seed = 1000, 60, 2
+    p = init_policy_params(seed=0, final_std=0.3)
+    env = VecReacher(num_envs=n, seed=seed)
+    env.reset()
+    out = env.rollout_policy(torch.from_numpy(p).cuda(), T, nout=2, mode=mode)
+    c = RC.ReacherOracleC(n, seed=seed); c.reset()
+    obs, pd, rew, done, _ = c.rollout_policy(T, p)
+    assert np.array_equal(out["done"].cpu().numpy(), done)
+    e_obs = np.abs(out["obs"].cpu().numpy() - obs).max()
+    e_pd = np.abs(out["pdflat"].cpu().numpy() - pd).max()
+    e_rew = np.abs(out["rew"].cpu().numpy() - rew).max()
+    print("fused rollout %s: obs %.3g pdflat %.3g rew %.3g" % (name, e_obs, e_pd, e_rew))
+    assert e_obs <= 1e-3 and e_pd <= 1e-3 and e_rew <= 1e-3
+    # teacher-forced check: the recorded pdflat is the policy of the recorded obs, to kernel precision
+    ref_pd = NN.policy_fwd(out["obs"].cpu().numpy().reshape(-1, 11), p).reshape(T, n, 4)
+    assert np.abs(out["pdflat"].cpu().numpy() - ref_pd).max() <= ptol
+    env.close()
+
+
+def test_rollout_host_entry_point_matches_device():
+    from reacherdistilation_b200 import MODE_FP32
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.teacher import init_policy_params
+    p = init_policy_params(seed=0)
+    a, b = VecReacher(num_envs=300, seed=1), VecReacher(num_envs=300, seed=1)
+    a.reset(); b.reset()
+    d = a.rollout_policy(torch.from_numpy(p).cuda(), 55, mode=MODE_FP32)
+    h = b.rollout_policy_host(torch.from_numpy(p), 55, mode=MODE_FP32)
+    for k in d:
+        assert torch.equal(d[k].cpu(), h[k]), k
+    a.close(); b.close()
