@@ -24,6 +24,10 @@ template <typename T> struct Model {
 __device__ __forceinline__ void sincos_t(float x, float* s, float* c) { sincosf(x, s, c); }
 __device__ __forceinline__ void sincos_t(double x, double* s, double* c) { sincos(x, s, c); }
 __device__ __forceinline__ float sqrt_t(float x) { return sqrtf(x); }
+__device__ __forceinline__ float fma_t(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+__device__ __forceinline__ double fma_t(double a, double b, double c) { return __fma_rn(a, b, c); }
+__device__ __forceinline__ float mul_t(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ double mul_t(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double sqrt_t(double x) { return sqrt(x); }
 
 // joint accelerations; u already clipped to ctrlrange
@@ -108,7 +112,8 @@ template <typename T> __device__ __forceinline__ void reset_env(EnvState<T>& e, 
 template <typename T>
 __device__ __forceinline__ T step_env(EnvState<T>& e, T a0, T a1, uint32_t k0, uint32_t k1, uint32_t gid, bool& done) {
     const T dx = e.px - e.tx, dy = e.py - e.ty;
-    const T rew = -sqrt_t(dx * dx + dy * dy) - (a0 * a0 + a1 * a1);   // stale fingertip, unclipped action
+    // stale fingertip, unclipped action; explicit fma/mul so every kernel that inlines this rounds identically
+    const T rew = -sqrt_t(fma_t(dx, dx, mul_t(dy, dy))) - fma_t(a0, a0, mul_t(a1, a1));
     const T u0 = a0 < T(-1) ? T(-1) : (a0 > T(1) ? T(1) : a0);
     const T u1 = a1 < T(-1) ? T(-1) : (a1 > T(1) ? T(1) : a1);
     T sq0, sq1;

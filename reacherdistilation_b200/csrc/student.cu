@@ -301,10 +301,10 @@ static int launch_student(const NetSpec& S, const float* params, const float* x,
     auto kern = k_student<TILE, TPS, WS>;
     static bool attr_set = false;
     if (!attr_set) {
-        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
         attr_set = true;
     }
-    RB_REQUIRE(smem <= 227 * 1024, "shared memory budget exceeded");
+    RB_REQUIRE(smem <= 224 * 1024, "shared memory budget exceeded");
     RB_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "params / x must be 16-byte aligned");
     kern<<<grid, TILE * TPS, smem, st>>>(S, params, x, tpd, B, loss_kind, fwd_only, (float4*)s_out, partials);
     RB_CUDA(cudaGetLastError());

@@ -27,9 +27,10 @@ def test_policy_forward_matches_oracle(n, nout):
     p = init_policy_params(seed=3, nout=nout, final_std=0.5, ob_mean=rng.standard_normal(11) * 0.1, ob_std=1 + rng.random(11))
     obs = (rng.standard_normal((n, 11)) * 3).astype(np.float32)     # exercises the +-5 clip
     ref = NN.policy_fwd(obs, p, nout=nout)
+    p_dev, obs_dev = torch.from_numpy(p).cuda(), torch.from_numpy(obs).cuda()      # keep alive across the async launch
     for name, mode, tol in _modes():
         out = torch.empty((n, 4), device="cuda")
-        check(lib().rb_policy_fwd(ptr(torch.from_numpy(p).cuda()), nout, ptr(torch.from_numpy(obs).cuda()), n, ptr(out), mode, stream_ptr()))
+        check(lib().rb_policy_fwd(ptr(p_dev), nout, ptr(obs_dev), n, ptr(out), mode, stream_ptr()))
         err = np.abs(out.cpu().numpy() - ref).max()
         print("policy_fwd %s n=%d nout=%d max err %.3g" % (name, n, nout, err))
         assert err <= tol, (name, err)
