@@ -55,7 +55,8 @@ int rb_version(void);
 int rb_device_count(void);
 int rb_sm_count(int device);
 /* 1 if the given RB_MODE_* is compiled into this build (RB_MODE_TC needs the tcgen05 kernels) */
-int rb_mode_available(int mode);
+int rb_mode_available(int mode);          /* policy / rollout kernels */
+int rb_student_mode_available(int mode);  /* student forward/backward kernels */
 
 /* ------------------------------------------------------------------------------------------------ env ----
  * rb_env = N lock-step Reacher-v2 environments resident in HBM.

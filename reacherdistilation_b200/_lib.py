@@ -25,6 +25,7 @@ _SIGS = {
     "rb_device_count": (C.c_int, []),
     "rb_sm_count": (C.c_int, [C.c_int]),
     "rb_mode_available": (C.c_int, [C.c_int]),
+    "rb_student_mode_available": (C.c_int, [C.c_int]),
     "rb_env_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_uint64, C.c_int, C.c_uint32]),
     "rb_env_destroy": (C.c_int, [_vp]),
     "rb_env_num_envs": (C.c_int64, [_vp]),

@@ -362,7 +362,7 @@ static int student_dispatch(int kind, const float* params, const float* x, const
 int rb_student_fwd(int kind, const float* params, const float* x, int64_t B, float* s_pd, int mode, void* stream) {
     RB_REQUIRE(params && x && s_pd, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
-    RB_REQUIRE(mode == RB_MODE_FP32 || mode == RB_MODE_TC, "unknown mode");
+    RB_REQUIRE(mode == RB_MODE_FP32, "rb_student_fwd: only RB_MODE_FP32 is built (see rb_student_mode_available)");
     if (B <= 0) return RB_OK;
     return student_dispatch(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, nullptr, (cudaStream_t)stream);
 }

@@ -1,0 +1,132 @@
+// tcgen05 / TMEM / mbarrier primitives for sm_100a (inline PTX), shared by the tensor-core kernels.
+//
+// Operand layout used everywhere here: UMMA "no-swizzle, K-major" canonical layout.  An operand tile [R rows x K] of
+// bf16 is stored as core matrices of 8 rows x 16 bytes (8 bf16 along K), each core matrix 128 contiguous bytes:
+//     byte_offset(r, k) = (k / 8) * LBO + (r / 8) * SBO + (r % 8) * 16 + (k % 8) * 2,   SBO = 128, LBO = R * 16
+// i.e. [K/8][R][8]: a thread that owns row r writes one 16-byte chunk per 8 k-values at chunk*LBO + r*16 -- consecutive
+// threads hit consecutive 16-byte slots (bank-conflict free 128-bit stores).  One tcgen05.mma kind::f16 consumes K = 16
+// (two chunks); advancing K by 16 adds 2*LBO to the descriptor start address.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace rb {
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// shared-memory matrix descriptor (64-bit): start address, leading (K-direction) and stride (row-group) byte offsets,
+// descriptor version 1 (Blackwell), no swizzle.
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFFu);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFFu) << 32;
+    d |= (uint64_t)1 << 46;
+    return d;
+}
+
+// instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, dense
+__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// D[tmem] (+)= A[smem] * B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
+// all previously issued MMAs of this thread arrive on the mbarrier when complete (implies fence::before_thread_sync)
+__device__ __forceinline__ void mma_commit(uint64_t* mbar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(mbar)) : "memory");
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* mbar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P1;\n\t"
+        "LAB_WAIT:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+        "@P1 bra DONE;\n\t"
+        "bra LAB_WAIT;\n\t"
+        "DONE:\n\t"
+        "}\n" ::"r"(smem_u32(mbar)), "r"(parity)
+        : "memory");
+}
+
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// TMEM allocation: one full warp; the base address lands in *dst (shared memory)
+template <int NCOLS> __device__ __forceinline__ void tmem_alloc(uint32_t* dst) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst)), "n"(NCOLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+template <int NCOLS> __device__ __forceinline__ void tmem_dealloc(uint32_t taddr) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "n"(NCOLS) : "memory");
+}
+
+// TMEM -> registers, shape 32x32b: thread `lane` of the warp reads TMEM lane (warp%4)*32 + lane, N consecutive columns
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float* v) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float* v) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr) : "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ---- bf16 hi/lo split (bf16x3 scheme): x ~= hi + lo, each bf16; two values packed per 32-bit word (first -> low half)
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
+    uint32_t d;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi_half), "f"(lo_half));
+    return d;
+}
+__device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi2, uint32_t& lo2) {
+    hi2 = pack_bf16x2(a, b);
+    const float ah = __uint_as_float(hi2 << 16), bh = __uint_as_float(hi2 & 0xFFFF0000u);
+    lo2 = pack_bf16x2(a - ah, b - bh);
+}
+__device__ __forceinline__ void split_scalar(float a, uint16_t& hi, uint16_t& lo) {
+    uint32_t h2, l2;
+    split_pair(a, 0.f, h2, l2);
+    hi = (uint16_t)(h2 & 0xFFFFu);
+    lo = (uint16_t)(l2 & 0xFFFFu);
+}
+
+// tanh(x) = 1 - 2 / (2^(2x log2 e) + 1) on the MUFU (ex2.approx + rcp.approx): absolute error ~3e-7
+__device__ __forceinline__ float tanh_mufu(float x) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * 2.8853900817779268f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
+// byte offset of element (r, k) inside a K-major no-swizzle tile with R rows
+__host__ __device__ constexpr uint32_t tile_off(int r, int k, int R) { return (uint32_t)((k >> 3) * (R * 16) + r * 16 + (k & 7) * 2); }
+
+}  // namespace tc
+}  // namespace rb

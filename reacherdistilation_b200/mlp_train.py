@@ -26,12 +26,15 @@ from .teacher import TeacherAgent
 class DaggerTrainer:
     def __init__(self, num_envs=NUM_ENVS, seed=SEED, device=0, student_kind=STUDENT_MLP, keep_prob=KEEP_PROB, mode=MODE_FP32,
                  teacher_params=None, teacher_seed=0, student_seed=1, env_offset=0, loss_kind=LOSS_KL_ST, lr=None, eps=None,
-                 process_group=None, average_grads=False, student_params=None):
+                 process_group=None, average_grads=False, student_params=None, student_mode=None):
         import ctypes as C
         self.env = VecReacher(num_envs=num_envs, seed=seed, device=device, env_offset=env_offset)
         self.device = self.env.device
         self.teacher = TeacherAgent(self.env, params=teacher_params, seed=teacher_seed, mode=mode)
-        self.student = StudentNet(kind=student_kind, seed=student_seed, device=self.device, mode=mode, lr=lr, eps=eps, params=student_params)
+        if student_mode is None:   # tensor-core student kernels only where this build has them; never a silent substitution of `mode`
+            student_mode = mode if lib().rb_student_mode_available(mode) else MODE_FP32
+        self.student_mode = student_mode
+        self.student = StudentNet(kind=student_kind, seed=student_seed, device=self.device, mode=student_mode, lr=lr, eps=eps, params=student_params)
         self.mode, self.loss_kind, self.n = mode, loss_kind, int(num_envs)
         h = C.c_void_p()
         check(lib().rb_dagger_create(C.byref(h), self.env._h, student_kind, float(keep_prob)))

@@ -12,7 +12,7 @@ def _modes():
     from reacherdistilation_b200 import MODE_FP32, MODE_TC
     from reacherdistilation_b200._lib import lib
     out = [("fp32", MODE_FP32, 3e-5)]
-    if lib().rb_mode_available(MODE_TC):
+    if lib().rb_student_mode_available(MODE_TC):
         out.append(("tc", MODE_TC, 2e-3))
     return out
 
