@@ -51,16 +51,11 @@ __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float
                                                     uint32_t offset) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float4 a = qv[i], b = tp[i];
-    const uint2 c = ctr[i];
-    EnvState<float> e;
-    e.q0 = a.x; e.q1 = a.y; e.v0 = a.z; e.v1 = a.w; e.tx = b.x; e.ty = b.y; e.px = b.z; e.py = b.w; e.step = (int)c.x; e.episode = c.y;
+    EnvState e = load_state(qv, tp, ctr, i);
     const float4 sp = __ldg(s_pd + i);
     bool d;
     const float r = step_env(e, sp.x, sp.y, k0, k1, offset + (uint32_t)i, d);
-    qv[i] = make_float4(e.q0, e.q1, e.v0, e.v1);
-    tp[i] = make_float4(e.tx, e.ty, e.px, e.py);
-    ctr[i] = make_uint2((uint32_t)e.step, e.episode);
+    store_state(qv, tp, ctr, i, e);
     if (t_pd) prev_t[i] = __ldg(t_pd + i);
     prev_rec_rew[i] = last_reward[i];
     last_reward[i] = r;

@@ -14,20 +14,6 @@ namespace rb {
 
 constexpr int ENV_BLOCK = 128;
 
-__device__ __forceinline__ EnvState<float> load_state(const float4* qv, const float4* tp, const uint2* ctr, int64_t i) {
-    const float4 a = qv[i], b = tp[i];
-    const uint2 c = ctr[i];
-    EnvState<float> e;
-    e.q0 = a.x; e.q1 = a.y; e.v0 = a.z; e.v1 = a.w; e.tx = b.x; e.ty = b.y; e.px = b.z; e.py = b.w;
-    e.step = (int)c.x; e.episode = c.y;
-    return e;
-}
-__device__ __forceinline__ void store_state(float4* qv, float4* tp, uint2* ctr, int64_t i, const EnvState<float>& e) {
-    qv[i] = make_float4(e.q0, e.q1, e.v0, e.v1);
-    tp[i] = make_float4(e.tx, e.ty, e.px, e.py);
-    ctr[i] = make_uint2((uint32_t)e.step, e.episode);
-}
-
 __global__ void __launch_bounds__(ENV_BLOCK) k_reset(int64_t n, float4* qv, float4* tp, uint2* ctr, float* obs, uint32_t k0,
                                                      uint32_t k1, uint32_t offset) {
     __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
@@ -38,7 +24,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_reset(int64_t n, float4* qv, floa
     const int nvalid = (int)min((int64_t)32, n - row0);
     float ob[OBS];
     if (i < n) {
-        EnvState<float> e;
+        EnvState e;
         e.episode = 0u;
         reset_env(e, k0, k1, offset + (uint32_t)i);
         store_state(qv, tp, ctr, i, e);
@@ -55,7 +41,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_observe(int64_t n, const float4* 
     if (row0 >= n) return;
     const int nvalid = (int)min((int64_t)32, n - row0);
     float ob[OBS];
-    if (i < n) { const EnvState<float> e = load_state(qv, tp, ctr, i); observe(e, ob); }
+    if (i < n) { const EnvState e = load_state(qv, tp, ctr, i); observe(e, ob); }
     warp_store_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
 }
 
@@ -71,7 +57,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_step(int64_t n, float4* __restric
     const int nvalid = (int)min((int64_t)32, n - row0);
     float ob[OBS];
     if (i < n) {
-        EnvState<float> e = load_state(qv, tp, ctr, i);
+        EnvState e = load_state(qv, tp, ctr, i);
         const float2 a = __ldg(act + i);
         bool d;
         const float r = step_env(e, a.x, a.y, k0, k1, offset + (uint32_t)i, d);
@@ -125,9 +111,9 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_rollout_random(int64_t n, float4*
     const int nvalid = (int)min((int64_t)32, n - row0);
     const bool valid = i < n;
     const uint32_t gid = offset + (uint32_t)i;
-    EnvState<float> e;
+    EnvState e;
     if (valid) e = load_state(qv, tp, ctr, i);
-    else { e.q0 = e.q1 = e.v0 = e.v1 = e.tx = e.ty = e.px = e.py = 0.f; e.step = 0; e.episode = 0; }
+    else e = zero_state();
     for (int t = 0; t < T; ++t) {
         const uint4 r = philox4x32_10(gid, step0 + (uint32_t)t, 0u, STREAM_ACTION, k0, k1);
         const float a0 = uniform_f32(r.x, -1.f, 1.f), a1 = uniform_f32(r.y, -1.f, 1.f);
@@ -186,9 +172,9 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, fl
     const int nvalid = (int)min((int64_t)32, n - row0);
     const bool valid = i < n;
     const uint32_t gid = offset + (uint32_t)i;
-    EnvState<float> e;
+    EnvState e;
     if (valid) e = load_state(qv, tp, ctr, i);
-    else { e.q0 = e.q1 = e.v0 = e.v1 = e.tx = e.ty = e.px = e.py = 0.f; e.step = 0; e.episode = 0; }
+    else e = zero_state();
     for (int t = 0; t < T; ++t) {
         float ob[OBS], pd[4];
         observe(e, ob);

@@ -2,17 +2,21 @@
 // Replaces sess.run((pi.pd.mean, pi.pd.flat)) (/root/reference src/distilation/mlp_train.py:123-125,165-167; network
 // teacher.py:12-16) and, fused with the env step, the teacher warm-up loop mlp_train.py:120-139.
 //
-// One CTA = 128 threads = 128 envs/samples = the 128 TMEM lanes of one M=128 accumulator tile; thread r owns row r
-// end to end (its env state lives in its registers, its accumulator row comes back through tcgen05.ld 32x32b).
-// Per policy evaluation the CTA runs three dependent GEMMs  [128 x K] * [K x N]:
-//     L1: K = 16 (11 obs + a ones column that carries b1 + zero pad), N = 64  -> TMEM cols   0.. 63
-//     L2: K = 64, N = 64                                                      -> TMEM cols  64..127
-//     L3: K = 64, N = 16 (nout padded)                                        -> TMEM cols   0.. 15
+// Work decomposition.  A *tile* = 128 envs/samples = the 128 TMEM lanes of one M=128 accumulator = 4 warps; thread r of a
+// tile owns row r end to end (env state in its registers, accumulator row through tcgen05.ld 32x32b).  A CTA holds NT tiles
+// that share ONE shared-memory copy of the split weights; each tile has its own A-operand buffers, its own 64 TMEM
+// columns, its own mbarrier and its own named barrier, so tiles run unsynchronised and hide each other's MMA / MUFU
+// latency.  One CTA per SM; envs are dealt to CTAs in units of one warp (32 envs) so every SM gets the same number of
+// warps +-1 whatever N is (65 536 envs = 2048 warp-units = 13.8 per SM; a 128-env granularity would leave a 15 % tail).
+//
+// Per policy evaluation a tile runs three dependent GEMMs [128 x K] * [K x N] (A, B in shared memory, D in TMEM):
+//     L1: K = 16 (11 obs + a ones column that carries b1 + zero pad), N = 64
+//     L2: K = 64 (+ one extra K = 16 step: a constant ones-tile times the b2 row), N = 64
+//     L3: K = 64, N = 16 (nout padded)
 // Operands are bf16 hi/lo splits of the fp32 values ("bf16x3": A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulate in
-// TMEM), which keeps the result within ~1e-5 of the fp32 network while running on tcgen05.  Weights are split once per
-// CTA into shared memory; activations are split in the epilogue (bias + MUFU tanh) and written straight into the next
-// layer's A tile (no-swizzle K-major layout, see tc_common.cuh).  One elected thread issues the MMAs; completion is
-// tracked with tcgen05.commit -> mbarrier.
+// TMEM), which keeps the result within ~1e-5 of the fp32 network.  W1/b1/W2/b2 are pre-multiplied by 2*log2(e) when they
+// are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  : FADD, 2 MUFU, FFMA per element, then the bf16
+// hi/lo split written straight into the next layer's A tile (no-swizzle K-major layout, see tc_common.cuh).
 #include "common.cuh"
 #include "physics.cuh"
 #include "tc_common.cuh"
@@ -21,55 +25,72 @@ namespace rb {
 
 using namespace tc;
 
-constexpr int TCB = 128;          // threads per CTA == rows per tile
-constexpr int N_TERMS = 3;        // bf16x3
+constexpr int TILE = 128;               // rows per tile == threads per tile
+constexpr int MAX_TILES = 6;
+constexpr float TANH_PRESCALE = 2.8853900817779268f;   // 2 * log2(e)
 
-struct __align__(128) PolicyTcSmem {
-    uint8_t A_hi[128 * 64 * 2];   // [8 chunks][128 rows][16 B]; the L1 tile (2 chunks) aliases its head; tail doubles as obs strips
-    uint8_t A_lo[128 * 64 * 2];
-    uint8_t B2_hi[64 * 64 * 2];
+struct __align__(128) TcShared {        // one per CTA: split weights + per-tile barriers
+    uint8_t B2_hi[64 * 64 * 2];         // [8 chunks][64 rows (n)][16 B]
     uint8_t B2_lo[64 * 64 * 2];
+    uint8_t B2b_hi[64 * 16 * 2];        // bias K-step of layer 2: k = 0 carries b2, k = 1..15 zero
+    uint8_t B2b_lo[64 * 16 * 2];
     uint8_t B1_hi[64 * 16 * 2];
     uint8_t B1_lo[64 * 16 * 2];
     uint8_t B3_hi[16 * 64 * 2];
     uint8_t B3_lo[16 * 64 * 2];
-    float b2[64];
+    uint8_t ONES[128 * 16 * 2];         // A operand of the bias K-step: column 0 = 1.0, rest 0
     float b3[4];
     float mu[12];
     float inv_sd[12];
     float logstd[4];
-    uint64_t mbar;
+    uint64_t mbar[MAX_TILES];
     uint32_t tmem_base;
 };
-constexpr uint32_t STRIP_OFF = 8192;   // obs staging strips live in A_hi[8192 .. 8192 + 4*1408)
+struct __align__(128) TcTile {
+    uint8_t A_hi[128 * 64 * 2];         // [8 chunks][128 rows][16 B]; the L1 tile (2 chunks) aliases its head; bytes 8192.. double as obs strips
+    uint8_t A_lo[128 * 64 * 2];
+};
+constexpr uint32_t STRIP_OFF = 8192;    // obs staging strips live in A_hi[8192 .. 8192 + 4*1408)
 
-// split W (fp32, row-major [K][N] in global) into the K-major B tiles (element (n,k) = W[k][n])
-__device__ inline void policy_tc_load_weights(PolicyTcSmem& S, const float* __restrict__ p, int nout) {
+template <int NT> __host__ __device__ constexpr int tmem_cols() { return NT * 64 <= 64 ? 64 : (NT * 64 <= 128 ? 128 : (NT * 64 <= 256 ? 256 : 512)); }
+template <int NT> constexpr size_t tc_smem_bytes() { return sizeof(TcShared) + (size_t)NT * sizeof(TcTile); }
+
+__device__ __forceinline__ void tile_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+
+// split W (fp32, row-major [K][N] in global) into the K-major B tiles (element (n,k) = W[k][n]); all threads of the CTA
+__device__ inline void policy_tc_load_weights(TcShared& S, const float* __restrict__ p, int nout) {
     const PolicyOffsets o = policy_offsets(nout);
-    const int tid = threadIdx.x;
-    for (int i = tid; i < 64 * 16; i += TCB) {          // B1: n = i % 64, k = i / 64 ; k == 11 carries the bias
+    const int tid = threadIdx.x, nt = blockDim.x;
+    for (int i = tid; i < 64 * 16; i += nt) {          // B1: n = i % 64, k = i / 64 ; k == 11 carries the bias
         const int n = i & 63, k = i >> 6;
         const float w = k < 11 ? __ldg(p + o.W1 + k * 64 + n) : (k == 11 ? __ldg(p + o.b1 + n) : 0.f);
         uint16_t h, l;
-        split_scalar(w, h, l);
+        split_scalar(w * TANH_PRESCALE, h, l);
         *reinterpret_cast<uint16_t*>(S.B1_hi + tile_off(n, k, 64)) = h;
         *reinterpret_cast<uint16_t*>(S.B1_lo + tile_off(n, k, 64)) = l;
+        const float bb = k == 0 ? __ldg(p + o.b2 + n) * TANH_PRESCALE : 0.f;   // B2b: k == 0 carries b2
+        split_scalar(bb, h, l);
+        *reinterpret_cast<uint16_t*>(S.B2b_hi + tile_off(n, k, 64)) = h;
+        *reinterpret_cast<uint16_t*>(S.B2b_lo + tile_off(n, k, 64)) = l;
     }
-    for (int i = tid; i < 64 * 64; i += TCB) {
+    for (int i = tid; i < 64 * 64; i += nt) {
         const int n = i & 63, k = i >> 6;
         uint16_t h, l;
-        split_scalar(__ldg(p + o.W2 + k * 64 + n), h, l);
+        split_scalar(__ldg(p + o.W2 + k * 64 + n) * TANH_PRESCALE, h, l);
         *reinterpret_cast<uint16_t*>(S.B2_hi + tile_off(n, k, 64)) = h;
         *reinterpret_cast<uint16_t*>(S.B2_lo + tile_off(n, k, 64)) = l;
     }
-    for (int i = tid; i < 16 * 64; i += TCB) {
+    for (int i = tid; i < 16 * 64; i += nt) {
         const int n = i & 15, k = i >> 4;
         uint16_t h, l;
         split_scalar(n < nout ? __ldg(p + o.W3 + k * nout + n) : 0.f, h, l);
         *reinterpret_cast<uint16_t*>(S.B3_hi + tile_off(n, k, 16)) = h;
         *reinterpret_cast<uint16_t*>(S.B3_lo + tile_off(n, k, 16)) = l;
     }
-    if (tid < 64) S.b2[tid] = __ldg(p + o.b2 + tid);
+    for (int i = tid; i < 128 * 16; i += nt) {
+        const int r = i & 127, k = i >> 7;
+        *reinterpret_cast<uint16_t*>(S.ONES + tile_off(r, k, 128)) = k == 0 ? (uint16_t)0x3F80u : (uint16_t)0u;
+    }
     if (tid < 4) {
         S.b3[tid] = tid < nout ? __ldg(p + o.b3 + tid) : 0.f;
         S.logstd[tid] = tid < 2 ? __ldg(p + o.logstd + tid) : 0.f;
@@ -80,52 +101,59 @@ __device__ inline void policy_tc_load_weights(PolicyTcSmem& S, const float* __re
     }
 }
 
-// issue one layer: D[tmem_d] = sum over k-steps and hi/lo terms of A * B^T.  Called by ONE thread.
-__device__ __forceinline__ void issue_layer(uint32_t tmem_d, const uint8_t* a_hi, const uint8_t* a_lo, const uint8_t* b_hi,
-                                            const uint8_t* b_lo, int ksteps, int n_rows_b, uint32_t idesc) {
+// D[tmem_d] (+)= sum over k-steps and hi/lo terms of A * B^T.  Called by ONE thread.  A tiles have 128 rows, B tiles n_rows_b.
+__device__ __forceinline__ void issue_bf16x3(uint32_t tmem_d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int ksteps, int n_rows_b,
+                                             uint32_t idesc, uint32_t acc) {
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)n_rows_b * 16;
-    const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
-    uint32_t acc = 0;
+#pragma unroll
     for (int ks = 0; ks < ksteps; ++ks) {
         const uint64_t dah = make_smem_desc(ah + ks * 2 * a_lbo, a_lbo, 128), dal = make_smem_desc(al + ks * 2 * a_lbo, a_lbo, 128);
         const uint64_t dbh = make_smem_desc(bh + ks * 2 * b_lbo, b_lbo, 128), dbl = make_smem_desc(bl + ks * 2 * b_lbo, b_lbo, 128);
         mma_bf16(tmem_d, dah, dbh, idesc, acc);
+        mma_bf16(tmem_d, dal, dbh, idesc, 1);
+        mma_bf16(tmem_d, dah, dbl, idesc, 1);
         acc = 1;
-        if (N_TERMS >= 2) mma_bf16(tmem_d, dal, dbh, idesc, 1);
-        if (N_TERMS >= 3) mma_bf16(tmem_d, dah, dbl, idesc, 1);
-        if (N_TERMS >= 4) mma_bf16(tmem_d, dal, dbl, idesc, 1);
     }
 }
 
-// epilogue of a 64-wide hidden layer: TMEM row -> (+bias) -> tanh -> bf16 hi/lo -> this thread's row of the next A tile
-__device__ __forceinline__ void hidden_epilogue(PolicyTcSmem& S, uint32_t taddr, const float* bias, int row) {
-    float v[64];
-    tmem_ld_x16(taddr, v);
-    tmem_ld_x16(taddr + 16, v + 16);
-    tmem_ld_x16(taddr + 32, v + 32);
-    tmem_ld_x16(taddr + 48, v + 48);
-    tmem_ld_wait();
+// 16 accumulator columns (already scaled by 2 log2 e) -> tanh -> bf16 hi/lo -> chunks 2*cc, 2*cc+1 of this thread's A row
+__device__ __forceinline__ void hidden_chunk(TcTile& T, const float* v, int cc, int row) {
 #pragma unroll
-    for (int c = 0; c < 8; ++c) {
+    for (int q8 = 0; q8 < 2; ++q8) {
         uint32_t h[4], l[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            float a = v[8 * c + 2 * q], b = v[8 * c + 2 * q + 1];
-            if (bias) { a += bias[8 * c + 2 * q]; b += bias[8 * c + 2 * q + 1]; }
-            split_pair(tanh_mufu(a), tanh_mufu(b), h[q], l[q]);
-        }
-        *reinterpret_cast<uint4*>(S.A_hi + c * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(S.A_lo + c * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+        for (int q = 0; q < 4; ++q) split_pair(tanh_from_scaled(v[8 * q8 + 2 * q]), tanh_from_scaled(v[8 * q8 + 2 * q + 1]), h[q], l[q]);
+        *reinterpret_cast<uint4*>(T.A_hi + (2 * cc + q8) * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        *reinterpret_cast<uint4*>(T.A_lo + (2 * cc + q8) * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
     }
 }
 
-// Full policy evaluation for the CTA's 128 rows.  Every thread of the CTA must call this (it contains CTA barriers).
-// ob: this thread's 11-d observation.  pd: (mean0, mean1, logstd0, logstd1) or the four raw outputs.
+// epilogue of a 64-wide hidden layer: TMEM row -> tanh -> split -> this thread's row of the next A tile; TMEM loads of
+// the next 16 columns are in flight while the current 16 are processed
+__device__ __forceinline__ void hidden_epilogue(TcTile& T, uint32_t taddr, int row) {
+    float va[16], vb[16];
+    tmem_ld_x16(taddr, va);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; cc += 2) {
+        tmem_ld_wait();
+        tmem_ld_x16(taddr + 16 * (cc + 1), vb);
+        hidden_chunk(T, va, cc, row);
+        tmem_ld_wait();
+        if (cc + 2 < 4) tmem_ld_x16(taddr + 16 * (cc + 2), va);
+        hidden_chunk(T, vb, cc + 1, row);
+    }
+}
+
+// Full policy evaluation for one tile.  Every ACTIVE thread of the tile must call this (it contains the tile barrier,
+// `bar_threads` = 32 * active warps of the tile).  ob: this thread's 11-d observation.  pd: (mean0, mean1, logstd0,
+// logstd1) or the four raw outputs.  issuer: exactly one active thread of the tile.
 template <int NOUT>
-__device__ __forceinline__ void policy_tc_eval(PolicyTcSmem& S, const float* ob, float* pd, uint32_t& phase) {
-    const int row = threadIdx.x;
-    const uint32_t tmem = S.tmem_base;
+__device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile, int row, int bar_threads, bool issuer, const float* ob,
+                                               float* pd, uint32_t& phase) {
+    const uint32_t tmem = S.tmem_base + (uint32_t)tile * 64u;
     const uint32_t lane_base = (uint32_t)(row & ~31) << 16;     // this warp's 32-lane TMEM window
+    uint64_t* mbar = &S.mbar[tile];
+    const uint32_t ah = smem_u32(T.A_hi), al = smem_u32(T.A_lo);
     // ---- A1 = [clip((ob - mu) * inv_sd), 1, 0...] --------------------------------------------------------------
     {
         float z[16];
@@ -137,41 +165,41 @@ __device__ __forceinline__ void policy_tc_eval(PolicyTcSmem& S, const float* ob,
             uint32_t h[4], l[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) split_pair(z[8 * c + 2 * q], z[8 * c + 2 * q + 1], h[q], l[q]);
-            *reinterpret_cast<uint4*>(S.A_hi + c * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-            *reinterpret_cast<uint4*>(S.A_lo + c * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+            *reinterpret_cast<uint4*>(T.A_hi + c * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+            *reinterpret_cast<uint4*>(T.A_lo + c * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
         }
     }
+#pragma unroll 1
+    for (int layer = 0; layer < 2; ++layer) {                     // the two 64-wide tanh layers share one copy of the epilogue code
+        fence_async_smem();
+        fence_before_sync();
+        tile_sync(1 + tile, bar_threads);
+        if (issuer) {
+            fence_after_sync();
+            const uint32_t idesc = make_idesc_bf16(128, 64);
+            if (layer == 0) {
+                issue_bf16x3(tmem, ah, al, smem_u32(S.B1_hi), smem_u32(S.B1_lo), 1, 64, idesc, 0);     // b1 rides in the ones column
+            } else {
+                const uint64_t ones = make_smem_desc(smem_u32(S.ONES), 128 * 16, 128);
+                mma_bf16(tmem, ones, make_smem_desc(smem_u32(S.B2b_hi), 64 * 16, 128), idesc, 0);     // D = 1 * b2 (hi + lo)
+                mma_bf16(tmem, ones, make_smem_desc(smem_u32(S.B2b_lo), 64 * 16, 128), idesc, 1);
+                issue_bf16x3(tmem, ah, al, smem_u32(S.B2_hi), smem_u32(S.B2_lo), 4, 64, idesc, 1);
+            }
+            mma_commit(mbar);
+        }
+        mbar_wait(mbar, phase); phase ^= 1u;
+        fence_after_sync();
+        hidden_epilogue(T, tmem + lane_base, row);
+    }
     fence_async_smem();
     fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x == 0) {
+    tile_sync(1 + tile, bar_threads);
+    if (issuer) {
         fence_after_sync();
-        issue_layer(tmem, S.A_hi, S.A_lo, S.B1_hi, S.B1_lo, 1, 64, make_idesc_bf16(128, 64));
-        mma_commit(&S.mbar);
+        issue_bf16x3(tmem, ah, al, smem_u32(S.B3_hi), smem_u32(S.B3_lo), 4, 16, make_idesc_bf16(128, 16), 0);
+        mma_commit(mbar);
     }
-    mbar_wait(&S.mbar, phase); phase ^= 1u;
-    fence_after_sync();
-    hidden_epilogue(S, tmem + lane_base, nullptr, row);           // b1 rides in the ones column
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        fence_after_sync();
-        issue_layer(tmem + 64, S.A_hi, S.A_lo, S.B2_hi, S.B2_lo, 4, 64, make_idesc_bf16(128, 64));
-        mma_commit(&S.mbar);
-    }
-    mbar_wait(&S.mbar, phase); phase ^= 1u;
-    fence_after_sync();
-    hidden_epilogue(S, tmem + lane_base + 64, S.b2, row);
-    fence_async_smem();
-    fence_before_sync();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        fence_after_sync();
-        issue_layer(tmem, S.A_hi, S.A_lo, S.B3_hi, S.B3_lo, 4, 16, make_idesc_bf16(128, 16));
-        mma_commit(&S.mbar);
-    }
-    mbar_wait(&S.mbar, phase); phase ^= 1u;
+    mbar_wait(mbar, phase); phase ^= 1u;
     fence_after_sync();
     float o[4];
     tmem_ld_x4(tmem + lane_base, o);
@@ -179,111 +207,131 @@ __device__ __forceinline__ void policy_tc_eval(PolicyTcSmem& S, const float* ob,
     pd[0] = o[0] + S.b3[0];
     pd[1] = o[1] + S.b3[1];
     if (NOUT == 4) { pd[2] = o[2] + S.b3[2]; pd[3] = o[3] + S.b3[3]; } else { pd[2] = S.logstd[0]; pd[3] = S.logstd[1]; }
-    fence_before_sync();       // orders this TMEM read before the next evaluation's MMA (issued after the next barrier)
+    fence_before_sync();       // orders this TMEM read before the next evaluation's MMA (issued after the next tile barrier)
 }
 
-__device__ __forceinline__ void policy_tc_setup(PolicyTcSmem& S, const float* params, int nout) {
-    if (threadIdx.x < 32) tmem_alloc<128>(&S.tmem_base);
-    if (threadIdx.x == 0) { mbar_init(&S.mbar, 1); fence_mbar_init(); }
+template <int NT> __device__ __forceinline__ void policy_tc_setup(TcShared& S, const float* params, int nout) {
+    if (threadIdx.x < 32) tmem_alloc<tmem_cols<NT>()>(&S.tmem_base);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < MAX_TILES; ++t) mbar_init(&S.mbar[t], 1);
+        fence_mbar_init();
+    }
     policy_tc_load_weights(S, params, nout);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
 }
-__device__ __forceinline__ void policy_tc_teardown(PolicyTcSmem& S) {
+template <int NT> __device__ __forceinline__ void policy_tc_teardown(TcShared& S) {
     fence_before_sync();
     __syncthreads();
-    if (threadIdx.x < 32) tmem_dealloc<128>(S.tmem_base);
+    if (threadIdx.x < 32) tmem_dealloc<tmem_cols<NT>()>(S.tmem_base);
 }
 
-template <int NOUT>
-__global__ void __launch_bounds__(TCB) k_policy_fwd_tc(const float* __restrict__ params, const float* __restrict__ obs, int64_t n,
-                                                       float4* __restrict__ pd_out) {
+// Standalone forward: every CTA strides over groups of NT tiles (all 4 warps of every tile take part; rows >= n are zeros)
+template <int NOUT, int NT>
+__global__ void __launch_bounds__(NT* TILE, 1) k_policy_fwd_tc(const float* __restrict__ params, const float* __restrict__ obs, int64_t n,
+                                                                float4* __restrict__ pd_out) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    PolicyTcSmem& S = *reinterpret_cast<PolicyTcSmem*>(smem_raw);
-    policy_tc_setup(S, params, NOUT);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* strip = reinterpret_cast<float*>(S.A_hi + STRIP_OFF) + warp * 32 * OBS;
+    TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
+    TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
+    policy_tc_setup<NT>(S, params, NOUT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tile = warp >> 2, row = threadIdx.x & (TILE - 1);
+    TcTile& T = tiles[tile];
+    float* strip = reinterpret_cast<float*>(T.A_hi + STRIP_OFF) + (warp & 3) * 32 * OBS;
     uint32_t phase = 0;
-    const int64_t ntiles = (n + TCB - 1) / TCB;
-    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-        const int64_t i = tile * TCB + threadIdx.x;
+    const int64_t ngroups = (n + (int64_t)NT * TILE - 1) / ((int64_t)NT * TILE);
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t i = g * NT * TILE + threadIdx.x;
         const int64_t row0 = i - lane;
         const int nvalid = (int)max((int64_t)0, min((int64_t)32, n - row0));
         float ob[OBS], pd[4];
         warp_load_rows<OBS>(obs, row0, nvalid, ob, strip, lane);
         __syncwarp();
-        policy_tc_eval<NOUT>(S, ob, pd, phase);
+        policy_tc_eval<NOUT>(S, T, tile, row, TILE, row == 0, ob, pd, phase);
         if (i < n) pd_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
     }
-    policy_tc_teardown(S);
+    policy_tc_teardown<NT>(S);
 }
 
-template <int NOUT>
-__global__ void __launch_bounds__(TCB) k_rollout_policy_tc(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
-                                                           int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
-                                                           float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf, uint32_t k0,
-                                                           uint32_t k1, uint32_t offset) {
+// Fused policy-in-the-loop rollout (teacher warm-up loop, mlp_train.py:120-139).  Envs are dealt to CTAs in warp units.
+template <int NOUT, int NT>
+__global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
+                                                                    int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
+                                                                    float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf, uint32_t k0,
+                                                                    uint32_t k1, uint32_t offset) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
-    PolicyTcSmem& S = *reinterpret_cast<PolicyTcSmem*>(smem_raw);
-    policy_tc_setup(S, params, NOUT);
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* strip = reinterpret_cast<float*>(S.A_hi + STRIP_OFF) + warp * 32 * OBS;
-    const int64_t i = (int64_t)blockIdx.x * TCB + threadIdx.x;
-    const int64_t row0 = i - lane;
-    const int nvalid = (int)max((int64_t)0, min((int64_t)32, n - row0));
-    const bool valid = i < n;
-    const uint32_t gid = offset + (uint32_t)i;
-    EnvState<float> e;
-    if (valid) {
-        const float4 a = qv[i], b = tp[i];
-        const uint2 c = ctr[i];
-        e.q0 = a.x; e.q1 = a.y; e.v0 = a.z; e.v1 = a.w; e.tx = b.x; e.ty = b.y; e.px = b.z; e.py = b.w; e.step = (int)c.x; e.episode = c.y;
-    } else { e.q0 = e.q1 = e.v0 = e.v1 = e.tx = e.ty = e.px = e.py = 0.f; e.step = 0; e.episode = 0; }
-    uint32_t phase = 0;
-    for (int t = 0; t < T; ++t) {
-        float ob[OBS], pd[4];
-        observe(e, ob);
-        if (obs_buf && nvalid > 0) warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strip, lane);
-        __syncwarp();
-        policy_tc_eval<NOUT>(S, ob, pd, phase);
-        bool d;
-        const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
-        const int64_t row = (int64_t)t * n + i;
-        if (valid) {
-            if (pd_buf) pd_buf[row] = make_float4(pd[0], pd[1], pd[2], pd[3]);
-            if (rew_buf) rew_buf[row] = rw;
-            if (done_buf) done_buf[row] = d ? 1 : 0;
+    TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
+    TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
+    // balanced contiguous split of the ceil(n/32) warp units over the grid
+    const int64_t units = (n + 31) >> 5, per = units / gridDim.x, rem = units % gridDim.x;
+    const int64_t unit0 = (int64_t)blockIdx.x * per + min((int64_t)blockIdx.x, rem);
+    const int nunits = (int)(per + ((int64_t)blockIdx.x < rem ? 1 : 0));       // <= 4 * NT (host guarantees)
+    if (nunits == 0) return;                                                  // CTA-uniform
+    policy_tc_setup<NT>(S, params, NOUT);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tile = warp >> 2, row = threadIdx.x & (TILE - 1);
+    if (warp < nunits) {
+        TcTile& Tl = tiles[tile];
+        const int bar_threads = 32 * min(4, nunits - 4 * tile);
+        float* strip = reinterpret_cast<float*>(Tl.A_hi + STRIP_OFF) + (warp & 3) * 32 * OBS;
+        const int64_t row0 = (unit0 + warp) << 5, i = row0 + lane;
+        const int nvalid = (int)min((int64_t)32, n - row0);
+        const bool valid = i < n;
+        const uint32_t gid = offset + (uint32_t)i;
+        EnvState e = valid ? load_state(qv, tp, ctr, i) : zero_state();
+        uint32_t phase = 0;
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) {
+            float ob[OBS], pd[4];
+            observe(e, ob);
+            if (obs_buf) warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strip, lane);
+            __syncwarp();
+            policy_tc_eval<NOUT>(S, Tl, tile, row, bar_threads, row == 0, ob, pd, phase);
+            bool d;
+            const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
+            const int64_t r = (int64_t)t * n + i;
+            if (valid) {
+                if (pd_buf) pd_buf[r] = make_float4(pd[0], pd[1], pd[2], pd[3]);
+                if (rew_buf) rew_buf[r] = rw;
+                if (done_buf) done_buf[r] = d ? 1 : 0;
+            }
         }
+        if (valid) store_state(qv, tp, ctr, i, e);
     }
-    if (valid) {
-        qv[i] = make_float4(e.q0, e.q1, e.v0, e.v1);
-        tp[i] = make_float4(e.tx, e.ty, e.px, e.py);
-        ctr[i] = make_uint2((uint32_t)e.step, e.episode);
-    }
-    policy_tc_teardown(S);
+    policy_tc_teardown<NT>(S);
 }
 
-template <typename K> static int set_smem_attr(K kern) {
-    RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(PolicyTcSmem)));
+template <typename K> static int set_smem_attr(K kern, size_t bytes) {
+    RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
     return RB_OK;
 }
 
-int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, float* pd, cudaStream_t s) {
-    int device = 0, sms = 148;
+static int sm_count_current(int* sms) {
+    int device = 0;
     RB_CUDA(cudaGetDevice(&device));
-    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    const int64_t ntiles = (n + TCB - 1) / TCB;
-    const unsigned grid = (unsigned)min((int64_t)sms * 3, ntiles);
+    RB_CUDA(cudaDeviceGetAttribute(sms, cudaDevAttrMultiProcessorCount, device));
+    return RB_OK;
+}
+
+constexpr int FWD_NT = 2;       // standalone forward: 2 tiles per CTA (97 KB) -> 2 CTAs per SM
+constexpr int ROLLOUT_NT = 4;   // fused rollout: 4 tiles = 16 warps per CTA, one CTA per SM
+
+int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, float* pd, cudaStream_t s) {
+    int sms = 148;
+    int rc = sm_count_current(&sms);
+    if (rc) return rc;
+    const int64_t ngroups = (n + FWD_NT * TILE - 1) / (FWD_NT * TILE);
+    const unsigned grid = (unsigned)min((int64_t)sms * 2, ngroups);
+    const size_t smem = tc_smem_bytes<FWD_NT>();
     if (nout == 2) {
-        int rc = set_smem_attr(k_policy_fwd_tc<2>);
+        rc = set_smem_attr(k_policy_fwd_tc<2, FWD_NT>, smem);
         if (rc) return rc;
-        k_policy_fwd_tc<2><<<grid, TCB, sizeof(PolicyTcSmem), s>>>(params, obs, n, (float4*)pd);
+        k_policy_fwd_tc<2, FWD_NT><<<grid, FWD_NT * TILE, smem, s>>>(params, obs, n, (float4*)pd);
     } else {
-        int rc = set_smem_attr(k_policy_fwd_tc<4>);
+        rc = set_smem_attr(k_policy_fwd_tc<4, FWD_NT>, smem);
         if (rc) return rc;
-        k_policy_fwd_tc<4><<<grid, TCB, sizeof(PolicyTcSmem), s>>>(params, obs, n, (float4*)pd);
+        k_policy_fwd_tc<4, FWD_NT><<<grid, FWD_NT * TILE, smem, s>>>(params, obs, n, (float4*)pd);
     }
     RB_CUDA(cudaGetLastError());
     return RB_OK;
@@ -291,18 +339,23 @@ int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, fl
 
 int rollout_policy_tc(rb_env* e, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf, uint8_t* done_buf,
                       cudaStream_t s) {
-    const unsigned grid = (unsigned)((e->n + TCB - 1) / TCB);
+    constexpr int NT = ROLLOUT_NT;
+    const int64_t units = (e->n + 31) / 32;
+    const int64_t per_round = (int64_t)4 * NT * e->sm_count;
+    const int64_t rounds = (units + per_round - 1) / per_round;
+    const unsigned grid = (unsigned)min(units, rounds * e->sm_count);        // units / grid <= 4 * NT
     const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+    const size_t smem = tc_smem_bytes<NT>();
     if (nout == 2) {
-        int rc = set_smem_attr(k_rollout_policy_tc<2>);
+        int rc = set_smem_attr(k_rollout_policy_tc<2, NT>, smem);
         if (rc) return rc;
-        k_rollout_policy_tc<2><<<grid, TCB, sizeof(PolicyTcSmem), s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf,
-                                                                        done_buf, k0, k1, e->offset);
+        k_rollout_policy_tc<2, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf,
+                                                                 k0, k1, e->offset);
     } else {
-        int rc = set_smem_attr(k_rollout_policy_tc<4>);
+        int rc = set_smem_attr(k_rollout_policy_tc<4, NT>, smem);
         if (rc) return rc;
-        k_rollout_policy_tc<4><<<grid, TCB, sizeof(PolicyTcSmem), s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf,
-                                                                        done_buf, k0, k1, e->offset);
+        k_rollout_policy_tc<4, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf,
+                                                                 k0, k1, e->offset);
     }
     RB_CUDA(cudaGetLastError());
     return RB_OK;

@@ -125,6 +125,14 @@ __device__ __forceinline__ float tanh_mufu(float x) {
     return fmaf(-2.0f, r, 1.0f);
 }
 
+// same with the argument already multiplied by 2 log2(e) (the kernels fold that factor into the weights)
+__device__ __forceinline__ float tanh_from_scaled(float y) {
+    float e, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(y));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(e + 1.0f));
+    return fmaf(-2.0f, r, 1.0f);
+}
+
 // byte offset of element (r, k) inside a K-major no-swizzle tile with R rows
 __host__ __device__ constexpr uint32_t tile_off(int r, int k, int R) { return (uint32_t)((k >> 3) * (R * 16) + r * 16 + (k & 7) * 2); }
 
