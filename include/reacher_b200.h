@@ -131,6 +131,9 @@ int rb_student_mlp_input(const float* obs_dev, const float* prev_pdflat_dev, con
 
 /* sess.run(s_pdflat)  src/distilation/mlp_train.py:173-186 -- forward only.  x_dev[B,in] -> s_pdflat_dev[B,4] */
 int rb_student_fwd(int kind, const float* params_dev, const float* x_dev, int64_t B, float* s_pdflat_dev, int mode, void* stream);
+/* same with a workspace (rb_student_workspace_bytes() bytes) -- required for RB_MODE_TC, which folds the linear layer first */
+int rb_student_fwd_ws(int kind, const float* params_dev, const float* x_dev, int64_t B, float* s_pdflat_dev, void* workspace_dev, int mode,
+                      void* stream);
 
 /* sess.run([loss, minimize_adam]) minus the Adam update  src/distilation/mlp_train.py:148-161 ;
  * lossandgrad  backup/student_rollout.py:646,708.

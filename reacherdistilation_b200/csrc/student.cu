@@ -316,9 +316,10 @@ static int launch_student(const NetSpec& S, const float* params, const float* x,
     return RB_OK;
 }
 
-// implemented in student_tc.cu
-int student_loss_grad_tc(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, float* s_out,
-                         float* gradloss, void* workspace, cudaStream_t st);
+// implemented in student_tc.cu (tcgen05 path)
+int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
+                   float* gradloss, void* workspace, cudaStream_t st);
+size_t student_tc_workspace_floats();
 
 }  // namespace rb
 
@@ -337,7 +338,8 @@ int rb_student_input_dim(int kind) {
 int64_t rb_student_workspace_bytes(int kind, int64_t batch, int device) {
     (void)batch; (void)device;
     if (kind != RB_STUDENT_POLICY64 && kind != RB_STUDENT_MLP) return -1;
-    return (int64_t)sizeof(float) * MAX_STUDENT_BLOCKS * (make_spec(kind).P + 1);
+    const size_t fp32_floats = (size_t)MAX_STUDENT_BLOCKS * (make_spec(kind).P + 1);
+    return (int64_t)(sizeof(float) * max(fp32_floats, student_tc_workspace_floats()));
 }
 
 int rb_student_mlp_input(const float* obs, const float* prev_pd, const float* prev_rew, int64_t B, float keep_prob, uint64_t seed,
@@ -359,10 +361,19 @@ static int student_dispatch(int kind, const float* params, const float* x, const
     return launch_student<64, 4, false>(S, params, x, tpd, B, loss_kind, fwd_only, s_out, gradloss, (float*)ws, st);
 }
 
+int rb_student_fwd_ws(int kind, const float* params, const float* x, int64_t B, float* s_pd, void* ws, int mode, void* stream) {
+    RB_REQUIRE(params && x && s_pd, "NULL argument");
+    RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
+    if (B <= 0) return RB_OK;
+    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, ws, (cudaStream_t)stream);
+    RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
+    return student_dispatch(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, nullptr, (cudaStream_t)stream);
+}
+
 int rb_student_fwd(int kind, const float* params, const float* x, int64_t B, float* s_pd, int mode, void* stream) {
     RB_REQUIRE(params && x && s_pd, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
-    RB_REQUIRE(mode == RB_MODE_FP32, "rb_student_fwd: only RB_MODE_FP32 is built (see rb_student_mode_available)");
+    RB_REQUIRE(mode == RB_MODE_FP32, "rb_student_fwd: RB_MODE_TC needs a workspace, use rb_student_fwd_ws");
     if (B <= 0) return RB_OK;
     return student_dispatch(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -373,7 +384,7 @@ int rb_student_loss_grad(int kind, const float* params, const float* x, const fl
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
     RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
     RB_REQUIRE(B > 0, "empty batch");
-    if (mode == RB_MODE_TC) return student_loss_grad_tc(kind, params, x, tpd, B, loss_kind, s_pd, gradloss, ws, (cudaStream_t)stream);
+    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, (cudaStream_t)stream);
     RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
     return student_dispatch(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, (cudaStream_t)stream);
 }

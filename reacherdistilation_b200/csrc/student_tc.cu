@@ -1,0 +1,523 @@
+// RB_MODE_TC student: forward, fused KL loss, backward (dgrad + wgrad) on the 5th-gen tensor cores.
+// Replaces sess.run([loss, minimize_adam]) minus Adam (/root/reference src/distilation/mlp_train.py:148-161), the student graph
+// student_nn.py:51-57 (16-24-128-128(lin)-32-4), the backup student backup/student_rollout.py:79-87 (11-64-64-4, obfilter),
+// kl_loss loss.py:3-13 and lossandgrad backup/student_rollout.py:639-646,708.
+//
+// One persistent CTA per SM (512 threads) walks over tiles of 128 samples.  Design:
+//  * ACTIVATIONS live in one feature-major shared-memory matrix per bf16 split half (ACT_HI, ACT_LO): "group" g = 8 features
+//    x 128 samples = 2048 B at byte g*2048, sample s at +s*16, feature f%8 at +(f%8)*2.  That is the UMMA no-swizzle K-major
+//    layout (LBO 2048, SBO 128) when a window of groups is used as the A operand of forward / dgrad GEMMs (M = samples), and
+//    the SAME BYTES are the MN-major layout (K-group stride 128, MN-group stride 2048) when a window is used as an operand of
+//    the wgrad GEMMs (K = samples), so nothing is ever transposed or copied.
+//  * Each layer input X_l is followed by a constant ONES group (feature 0 == 1): the forward GEMM picks the bias up from an
+//    extra K row of the weight tile, and the wgrad GEMM  G_l[out, in|1] += dZ_l^T [X_l | 1]  yields the bias gradient as one
+//    more column.  dZ_l (gradient w.r.t. the pre-activation of layer l) overwrites X_{l+1} in place.
+//  * WEIGHTS: one K-major tile per layer (hi and lo), element (n = out, k = in); the dgrad GEMM reads the same tile through
+//    an MN-major descriptor (dX = dZ W^T).
+//  * ACCUMULATORS in TMEM: columns [0,128) forward / dgrad results; G_l of every layer behind them.  The weight-gradient
+//    accumulators stay in TMEM across ALL tiles of the CTA and are written out once (fixed order => bit-reproducible).
+//  * bf16x3 operand splitting (hi*hi + lo*hi + hi*lo, fp32 accumulate) keeps results ~1e-5 of fp32.
+//  * The reference's third layer is LINEAR (student_nn.py:55), so layers 3 and 4 are folded for the GEMMs:
+//    W34 = W3 W4, b34 = b3 W4 + b4 (k_fold34, fp32).  The tile kernel accumulates G34 = dL/dW34, g34 = dL/db34 and
+//    k_student_finish maps them back exactly:  dW3 = G34 W4^T, db3 = W4 g34, dW4 = W3^T G34 + b3 (x) g34, db4 = g34.
+//    This removes the 128x128 layer (60 % of the MMA work and 100 KB of shared memory) without changing the function.
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace rb {
+
+using namespace tc;
+
+constexpr int ST_THREADS = 512;
+constexpr int ST_TILE = 128;
+constexpr int ST_GROUPS = 32;                         // groups per ACT half
+constexpr int ST_ACT_BYTES = ST_GROUPS * 2048;        // 64 KB
+constexpr int ST_MAXL = 4;
+
+// ---- network specs (the folded MLP and the 2x64 policy student) ---------------------------------------------------------
+struct SpecMLP {   // 16 -> 24 tanh -> 128 tanh -> [128 lin -> ] 32 tanh -> 4
+    static constexpr int L = 4, IN0 = 16, OBFILTER = 0;
+    __host__ __device__ static constexpr int in(int l) { return l == 0 ? 16 : l == 1 ? 24 : l == 2 ? 128 : 32; }
+    __host__ __device__ static constexpr int out(int l) { return l == 0 ? 24 : l == 1 ? 128 : l == 2 ? 32 : 4; }
+    // group index of X_l in the ACT halves (ONES group follows each); dZ of the last layer sits at group 0
+    __host__ __device__ static constexpr int slot(int l) { return l == 0 ? 7 : l == 1 ? 10 : l == 2 ? 14 : 2; }
+};
+struct SpecPOL {   // 11 -> 64 tanh -> 64 tanh -> 4, input z = clip((x - mu) / sd, +-5)
+    static constexpr int L = 3, IN0 = 11, OBFILTER = 1;
+    __host__ __device__ static constexpr int in(int l) { return l == 0 ? 11 : 64; }
+    __host__ __device__ static constexpr int out(int l) { return l == 2 ? 4 : 64; }
+    __host__ __device__ static constexpr int slot(int l) { return l == 0 ? 2 : l == 1 ? 5 : 14; }
+};
+template <class S> struct Geo {
+    __host__ __device__ static constexpr int ig(int l) { return (S::in(l) + 7) / 8; }                  // feature groups of X_l
+    __host__ __device__ static constexpr int K(int l) { return ((ig(l) * 8 + 1 + 15) / 16) * 16; }     // forward K incl. ones
+    __host__ __device__ static constexpr int N(int l) { return ((S::out(l) + 15) / 16) * 16; }         // forward N
+    __host__ __device__ static constexpr int inpad(int l) { return ((S::in(l) + 15) / 16) * 16; }      // dgrad N
+    __host__ __device__ static constexpr int dzslot(int l) { return l == S::L - 1 ? 0 : S::slot(l + 1); }
+    __host__ __device__ static constexpr int wtile_off(int l) { return l == 0 ? 0 : wtile_off(l - 1) + N(l - 1) * K(l - 1) * 2; }   // bytes
+    __host__ __device__ static constexpr int wtile_bytes() { return wtile_off(S::L); }
+    __host__ __device__ static constexpr int gcol(int l) { return l == 0 ? 128 : gcol(l - 1) + K(l - 1); }   // TMEM column of G_l
+};
+
+struct StudentTcArgs {
+    const float* w[ST_MAXL];      // W_l row-major [in][out]
+    const float* b[ST_MAXL];      // b_l [out]
+    int pw[ST_MAXL], pb[ST_MAXL]; // offsets of dW_l / db_l inside one partial vector
+    int ploss, pstride;           // offset of the loss, floats per partial vector
+    const float* obf;             // SpecPOL: ob_mean[11] ob_std[11]
+    const float* x;               // [B, IN0]
+    const float* t;               // [B, 4] teacher pdflat (NULL: forward only)
+    float4* s_out;                // [B] student pdflat (may be NULL)
+    float* partials;              // [grid][pstride]
+    int64_t B;
+    int loss_kind, fwd_only;
+};
+
+struct __align__(16) StudentTcCtl {
+    uint64_t mbar;
+    uint32_t tmem_base;
+    float red[ST_THREADS / 32];
+};
+
+__device__ __forceinline__ uint32_t make_idesc_bf16_ex(int M, int N, int a_mn, int b_mn) {
+    return make_idesc_bf16(M, N) | ((uint32_t)a_mn << 15) | ((uint32_t)b_mn << 16);
+}
+__device__ __forceinline__ void tmem_ld_x8(uint32_t taddr, float* v) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ float bf16lo_to_f32(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf16hi_to_f32(uint32_t w) { return __uint_as_float(w & 0xFFFF0000u); }
+
+// three bf16x3 terms for one K-step
+__device__ __forceinline__ void mma3(uint32_t d, uint64_t ah, uint64_t al, uint64_t bh, uint64_t bl, uint32_t idesc, uint32_t acc) {
+    mma_bf16(d, ah, bh, idesc, acc);
+    mma_bf16(d, al, bh, idesc, 1);
+    mma_bf16(d, ah, bl, idesc, 1);
+}
+
+template <class S, int l> __device__ __forceinline__ void issue_fwd(uint32_t tmem, uint32_t act_hi, uint32_t act_lo, uint32_t w_hi, uint32_t w_lo) {
+    using G = Geo<S>;
+    constexpr int K = G::K(l), N = G::N(l);
+    const uint32_t idesc = make_idesc_bf16_ex(128, N, 0, 0);
+    const uint32_t a0 = S::slot(l) * 2048, b0 = G::wtile_off(l);
+#pragma unroll
+    for (int ks = 0; ks < K / 16; ++ks) {
+        const uint32_t ao = a0 + ks * 2 * 2048, bo = b0 + ks * 2 * (N * 16);
+        mma3(tmem, make_smem_desc(act_hi + ao, 2048, 128), make_smem_desc(act_lo + ao, 2048, 128), make_smem_desc(w_hi + bo, N * 16, 128),
+             make_smem_desc(w_lo + bo, N * 16, 128), idesc, ks > 0);
+    }
+}
+// dX_l[128, inpad] = dZ_l[128, N_l] * W_l^T : A = dZ window (K-major), B = weight tile through an MN-major descriptor
+template <class S, int l> __device__ __forceinline__ void issue_dgrad(uint32_t tmem, uint32_t act_hi, uint32_t act_lo, uint32_t w_hi, uint32_t w_lo) {
+    using G = Geo<S>;
+    constexpr int N = G::N(l), NP = G::inpad(l);
+    const uint32_t idesc = make_idesc_bf16_ex(128, NP, 0, 1);
+    const uint32_t a0 = G::dzslot(l) * 2048, b0 = G::wtile_off(l);
+#pragma unroll
+    for (int ks = 0; ks < N / 16; ++ks) {
+        const uint32_t ao = a0 + ks * 2 * 2048, bo = b0 + ks * 2 * 128;
+        mma3(tmem, make_smem_desc(act_hi + ao, 2048, 128), make_smem_desc(act_lo + ao, 2048, 128), make_smem_desc(w_hi + bo, 128, N * 16),
+             make_smem_desc(w_lo + bo, 128, N * 16), idesc, ks > 0);
+    }
+}
+// G_l[128 (out features of the dZ window), K_l] += dZ_l^T [X_l | ONES | .] : both operands MN-major windows of ACT, K = samples
+template <class S, int l> __device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t act_hi, uint32_t act_lo, uint32_t first) {
+    using G = Geo<S>;
+    constexpr int K = G::K(l);
+    const uint32_t idesc = make_idesc_bf16_ex(128, K, 1, 1);
+    const uint32_t a0 = G::dzslot(l) * 2048, b0 = S::slot(l) * 2048, d = tmem + G::gcol(l);
+#pragma unroll
+    for (int ks = 0; ks < ST_TILE / 16; ++ks) {
+        const uint32_t ao = a0 + ks * 256, bo = b0 + ks * 256;
+        mma3(d, make_smem_desc(act_hi + ao, 128, 2048), make_smem_desc(act_lo + ao, 128, 2048), make_smem_desc(act_hi + bo, 128, 2048),
+             make_smem_desc(act_lo + bo, 128, 2048), idesc, (ks > 0) || !first);
+    }
+}
+
+// write 8 fp32 values as one bf16 hi group row and one lo group row
+__device__ __forceinline__ void store_split8(uint8_t* act_hi, uint8_t* act_lo, int group, int row, const float* v) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
+    *reinterpret_cast<uint4*>(act_hi + group * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+    *reinterpret_cast<uint4*>(act_lo + group * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
+}
+
+// forward epilogue of hidden layer l: ACC -> tanh -> X_{l+1}
+template <class S, int l> __device__ __forceinline__ void epi_fwd(uint32_t tacc, uint8_t* act_hi, uint8_t* act_lo, int row, int part) {
+    constexpr int og = S::out(l) / 8, gpp = (og + 3) / 4;
+    static_assert(S::out(l) % 8 == 0, "hidden widths are multiples of 8");
+    float v[gpp][8];
+#pragma unroll
+    for (int i = 0; i < gpp; ++i)
+        if (part * gpp + i < og) tmem_ld_x8(tacc + (part * gpp + i) * 8, v[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < gpp; ++i) {
+        const int g = part * gpp + i;
+        if (g < og) {
+#pragma unroll
+            for (int k = 0; k < 8; ++k) v[i][k] = tanh_mufu(v[i][k]);
+            store_split8(act_hi, act_lo, S::slot(l + 1) + g, row, v[i]);
+        }
+    }
+}
+// backward epilogue: dX_l (ACC) * tanh'(X_l) -> dZ_{l-1}, in place over X_l
+template <class S, int l> __device__ __forceinline__ void epi_bwd(uint32_t tacc, uint8_t* act_hi, uint8_t* act_lo, int row, int part) {
+    constexpr int ig = S::in(l) / 8, gpp = (ig + 3) / 4;
+    static_assert(S::in(l) % 8 == 0, "hidden widths are multiples of 8");
+    float v[gpp][8];
+#pragma unroll
+    for (int i = 0; i < gpp; ++i)
+        if (part * gpp + i < ig) tmem_ld_x8(tacc + (part * gpp + i) * 8, v[i]);
+    tmem_ld_wait();
+#pragma unroll
+    for (int i = 0; i < gpp; ++i) {
+        const int g = part * gpp + i;
+        if (g < ig) {
+            const uint4 hh = *reinterpret_cast<const uint4*>(act_hi + (S::slot(l) + g) * 2048 + row * 16);
+            const uint4 ll = *reinterpret_cast<const uint4*>(act_lo + (S::slot(l) + g) * 2048 + row * 16);
+            const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w}, lw[4] = {ll.x, ll.y, ll.z, ll.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float h0 = bf16lo_to_f32(hw[q]) + bf16lo_to_f32(lw[q]), h1 = bf16hi_to_f32(hw[q]) + bf16hi_to_f32(lw[q]);
+                v[i][2 * q] *= fmaf(-h0, h0, 1.f);
+                v[i][2 * q + 1] *= fmaf(-h1, h1, 1.f);
+            }
+            store_split8(act_hi, act_lo, S::slot(l) + g, row, v[i]);
+        }
+    }
+}
+
+template <class S> struct LayerLoop {
+    // weights -> K-major hi/lo tiles: element (n, k) = W[k][n] for k < in, b[n] at k == 8 * ig (the ONES feature), else 0
+    template <int l> __device__ static void load_weights(const StudentTcArgs& a, uint8_t* w_hi, uint8_t* w_lo) {
+        using G = Geo<S>;
+        constexpr int K = G::K(l), N = G::N(l), in = S::in(l), out = S::out(l), kb = G::ig(l) * 8;
+        const float* __restrict__ W = a.w[l];
+        const float* __restrict__ bb = a.b[l];
+        for (int i = threadIdx.x; i < N * K; i += ST_THREADS) {
+            const int n = i % N, k = i / N;
+            float v = 0.f;
+            if (n < out) v = k < in ? __ldg(W + k * out + n) : (k == kb ? __ldg(bb + n) : 0.f);
+            uint16_t h, lo;
+            split_scalar(v, h, lo);
+            const uint32_t off = G::wtile_off(l) + tile_off(n, k, N);
+            *reinterpret_cast<uint16_t*>(w_hi + off) = h;
+            *reinterpret_cast<uint16_t*>(w_lo + off) = lo;
+        }
+        if constexpr (l + 1 < S::L) load_weights<l + 1>(a, w_hi, w_lo);
+    }
+    // G_l (TMEM) -> partial gradient vector: lane j = out feature, column i = in feature, column 8*ig = bias
+    template <int l> __device__ static void dump_grads(const StudentTcArgs& a, uint32_t tmem, float* __restrict__ part_out, int sub, int part, int lane) {
+        using G = Geo<S>;
+        constexpr int in = S::in(l), out = S::out(l), kb = G::ig(l) * 8, ncol8 = G::ig(l) + 1;      // 8-column chunks incl. the bias chunk
+        if (sub * 32 < out) {                                                                      // warp-uniform
+            const int j = sub * 32 + lane;
+            const uint32_t t0 = tmem + ((uint32_t)(sub * 32) << 16) + G::gcol(l);
+            for (int c = part; c < ncol8; c += 4) {
+                float v[8];
+                tmem_ld_x8(t0 + c * 8, v);
+                tmem_ld_wait();
+                if (j < out) {
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) {
+                        const int i = c * 8 + k;
+                        if (i < in) part_out[a.pw[l] + i * out + j] = v[k];
+                        else if (i == kb) part_out[a.pb[l] + j] = v[k];
+                    }
+                }
+            }
+        }
+        if constexpr (l + 1 < S::L) dump_grads<l + 1>(a, tmem, part_out, sub, part, lane);
+    }
+};
+
+template <class S>
+__global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArgs a) {
+    using G = Geo<S>;
+    constexpr int L = S::L;
+    extern __shared__ __align__(128) uint8_t smem[];
+    uint8_t* act_hi = smem;
+    uint8_t* act_lo = smem + ST_ACT_BYTES;
+    uint8_t* w_hi = smem + 2 * ST_ACT_BYTES;
+    uint8_t* w_lo = w_hi + G::wtile_bytes();
+    StudentTcCtl& ctl = *reinterpret_cast<StudentTcCtl*>(w_lo + G::wtile_bytes());
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = warp & 3, part = warp >> 2, row = sub * 32 + lane;
+
+    // ---- one-time setup: TMEM, barrier, zeroed activations + ONES groups, split weights -----------------------------------
+    if (warp == 0) tmem_alloc<512>(&ctl.tmem_base);
+    if (tid == 0) { mbar_init(&ctl.mbar, 1); fence_mbar_init(); }
+    for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
+    __syncthreads();
+    if (tid < ST_TILE) {
+#pragma unroll
+        for (int l = 0; l < L; ++l) *reinterpret_cast<uint16_t*>(act_hi + (S::slot(l) + G::ig(l)) * 2048 + tid * 16) = (uint16_t)0x3F80u;
+    }
+    LayerLoop<S>::template load_weights<0>(a, w_hi, w_lo);
+    fence_async_smem();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = ctl.tmem_base;
+    const uint32_t tacc = tmem + ((uint32_t)(sub * 32) << 16);
+    const uint32_t ah = smem_u32(act_hi), al = smem_u32(act_lo), wh = smem_u32(w_hi), wl = smem_u32(w_lo);
+    uint32_t phase = 0;
+    float loss_acc = 0.f;
+    bool first = true;
+
+    const int64_t ntiles = (a.B + ST_TILE - 1) / ST_TILE;
+    for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t base = tile * ST_TILE;
+        const int nvalid = (int)min((int64_t)ST_TILE, a.B - base);
+        // ---- X0: global fp32 -> (obfilter) -> bf16 hi/lo rows ---------------------------------------------------------------
+        if constexpr (S::IN0 == 16) {
+            const int r = tid >> 2, q = tid & 3;                       // 4 threads per sample row, 4 features each
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r < nvalid) v = __ldg(reinterpret_cast<const float4*>(a.x + (base + r) * 16) + q);
+            uint32_t h0, l0, h1, l1;
+            split_pair(v.x, v.y, h0, l0);
+            split_pair(v.z, v.w, h1, l1);
+            const uint32_t off = (S::slot(0) + (q >> 1)) * 2048 + r * 16 + (q & 1) * 8;
+            *reinterpret_cast<uint2*>(act_hi + off) = make_uint2(h0, h1);
+            *reinterpret_cast<uint2*>(act_lo + off) = make_uint2(l0, l1);
+        } else {
+            for (int e = tid; e < ST_TILE * S::IN0; e += ST_THREADS) {
+                const int r = e / S::IN0, f = e - r * S::IN0;
+                float v = 0.f;
+                if (r < nvalid) {
+                    v = __ldg(a.x + base * S::IN0 + e);
+                    if (S::OBFILTER) v = fminf(5.f, fmaxf(-5.f, (v - __ldg(a.obf + f)) / __ldg(a.obf + 11 + f)));
+                }
+                uint16_t h, lo;
+                split_scalar(v, h, lo);
+                const uint32_t off = (S::slot(0) + (f >> 3)) * 2048 + r * 16 + (f & 7) * 2;
+                *reinterpret_cast<uint16_t*>(act_hi + off) = h;
+                *reinterpret_cast<uint16_t*>(act_lo + off) = lo;
+            }
+        }
+        float4 tpd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!a.fwd_only && part == 0 && row < nvalid) tpd = __ldg(reinterpret_cast<const float4*>(a.t) + base + row);
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+
+        // ---- forward ----------------------------------------------------------------------------------------------------
+#define RB_ST_FWD(l)                                                               \
+        if constexpr (l < L) {                                                     \
+            if (tid == 0) {                                                        \
+                fence_after_sync();                                                \
+                issue_fwd<S, (l < L ? l : 0)>(tmem, ah, al, wh, wl);               \
+                mma_commit(&ctl.mbar);                                             \
+            }                                                                      \
+            mbar_wait(&ctl.mbar, phase); phase ^= 1u;                              \
+            fence_after_sync();                                                    \
+            if constexpr (l < L - 1) {                                             \
+                epi_fwd<S, (l < L - 1 ? l : 0)>(tacc, act_hi, act_lo, row, part);  \
+                fence_async_smem();                                                \
+                fence_before_sync();                                               \
+                __syncthreads();                                                   \
+            }                                                                      \
+        }
+        RB_ST_FWD(0) RB_ST_FWD(1) RB_ST_FWD(2) RB_ST_FWD(3)
+#undef RB_ST_FWD
+        // ---- output epilogue: s = ACC[:, 0:4]; KL loss and dL/ds (loss.py:8-13; reverse: backup/student_rollout.py:639-640) ---
+        if (part == 0) {
+            float s[4];
+            tmem_ld_x4(tacc, s);
+            tmem_ld_wait();
+            if (row < nvalid && a.s_out) a.s_out[base + row] = make_float4(s[0], s[1], s[2], s[3]);
+            if (!a.fwd_only) {
+                float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (row < nvalid) {
+                    const float m0 = s[0], m1 = s[1], l0 = s[2], l1 = s[3];
+                    const float vs0 = expf(2.f * l0), vs1 = expf(2.f * l1), vt0 = expf(2.f * tpd.z), vt1 = expf(2.f * tpd.w);
+                    const float e0 = m0 - tpd.x, e1 = m1 - tpd.y;
+                    if (a.loss_kind == RB_LOSS_KL_ST) {
+                        loss_acc += (tpd.z - l0 + (vs0 + e0 * e0) / (2.f * vt0) - 0.5f) + (tpd.w - l1 + (vs1 + e1 * e1) / (2.f * vt1) - 0.5f);
+                        d[0] = e0 / vt0; d[1] = e1 / vt1; d[2] = vs0 / vt0 - 1.f; d[3] = vs1 / vt1 - 1.f;
+                    } else {
+                        loss_acc += (l0 - tpd.z + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (l1 - tpd.w + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
+                        d[0] = e0 / vs0; d[1] = e1 / vs1; d[2] = 1.f - (vt0 + e0 * e0) / vs0; d[3] = 1.f - (vt1 + e1 * e1) / vs1;
+                    }
+                }
+                store_split8(act_hi, act_lo, 0, row, d);
+            }
+        }
+        fence_async_smem();
+        fence_before_sync();
+        __syncthreads();
+        if (a.fwd_only) continue;
+
+        // ---- backward: wgrad_l (accumulates in TMEM) + dgrad_l, then dZ_{l-1} in place over X_l ------------------------------
+#define RB_ST_BWD(l)                                                               \
+        if constexpr (l < L) {                                                     \
+            if (tid == 0) {                                                        \
+                fence_after_sync();                                                \
+                issue_wgrad<S, (l < L ? l : 0)>(tmem, ah, al, first ? 1u : 0u);    \
+                if constexpr (l > 0) issue_dgrad<S, (l < L ? l : 0)>(tmem, ah, al, wh, wl); \
+                mma_commit(&ctl.mbar);                                             \
+            }                                                                      \
+            mbar_wait(&ctl.mbar, phase); phase ^= 1u;                              \
+            fence_after_sync();                                                    \
+            if constexpr (l > 0) {                                                 \
+                epi_bwd<S, (l > 0 && l < L ? l : 1)>(tacc, act_hi, act_lo, row, part); \
+                fence_async_smem();                                                \
+            }                                                                      \
+            fence_before_sync();                                                   \
+            __syncthreads();                                                       \
+        }
+        RB_ST_BWD(3) RB_ST_BWD(2) RB_ST_BWD(1) RB_ST_BWD(0)
+#undef RB_ST_BWD
+        first = false;
+    }
+
+    // ---- write this CTA's partial gradient + loss -----------------------------------------------------------------------------
+    if (!a.fwd_only) {
+        float* part_out = a.partials + (size_t)blockIdx.x * a.pstride;
+        fence_after_sync();
+        LayerLoop<S>::template dump_grads<0>(a, tmem, part_out, sub, part, lane);
+        float v = loss_acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) ctl.red[warp] = v;
+        __syncthreads();
+        if (tid == 0) part_out[a.ploss] = (ctl.red[0] + ctl.red[1]) + (ctl.red[2] + ctl.red[3]);     // part 0 = warps 0..3
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+// ---- MLP folding helpers -----------------------------------------------------------------------------------------------------
+// flat MLP parameter layout (include/reacher_b200.h): for each layer W[in][out] then b[out], layers 16-24-128-128-32-4
+constexpr int M_W1 = 0, M_B1 = 384, M_W2 = 408, M_B2 = 3480, M_W3 = 3608, M_B3 = 19992, M_W4 = 20120, M_B4 = 24216, M_W5 = 24248, M_B5 = 24376,
+              M_P = 24380;
+// partial / reduced vector of the folded network: [dW1 db1 dW2 db2 G34(128x32) g34(32) dW5 db5 loss]
+constexpr int R_W1 = 0, R_B1 = 384, R_W2 = 408, R_B2 = 3480, R_G34 = 3608, R_g34 = 7704, R_W5 = 7736, R_B5 = 7864, R_LOSS = 7868, R_N = 7872;
+
+// fold[0 : 4096] = W34 = W3 W4 (128 x 32), fold[4096 : 4128] = b34 = b3 W4 + b4
+__global__ void k_fold34(const float* __restrict__ p, float* __restrict__ fold) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx < 128 * 32) {
+        const int i = idx >> 5, j = idx & 31;
+        float acc = 0.f;
+        for (int k = 0; k < 128; ++k) acc = fmaf(__ldg(p + M_W3 + i * 128 + k), __ldg(p + M_W4 + k * 32 + j), acc);
+        fold[idx] = acc;
+    } else if (idx < 128 * 32 + 32) {
+        const int j = idx - 128 * 32;
+        float acc = __ldg(p + M_B4 + j);
+        for (int k = 0; k < 128; ++k) acc = fmaf(__ldg(p + M_B3 + k), __ldg(p + M_W4 + k * 32 + j), acc);
+        fold[idx] = acc;
+    }
+}
+
+// sum the per-CTA partial vectors in CTA order (deterministic)
+__global__ void k_student_reduce(const float* __restrict__ partials, int nparts, int stride, int n, float* __restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float acc = 0.f;
+    for (int b = 0; b < nparts; ++b) acc += partials[(size_t)b * stride + i];
+    out[i] = acc;
+}
+
+// reduced folded gradient -> flat MLP gradient [P] + loss
+__global__ void k_student_finish_mlp(const float* __restrict__ p, const float* __restrict__ red, float* __restrict__ gradloss) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > M_P) return;
+    float v;
+    if (i == M_P) v = red[R_LOSS];
+    else if (i < M_W3) v = red[i];                                  // dW1 db1 dW2 db2 share offsets
+    else if (i < M_B3) {                                            // dW3[a][k] = sum_j G34[a][j] W4[k][j]
+        const int aa = (i - M_W3) >> 7, k = (i - M_W3) & 127;
+        float acc = 0.f;
+        for (int j = 0; j < 32; ++j) acc = fmaf(red[R_G34 + aa * 32 + j], __ldg(p + M_W4 + k * 32 + j), acc);
+        v = acc;
+    } else if (i < M_W4) {                                          // db3[k] = sum_j W4[k][j] g34[j]
+        const int k = i - M_B3;
+        float acc = 0.f;
+        for (int j = 0; j < 32; ++j) acc = fmaf(__ldg(p + M_W4 + k * 32 + j), red[R_g34 + j], acc);
+        v = acc;
+    } else if (i < M_B4) {                                          // dW4[k][j] = sum_a W3[a][k] G34[a][j] + b3[k] g34[j]
+        const int k = (i - M_W4) >> 5, j = (i - M_W4) & 31;
+        float acc = __ldg(p + M_B3 + k) * red[R_g34 + j];
+        for (int aa = 0; aa < 128; ++aa) acc = fmaf(__ldg(p + M_W3 + aa * 128 + k), red[R_G34 + aa * 32 + j], acc);
+        v = acc;
+    } else if (i < M_W5) v = red[R_g34 + (i - M_B4)];                // db4 = g34
+    else v = red[R_W5 + (i - M_W5)];                                // dW5 db5
+    gradloss[i] = v;
+}
+
+template <class S> static size_t student_tc_smem() { return 2 * (size_t)ST_ACT_BYTES + 2 * (size_t)Geo<S>::wtile_bytes() + sizeof(StudentTcCtl); }
+
+static int tc_grid(int64_t B, int* grid) {
+    int device = 0, sms = 148;
+    RB_CUDA(cudaGetDevice(&device));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    *grid = (int)min((int64_t)min(sms, 160), (B + ST_TILE - 1) / ST_TILE);
+    return RB_OK;
+}
+
+constexpr int ST_MAX_GRID = 160;
+// workspace (floats): [fold 4128 -> 4160][reduced R_N][partials ST_MAX_GRID * stride]
+constexpr size_t WS_FOLD = 0, WS_RED = 4160, WS_PART = 4160 + 8192, WS_PSTRIDE_MAX = 8192;
+
+size_t student_tc_workspace_floats() { return WS_PART + (size_t)ST_MAX_GRID * WS_PSTRIDE_MAX; }
+
+int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
+                   float* gradloss, void* workspace, cudaStream_t st) {
+    RB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(params) & 3) == 0, "x must be 16-byte aligned");
+    RB_REQUIRE(workspace != nullptr, "workspace is NULL");
+    float* ws = (float*)workspace;
+    int grid = 1;
+    int rc = tc_grid(B, &grid);
+    if (rc) return rc;
+    StudentTcArgs a{};
+    a.x = x; a.t = tpd; a.s_out = (float4*)s_out; a.B = B; a.loss_kind = loss_kind; a.fwd_only = fwd_only; a.partials = ws + WS_PART;
+    if (kind == RB_STUDENT_MLP) {
+        k_fold34<<<(4128 + 127) / 128, 128, 0, st>>>(params, ws + WS_FOLD);
+        RB_CUDA(cudaGetLastError());
+        a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
+        a.w[2] = ws + WS_FOLD; a.b[2] = ws + WS_FOLD + 4096; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
+        a.pw[0] = R_W1; a.pb[0] = R_B1; a.pw[1] = R_W2; a.pb[1] = R_B2; a.pw[2] = R_G34; a.pb[2] = R_g34; a.pw[3] = R_W5; a.pb[3] = R_B5;
+        a.ploss = R_LOSS; a.pstride = R_N;
+        const size_t smem = student_tc_smem<SpecMLP>();
+        static bool attr = false;
+        if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<SpecMLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        k_student_tc<SpecMLP><<<grid, ST_THREADS, smem, st>>>(a);
+        RB_CUDA(cudaGetLastError());
+        if (!fwd_only) {
+            k_student_reduce<<<(R_N + 255) / 256, 256, 0, st>>>(ws + WS_PART, grid, R_N, R_N, ws + WS_RED);
+            k_student_finish_mlp<<<(M_P + 1 + 127) / 128, 128, 0, st>>>(params, ws + WS_RED, gradloss);
+            RB_CUDA(cudaGetLastError());
+        }
+    } else {
+        const PolicyOffsets o = policy_offsets(4);
+        a.obf = params;
+        a.w[0] = params + o.W1; a.b[0] = params + o.b1; a.w[1] = params + o.W2; a.b[1] = params + o.b2; a.w[2] = params + o.W3; a.b[2] = params + o.b3;
+        a.pw[0] = o.W1; a.pb[0] = o.b1; a.pw[1] = o.W2; a.pb[1] = o.b2; a.pw[2] = o.W3; a.pb[2] = o.b3;
+        a.ploss = o.total; a.pstride = o.total + 1;       // obfilter / logstd entries of the partials stay zero (memset below)
+        const size_t smem = student_tc_smem<SpecPOL>();
+        static bool attr = false;
+        if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<SpecPOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+        if (!fwd_only) RB_CUDA(cudaMemsetAsync(ws + WS_PART, 0, sizeof(float) * (size_t)grid * a.pstride, st));
+        k_student_tc<SpecPOL><<<grid, ST_THREADS, smem, st>>>(a);
+        RB_CUDA(cudaGetLastError());
+        if (!fwd_only) {
+            k_student_reduce<<<(a.pstride + 255) / 256, 256, 0, st>>>(ws + WS_PART, grid, a.pstride, a.pstride, gradloss);
+            RB_CUDA(cudaGetLastError());
+        }
+    }
+    return RB_OK;
+}
+
+}  // namespace rb
+
+extern "C" int rb_student_mode_available(int mode) { return mode == RB_MODE_FP32 || mode == RB_MODE_TC; }
+extern "C" int rb_mode_available(int mode) { return mode == RB_MODE_FP32 || mode == RB_MODE_TC; }

@@ -50,7 +50,7 @@ class StudentNet:
         x = x.reshape(-1, self.in_dim).contiguous()
         if out is None:
             out = torch.empty((x.shape[0], 4), dtype=torch.float32, device=self.device)
-        check(lib().rb_student_fwd(self.kind, ptr(self.params), ptr(x), x.shape[0], ptr(out), self.mode, stream_ptr()))
+        check(lib().rb_student_fwd_ws(self.kind, ptr(self.params), ptr(x), x.shape[0], ptr(out), ptr(self.workspace), self.mode, stream_ptr()))
         return out
 
     def loss_grad(self, x, t_pdflat, loss_kind=LOSS_KL_ST, s_out=None):
