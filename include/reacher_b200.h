@@ -150,6 +150,12 @@ int rb_student_loss_grad(int kind, const float* params_dev, const float* x_dev, 
 int rb_adam_step(float* params_dev, float* m_dev, float* v_dev, const float* grad_dev, int64_t P, int64_t step_t, float lr,
                  float beta1, float beta2, float eps, float grad_scale, void* stream);
 
+/* rb_student_loss_grad immediately followed by rb_adam_step on the same parameters (single rank: nothing to all-reduce).
+ * RB_MODE_TC runs both inside ONE cooperative kernel launch.                                                     */
+int rb_student_step(int kind, float* params_dev, float* m_dev, float* v_dev, const float* x_dev, const float* t_pdflat_dev, int64_t B,
+                    int loss_kind, float* s_pdflat_dev, float* gradloss_dev, void* workspace_dev, int64_t step_t, float lr, float beta1,
+                    float beta2, float eps, float grad_scale, int mode, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ DAgger --
  * One lock-step DAgger iteration pieces (src/distilation/mlp_train.py:143-204 batched):
  * rb_dagger_observe: for every env write ob[N,11], teacher label t_pdflat[N,4] and the student input x[N,in]

@@ -49,6 +49,8 @@ _SIGS = {
     "rb_student_fwd": (C.c_int, [C.c_int, _fp, _fp, C.c_int64, _fp, C.c_int, _vp]),
     "rb_student_fwd_ws": (C.c_int, [C.c_int, _fp, _fp, C.c_int64, _fp, _vp, C.c_int, _vp]),
     "rb_student_loss_grad": (C.c_int, [C.c_int, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, _fp, _vp, C.c_int, _vp]),
+    "rb_student_step": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, _fp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float,
+                                  C.c_float, C.c_float, C.c_int, _vp]),
     "rb_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "rb_dagger_create": (C.c_int, [C.POINTER(C.c_void_p), _vp, C.c_int, C.c_float]),
     "rb_dagger_destroy": (C.c_int, [_vp]),

@@ -80,6 +80,15 @@ __device__ __forceinline__ void warp_load_rows(const float* __restrict__ g, int6
     for (int k = 0; k < W; ++k) vals[k] = lane < nvalid ? strip[lane * W + k] : 0.f;
 }
 
+// TF1 Adam update of one element (mlp_train.py:75-80; eps added to the un-corrected sqrt(v)).  Explicit roundings: the stand-alone
+// kernel and the update fused into the student kernel give bit-identical parameters.
+__device__ __forceinline__ void adam_update(float& p, float& m, float& v, float g, float lr_t, float b1, float b2, float eps, float gscale) {
+    const float gi = __fmul_rn(g, gscale);
+    m = __fmaf_rn(b1, m, __fmul_rn(__fsub_rn(1.f, b1), gi));
+    v = __fmaf_rn(b2, v, __fmul_rn(__fsub_rn(1.f, b2), __fmul_rn(gi, gi)));
+    p = __fsub_rn(p, __fdiv_rn(__fmul_rn(lr_t, m), __fadd_rn(__fsqrt_rn(v), eps)));
+}
+
 // ---- policy parameters (MlpPolicy 11-64-64-nout) ------------------------------------------------------------
 // global flat layout (include/reacher_b200.h): ob_mean[11] ob_std[11] W1[11][64] b1[64] W2[64][64] b2[64] W3[64][nout]
 // b3[nout] logstd[2]

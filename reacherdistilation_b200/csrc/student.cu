@@ -239,11 +239,9 @@ __global__ void k_adam(float* __restrict__ p, float* __restrict__ m, float* __re
                        float lr_t, float b1, float b2, float eps, float gscale) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    const float gi = g[i] * gscale;
-    const float mi = b1 * m[i] + (1.f - b1) * gi;
-    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
-    m[i] = mi; v[i] = vi;
-    p[i] = p[i] - lr_t * mi / (sqrtf(vi) + eps);
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, g[i], lr_t, b1, b2, eps, gscale);
+    p[i] = pi; m[i] = mi; v[i] = vi;
 }
 
 // mlp_train.py:50-52: x = concat(dropout(ob, kp), prev_pdflat, prev_rew)
@@ -317,8 +315,9 @@ static int launch_student(const NetSpec& S, const float* params, const float* x,
 }
 
 // implemented in student_tc.cu (tcgen05 path)
+struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
-                   float* gradloss, void* workspace, cudaStream_t st);
+                   float* gradloss, void* workspace, const AdamFuse* adam, cudaStream_t st);
 size_t student_tc_workspace_floats();
 
 }  // namespace rb
@@ -365,7 +364,7 @@ int rb_student_fwd_ws(int kind, const float* params, const float* x, int64_t B, 
     RB_REQUIRE(params && x && s_pd, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
     if (B <= 0) return RB_OK;
-    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, ws, (cudaStream_t)stream);
+    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, ws, nullptr, (cudaStream_t)stream);
     RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
     return student_dispatch(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -384,16 +383,35 @@ int rb_student_loss_grad(int kind, const float* params, const float* x, const fl
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
     RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
     RB_REQUIRE(B > 0, "empty batch");
-    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, (cudaStream_t)stream);
+    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, nullptr, (cudaStream_t)stream);
     RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
     return student_dispatch(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, (cudaStream_t)stream);
+}
+
+static float adam_lr_t(float lr, float b1, float b2, int64_t t) {
+    return (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
+}
+
+int rb_student_step(int kind, float* params, float* m, float* v, const float* x, const float* tpd, int64_t B, int loss_kind, float* s_pd,
+                    float* gradloss, void* ws, int64_t t, float lr, float b1, float b2, float eps, float gscale, int mode, void* stream) {
+    RB_REQUIRE(params && m && v && x && tpd && gradloss && ws, "NULL argument");
+    RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
+    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    RB_REQUIRE(B > 0 && t >= 1, "empty batch / bad step");
+    if (mode == RB_MODE_TC) {
+        const AdamFuse af{params, m, v, adam_lr_t(lr, b1, b2, t), b1, b2, eps, gscale};
+        return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, &af, (cudaStream_t)stream);
+    }
+    int rc = rb_student_loss_grad(kind, params, x, tpd, B, loss_kind, s_pd, gradloss, ws, mode, stream);
+    if (rc) return rc;
+    return rb_adam_step(params, m, v, gradloss, rb_student_param_count(kind), t, lr, b1, b2, eps, gscale, stream);
 }
 
 int rb_adam_step(float* p, float* m, float* v, const float* g, int64_t P, int64_t t, float lr, float b1, float b2, float eps,
                  float gscale, void* stream) {
     RB_REQUIRE(p && m && v && g, "NULL argument");
     RB_REQUIRE(P > 0 && t >= 1, "bad size / step");
-    const double lr_t = (double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t));
+    const double lr_t = adam_lr_t(lr, b1, b2, t);
     k_adam<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, m, v, g, P, (float)lr_t, b1, b2, eps, gscale);
     RB_CUDA(cudaGetLastError());
     return RB_OK;

@@ -21,6 +21,8 @@
 //    W34 = W3 W4, b34 = b3 W4 + b4 (k_fold34, fp32).  The tile kernel accumulates G34 = dL/dW34, g34 = dL/db34 and
 //    k_student_finish maps them back exactly:  dW3 = G34 W4^T, db3 = W4 g34, dW4 = W3^T G34 + b3 (x) g34, db4 = g34.
 //    This removes the 128x128 layer (60 % of the MMA work and 100 KB of shared memory) without changing the function.
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -71,6 +73,17 @@ struct StudentTcArgs {
     float* partials;              // [grid][pstride]
     int64_t B;
     int loss_kind, fwd_only;
+    // cooperative phases (all global scratch lives in the caller's workspace)
+    const float* params;          // flat parameter vector (fold / finish / Adam)
+    float* fold;                  // SpecMLP: W34 (128x32) | b34 (32)
+    uint8_t* wimg;                // split weight image: hi tiles then lo tiles, exactly the shared-memory layout
+    float* red;                   // reduced partial vector [pstride]
+    float* gradloss;              // final flat gradient [P] + loss
+    int P;                        // parameter count
+    // optional fused TF-form Adam (single rank: no all-reduce between gradient and update)
+    int do_adam;
+    float* adam_p; float* adam_m; float* adam_v;
+    float lr_t, beta1, beta2, eps, gscale;
 };
 
 struct __align__(16) StudentTcCtl {
@@ -196,23 +209,30 @@ template <class S, int l> __device__ __forceinline__ void epi_bwd(uint32_t tacc,
 }
 
 template <class S> struct LayerLoop {
-    // weights -> K-major hi/lo tiles: element (n, k) = W[k][n] for k < in, b[n] at k == 8 * ig (the ONES feature), else 0
-    template <int l> __device__ static void load_weights(const StudentTcArgs& a, uint8_t* w_hi, uint8_t* w_lo) {
+    // weights -> global image of the K-major hi/lo tiles: element (n, k) = W[k][n] for k < in, b[n] at k == 8 * ig (the ONES
+    // feature), else 0.  e = flat element index over all layers (so every layer is built concurrently, one element per thread).
+    template <int l> __device__ static void image_element(const StudentTcArgs& a, int e) {
         using G = Geo<S>;
         constexpr int K = G::K(l), N = G::N(l), in = S::in(l), out = S::out(l), kb = G::ig(l) * 8;
-        const float* __restrict__ W = a.w[l];
-        const float* __restrict__ bb = a.b[l];
-        for (int i = threadIdx.x; i < N * K; i += ST_THREADS) {
-            const int n = i % N, k = i / N;
+        if (e < N * K) {
+            const int n = e % N, k = e / N;
             float v = 0.f;
-            if (n < out) v = k < in ? __ldg(W + k * out + n) : (k == kb ? __ldg(bb + n) : 0.f);
+            if (S::L == 4 && l == 2) {                       // SpecMLP folded layer: its non-zero elements come from fold_into_image()
+                if (n < out && (k < in || k == kb)) return;
+            } else if (n < out) v = k < in ? __ldcg(a.w[l] + k * out + n) : (k == kb ? __ldcg(a.b[l] + n) : 0.f);
             uint16_t h, lo;
             split_scalar(v, h, lo);
             const uint32_t off = G::wtile_off(l) + tile_off(n, k, N);
-            *reinterpret_cast<uint16_t*>(w_hi + off) = h;
-            *reinterpret_cast<uint16_t*>(w_lo + off) = lo;
+            *reinterpret_cast<uint16_t*>(a.wimg + off) = h;
+            *reinterpret_cast<uint16_t*>(a.wimg + G::wtile_bytes() + off) = lo;
+            return;
         }
-        if constexpr (l + 1 < S::L) load_weights<l + 1>(a, w_hi, w_lo);
+        if constexpr (l + 1 < S::L) image_element<l + 1>(a, e - N * K);
+    }
+    // the image elements are dealt to the LAST threads of the grid (the fold, which is the long job, starts at the first)
+    __device__ static void build_image(const StudentTcArgs& a, int gtid, int gthreads) {
+        constexpr int total = Geo<S>::wtile_bytes() / 2;
+        for (int e = gthreads - 1 - gtid; e < total; e += gthreads) image_element<0>(a, e);
     }
     // G_l (TMEM) -> partial gradient vector: lane j = out feature, column i = in feature, column 8*ig = bias
     template <int l> __device__ static void dump_grads(const StudentTcArgs& a, uint32_t tmem, float* __restrict__ part_out, int sub, int part, int lane) {
@@ -239,10 +259,86 @@ template <class S> struct LayerLoop {
     }
 };
 
+// ---- MLP folding ----------------------------------------------------------------------------------------------------------
+// flat MLP parameter layout (include/reacher_b200.h): for each layer W[in][out] then b[out], layers 16-24-128-128-32-4
+constexpr int M_W1 = 0, M_B1 = 384, M_W2 = 408, M_B2 = 3480, M_W3 = 3608, M_B3 = 19992, M_W4 = 20120, M_B4 = 24216, M_W5 = 24248, M_B5 = 24376,
+              M_P = 24380;
+// partial / reduced vector of the folded network: [dW1 db1 dW2 db2 G34(128x32) g34(32) dW5 db5 loss]
+constexpr int R_W1 = 0, R_B1 = 384, R_W2 = 408, R_B2 = 3480, R_G34 = 3608, R_g34 = 7704, R_W5 = 7736, R_B5 = 7864, R_LOSS = 7868, R_N = 7872;
+
+// SpecMLP layer 2 of the weight image: W34 = W3 W4 (128 x 32) and b34 = b3 W4 + b4, computed in fp32 (16 lanes per element, fixed
+// reduction tree), split and written straight into the K-major tile (element (n = j, k = i); bias row k = 128).
+__device__ __forceinline__ void fold_into_image(const float* p, uint8_t* img, int gtid, int gthreads) {
+    using G = Geo<SpecMLP>;
+    const int sub = gtid & 15;
+    for (int idx = gtid >> 4; idx < 4128; idx += gthreads >> 4) {            // 4128 is even: both half-warps of a warp stay together
+        float acc = 0.f;
+        const int i = idx < 4096 ? idx >> 5 : 128, j = idx & 31;
+        const float* lhs = idx < 4096 ? p + M_W3 + i * 128 : p + M_B3;
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { const int k = sub + 16 * m; acc = fmaf(__ldcg(lhs + k), __ldcg(p + M_W4 + k * 32 + j), acc); }
+#pragma unroll
+        for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (sub == 0) {
+            if (idx >= 4096) acc += __ldcg(p + M_B4 + j);
+            uint16_t h, lo;
+            split_scalar(acc, h, lo);
+            const uint32_t off = G::wtile_off(2) + tile_off(j, i, G::N(2));
+            *reinterpret_cast<uint16_t*>(img + off) = h;
+            *reinterpret_cast<uint16_t*>(img + G::wtile_bytes() + off) = lo;
+        }
+    }
+}
+
+// reduced folded gradient -> flat MLP gradient.  dW3 = G34 W4^T and dW4 = W3^T G34 + b3 (x) g34 are dealt one row per CTA
+// (row-contiguous loads); the pass-through entries and db3 go to the last threads of the grid.
+__device__ __forceinline__ void finish_mlp(const float* p, const float* red, float* gradloss, int gtid, int gthreads) {
+    const int tid = threadIdx.x;
+    for (int r = blockIdx.x; r < 128; r += gridDim.x) {
+        if (tid < 128) {                                             // dW3[r][k] = sum_j G34[r][j] W4[k][j],  k = tid
+            float acc = 0.f;
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                const float4 g = __ldcg(reinterpret_cast<const float4*>(red + R_G34 + r * 32) + j4);
+                const float4 w = __ldcg(reinterpret_cast<const float4*>(p + M_W4 + tid * 32) + j4);
+                acc = fmaf(g.x, w.x, acc); acc = fmaf(g.y, w.y, acc); acc = fmaf(g.z, w.z, acc); acc = fmaf(g.w, w.w, acc);
+            }
+            gradloss[M_W3 + r * 128 + tid] = acc;
+        }
+        {                                                            // dW4[r][j] = sum_a W3[a][r] G34[a][j] + b3[r] g34[j],  16 lanes per j
+            const int j = tid >> 4, sub = tid & 15;
+            float acc = 0.f;
+#pragma unroll
+            for (int m = 0; m < 8; ++m) { const int aa = sub + 16 * m; acc = fmaf(__ldcg(p + M_W3 + aa * 128 + r), __ldcg(red + R_G34 + aa * 32 + j), acc); }
+#pragma unroll
+            for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (sub == 0) gradloss[M_W4 + r * 32 + j] = fmaf(__ldcg(p + M_B3 + r), __ldcg(red + R_g34 + j), acc);
+        }
+    }
+    constexpr int n_a = M_W3, n_b = M_W4 - M_B3, n_c = M_P + 1 - M_B4;       // [0, W3) | db3 | [db4 .. loss]
+    for (int q = gthreads - 1 - gtid; q < n_a + n_b + n_c; q += gthreads) {
+        if (q < n_a) gradloss[q] = __ldcg(red + q);                  // dW1 db1 dW2 db2 share offsets
+        else if (q < n_a + n_b) {                                    // db3[k] = sum_j W4[k][j] g34[j]
+            const int k = q - n_a;
+            float acc = 0.f;
+#pragma unroll 8
+            for (int j = 0; j < 32; ++j) acc = fmaf(__ldcg(p + M_W4 + k * 32 + j), __ldcg(red + R_g34 + j), acc);
+            gradloss[M_B3 + k] = acc;
+        } else {
+            const int i = M_B4 + (q - n_a - n_b);
+            gradloss[i] = i == M_P ? __ldcg(red + R_LOSS) : (i < M_W5 ? __ldcg(red + R_g34 + (i - M_B4)) : __ldcg(red + R_W5 + (i - M_W5)));
+        }
+    }
+}
+
+// One cooperative launch = fold + weight split (spread over the grid) -> tiles (forward, loss, backward; weight gradients in
+// TMEM) -> partials -> grid-wide fixed-order reduction -> gradient of the un-folded parameters [-> Adam].
 template <class S>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArgs a) {
     using G = Geo<S>;
     constexpr int L = S::L;
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
     extern __shared__ __align__(128) uint8_t smem[];
     uint8_t* act_hi = smem;
     uint8_t* act_lo = smem + ST_ACT_BYTES;
@@ -250,17 +346,20 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     uint8_t* w_lo = w_hi + G::wtile_bytes();
     StudentTcCtl& ctl = *reinterpret_cast<StudentTcCtl*>(w_lo + G::wtile_bytes());
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = warp & 3, part = warp >> 2, row = sub * 32 + lane;
+    const int gtid = blockIdx.x * ST_THREADS + tid, gthreads = gridDim.x * ST_THREADS;
 
-    // ---- one-time setup: TMEM, barrier, zeroed activations + ONES groups, split weights -----------------------------------
+    // ---- phase 0: TMEM, barrier, zeroed activations + ONES groups; fold and split the weights once for the whole grid -----
     if (warp == 0) tmem_alloc<512>(&ctl.tmem_base);
     if (tid == 0) { mbar_init(&ctl.mbar, 1); fence_mbar_init(); }
     for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-    __syncthreads();
+    if constexpr (S::L == 4) fold_into_image(a.params, a.wimg, gtid, gthreads);       // SpecMLP: W34, b34
+    LayerLoop<S>::build_image(a, gtid, gthreads);
+    grid.sync();
     if (tid < ST_TILE) {
 #pragma unroll
         for (int l = 0; l < L; ++l) *reinterpret_cast<uint16_t*>(act_hi + (S::slot(l) + G::ig(l)) * 2048 + tid * 16) = (uint16_t)0x3F80u;
     }
-    LayerLoop<S>::template load_weights<0>(a, w_hi, w_lo);
+    for (int i = tid; i < 2 * G::wtile_bytes() / 16; i += ST_THREADS) reinterpret_cast<uint4*>(w_hi)[i] = __ldcg(reinterpret_cast<const uint4*>(a.wimg) + i);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -273,20 +372,27 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     bool first = true;
 
     const int64_t ntiles = (a.B + ST_TILE - 1) / ST_TILE;
+    // software prefetch of the next tile's inputs (SpecMLP: one float4 of x per thread) while the current tile computes
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    if constexpr (S::IN0 == 16) {
+        const int64_t r0 = (int64_t)blockIdx.x * ST_TILE + (tid >> 2);
+        if (blockIdx.x < ntiles && r0 < a.B) xv = __ldg(reinterpret_cast<const float4*>(a.x + r0 * 16) + (tid & 3));
+    }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * ST_TILE;
         const int nvalid = (int)min((int64_t)ST_TILE, a.B - base);
         // ---- X0: global fp32 -> (obfilter) -> bf16 hi/lo rows ---------------------------------------------------------------
         if constexpr (S::IN0 == 16) {
             const int r = tid >> 2, q = tid & 3;                       // 4 threads per sample row, 4 features each
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r < nvalid) v = __ldg(reinterpret_cast<const float4*>(a.x + (base + r) * 16) + q);
             uint32_t h0, l0, h1, l1;
-            split_pair(v.x, v.y, h0, l0);
-            split_pair(v.z, v.w, h1, l1);
+            split_pair(xv.x, xv.y, h0, l0);
+            split_pair(xv.z, xv.w, h1, l1);
             const uint32_t off = (S::slot(0) + (q >> 1)) * 2048 + r * 16 + (q & 1) * 8;
             *reinterpret_cast<uint2*>(act_hi + off) = make_uint2(h0, h1);
             *reinterpret_cast<uint2*>(act_lo + off) = make_uint2(l0, l1);
+            const int64_t rn = (tile + gridDim.x) * ST_TILE + r;
+            xv = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (rn < a.B) xv = __ldg(reinterpret_cast<const float4*>(a.x + rn * 16) + q);
         } else {
             for (int e = tid; e < ST_TILE * S::IN0; e += ST_THREADS) {
                 const int r = e / S::IN0, f = e - r * S::IN0;
@@ -378,80 +484,48 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         first = false;
     }
 
-    // ---- write this CTA's partial gradient + loss -----------------------------------------------------------------------------
     if (!a.fwd_only) {
+        // ---- this CTA's partial gradient + loss -> global ---------------------------------------------------------------------
         float* part_out = a.partials + (size_t)blockIdx.x * a.pstride;
         fence_after_sync();
-        LayerLoop<S>::template dump_grads<0>(a, tmem, part_out, sub, part, lane);
+        if (!first) LayerLoop<S>::template dump_grads<0>(a, tmem, part_out, sub, part, lane);
         float v = loss_acc;
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
         if (lane == 0) ctl.red[warp] = v;
         __syncthreads();
         if (tid == 0) part_out[a.ploss] = (ctl.red[0] + ctl.red[1]) + (ctl.red[2] + ctl.red[3]);     // part 0 = warps 0..3
+        grid.sync();
+        // ---- grid-wide reduction of the partial vectors: 8 lanes per element, CTA order, fixed tree => bit-reproducible -----------
+        {
+            const int nparts = (int)min((int64_t)gridDim.x, ntiles), l8 = gtid & 7;
+            for (int i = gtid >> 3; i < ((a.pstride + 3) & ~3); i += gthreads >> 3) {
+                float acc = 0.f;
+                if (i < a.pstride)
+                    for (int b = l8; b < nparts; b += 8) acc += __ldcg(a.partials + (size_t)b * a.pstride + i);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
+                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
+                if (l8 == 0 && i < a.pstride) a.red[i] = acc;
+            }
+        }
+        grid.sync();
+        // ---- gradient of the un-folded parameters ---------------------------------------------------------------------------------
+        if constexpr (S::L == 4) finish_mlp(a.params, a.red, a.gradloss, gtid, gthreads);
+        else
+            for (int i = gtid; i <= a.P; i += gthreads) a.gradloss[i] = __ldcg(a.red + i);
+        if (a.do_adam) {                   // TF1 Adam, same arithmetic as k_adam (student.cu)
+            grid.sync();                   // every read of the old parameters (finish) is done, every gradloss entry written
+            for (int i = gtid; i < a.P; i += gthreads) {
+                float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
+                adam_update(pi, mi, vi, __ldcg(a.gradloss + i), a.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
+            }
+        }
     }
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
-}
-
-// ---- MLP folding helpers -----------------------------------------------------------------------------------------------------
-// flat MLP parameter layout (include/reacher_b200.h): for each layer W[in][out] then b[out], layers 16-24-128-128-32-4
-constexpr int M_W1 = 0, M_B1 = 384, M_W2 = 408, M_B2 = 3480, M_W3 = 3608, M_B3 = 19992, M_W4 = 20120, M_B4 = 24216, M_W5 = 24248, M_B5 = 24376,
-              M_P = 24380;
-// partial / reduced vector of the folded network: [dW1 db1 dW2 db2 G34(128x32) g34(32) dW5 db5 loss]
-constexpr int R_W1 = 0, R_B1 = 384, R_W2 = 408, R_B2 = 3480, R_G34 = 3608, R_g34 = 7704, R_W5 = 7736, R_B5 = 7864, R_LOSS = 7868, R_N = 7872;
-
-// fold[0 : 4096] = W34 = W3 W4 (128 x 32), fold[4096 : 4128] = b34 = b3 W4 + b4
-__global__ void k_fold34(const float* __restrict__ p, float* __restrict__ fold) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx < 128 * 32) {
-        const int i = idx >> 5, j = idx & 31;
-        float acc = 0.f;
-        for (int k = 0; k < 128; ++k) acc = fmaf(__ldg(p + M_W3 + i * 128 + k), __ldg(p + M_W4 + k * 32 + j), acc);
-        fold[idx] = acc;
-    } else if (idx < 128 * 32 + 32) {
-        const int j = idx - 128 * 32;
-        float acc = __ldg(p + M_B4 + j);
-        for (int k = 0; k < 128; ++k) acc = fmaf(__ldg(p + M_B3 + k), __ldg(p + M_W4 + k * 32 + j), acc);
-        fold[idx] = acc;
-    }
-}
-
-// sum the per-CTA partial vectors in CTA order (deterministic)
-__global__ void k_student_reduce(const float* __restrict__ partials, int nparts, int stride, int n, float* __restrict__ out) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n) return;
-    float acc = 0.f;
-    for (int b = 0; b < nparts; ++b) acc += partials[(size_t)b * stride + i];
-    out[i] = acc;
-}
-
-// reduced folded gradient -> flat MLP gradient [P] + loss
-__global__ void k_student_finish_mlp(const float* __restrict__ p, const float* __restrict__ red, float* __restrict__ gradloss) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i > M_P) return;
-    float v;
-    if (i == M_P) v = red[R_LOSS];
-    else if (i < M_W3) v = red[i];                                  // dW1 db1 dW2 db2 share offsets
-    else if (i < M_B3) {                                            // dW3[a][k] = sum_j G34[a][j] W4[k][j]
-        const int aa = (i - M_W3) >> 7, k = (i - M_W3) & 127;
-        float acc = 0.f;
-        for (int j = 0; j < 32; ++j) acc = fmaf(red[R_G34 + aa * 32 + j], __ldg(p + M_W4 + k * 32 + j), acc);
-        v = acc;
-    } else if (i < M_W4) {                                          // db3[k] = sum_j W4[k][j] g34[j]
-        const int k = i - M_B3;
-        float acc = 0.f;
-        for (int j = 0; j < 32; ++j) acc = fmaf(__ldg(p + M_W4 + k * 32 + j), red[R_g34 + j], acc);
-        v = acc;
-    } else if (i < M_B4) {                                          // dW4[k][j] = sum_a W3[a][k] G34[a][j] + b3[k] g34[j]
-        const int k = (i - M_W4) >> 5, j = (i - M_W4) & 31;
-        float acc = __ldg(p + M_B3 + k) * red[R_g34 + j];
-        for (int aa = 0; aa < 128; ++aa) acc = fmaf(__ldg(p + M_W3 + aa * 128 + k), red[R_G34 + aa * 32 + j], acc);
-        v = acc;
-    } else if (i < M_W5) v = red[R_g34 + (i - M_B4)];                // db4 = g34
-    else v = red[R_W5 + (i - M_W5)];                                // dW5 db5
-    gradloss[i] = v;
 }
 
 template <class S> static size_t student_tc_smem() { return 2 * (size_t)ST_ACT_BYTES + 2 * (size_t)Geo<S>::wtile_bytes() + sizeof(StudentTcCtl); }
@@ -465,56 +539,53 @@ static int tc_grid(int64_t B, int* grid) {
 }
 
 constexpr int ST_MAX_GRID = 160;
-// workspace (floats): [fold 4128 -> 4160][reduced R_N][partials ST_MAX_GRID * stride]
-constexpr size_t WS_FOLD = 0, WS_RED = 4160, WS_PART = 4160 + 8192, WS_PSTRIDE_MAX = 8192;
+// workspace (floats): [fold 4160][reduced 8192][weight image 12288 (48 KB)][partials ST_MAX_GRID * 8192]
+constexpr size_t WS_FOLD = 0, WS_RED = 4160, WS_IMG = WS_RED + 8192, WS_PART = WS_IMG + 12288, WS_PSTRIDE_MAX = 8192;
 
 size_t student_tc_workspace_floats() { return WS_PART + (size_t)ST_MAX_GRID * WS_PSTRIDE_MAX; }
 
+template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cudaStream_t st) {
+    static_assert(2 * Geo<S>::wtile_bytes() <= 12288 * 4, "weight image does not fit its workspace slot");
+    const size_t smem = student_tc_smem<S>();
+    static bool attr = false;
+    if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    void* args[] = {(void*)&a};
+    RB_CUDA(cudaLaunchCooperativeKernel((const void*)k_student_tc<S>, dim3(grid), dim3(ST_THREADS), args, smem, st));
+    return RB_OK;
+}
+
+struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
+
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
-                   float* gradloss, void* workspace, cudaStream_t st) {
+                   float* gradloss, void* workspace, const AdamFuse* adam, cudaStream_t st) {
     RB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(params) & 3) == 0, "x must be 16-byte aligned");
-    RB_REQUIRE(workspace != nullptr, "workspace is NULL");
+    RB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     float* ws = (float*)workspace;
     int grid = 1;
     int rc = tc_grid(B, &grid);
     if (rc) return rc;
     StudentTcArgs a{};
     a.x = x; a.t = tpd; a.s_out = (float4*)s_out; a.B = B; a.loss_kind = loss_kind; a.fwd_only = fwd_only; a.partials = ws + WS_PART;
-    if (kind == RB_STUDENT_MLP) {
-        k_fold34<<<(4128 + 127) / 128, 128, 0, st>>>(params, ws + WS_FOLD);
-        RB_CUDA(cudaGetLastError());
-        a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
-        a.w[2] = ws + WS_FOLD; a.b[2] = ws + WS_FOLD + 4096; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
-        a.pw[0] = R_W1; a.pb[0] = R_B1; a.pw[1] = R_W2; a.pb[1] = R_B2; a.pw[2] = R_G34; a.pb[2] = R_g34; a.pw[3] = R_W5; a.pb[3] = R_B5;
-        a.ploss = R_LOSS; a.pstride = R_N;
-        const size_t smem = student_tc_smem<SpecMLP>();
-        static bool attr = false;
-        if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<SpecMLP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-        k_student_tc<SpecMLP><<<grid, ST_THREADS, smem, st>>>(a);
-        RB_CUDA(cudaGetLastError());
-        if (!fwd_only) {
-            k_student_reduce<<<(R_N + 255) / 256, 256, 0, st>>>(ws + WS_PART, grid, R_N, R_N, ws + WS_RED);
-            k_student_finish_mlp<<<(M_P + 1 + 127) / 128, 128, 0, st>>>(params, ws + WS_RED, gradloss);
-            RB_CUDA(cudaGetLastError());
-        }
-    } else {
-        const PolicyOffsets o = policy_offsets(4);
-        a.obf = params;
-        a.w[0] = params + o.W1; a.b[0] = params + o.b1; a.w[1] = params + o.W2; a.b[1] = params + o.b2; a.w[2] = params + o.W3; a.b[2] = params + o.b3;
-        a.pw[0] = o.W1; a.pb[0] = o.b1; a.pw[1] = o.W2; a.pb[1] = o.b2; a.pw[2] = o.W3; a.pb[2] = o.b3;
-        a.ploss = o.total; a.pstride = o.total + 1;       // obfilter / logstd entries of the partials stay zero (memset below)
-        const size_t smem = student_tc_smem<SpecPOL>();
-        static bool attr = false;
-        if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<SpecPOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-        if (!fwd_only) RB_CUDA(cudaMemsetAsync(ws + WS_PART, 0, sizeof(float) * (size_t)grid * a.pstride, st));
-        k_student_tc<SpecPOL><<<grid, ST_THREADS, smem, st>>>(a);
-        RB_CUDA(cudaGetLastError());
-        if (!fwd_only) {
-            k_student_reduce<<<(a.pstride + 255) / 256, 256, 0, st>>>(ws + WS_PART, grid, a.pstride, a.pstride, gradloss);
-            RB_CUDA(cudaGetLastError());
-        }
+    a.params = params; a.fold = ws + WS_FOLD; a.wimg = (uint8_t*)(ws + WS_IMG); a.red = ws + WS_RED; a.gradloss = gradloss;
+    if (adam && !fwd_only) {
+        a.do_adam = 1; a.adam_p = adam->p; a.adam_m = adam->m; a.adam_v = adam->v;
+        a.lr_t = adam->lr_t; a.beta1 = adam->beta1; a.beta2 = adam->beta2; a.eps = adam->eps; a.gscale = adam->gscale;
     }
-    return RB_OK;
+    if (kind == RB_STUDENT_MLP) {
+        a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
+        a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
+        a.pw[0] = R_W1; a.pb[0] = R_B1; a.pw[1] = R_W2; a.pb[1] = R_B2; a.pw[2] = R_G34; a.pb[2] = R_g34; a.pw[3] = R_W5; a.pb[3] = R_B5;
+        a.ploss = R_LOSS; a.pstride = R_LOSS + 1; a.P = M_P;
+        return launch_student_tc<SpecMLP>(a, grid, st);
+    }
+    const PolicyOffsets o = policy_offsets(4);
+    a.obf = params;
+    a.w[0] = params + o.W1; a.b[0] = params + o.b1; a.w[1] = params + o.W2; a.b[1] = params + o.b2; a.w[2] = params + o.W3; a.b[2] = params + o.b3;
+    a.pw[0] = o.W1; a.pb[0] = o.b1; a.pw[1] = o.W2; a.pb[1] = o.b2; a.pw[2] = o.W3; a.pb[2] = o.b3;
+    a.ploss = o.total; a.pstride = o.total + 1; a.P = o.total;
+    // obfilter / logstd entries of the partial vectors are never written by the kernel: keep them zero
+    if (!fwd_only) RB_CUDA(cudaMemsetAsync(ws + WS_PART, 0, sizeof(float) * (size_t)grid * a.pstride, st));
+    return launch_student_tc<SpecPOL>(a, grid, st);
 }
 
 }  // namespace rb

@@ -64,10 +64,12 @@ class DaggerTrainer:
         """One DAgger iteration over all envs.  Asynchronous; returns nothing (loss: self.last_loss())."""
         L, st = lib(), stream_ptr()
         check(L.rb_dagger_observe(self._h, ptr(self.teacher.params), self.iteration, ptr(self.obs), ptr(self.t_pd), ptr(self.x), self.mode, st))
-        self.student.loss_grad(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd)
         if self.world > 1:
+            self.student.loss_grad(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd)
             torch.distributed.all_reduce(self.student.gradloss, group=self.pg)
-        self.student.adam_step(self.grad_scale)
+            self.student.adam_step(self.grad_scale)
+        else:
+            self.student.step(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd, grad_scale=self.grad_scale)
         check(L.rb_dagger_act(self._h, ptr(self.s_pd), ptr(self.t_pd), ptr(self.rew), ptr(self.done), st))
         self.iteration += 1
 

@@ -64,6 +64,19 @@ class StudentNet:
                                          ptr(self.workspace), self.mode, stream_ptr()))
         return s_out
 
+    def step(self, x, t_pdflat, loss_kind=LOSS_KL_ST, s_out=None, grad_scale=1.0):
+        """loss_grad + adam_step in one C-ABI call (single rank); RB_MODE_TC: one cooperative kernel launch."""
+        x = x.reshape(-1, self.in_dim).contiguous()
+        t_pdflat = t_pdflat.reshape(-1, 4).contiguous()
+        B = x.shape[0]
+        if s_out is None:
+            s_out = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+        self.t += 1
+        check(lib().rb_student_step(self.kind, ptr(self.params), ptr(self.m), ptr(self.v), ptr(x), ptr(t_pdflat), B, loss_kind, ptr(s_out),
+                                    ptr(self.gradloss), ptr(self.workspace), self.t, self.lr, self.beta1, self.beta2, self.eps, grad_scale,
+                                    self.mode, stream_ptr()))
+        return s_out
+
     def adam_step(self, grad_scale=1.0):
         self.t += 1
         check(lib().rb_adam_step(ptr(self.params), ptr(self.m), ptr(self.v), ptr(self.gradloss), self.P, self.t, self.lr, self.beta1, self.beta2,

@@ -41,15 +41,17 @@ def _oracle_loop(kind, n, iters, seed, teacher_p, student_p, keep_prob, lr, eps,
     return np.array(losses), np.array(rews), theta
 
 
+@pytest.mark.parametrize("mode_name", ["fp32", "tc"])
 @pytest.mark.parametrize("kind_name,keep_prob", [("mlp", 0.5), ("mlp", 1.0), ("policy64", 1.0)])
-def test_loss_curve_matches_cpu_restatement(kind_name, keep_prob):
-    from reacherdistilation_b200 import STUDENT_MLP, STUDENT_POLICY64
+def test_loss_curve_matches_cpu_restatement(kind_name, keep_prob, mode_name):
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC, STUDENT_MLP, STUDENT_POLICY64
+    mode = MODE_TC if mode_name == "tc" else MODE_FP32
     from reacherdistilation_b200.mlp_train import DaggerTrainer
     from reacherdistilation_b200.teacher import init_policy_params
     kind = STUDENT_MLP if kind_name == "mlp" else STUDENT_POLICY64
     n, iters, seed = 256, 70, 4
     tp = init_policy_params(seed=0, final_std=0.3)
-    tr = DaggerTrainer(num_envs=n, seed=seed, student_kind=kind, keep_prob=keep_prob, teacher_params=tp, student_seed=1, lr=1e-3, eps=1e-8)
+    tr = DaggerTrainer(num_envs=n, seed=seed, student_kind=kind, keep_prob=keep_prob, teacher_params=tp, student_seed=1, lr=1e-3, eps=1e-8, mode=mode)
     sp = tr.student.params.cpu().numpy().copy()
     dev_losses, dev_rews = [], []
     for it in range(iters):
@@ -57,12 +59,15 @@ def test_loss_curve_matches_cpu_restatement(kind_name, keep_prob):
         dev_losses.append(float(tr.last_loss())); dev_rews.append(float(tr.rew.mean()))
     ref_losses, ref_rews, theta = _oracle_loop(kind, n, iters, seed, tp, sp, keep_prob, 1e-3, 1e-8)
     rel = np.abs(np.array(dev_losses) - ref_losses) / np.maximum(1.0, np.abs(ref_losses))
-    print("%s kp=%.1f loss curve: first %.4g last %.4g, max rel err %.3g; reward err %.3g" %
-          (kind_name, keep_prob, ref_losses[0], ref_losses[-1], rel.max(), np.abs(np.array(dev_rews) - ref_rews).max()))
+    print("%s %s kp=%.1f loss curve: first %.4g last %.4g, max rel err %.3g; reward err %.3g" %
+          (kind_name, mode_name, keep_prob, ref_losses[0], ref_losses[-1], rel.max(), np.abs(np.array(dev_rews) - ref_rews).max()))
     assert ref_losses[-1] < ref_losses[0]                 # it learns
-    assert rel.max() <= 2e-3                              # stated loss-curve tolerance (fp32 device vs float64 restatement, closed loop)
-    assert np.abs(np.array(dev_rews) - ref_rews).max() <= 2e-3
-    assert np.abs(tr.student.params.cpu().numpy() - theta).max() <= 2e-3
+    # stated loss-curve tolerance, closed loop over 70 iterations vs the float64 restatement: 2e-3 (fp32 kernels); 1e-2 for the
+    # tensor-core kernels, whose bf16x3 products are good to ~1e-5 per evaluation (teacher label AND student) before feedback
+    tol = 2e-3 if mode_name == "fp32" else 1e-2
+    assert rel.max() <= tol
+    assert np.abs(np.array(dev_rews) - ref_rews).max() <= tol
+    assert np.abs(tr.student.params.cpu().numpy() - theta).max() <= tol
     tr.close()
 
 

@@ -96,3 +96,41 @@ def test_student_input_and_dropout_mask_bit_exact():
         x = student_mlp_input(torch.from_numpy(obs).cuda(), torch.from_numpy(pp).cuda(), torch.from_numpy(pr).cuda(), kp, seed, sid0, it)
         ref = NN.student_input(obs, pp, pr, kp, seed, np.arange(B, dtype=np.uint32) + sid0, it, dtype=np.float32)
         assert np.array_equal(x.cpu().numpy(), ref.astype(np.float32)), kp
+
+
+@pytest.mark.parametrize("kind_name", ["mlp", "policy64"])
+def test_fused_step_equals_loss_grad_then_adam(kind_name):
+    """rb_student_step (one cooperative launch in RB_MODE_TC) == rb_student_loss_grad followed by rb_adam_step."""
+    from reacherdistilation_b200 import STUDENT_MLP, STUDENT_POLICY64
+    from reacherdistilation_b200.student_nn import StudentNet
+    kind = STUDENT_MLP if kind_name == "mlp" else STUDENT_POLICY64
+    rng = np.random.default_rng(5)
+    for name, mode, tol in _modes():
+        a, b = StudentNet(kind=kind, seed=2, mode=mode, lr=1e-3), StudentNet(kind=kind, seed=2, mode=mode, lr=1e-3)
+        for it in range(3):
+            B = (300, 5000, 129)[it]
+            x = torch.from_numpy((rng.standard_normal((B, a.in_dim))).astype(np.float32)).cuda()
+            t = torch.from_numpy(np.concatenate([rng.standard_normal((B, 2)) * 0.3, -1.0 + 0.2 * rng.standard_normal((B, 2))], -1).astype(np.float32)).cuda()
+            sa = a.step(x, t, grad_scale=0.5)
+            sb = b.loss_grad(x, t)
+            b.adam_step(grad_scale=0.5)
+            assert torch.equal(sa, sb)
+            assert torch.equal(a.gradloss, b.gradloss), name          # same kernel, same order: bit-identical gradient
+            assert torch.equal(a.params, b.params), name              # shared adam_update(): bit-identical update
+            assert a.t == b.t
+
+
+def test_tc_gradient_is_bit_reproducible():
+    from reacherdistilation_b200 import MODE_TC, STUDENT_MLP
+    from reacherdistilation_b200._lib import lib
+    from reacherdistilation_b200.student_nn import StudentNet
+    if not lib().rb_student_mode_available(MODE_TC):
+        pytest.skip("RB_MODE_TC student not built")
+    rng = np.random.default_rng(0)
+    net = StudentNet(kind=STUDENT_MLP, seed=1, mode=MODE_TC)
+    x = torch.from_numpy(rng.standard_normal((50000, 16)).astype(np.float32)).cuda()
+    t = torch.from_numpy((rng.standard_normal((50000, 4)) * 0.3).astype(np.float32)).cuda()
+    net.loss_grad(x, t)
+    a = net.gradloss.clone()
+    net.loss_grad(x, t)
+    assert torch.equal(a, net.gradloss)
