@@ -167,6 +167,9 @@ int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_
 int rb_dagger_destroy(rb_dagger* d);
 int rb_dagger_observe(rb_dagger* d, const float* teacher_params_dev, uint32_t iteration, float* obs_dev, float* t_pdflat_dev,
                       float* x_dev, int mode, void* stream);
+/* RB_MODE_TC observe caches the split-weight image of the (frozen, teacher.py:17-20) teacher keyed by the parameter POINTER;
+ * call this after modifying the teacher parameters in place.                                                                */
+int rb_dagger_invalidate_teacher(rb_dagger* d);
 int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
                   void* stream);
 

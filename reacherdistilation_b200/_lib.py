@@ -55,6 +55,7 @@ _SIGS = {
     "rb_dagger_create": (C.c_int, [C.POINTER(C.c_void_p), _vp, C.c_int, C.c_float]),
     "rb_dagger_destroy": (C.c_int, [_vp]),
     "rb_dagger_observe": (C.c_int, [_vp, _fp, C.c_uint32, _fp, _fp, _fp, C.c_int, _vp]),
+    "rb_dagger_invalidate_teacher": (C.c_int, [_vp]),
     "rb_dagger_act": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
 }
 

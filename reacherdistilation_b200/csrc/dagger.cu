@@ -2,10 +2,14 @@
 // Replaces the per-env-step body of /root/reference src/distilation/mlp_train.py:143-204 (teacher label :165-167, record
 // :188-193 with dataset.py:118-143 `prev` / `prew` semantics, env.step(s_ac) :196) for N envs at once.
 #include "common.cuh"
+#include "dagger_input.cuh"
 #include "physics.cuh"
 
 struct rb_dagger {
     rb_env* env = nullptr;
+    // split-weight image of the (frozen) teacher for the tensor-core observe kernel, keyed by the parameter pointer
+    void* teacher_img = nullptr;
+    const float* teacher_img_src = nullptr;
     int kind = 0;
     float keep_prob = 1.f;
     float4* prev_t = nullptr;      // teacher pdflat of the previous record of the current episode
@@ -20,29 +24,15 @@ __global__ void k_dagger_input(int64_t n, const uint2* __restrict__ ctr, const f
                                uint32_t iteration, float4* __restrict__ x) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
-    float ob[12];
+    float ob[11];
 #pragma unroll
     for (int k = 0; k < 11; ++k) ob[k] = __ldg(obs + i * 11 + k);
-    ob[11] = 0.f;
-    if (keep_prob < 1.f) {
-#pragma unroll
-        for (int blk = 0; blk < 3; ++blk) {
-            const uint4 r = philox4x32_10(offset + (uint32_t)i, iteration, (uint32_t)blk, STREAM_DROPOUT, k0, k1);
-            const uint32_t rr[4] = {r.x, r.y, r.z, r.w};
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                const float u = (float)(rr[c] >> 8) * 5.9604644775390625e-08f;
-                ob[4 * blk + c] = __fdiv_rn(ob[4 * blk + c], keep_prob) * floorf(keep_prob + u);
-            }
-        }
-    }
     const bool first = ctr[i].x == 0u;   // first record of an episode: prev / prew are zeros (dataset.py:151-164)
     const float4 pp = first ? make_float4(0.f, 0.f, 0.f, 0.f) : prev_t[i];
     const float pr = first ? 0.f : prev_rec_rew[i];
-    x[i * 4 + 0] = make_float4(ob[0], ob[1], ob[2], ob[3]);
-    x[i * 4 + 1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
-    x[i * 4 + 2] = make_float4(ob[8], ob[9], ob[10], pp.x);
-    x[i * 4 + 3] = make_float4(pp.y, pp.z, pp.w, pr);
+    float4 o[4];
+    mlp_input_row(ob, keep_prob, k0, k1, offset + (uint32_t)i, iteration, pp, pr, o);
+    x[i * 4 + 0] = o[0]; x[i * 4 + 1] = o[1]; x[i * 4 + 2] = o[2]; x[i * 4 + 3] = o[3];
 }
 
 __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint2* ctr, const float4* __restrict__ s_pd,
@@ -62,6 +52,12 @@ __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float
     if (rew) rew[i] = r;
     if (done) done[i] = d ? 1 : 0;
 }
+
+// implemented in policy_tc.cu
+size_t policy_tc_image_bytes();
+int policy_tc_build_image(const float* params, int nout, void* img, cudaStream_t s);
+int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, float keep_prob, const float4* prev_t, const float* prev_rec_rew,
+                      uint32_t iteration, float* obs, float* t_pd, float* x, cudaStream_t s);
 
 }  // namespace rb
 
@@ -89,7 +85,7 @@ int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_
 
 int rb_dagger_destroy(rb_dagger* d) {
     if (!d) return RB_OK;
-    cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward);
+    cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward); cudaFree(d->teacher_img);
     delete d;
     return RB_OK;
 }
@@ -97,6 +93,16 @@ int rb_dagger_destroy(rb_dagger* d) {
 int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iteration, float* obs, float* t_pd, float* x, int mode, void* stream) {
     RB_REQUIRE(d && teacher_params && obs && t_pd && x, "NULL argument");
     rb_env* e = d->env;
+    if (mode == RB_MODE_TC) {            // one fused kernel: observe + teacher (tcgen05) + student input
+        if (!d->teacher_img) RB_CUDA(cudaMalloc(&d->teacher_img, policy_tc_image_bytes()));
+        if (d->teacher_img_src != teacher_params) {
+            int rc0 = policy_tc_build_image(teacher_params, 2, d->teacher_img, (cudaStream_t)stream);
+            if (rc0) return rc0;
+            d->teacher_img_src = teacher_params;
+        }
+        return dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, iteration, obs, t_pd, x,
+                                 (cudaStream_t)stream);
+    }
     int rc = rb_env_observe(e, obs, stream);
     if (rc) return rc;
     rc = rb_policy_fwd(teacher_params, 2, obs, e->n, t_pd, mode, stream);
@@ -109,6 +115,12 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iterat
                                                                                         iteration, (float4*)x);
         RB_CUDA(cudaGetLastError());
     }
+    return RB_OK;
+}
+
+int rb_dagger_invalidate_teacher(rb_dagger* d) {
+    RB_REQUIRE(d != nullptr, "NULL argument");
+    d->teacher_img_src = nullptr;
     return RB_OK;
 }
 

@@ -17,7 +17,10 @@
 // TMEM), which keeps the result within ~1e-5 of the fp32 network.  W1/b1/W2/b2 are pre-multiplied by 2*log2(e) when they
 // are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  : FADD, 2 MUFU, FFMA per element, then the bf16
 // hi/lo split written straight into the next layer's A tile (no-swizzle K-major layout, see tc_common.cuh).
+#include <cstddef>
+
 #include "common.cuh"
+#include "dagger_input.cuh"
 #include "physics.cuh"
 #include "tc_common.cuh"
 
@@ -43,9 +46,12 @@ struct __align__(128) TcShared {        // one per CTA: split weights + per-tile
     float mu[12];
     float inv_sd[12];
     float logstd[4];
-    uint64_t mbar[MAX_TILES];
+    uint64_t mbar[MAX_TILES];           // ---- everything above this line is the "weight image" (built once, bulk-copied by TMA)
+    uint64_t mbar_load;
     uint32_t tmem_base;
 };
+constexpr uint32_t TC_IMAGE_BYTES = (uint32_t)offsetof(TcShared, mbar);
+static_assert(TC_IMAGE_BYTES % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
 struct __align__(128) TcTile {
     uint8_t A_hi[128 * 64 * 2];         // [8 chunks][128 rows][16 B]; the L1 tile (2 chunks) aliases its head; bytes 8192.. double as obs strips
     uint8_t A_lo[128 * 64 * 2];
@@ -223,6 +229,23 @@ template <int NT> __device__ __forceinline__ void policy_tc_setup(TcShared& S, c
     __syncthreads();
     fence_after_sync();
 }
+// same, with the split weights coming from a prebuilt global image (k_policy_tc_build_image) through one TMA bulk copy
+template <int NT> __device__ __forceinline__ void policy_tc_setup_from_image(TcShared& S, const void* img) {
+    if (threadIdx.x < 32) tmem_alloc<tmem_cols<NT>()>(&S.tmem_base);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int t = 0; t < MAX_TILES; ++t) mbar_init(&S.mbar[t], 1);
+        mbar_init(&S.mbar_load, 1);
+        fence_mbar_init();
+        mbar_expect_tx(&S.mbar_load, TC_IMAGE_BYTES);
+        bulk_g2s(&S, img, TC_IMAGE_BYTES, &S.mbar_load);
+    }
+    __syncthreads();                      // barrier inits visible before anyone waits
+    mbar_wait(&S.mbar_load, 0);
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+}
 template <int NT> __device__ __forceinline__ void policy_tc_teardown(TcShared& S) {
     fence_before_sync();
     __syncthreads();
@@ -251,6 +274,63 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_policy_fwd_tc(const float* __re
         __syncwarp();
         policy_tc_eval<NOUT>(S, T, tile, row, TILE, row == 0, ob, pd, phase);
         if (i < n) pd_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
+    }
+    policy_tc_teardown<NT>(S);
+}
+
+__global__ void k_policy_tc_build_image(const float* __restrict__ params, int nout, TcShared* img) { policy_tc_load_weights(*img, params, nout); }
+
+// DAgger observe, fused: for every env the observation, the teacher label t = teacher(ob) (mlp_train.py:165-167) and the student
+// input row (MLP student: [dropout(ob), prev teacher pdflat, prev recorded reward], zeros at the first step of an episode --
+// mlp_train.py:50-52, dataset.py:118-143; 2x64 student: x = ob).  One pass over the env state, teacher on tcgen05.
+template <int KIND, int NT>
+__global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, const float4* __restrict__ qv, const float4* __restrict__ tp,
+                                                                    const uint2* __restrict__ ctr, const void* __restrict__ teacher_img,
+                                                                    const float4* __restrict__ prev_t, const float* __restrict__ prev_rec_rew,
+                                                                    float keep_prob, uint32_t k0, uint32_t k1, uint32_t offset, uint32_t iteration,
+                                                                    float* __restrict__ obs_out, float4* __restrict__ t_out, float* __restrict__ x_out) {
+    extern __shared__ __align__(128) uint8_t smem_raw[];
+    TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
+    TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
+    policy_tc_setup_from_image<NT>(S, teacher_img);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, tile = warp >> 2, row = threadIdx.x & (TILE - 1);
+    TcTile& T = tiles[tile];
+    float* strip = reinterpret_cast<float*>(T.A_hi + STRIP_OFF) + (warp & 3) * 32 * OBS;
+    uint32_t phase = 0;
+    const int64_t ngroups = (n + (int64_t)NT * TILE - 1) / ((int64_t)NT * TILE);
+    for (int64_t g = blockIdx.x; g < ngroups; g += gridDim.x) {
+        const int64_t i = g * NT * TILE + threadIdx.x;
+        const int64_t row0 = i - lane;
+        const int nvalid = (int)max((int64_t)0, min((int64_t)32, n - row0));
+        const bool valid = i < n;
+        float ob[OBS], pd[4];
+        uint32_t step = 1u;
+        if (valid) {
+            const EnvState e = load_state(qv, tp, ctr, i);
+            observe(e, ob);
+            step = (uint32_t)e.step;
+        } else {
+#pragma unroll
+            for (int k = 0; k < OBS; ++k) ob[k] = 0.f;
+        }
+        if (nvalid > 0) {
+            warp_store_rows<OBS>(obs_out, row0, nvalid, ob, strip, lane);
+            if (KIND == RB_STUDENT_POLICY64 && x_out != obs_out) warp_store_rows<OBS>(x_out, row0, nvalid, ob, strip, lane);
+        }
+        __syncwarp();
+        policy_tc_eval<2>(S, T, tile, row, TILE, row == 0, ob, pd, phase);
+        if (valid) {
+            t_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
+            if (KIND == RB_STUDENT_MLP) {
+                const bool first = step == 0u;   // first record of an episode: prev / prew are zeros (dataset.py:151-164)
+                const float4 pp = first ? make_float4(0.f, 0.f, 0.f, 0.f) : __ldg(prev_t + i);
+                const float pr = first ? 0.f : __ldg(prev_rec_rew + i);
+                float4 o[4];
+                mlp_input_row(ob, keep_prob, k0, k1, offset + (uint32_t)i, iteration, pp, pr, o);
+                float4* xr = reinterpret_cast<float4*>(x_out) + i * 4;
+                xr[0] = o[0]; xr[1] = o[1]; xr[2] = o[2]; xr[3] = o[3];
+            }
+        }
     }
     policy_tc_teardown<NT>(S);
 }
@@ -332,6 +412,36 @@ int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, fl
         rc = set_smem_attr(k_policy_fwd_tc<4, FWD_NT>, smem);
         if (rc) return rc;
         k_policy_fwd_tc<4, FWD_NT><<<grid, FWD_NT * TILE, smem, s>>>(params, obs, n, (float4*)pd);
+    }
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+size_t policy_tc_image_bytes() { return TC_IMAGE_BYTES; }
+
+int policy_tc_build_image(const float* params, int nout, void* img, cudaStream_t s) {
+    k_policy_tc_build_image<<<1, 256, 0, s>>>(params, nout, (TcShared*)img);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, float keep_prob, const float4* prev_t, const float* prev_rec_rew,
+                      uint32_t iteration, float* obs, float* t_pd, float* x, cudaStream_t s) {
+    constexpr int NT = FWD_NT;
+    const int64_t ngroups = (e->n + NT * TILE - 1) / (NT * TILE);
+    const unsigned grid = (unsigned)min((int64_t)e->sm_count * 2, ngroups);
+    const size_t smem = tc_smem_bytes<NT>();
+    const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
+    if (student_kind == RB_STUDENT_MLP) {
+        int rc = set_smem_attr(k_dagger_observe_tc<RB_STUDENT_MLP, NT>, smem);
+        if (rc) return rc;
+        k_dagger_observe_tc<RB_STUDENT_MLP, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, teacher_img, prev_t, prev_rec_rew, keep_prob, k0,
+                                                                            k1, e->offset, iteration, obs, (float4*)t_pd, x);
+    } else {
+        int rc = set_smem_attr(k_dagger_observe_tc<RB_STUDENT_POLICY64, NT>, smem);
+        if (rc) return rc;
+        k_dagger_observe_tc<RB_STUDENT_POLICY64, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, teacher_img, prev_t, prev_rec_rew,
+                                                                                 keep_prob, k0, k1, e->offset, iteration, obs, (float4*)t_pd, x);
     }
     RB_CUDA(cudaGetLastError());
     return RB_OK;

@@ -65,6 +65,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* mbar, uint32_t parity) {
         : "memory");
 }
 
+// TMA bulk copy global -> shared (1-D), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* mbar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* mbar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)), "l"(src_gmem),
+                 "r"(bytes), "r"(smem_u32(mbar))
+                 : "memory");
+}
+
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (tensor core operand reads)
