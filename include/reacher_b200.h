@@ -173,6 +173,32 @@ int rb_dagger_invalidate_teacher(rb_dagger* d);
 int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------ dataset -
+ * Device-resident rollout buffer with the semantics of the reference Dataset (src/distilation/dataset.py:72-296) for N lock-step
+ * envs: a ring of `generations` x 50 steps x N records {ob[11], rew, t[4], s[4], with}; prev / prew of record j are t / rew of
+ * record j-1 (zeros at j = 0: pdflat_at / rew_at, dataset.py:151-164).  The cursor (step in episode, generation) lives on the host;
+ * all data movement is asynchronous on `stream`.                                                                          */
+typedef struct rb_dataset rb_dataset;
+int rb_dataset_create(rb_dataset** out, int64_t num_envs, int64_t generations, int device);
+int rb_dataset_destroy(rb_dataset* d);
+/* Dataset.write  dataset.py:118-143: append one record per env.  rew / t / s may be NULL (zeros).  stepped_with: 0 = 't', 1 = 's'. */
+int rb_dataset_write(rb_dataset* d, const float* ob_dev, const float* rew_dev, const float* t_pdflat_dev, const float* s_pdflat_dev,
+                     int stepped_with, void* stream);
+/* Dataset.flush  dataset.py:146-149: close the N current episodes (they must hold exactly 50 records, as in the reference). */
+int rb_dataset_flush(rb_dataset* d);
+int64_t rb_dataset_num_episodes(const rb_dataset* d);   /* Dataset.num_episodes: episodes flushed so far                       */
+int64_t rb_dataset_num_available(const rb_dataset* d);  /* complete episodes still in the ring                                 */
+int rb_dataset_episode_len(const rb_dataset* d);        /* len(curr_episode)                                                   */
+/* Dataset.training_batches  dataset.py:179-210: B episodes drawn with replacement and ONE shared start in [0, 50-T], Philox keyed
+ * (seed; draw, b).  Time-major outputs ob[T,B,11], t[T,B,4], prev[T,B,4], prew[T,B,1]; episodes_out[B] / start_out[1] (optional)
+ * report what was drawn.                                                                                                      */
+int rb_dataset_training_batch(rb_dataset* d, uint64_t seed, uint32_t draw, int B, int T, float* ob_out_dev, float* t_out_dev, float* prev_out_dev,
+                              float* prew_out_dev, int32_t* episodes_out_dev, int32_t* start_out_dev, void* stream);
+/* Dataset.test_batch  dataset.py:213-290, for every env at once: ob[T,N,11] = last T-1 observations of the current episode
+ * (left zero padded) + ob_cur; prev[T,N,4] / prew[T,N,1] = t / rew of the records one step earlier (zero padded).  The reference
+ * places the single env's window in the LAST batch row of a zero batch; env.py does that for num_envs == 1.                  */
+int rb_dataset_test_batch(rb_dataset* d, const float* ob_cur_dev, int T, float* ob_out_dev, float* prev_out_dev, float* prew_out_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

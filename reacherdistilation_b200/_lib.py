@@ -57,6 +57,15 @@ _SIGS = {
     "rb_dagger_observe": (C.c_int, [_vp, _fp, C.c_uint32, _fp, _fp, _fp, C.c_int, _vp]),
     "rb_dagger_invalidate_teacher": (C.c_int, [_vp]),
     "rb_dagger_act": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
+    "rb_dataset_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int]),
+    "rb_dataset_destroy": (C.c_int, [_vp]),
+    "rb_dataset_write": (C.c_int, [_vp, _fp, _fp, _fp, _fp, C.c_int, _vp]),
+    "rb_dataset_flush": (C.c_int, [_vp]),
+    "rb_dataset_num_episodes": (C.c_int64, [_vp]),
+    "rb_dataset_num_available": (C.c_int64, [_vp]),
+    "rb_dataset_episode_len": (C.c_int, [_vp]),
+    "rb_dataset_training_batch": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _i32p, _i32p, _vp]),
+    "rb_dataset_test_batch": (C.c_int, [_vp, _fp, C.c_int, _fp, _fp, _fp, _vp]),
 }
 
 MODE_FP32, MODE_TC = 0, 1
