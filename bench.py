@@ -31,7 +31,11 @@ ENVS_PER_GPU = 65536
 CHUNK_T = 50
 DISTILL_ENVS_PER_GPU = 32768
 STEP_API_ENVS = 1 << 22
-ALG_BYTES_ROLLOUT = 68.0      # fused rollout writes one 17-float buffer row per env-step
+ALG_BYTES_ROLLOUT = 65.0      # fused rollout writes one buffer row per env-step: ob 44 + pdflat 16 + rew 4 + done 1 B (17 scalars)
+ROLLOUT_TRAFFIC_NCU = 158.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
+                                # profiles/r01_ncu_full_k_rollout_policy_tc.csv; the rest of the 213 MB is still dirty in L2 at kernel end
+MUFU_PER_ENV_STEP = 265.0       # 128 tanh x (ex2 + rcp) + 8 rcp + 1 sqrt (profiles: MUFU instructions / warp-step)
+XU_LANES_PER_CLK_PER_SM = 16.0  # B200 MUFU rate
 ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 FLOP_PER_ENV_STEP = 450.0 + 9856.0          # physics + teacher MLP
@@ -54,7 +58,7 @@ class ClockSampler:
     def __init__(self, index=0):
         self.lines, self.proc = [], None
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.th = threading.Thread(target=self._read, daemon=True)
             self.th.start()
@@ -66,7 +70,11 @@ class ClockSampler:
             self.lines.append((time.time(), line.strip()))
 
     def window(self, t0, t1):
-        rows = [l for (t, l) in self.lines if t0 <= t <= t1] or [l for (_, l) in self.lines[-3:]]
+        if not [1 for (t, _) in self.lines if t0 <= t <= t1]:
+            time.sleep(0.2)                               # very short timed region: take the samples closest to it
+        rows = [l for (t, l) in self.lines if t0 <= t <= t1]
+        if not rows:
+            rows = [l for (_, l) in sorted(self.lines, key=lambda tl: abs(tl[0] - 0.5 * (t0 + t1)))[:3]]
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in rows:
@@ -99,11 +107,14 @@ def cpu_reference_leg(seconds=12.0, nthreads=0):
     n = int(min(ENVS_PER_GPU, max(2048, rate * seconds / CHUNK_T)))
     env = RC.ReacherOracleC(n, seed=0, nthreads=nthreads); env.reset()
     obs, pd, rw, dn = (np.zeros((CHUNK_T, n, 11)), np.zeros((CHUNK_T, n, 4)), np.zeros((CHUNK_T, n)), np.zeros((CHUNK_T, n), np.uint8))
-    t0 = time.perf_counter()
-    env.rollout_policy(CHUNK_T, p, record=True)
+    reps, t0 = 0, time.perf_counter()
+    while reps == 0 or time.perf_counter() - t0 < seconds:          # bounded sample: ~`seconds` of CPU work on all host cores
+        env.rollout_policy(CHUNK_T, p, record=True)
+        reps += 1
     dt = time.perf_counter() - t0
-    return dict(value=n * CHUNK_T / dt, unit="env-steps/s", cores=cores, kind="port",
-                sample="%d envs x %d steps teacher-in-the-loop rollout, float64 C restatement (oracle/reacher_oracle.c), %.1f s" % (n, CHUNK_T, dt)), n, dt
+    return dict(value=n * CHUNK_T * reps / dt, unit="env-steps/s", cores=cores, kind="port",
+                sample="%d x (%d envs x %d steps) teacher-in-the-loop rollout chunks, float64 C restatement (oracle/reacher_oracle.c, OpenMP), %.1f s"
+                       % (reps, n, CHUNK_T, dt)), n, dt
 
 
 def cpu_distill_leg(kind="mlp", seconds=6.0):
@@ -261,12 +272,18 @@ def main():
                                % (n * CHUNK_T * 68 / 1e6), seed=0, mean_teacher_reward=mean_rew),
                 e2e=e2e, gpu_launches=K, clocks=clocks)
     line["roofline"] = dict(bound="hbm", achieved=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9, peak=pk["hbm"], unit="GB/s",
-                            frac=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9 / pk["hbm"], traffic=None, peak_source=pk["src"],
+                            frac=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9 / pk["hbm"],
+                            traffic=(ROLLOUT_TRAFFIC_NCU if (mode == MODE_TC and n == 65536) else None), peak_source=pk["src"],
                             kernel="k_rollout_policy_%s" % ("tc" if mode == MODE_TC else "fp32"),
-                            note="fused rollout is FP32/MUFU-pipe bound, not HBM bound (SURVEY 8(d)); see fp32_pipe")
-    line["fp32_pipe"] = dict(achieved_tflops=FLOP_PER_ENV_STEP * n * CHUNK_T / kernel_s / 1e12, peak_tflops=FP32_PEAK_TFLOPS,
-                             frac=FLOP_PER_ENV_STEP * n * CHUNK_T / kernel_s / 1e12 / FP32_PEAK_TFLOPS,
-                             flop_per_env_step=FLOP_PER_ENV_STEP, note="algorithmic FLOP (physics 450 + teacher 9856) vs 148 SM x 128 lanes x 2 x 1.965 GHz")
+                            note="HBM is NOT the limiter of the fused rollout (it only writes the 65 B buffer row per env-step, state stays in "
+                                 "registers, SURVEY 8(d)); the binding resources are instruction issue and the XU (MUFU) pipe: see `pipes`")
+    sms = L.rb_sm_count(local)
+    xu_ceiling = sms * XU_LANES_PER_CLK_PER_SM * 1.965e9 / MUFU_PER_ENV_STEP
+    line["pipes"] = dict(xu_mufu_per_env_step=MUFU_PER_ENV_STEP, xu_ceiling_env_steps_per_s=xu_ceiling, frac_of_xu_ceiling=value / world / xu_ceiling,
+                         tensor_tflops_bf16x3=3 * 9856.0 * n * CHUNK_T / kernel_s / 1e12, tensor_peak_tflops=pk["bf16_burst"],
+                         physics_flop_per_env_step=450.0, teacher_flop_per_env_step=9856.0,
+                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 265 MUFU per env-step; ncu (profiles/): XU pipe 45 % of active cycles, "
+                              "issue slots 47 %, tensor pipe 12 %")
 
     if not args.quick:
         # ---- distill: DAgger iterations on the config-4 shard ---------------------------------------------------
@@ -279,7 +296,7 @@ def main():
             tr.step()
         dsec, _ = timed(tr.step, Kd)
         # student kernel alone (device time of the dominant kernel of this loop)
-        lg = lambda: tr.student.loss_grad(tr.x, tr.t_pd, s_out=tr.s_pd)
+        lg = lambda: tr.student.loss_grad(tr.x, tr.t_pd, s_out=tr.s_pd)      # ONE cooperative launch in tc mode (fold, tiles, reduce, un-fold)
         for _ in range(3):
             lg()
         ksec, _ = timed(lg, 20)
@@ -298,11 +315,28 @@ def main():
                                ms_per_step=1e3 * dsec / Kd, workload="config4 shard: %d envs/GPU, student %s, KL(s||t), TF-Adam, %s"
                                % (nd, args.student, "NCCL all-reduce of flat grad" if world > 1 else "single GPU"),
                                e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=4),
-                               gpu_launches_per_step=7, last_loss=float(tr.last_loss()),
+                               gpu_launches_per_step=(3 if (mode == MODE_TC and world == 1) else 8), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
+                               last_loss=float(tr.last_loss()),
                                roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",
                                              frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"], traffic=None, peak_source=pk["src"],
-                                             kernel="k_student(loss_grad) + k_reduce_partials", kernel_ms=1e3 * ksec / 20))
+                                             kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
+                                                     else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
+                                             note="tile GEMMs run bf16x3 (3 MMAs per product): tensor-pipe work is 3x the algorithmic FLOP"))
         tr.close()
+        if world == 1:
+            # the whole config-4 batch (262 144 envs) on ONE GPU: fixed phases of the cooperative kernel amortise over 14 tiles per SM
+            nl = 8 * DISTILL_ENVS_PER_GPU
+            trl = DaggerTrainer(num_envs=nl, seed=0, device=local, student_kind=kind, mode=mode)
+            for _ in range(W):
+                trl.step()
+            lsec, _ = timed(trl.step, 30)
+            lgl = lambda: trl.student.loss_grad(trl.x, trl.t_pd, s_out=trl.s_pd)
+            lgl()
+            lksec, _ = timed(lgl, 10)
+            line["distill"]["full_batch_one_gpu"] = dict(envs=nl, value=float(nl) * 30 / lsec, unit="samples/s", ms_per_step=1e3 * lsec / 30,
+                                                         kernel_ms=1e3 * lksec / 10, tensor_tflops=fl * nl / (lksec / 10) / 1e12,
+                                                         frac_of_bf16_peak=fl * nl / (lksec / 10) / 1e12 / pk["bf16_burst"])
+            trl.close()
         # ---- step API: HBM-bound single-step kernel at 4M envs ---------------------------------------------------
         ns = STEP_API_ENVS
         env2 = VecReacher(num_envs=ns, seed=0, device=local, env_offset=0)
