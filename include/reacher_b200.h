@@ -156,6 +156,19 @@ int rb_student_step(int kind, float* params_dev, float* m_dev, float* v_dev, con
                     int loss_kind, float* s_pdflat_dev, float* gradloss_dev, void* workspace_dev, int64_t step_t, float lr, float beta1,
                     float beta2, float eps, float grad_scale, int mode, void* stream);
 
+/* Data-parallel form of rb_student_step (MpiAdam.update = Allreduce + Adam, backup/student_rollout.py:658,709), RB_MODE_TC only:
+ * ONE cooperative kernel per rank computes the local [grad | loss], exchanges it with a one-shot all-reduce over NVLink peer
+ * memory (every rank adds all ranks' slots in rank order => bit-identical sums everywhere) and applies Adam.
+ *   peer_grad_slots[world]: device address, valid on THIS rank, of every rank's slot of rb_student_param_count+1 floats for this
+ *                           step (symmetric / IPC-mapped memory; the caller alternates two slots per rank from step to step),
+ *   peer_flags[world]     : device address of every rank's flag array (uint32[world], zero before the first step),
+ *   epoch                 : 1, 2, 3, ... identical on all ranks.  gradloss_dev receives the all-reduced [grad | loss].
+ * All ranks must launch the same step; the kernels wait for one another.                                               */
+int rb_student_step_dp(int kind, float* params_dev, float* m_dev, float* v_dev, const float* x_dev, const float* t_pdflat_dev, int64_t B,
+                       int loss_kind, float* s_pdflat_dev, float* gradloss_dev, void* workspace_dev, int64_t step_t, float lr, float beta1,
+                       float beta2, float eps, float grad_scale, int rank, int world, const uint64_t* peer_grad_slots,
+                       const uint64_t* peer_flags, uint32_t epoch, void* stream);
+
 /* ------------------------------------------------------------------------------------------------ DAgger --
  * One lock-step DAgger iteration pieces (src/distilation/mlp_train.py:143-204 batched):
  * rb_dagger_observe: for every env write ob[N,11], teacher label t_pdflat[N,4] and the student input x[N,in]

@@ -84,7 +84,26 @@ struct StudentTcArgs {
     int do_adam;
     float* adam_p; float* adam_m; float* adam_v;
     float lr_t, beta1, beta2, eps, gscale;
+    // optional data-parallel exchange fused in front of the update: one-shot all-reduce over NVLink peer memory.
+    // peer_gl[r] = rank r's [P+1] gradient slot of this step (symmetric allocation, double buffered by the caller),
+    // peer_flag[r] = rank r's flag array (uint32[world]); this rank writes `epoch` into peer_flag[r][rank].
+    int world, rank;
+    uint32_t epoch;
+    float* peer_gl[8];
+    uint32_t* peer_flag[8];
 };
+
+__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
 
 struct __align__(16) StudentTcCtl {
     uint64_t mbar;
@@ -511,14 +530,32 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         }
         grid.sync();
         // ---- gradient of the un-folded parameters ---------------------------------------------------------------------------------
-        if constexpr (S::L == 4) finish_mlp(a.params, a.red, a.gradloss, gtid, gthreads);
+        float* gl = a.world > 1 ? a.peer_gl[a.rank] : a.gradloss;          // data parallel: this rank's slot of the symmetric buffer
+        if constexpr (S::L == 4) finish_mlp(a.params, a.red, gl, gtid, gthreads);
         else
-            for (int i = gtid; i <= a.P; i += gthreads) a.gradloss[i] = __ldcg(a.red + i);
+            for (int i = gtid; i <= a.P; i += gthreads) gl[i] = __ldcg(a.red + i);
+        if (a.world > 1) {
+            // ---- one-shot all-reduce over NVLink peer memory (MpiAdam.update's Allreduce, backup/student_rollout.py:709) ----------
+            __threadfence_system();
+            grid.sync();                                                   // the whole local gradient is written and fenced
+            if (blockIdx.x == 0 && tid < a.world) {
+                __threadfence_system();
+                st_release_sys(a.peer_flag[tid] + a.rank, a.epoch);        // tell rank `tid` that this rank's slot is ready
+                while (ld_acquire_sys(a.peer_flag[a.rank] + tid) < a.epoch) { }     // ... and wait for rank `tid`'s slot
+            }
+            grid.sync();
+            for (int i = gtid; i <= a.P; i += gthreads) {                  // every rank adds the slots in rank order: identical sums
+                float tot = 0.f;
+                for (int r = 0; r < a.world; ++r) tot += ld_relaxed_sys(a.peer_gl[r] + i);
+                a.gradloss[i] = tot;
+            }
+        }
         if (a.do_adam) {                   // TF1 Adam, same arithmetic as k_adam (student.cu)
-            grid.sync();                   // every read of the old parameters (finish) is done, every gradloss entry written
+            if (a.world <= 1) grid.sync(); // every read of the old parameters (finish) is done, every gradloss entry written
+            else __syncthreads();          // (the exchange above already separated finish from here; own-thread gradloss entries)
             for (int i = gtid; i < a.P; i += gthreads) {
                 float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
-                adam_update(pi, mi, vi, __ldcg(a.gradloss + i), a.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                adam_update(pi, mi, vi, a.world > 1 ? a.gradloss[i] : __ldcg(a.gradloss + i), a.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
                 a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
             }
         }
@@ -555,9 +592,10 @@ template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cuda
 }
 
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
+struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; };
 
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
-                   float* gradloss, void* workspace, const AdamFuse* adam, cudaStream_t st) {
+                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, cudaStream_t st) {
     RB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(params) & 3) == 0, "x must be 16-byte aligned");
     RB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     float* ws = (float*)workspace;
@@ -570,6 +608,12 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
     if (adam && !fwd_only) {
         a.do_adam = 1; a.adam_p = adam->p; a.adam_m = adam->m; a.adam_v = adam->v;
         a.lr_t = adam->lr_t; a.beta1 = adam->beta1; a.beta2 = adam->beta2; a.eps = adam->eps; a.gscale = adam->gscale;
+    }
+    a.world = 1;
+    if (px && !fwd_only && px->world > 1) {
+        RB_REQUIRE(px->world <= 8 && px->rank >= 0 && px->rank < px->world, "peer exchange supports 2..8 ranks");
+        a.world = px->world; a.rank = px->rank; a.epoch = px->epoch;
+        for (int r = 0; r < px->world; ++r) { a.peer_gl[r] = (float*)px->gl_ptrs[r]; a.peer_flag[r] = (uint32_t*)px->flag_ptrs[r]; }
     }
     if (kind == RB_STUDENT_MLP) {
         a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;

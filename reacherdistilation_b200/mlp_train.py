@@ -26,7 +26,7 @@ from .teacher import TeacherAgent
 class DaggerTrainer:
     def __init__(self, num_envs=NUM_ENVS, seed=SEED, device=0, student_kind=STUDENT_MLP, keep_prob=KEEP_PROB, mode=MODE_FP32,
                  teacher_params=None, teacher_seed=0, student_seed=1, env_offset=0, loss_kind=LOSS_KL_ST, lr=None, eps=None,
-                 process_group=None, average_grads=False, student_params=None, student_mode=None):
+                 process_group=None, average_grads=False, student_params=None, student_mode=None, fused_allreduce=None):
         import ctypes as C
         self.env = VecReacher(num_envs=num_envs, seed=seed, device=device, env_offset=env_offset)
         self.device = self.env.device
@@ -52,6 +52,10 @@ class DaggerTrainer:
         if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
             self.world = torch.distributed.get_world_size(process_group)
         self.grad_scale = (1.0 / self.world) if average_grads else 1.0   # MpiAdam averages (backup :709); KL sum = concatenated batch
+        # world > 1: exchange the gradient inside the student kernel over NVLink peer memory (tensor-core path) unless told to use NCCL
+        self.fused_allreduce = (self.world > 1 and self.student_mode == _lib.MODE_TC) if fused_allreduce is None else bool(fused_allreduce)
+        if self.fused_allreduce:
+            self.student.enable_peer_exchange(process_group)
         self.iteration = 0
         self.env.reset()
 
@@ -64,7 +68,9 @@ class DaggerTrainer:
         """One DAgger iteration over all envs.  Asynchronous; returns nothing (loss: self.last_loss())."""
         L, st = lib(), stream_ptr()
         check(L.rb_dagger_observe(self._h, ptr(self.teacher.params), self.iteration, ptr(self.obs), ptr(self.t_pd), ptr(self.x), self.mode, st))
-        if self.world > 1:
+        if self.fused_allreduce:
+            self.student.step_dp(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd, grad_scale=self.grad_scale)
+        elif self.world > 1:
             self.student.loss_grad(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd)
             torch.distributed.all_reduce(self.student.gradloss, group=self.pg)
             self.student.adam_step(self.grad_scale)

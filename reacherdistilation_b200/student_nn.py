@@ -77,6 +77,46 @@ class StudentNet:
                                     self.mode, stream_ptr()))
         return s_out
 
+    # ---- data parallel: one-shot all-reduce over NVLink peer memory fused into the step kernel -------------------------
+    def enable_peer_exchange(self, group=None):
+        """Allocate this rank's symmetric buffer [flags(64 u32) | slot 0 | slot 1] and exchange the peer mappings
+        (torch.distributed._symmetric_memory: CUDA VMM handles over the process group's store).  RB_MODE_TC only."""
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        assert self.mode == _lib.MODE_TC, "the fused exchange lives in the tcgen05 student kernel"
+        group = group if group is not None else dist.group.WORLD
+        self._px_world, self._px_rank = dist.get_world_size(group), dist.get_rank(group)
+        assert 2 <= self._px_world <= 8
+        slot = (self.P + 1 + 63) // 64 * 64
+        with torch.cuda.device(self.device):
+            self._px_buf = symm.empty(64 + 2 * slot, dtype=torch.float32, device=self.device)
+        self._px_buf.zero_()
+        hdl = symm.rendezvous(self._px_buf, group.group_name)
+        self._px_hdl = hdl
+        base = [int(p) for p in hdl.buffer_ptrs]
+        mk = lambda vals: torch.tensor(vals, dtype=torch.int64).numpy().astype(np.uint64)
+        self._px_flags = mk(base)
+        self._px_slots = [mk([b + 4 * (64 + k * slot) for b in base]) for k in (0, 1)]
+        self._px_epoch = 0
+        torch.cuda.synchronize(self.device)
+        hdl.barrier()                                   # every rank's flags are zero before anyone steps
+        torch.cuda.synchronize(self.device)
+
+    def step_dp(self, x, t_pdflat, loss_kind=LOSS_KL_ST, s_out=None, grad_scale=1.0):
+        """Data-parallel rb_student_step: local [grad|loss] -> all-reduce over peer memory -> Adam, in one kernel per rank."""
+        x = x.reshape(-1, self.in_dim).contiguous()
+        t_pdflat = t_pdflat.reshape(-1, 4).contiguous()
+        B = x.shape[0]
+        if s_out is None:
+            s_out = torch.empty((B, 4), dtype=torch.float32, device=self.device)
+        self.t += 1
+        self._px_epoch += 1
+        slots = self._px_slots[self._px_epoch & 1]
+        check(lib().rb_student_step_dp(self.kind, ptr(self.params), ptr(self.m), ptr(self.v), ptr(x), ptr(t_pdflat), B, loss_kind, ptr(s_out),
+                                       ptr(self.gradloss), ptr(self.workspace), self.t, self.lr, self.beta1, self.beta2, self.eps, grad_scale,
+                                       self._px_rank, self._px_world, slots.ctypes.data, self._px_flags.ctypes.data, self._px_epoch, stream_ptr()))
+        return s_out
+
     def adam_step(self, grad_scale=1.0):
         self.t += 1
         check(lib().rb_adam_step(ptr(self.params), ptr(self.m), ptr(self.v), ptr(self.gradloss), self.P, self.t, self.lr, self.beta1, self.beta2,
