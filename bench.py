@@ -315,14 +315,25 @@ def main():
                                ms_per_step=1e3 * dsec / Kd, workload="config4 shard: %d envs/GPU, student %s, KL(s||t), TF-Adam, %s"
                                % (nd, args.student, "NCCL all-reduce of flat grad" if world > 1 else "single GPU"),
                                e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=4),
-                               gpu_launches_per_step=(3 if (mode == MODE_TC and world == 1) else 8), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
+                               gpu_launches_per_step=(3 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
                                last_loss=float(tr.last_loss()),
                                roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",
                                              frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"], traffic=None, peak_source=pk["src"],
                                              kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
                                                      else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
                                              note="tile GEMMs run bf16x3 (3 MMAs per product): tensor-pipe work is 3x the algorithmic FLOP"))
+        line["distill"]["exchange"] = ("none (single rank)" if world == 1 else
+                                       "one-shot all-reduce over NVLink peer memory fused into k_student_tc" if tr.fused_allreduce else "NCCL all-reduce")
         tr.close()
+        if world > 1:
+            # same loop with the gradient exchange done by NCCL (all-reduce kernel + separate Adam launch): the baseline of the fused kernel
+            trn = DaggerTrainer(num_envs=nd, seed=0, device=local, student_kind=kind, mode=mode, env_offset=rank * nd, fused_allreduce=False)
+            trn.sync_params()
+            for _ in range(W):
+                trn.step()
+            nsec, _ = timed(trn.step, Kd)
+            line["distill"]["nccl_baseline"] = dict(value=float(nd) * Kd * world / nsec, unit="samples/s", ms_per_step=1e3 * nsec / Kd)
+            trn.close()
         if world == 1:
             # the whole config-4 batch (262 144 envs) on ONE GPU: fixed phases of the cooperative kernel amortise over 14 tiles per SM
             nl = 8 * DISTILL_ENVS_PER_GPU

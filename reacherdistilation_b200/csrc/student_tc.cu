@@ -536,9 +536,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             for (int i = gtid; i <= a.P; i += gthreads) gl[i] = __ldcg(a.red + i);
         if (a.world > 1) {
             // ---- one-shot all-reduce over NVLink peer memory (MpiAdam.update's Allreduce, backup/student_rollout.py:709) ----------
-            __threadfence_system();
-            grid.sync();                                                   // the whole local gradient is written and fenced
-            if (blockIdx.x == 0 && tid < a.world) {
+            grid.sync();                                                   // the whole local gradient is written (gpu scope)
+            if (blockIdx.x == 0 && tid < a.world) {                        // fence.sys + release.sys are cumulative over what the barrier ordered
                 __threadfence_system();
                 st_release_sys(a.peer_flag[tid] + a.rank, a.epoch);        // tell rank `tid` that this rank's slot is ready
                 while (ld_acquire_sys(a.peer_flag[a.rank] + tid) < a.epoch) { }     // ... and wait for rank `tid`'s slot
