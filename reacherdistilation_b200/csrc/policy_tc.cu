@@ -18,11 +18,16 @@
 // are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  : FADD, 2 MUFU, FFMA per element, then the bf16
 // hi/lo split written straight into the next layer's A tile (no-swizzle K-major layout, see tc_common.cuh).
 #include <cstddef>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "dagger_input.cuh"
 #include "physics.cuh"
 #include "tc_common.cuh"
+
+#ifndef RB_TANH_VARIANT
+#define RB_TANH_VARIANT 1
+#endif
 
 namespace rb {
 
@@ -127,8 +132,28 @@ __device__ __forceinline__ void hidden_chunk(TcTile& T, const float* v, int cc, 
 #pragma unroll
     for (int q8 = 0; q8 < 2; ++q8) {
         uint32_t h[4], l[4];
+#if RB_TANH_VARIANT == 3
 #pragma unroll
-        for (int q = 0; q < 4; ++q) split_pair(tanh_from_scaled(v[8 * q8 + 2 * q]), tanh_from_scaled(v[8 * q8 + 2 * q + 1]), h[q], l[q]);
+        for (int q = 0; q < 2; ++q) {
+            float t[4];
+            tanh_quad_from_scaled(v + 8 * q8 + 4 * q, t);
+            split_pair(t[0], t[1], h[2 * q], l[2 * q]);
+            split_pair(t[2], t[3], h[2 * q + 1], l[2 * q + 1]);
+        }
+#else
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            float t0, t1;
+#if RB_TANH_VARIANT == 1
+            tanh_pair_from_scaled(v[8 * q8 + 2 * q], v[8 * q8 + 2 * q + 1], t0, t1);
+#elif RB_TANH_VARIANT == 2
+            t0 = tanh_from_scaled_newton(v[8 * q8 + 2 * q]); t1 = tanh_from_scaled_newton(v[8 * q8 + 2 * q + 1]);
+#else
+            t0 = tanh_from_scaled(v[8 * q8 + 2 * q]); t1 = tanh_from_scaled(v[8 * q8 + 2 * q + 1]);
+#endif
+            split_pair(t0, t1, h[q], l[q]);
+        }
+#endif
         *reinterpret_cast<uint4*>(T.A_hi + (2 * cc + q8) * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
         *reinterpret_cast<uint4*>(T.A_lo + (2 * cc + q8) * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
     }
@@ -340,7 +365,7 @@ template <int NOUT, int NT>
 __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
                                                                     int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
                                                                     float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf, uint32_t k0,
-                                                                    uint32_t k1, uint32_t offset) {
+                                                                    uint32_t k1, uint32_t offset, uint32_t stagger_ns) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
     TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
@@ -361,6 +386,10 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
         const uint32_t gid = offset + (uint32_t)i;
         EnvState e = valid ? load_state(qv, tp, ctr, i) : zero_state();
         uint32_t phase = 0;
+        // The tiles of a CTA alternate between an XU-bound phase (tanh epilogues: 2 MUFU per element) and an issue-bound phase
+        // (physics).  Started together they stay in lock step and fight for the same pipe; a one-time offset of a fraction of the
+        // step period lets one tile's epilogue overlap another tile's physics.
+        for (uint32_t w = 0; w < (uint32_t)tile * stagger_ns; w += 1000u) __nanosleep(1000u);
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             float ob[OBS], pd[4];
@@ -396,6 +425,7 @@ static int sm_count_current(int* sms) {
 
 constexpr int FWD_NT = 2;       // standalone forward: 2 tiles per CTA (97 KB) -> 2 CTAs per SM
 constexpr int ROLLOUT_NT = 4;   // fused rollout: 4 tiles = 16 warps per CTA, one CTA per SM
+constexpr int ROLLOUT_STAGGER_NS = 2000;   // start offset between consecutive tiles of a CTA (step period ~ 8 us)
 
 int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, float* pd, cudaStream_t s) {
     int sms = 148;
@@ -447,28 +477,40 @@ int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, floa
     return RB_OK;
 }
 
-int rollout_policy_tc(rb_env* e, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf, uint8_t* done_buf,
-                      cudaStream_t s) {
-    constexpr int NT = ROLLOUT_NT;
+template <int NOUT, int NT>
+static int launch_rollout_tc(rb_env* e, const float* params, int T, float* obs_buf, float* pd_buf, float* rew_buf, uint8_t* done_buf, cudaStream_t s) {
     const int64_t units = (e->n + 31) / 32;
     const int64_t per_round = (int64_t)4 * NT * e->sm_count;
     const int64_t rounds = (units + per_round - 1) / per_round;
     const unsigned grid = (unsigned)min(units, rounds * e->sm_count);        // units / grid <= 4 * NT
     const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
     const size_t smem = tc_smem_bytes<NT>();
-    if (nout == 2) {
-        int rc = set_smem_attr(k_rollout_policy_tc<2, NT>, smem);
-        if (rc) return rc;
-        k_rollout_policy_tc<2, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf,
-                                                                 k0, k1, e->offset);
-    } else {
-        int rc = set_smem_attr(k_rollout_policy_tc<4, NT>, smem);
-        if (rc) return rc;
-        k_rollout_policy_tc<4, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf,
-                                                                 k0, k1, e->offset);
-    }
+    int rc = set_smem_attr(k_rollout_policy_tc<NOUT, NT>, smem);
+    if (rc) return rc;
+    static int stagger = -1;
+    if (stagger < 0) { const char* v = getenv("RB_ROLLOUT_STAGGER_NS"); stagger = v ? atoi(v) : ROLLOUT_STAGGER_NS; }
+    k_rollout_policy_tc<NOUT, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf, k0, k1,
+                                                                e->offset, (uint32_t)stagger);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
+}
+
+int rollout_policy_tc(rb_env* e, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf, uint8_t* done_buf,
+                      cudaStream_t s) {
+    static int nt = 0;
+    if (nt == 0) {                                   // tiles per CTA: RB_ROLLOUT_NT = 4 | 5 | 6 (tuning knob, default ROLLOUT_NT)
+        const char* v = getenv("RB_ROLLOUT_NT");
+        nt = v ? atoi(v) : ROLLOUT_NT;
+        if (nt < 4 || nt > 6) nt = ROLLOUT_NT;
+    }
+    if (nout == 2) {
+        if (nt == 5) return launch_rollout_tc<2, 5>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+        if (nt == 6) return launch_rollout_tc<2, 6>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+        return launch_rollout_tc<2, 4>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+    }
+    if (nt == 5) return launch_rollout_tc<4, 5>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+    if (nt == 6) return launch_rollout_tc<4, 6>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+    return launch_rollout_tc<4, 4>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
 }
 
 }  // namespace rb

@@ -143,6 +143,46 @@ __device__ __forceinline__ float tanh_from_scaled(float y) {
     return fmaf(-2.0f, r, 1.0f);
 }
 
+// tanh of a PAIR from scaled arguments with ONE reciprocal: 1/(a b) shared, 1/a = b/(a b).  3 MUFU per pair instead of 4 (the XU
+// pipe is the busiest pipe of the rollout kernel).  y is clamped to 60 so (e0+1)(e1+1) <= 2^121 stays finite; tanh(60/(2 log2 e)) == 1.
+__device__ __forceinline__ void tanh_pair_from_scaled(float y0, float y1, float& t0, float& t1) {
+    float e0, e1, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(y0, 60.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(y1, 60.f)));
+    const float a0 = e0 + 1.0f, a1 = e1 + 1.0f;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
+    t0 = fmaf(-2.0f * a1, r, 1.0f);
+    t1 = fmaf(-2.0f * a0, r, 1.0f);
+}
+// same for FOUR values with one reciprocal (5 MUFU per 4 elements); y clamped to 30: tanh(30 / (2 log2 e)) rounds to 1.0f exactly and
+// the product of four (e + 1) <= 2^121 stays finite.
+__device__ __forceinline__ void tanh_quad_from_scaled(const float* y, float* t) {
+    float e[4], a[4], r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(fminf(y[i], 30.f)));
+        a[i] = e[i] + 1.0f;
+    }
+    const float p01 = a[0] * a[1], p23 = a[2] * a[3];
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    const float r01 = -2.0f * (r * p23), r23 = -2.0f * (r * p01);      // -2 / (a0 a1), -2 / (a2 a3)
+    t[0] = fmaf(r01, a[1], 1.0f);
+    t[1] = fmaf(r01, a[0], 1.0f);
+    t[2] = fmaf(r23, a[3], 1.0f);
+    t[3] = fmaf(r23, a[2], 1.0f);
+}
+// variant with the reciprocal on the FMA pipe (integer seed + 3 Newton steps, rel. error < 1e-7): 1 MUFU per element
+__device__ __forceinline__ float tanh_from_scaled_newton(float y) {
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(fminf(y, 100.f)));
+    const float a = e + 1.0f;
+    float r = __uint_as_float(0x7EF311C7u - __float_as_uint(a));
+    r = r * fmaf(-a, r, 2.0f);
+    r = r * fmaf(-a, r, 2.0f);
+    r = r * fmaf(-a, r, 2.0f);
+    return fmaf(-2.0f, r, 1.0f);
+}
+
 // byte offset of element (r, k) inside a K-major no-swizzle tile with R rows
 __host__ __device__ constexpr uint32_t tile_off(int r, int k, int R) { return (uint32_t)((k >> 3) * (R * 16) + r * 16 + (k & 7) * 2); }
 

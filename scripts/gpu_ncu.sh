@@ -1,12 +1,10 @@
 #!/bin/bash
-# parity tests, then launch list + one full capture of the tensor-core rollout kernel
+# launch list + one full capture of the tensor-core rollout kernel (bench --quick = headline section only)
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests -m gpu -q -x > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu.log
-tail -4 gpurun_out/pytest_gpu.log
 CMD="python bench.py --steps 5 --warmup 3 --quick"
 $CMD > gpurun_out/plain.log 2>&1 &&
-ncu --metrics gpu__time_duration.sum --clock-control none -c 80 --csv --log-file gpurun_out/launches_tc.csv $CMD > gpurun_out/ncu1.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_tc.csv $CMD > gpurun_out/ncu1.log 2>&1
 $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_rollout_policy_tc -s 3 -c 1 -f -o gpurun_out/prof_rollout_tc $CMD > gpurun_out/ncu2.log 2>&1
-tail -3 gpurun_out/ncu1.log gpurun_out/ncu2.log
-ls -la gpurun_out
+tail -n 3 gpurun_out/ncu1.log gpurun_out/ncu2.log
+for nt in 4 5 6; do RB_ROLLOUT_NT=$nt python bench.py --steps 50 --warmup 5 --quick 2>&1 | grep -o '"value": [0-9.]*' | head -1; done
