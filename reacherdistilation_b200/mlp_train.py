@@ -130,3 +130,61 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
         torch.save(tr.student.state_dict(), ckpt)
     out = dict(losses=losses, rewards=rewards, teacher_reward=teacher_reward, iterations=iterations, trainer=tr)
     return out
+
+
+def train_replay(train=True, restore=False, num_envs=64, total_episodes=5000, iterations=None, seed=SEED, device=0, keep_prob=KEEP_PROB,
+                 mode=MODE_FP32, batch_size=MLP_BATCH_SIZE, steps_unrolled=None, generations=64, lr=None, verbose=True):
+    """The reference loop in its own shape (mlp_train.py:110-204), N envs wide, with the device Dataset as replay buffer:
+
+    phase A (:120-139)  teacher acts; every record {ob, reward, t_pdflat, s=0, 't'} is written; flush on done, until more than
+                        2 * MLP_BATCH_SIZE episodes exist;
+    phase B (:143-204)  per env step: one optimiser step per Dataset.training_batches() batch (windows [T,B,.] drawn from the
+                        buffer, student input = [dropout(ob), prev, prew], loss.py KL vs the recorded teacher pdflat); teacher label
+                        for the current observation; student action from [ob, prev, prew] with keep_prob 1 (the last row of
+                        Dataset.test_batch -- the MLP graph only uses that row, :63-66); write the record ('s'); step with the
+                        student's mean; flush on done.
+    The reference feeds random noise for prev/prew in this file ("TODO: revert this back", :157-158); the reverted form is used."""
+    from .config import STEPS_UNROLLED
+    from .dataset import Dataset
+    from .student_nn import student_mlp_input
+    T = steps_unrolled or STEPS_UNROLLED
+    env = VecReacher(num_envs=num_envs, seed=seed, device=device)
+    teacher = TeacherAgent(env, restore=restore, mode=mode)
+    student = StudentNet(kind=STUDENT_MLP, seed=1, device=env.device, mode=mode, lr=lr)
+    dataset = Dataset(num_envs=num_envs, generations=generations, device=device, seed=seed)
+    ob = env.reset()
+    reward = torch.zeros(num_envs, device=env.device)
+    if not train:
+        return dict(env=env, teacher=teacher, student=student, dataset=dataset)
+    if verbose:
+        print("Begin Training! First Accumulate observation with teacher")
+    while dataset.num_episodes() <= 2 * MLP_BATCH_SIZE:
+        t_pdflat = teacher.pdflat(ob)
+        dataset.write(ob, reward, t_pdflat, None, "t")
+        ob, reward, new, _ = env.step(t_pdflat[:, :2].contiguous())
+        if dataset.last_step() + 1 == 50:                      # lock-step envs: every episode ends on the same step (TimeLimit 50)
+            dataset.flush()
+    if verbose:
+        print("Accumulated sufficient data points from teacher. now train")
+    losses, rewards, it = [], [], 0
+    max_it = iterations if iterations is not None else 50 * max(1, -(-total_episodes // num_envs))
+    while it < max_it:
+        total_loss = 0.0
+        for (ob_b, t_b, prev_b, prew_b) in dataset.training_batches(batch_size, T):
+            x = student_mlp_input(ob_b.reshape(-1, 11), prev_b.reshape(-1, 4), prew_b.reshape(-1), keep_prob, seed, 0, it)
+            student.step(x, t_b.reshape(-1, 4))
+            total_loss = student.gradloss[student.P]
+        t_pdflat = teacher.pdflat(ob)
+        _, prev_p, prev_r = dataset.test_batch(ob, steps=1) if num_envs > 1 else [a[:, -1:, :] for a in dataset.test_batch(ob, steps=1)]
+        x_act = student_mlp_input(ob, prev_p.reshape(-1, 4), prev_r.reshape(-1), 1.0, seed, 0, it)
+        s_pdflat = student.forward(x_act)
+        dataset.write(ob, reward, t_pdflat, s_pdflat, "s")
+        ob, reward, new, _ = env.step(s_pdflat[:, :2].contiguous())
+        it += 1
+        if dataset.last_step() + 1 == 50:
+            dataset.flush()
+            losses.append(float(total_loss)); rewards.append(float(reward.mean()))
+            if verbose:
+                print("************** Episode %d ****************" % dataset.num_episodes())
+                print("recent loss: %f " % losses[-1])
+    return dict(losses=losses, rewards=rewards, iterations=it, env=env, teacher=teacher, student=student, dataset=dataset)

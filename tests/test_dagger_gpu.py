@@ -77,3 +77,18 @@ def test_train_entry_point_runs():
     assert len(out["losses"]) == 4 and out["losses"][-1] < out["losses"][0]
     assert -1.0 < out["teacher_reward"] < 0.0
     out["trainer"].close()
+
+
+@pytest.mark.parametrize("num_envs", [1, 48])
+def test_reference_shaped_replay_loop(num_envs):
+    """mlp_train.train_replay: the reference's loop shape (warm-up into the Dataset, window batches, test-batch acting)."""
+    from reacherdistilation_b200 import mlp_train
+    out = mlp_train.train_replay(True, False, num_envs=num_envs, iterations=150 if num_envs > 1 else 60, lr=1e-3, verbose=False,
+                                 generations=64 if num_envs == 1 else 8)
+    ds = out["dataset"]
+    warm = -(-41 // num_envs) * num_envs                    # episodes recorded by the teacher before training starts (> 2 * MLP_BATCH_SIZE)
+    assert ds.num_episodes() == warm + (150 // 50 if num_envs > 1 else 1) * num_envs
+    assert len(out["losses"]) >= 1 and np.isfinite(out["losses"]).all()
+    if num_envs > 1:
+        assert out["losses"][-1] < out["losses"][0]
+    ds.close(); out["env"].close()
