@@ -202,6 +202,10 @@ int rb_dataset_flush(rb_dataset* d);
 int64_t rb_dataset_num_episodes(const rb_dataset* d);   /* Dataset.num_episodes: episodes flushed so far                       */
 int64_t rb_dataset_num_available(const rb_dataset* d);  /* complete episodes still in the ring                                 */
 int rb_dataset_episode_len(const rb_dataset* d);        /* len(curr_episode)                                                   */
+/* Copy one flushed generation (absolute index, must still be in the ring) to HOST buffers ob[50,N,11] rew[50,N] t[50,N,4] s[50,N,4]
+ * with[50,N] -- what Dataset.dump (dataset.py:80-85 -> DatasetStore.store :31-40) serialises into gzip-JSON pages.  Synchronises.  */
+int64_t rb_dataset_generations(const rb_dataset* d);
+int rb_dataset_export_host(rb_dataset* d, int64_t generation, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host);
 /* Dataset.training_batches  dataset.py:179-210: B episodes drawn with replacement and ONE shared start in [0, 50-T], Philox keyed
  * (seed; draw, b).  Time-major outputs ob[T,B,11], t[T,B,4], prev[T,B,4], prew[T,B,1]; episodes_out[B] / start_out[1] (optional)
  * report what was drawn.                                                                                                      */

@@ -66,6 +66,8 @@ _SIGS = {
     "rb_dataset_num_episodes": (C.c_int64, [_vp]),
     "rb_dataset_num_available": (C.c_int64, [_vp]),
     "rb_dataset_episode_len": (C.c_int, [_vp]),
+    "rb_dataset_generations": (C.c_int64, [_vp]),
+    "rb_dataset_export_host": (C.c_int, [_vp, C.c_int64, _fp, _fp, _fp, _fp, _u8p]),
     "rb_dataset_training_batch": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _i32p, _i32p, _vp]),
     "rb_dataset_test_batch": (C.c_int, [_vp, _fp, C.c_int, _fp, _fp, _fp, _vp]),
 }

@@ -153,6 +153,22 @@ int64_t rb_dataset_num_episodes(const rb_dataset* d) { return d ? d->gen * d->n 
 int64_t rb_dataset_num_available(const rb_dataset* d) { return d ? (d->gen < d->G ? d->gen : d->G - (d->k > 0 ? 1 : 0)) * d->n : 0; }
 int rb_dataset_episode_len(const rb_dataset* d) { return d ? d->k : 0; }
 
+int64_t rb_dataset_generations(const rb_dataset* d) { return d ? d->gen : 0; }
+
+int rb_dataset_export_host(rb_dataset* d, int64_t generation, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host) {
+    RB_REQUIRE(d != nullptr, "NULL argument");
+    RB_REQUIRE(generation >= 0 && generation < d->gen && generation >= d->gen - d->G + (d->k > 0 ? 1 : 0), "generation is not in the ring any more");
+    RB_CUDA(cudaSetDevice(d->device));
+    const size_t rows = (size_t)EP * d->n, r0 = (size_t)(generation % d->G) * rows;
+    RB_CUDA(cudaDeviceSynchronize());
+    if (ob_host) RB_CUDA(cudaMemcpy(ob_host, d->ob + r0 * 11, rows * 11 * sizeof(float), cudaMemcpyDeviceToHost));
+    if (rew_host) RB_CUDA(cudaMemcpy(rew_host, d->rew + r0, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    if (t_host) RB_CUDA(cudaMemcpy(t_host, d->t + r0, rows * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (s_host) RB_CUDA(cudaMemcpy(s_host, d->s + r0, rows * sizeof(float4), cudaMemcpyDeviceToHost));
+    if (with_host) RB_CUDA(cudaMemcpy(with_host, d->with + r0, rows, cudaMemcpyDeviceToHost));
+    return RB_OK;
+}
+
 int rb_dataset_training_batch(rb_dataset* d, uint64_t seed, uint32_t draw, int B, int T, float* ob_out, float* t_out, float* prev_out, float* prew_out,
                               int32_t* episodes_out, int32_t* start_out, void* stream) {
     RB_REQUIRE(d && ob_out && t_out && prev_out && prew_out, "NULL argument");

@@ -1,17 +1,60 @@
 """Dataset -- the reference's rollout buffer (/root/reference src/distilation/dataset.py:72-296) on the device.
 
 Same method names: write / flush / training_batches / test_batch / num_episodes / last_step.  N lock-step envs append one
-record each per call; sampling uses Philox (seed, draw counter) instead of Python's `random`.  The gzip-JSON page store
-(DatasetStore, dataset.py:14-65: dump / pages / switch) is the next row of the build and raises here.
+record each per call; sampling uses Philox (seed, draw counter) instead of Python's `random`.  DatasetStore keeps the reference's
+on-disk page format (dataset.py:14-65): `dataset_<k>.json` = gzip(JSON list[episode][step]{ob, rew, t, s, with, prev, prew}), at most
+MAX_CAPACITY episodes per page, so extract_reward.py / plot.py keep working on exported rollouts.
 """
 import ctypes as C
+import gzip
+import json
+import os
+import re
 
+import numpy as np
 import torch
 
 from ._lib import check, lib, ptr, stream_ptr
-from .config import EPISODE_STEPS, LSTM_BATCH_SIZE, STEPS_UNROLLED, TRAINING_EPOCHS
+from .config import EPISODE_STEPS, LSTM_BATCH_SIZE, MAX_CAPACITY, STEPS_UNROLLED, TRAINING_EPOCHS
 
-__all__ = ["Dataset"]
+__all__ = ["Dataset", "DatasetStore"]
+
+
+class DatasetStore:
+    """Page files of the reference (dataset.py:14-65).  json_tricks(primitives=True, compression=True) == gzip(json) of plain lists."""
+
+    def __init__(self, dir_path):
+        self.dir_path = dir_path
+        os.makedirs(dir_path, exist_ok=True)
+        self.pages = self.collect_pages(dir_path)
+
+    def get_full_path(self, page):
+        return os.path.join(self.dir_path, "dataset_%d.json" % page)
+
+    def collect_pages(self, dir_path):
+        fs = [f for f in os.listdir(dir_path) if re.fullmatch(r"dataset_(\d+)\.json", f)]
+        return [os.path.join(dir_path, f) for f in sorted(fs, key=lambda f: int(re.search(r"(\d+)", f).group(1)))]
+
+    def store(self, episodes):
+        """Write `episodes` (list[episode][step] of dicts) as ONE new page; refuses to overwrite (dataset.py:55-61)."""
+        path = self.get_full_path(len(self.pages))
+        if os.path.exists(path):
+            raise FileExistsError("current page already exists. will not overwrite")
+        with open(path, "wb") as fh:
+            fh.write(gzip.compress(json.dumps(episodes).encode()))
+        self.pages.append(path)
+        return path
+
+    @staticmethod
+    def load(page):
+        with open(page, "rb") as fh:
+            return json.loads(gzip.decompress(fh.read()))
+
+    def rand_pages(self, num_pages, rng=None):
+        if not self.pages:
+            return None
+        rng = rng or np.random.default_rng(0)
+        return [self.pages[i] for i in rng.choice(len(self.pages), size=min(num_pages, len(self.pages)), replace=False)]
 
 
 class Dataset:
@@ -22,6 +65,9 @@ class Dataset:
         check(lib().rb_dataset_create(C.byref(h), self.num_envs, int(generations), self.device.index))
         self._h = h
         self._draw = 0
+        self.dstore = DatasetStore(dir_path) if dir_path else None
+        self.data_in_memory = []          # host copy of the page last loaded with switch() (what extract_reward.py iterates)
+        self._dumped = 0                  # generations already written to pages
 
     # ---- recording -----------------------------------------------------------------------------------------
     def _dev(self, a, width):
@@ -79,11 +125,57 @@ class Dataset:
             dst[:, batch_size - 1, :] = src[:, 0, :]
         return tuple(out)
 
-    # ---- page store: next row of the build -----------------------------------------------------------------
-    def dump(self):
-        raise NotImplementedError("gzip-JSON page store (dataset.py:14-65) is the next row of the build; the buffer is device-resident")
+    # ---- page store (dataset.py:80-116) -----------------------------------------------------------------------
+    def export_generation(self, generation):
+        """One flushed generation as host episodes: list[N] of list[50] of dicts in the reference's record format."""
+        n = self.num_envs
+        ob, rew = np.empty((EPISODE_STEPS, n, 11), np.float32), np.empty((EPISODE_STEPS, n), np.float32)
+        t, s = np.empty((EPISODE_STEPS, n, 4), np.float32), np.empty((EPISODE_STEPS, n, 4), np.float32)
+        w = np.empty((EPISODE_STEPS, n), np.uint8)
+        check(lib().rb_dataset_export_host(self._h, int(generation), ob.ctypes.data, rew.ctypes.data, t.ctypes.data, s.ctypes.data, w.ctypes.data))
+        eps = []
+        for e in range(n):
+            ep = []
+            for k in range(EPISODE_STEPS):
+                ep.append({"ob": ob[k, e].astype(float).tolist(), "rew": [float(rew[k, e])], "t": t[k, e].astype(float).tolist(),
+                           "s": s[k, e].astype(float).tolist(), "with": "s" if w[k, e] else "t",
+                           "prev": t[k - 1, e].astype(float).tolist() if k else [0.0] * 4, "prew": [float(rew[k - 1, e])] if k else [0]})
+            eps.append(ep)
+        return eps
 
-    pages = switch = dump
+    def dump(self):
+        """Write every flushed generation not yet on disk as pages of MAX_CAPACITY episodes (dataset.py:80-85, :31-40)."""
+        if self.dstore is None:
+            raise ValueError("Dataset was created without dir_path")
+        written = []
+        gens = int(lib().rb_dataset_generations(self._h))
+        for g in range(self._dumped, gens):
+            eps = self.export_generation(g)
+            for i in range(0, len(eps), MAX_CAPACITY):
+                written.append(self.dstore.store(eps[i:i + MAX_CAPACITY]))
+        self._dumped = gens
+        return written
+
+    def pages(self):
+        return tuple(self.dstore.pages) if self.dstore else ()
+
+    def switch(self, page):
+        """Load a page into data_in_memory (host), as the reference's analysis scripts expect (extract_reward.py:25-31)."""
+        self.data_in_memory = DatasetStore.load(page)
+        return self.data_in_memory
+
+    def load_page_into_ring(self, page):
+        """Replay a page (episodes of 50 records) into the device ring, num_envs episodes at a time; returns episodes loaded."""
+        eps = [ep for ep in DatasetStore.load(page) if len(ep) == EPISODE_STEPS]
+        n, loaded = self.num_envs, 0
+        for i in range(0, len(eps) - n + 1, n):
+            grp = eps[i:i + n]
+            for k in range(EPISODE_STEPS):
+                self.write(np.array([ep[k]["ob"] for ep in grp], np.float32), np.array([np.ravel(ep[k]["rew"])[0] for ep in grp], np.float32),
+                           np.array([ep[k]["t"] for ep in grp], np.float32), np.array([ep[k]["s"] for ep in grp], np.float32), grp[0][k]["with"])
+            self.flush()
+            loaded += n
+        return loaded
 
     def close(self):
         if getattr(self, "_h", None):

@@ -26,3 +26,14 @@ with_s = np.array([[1 if s["with"] == "s" else 0 for s in ep] for ep in d], dtyp
 assert ob.shape == (E, T, 11) and t.shape == (E, T, 4)
 np.savez_compressed(DST, ob=ob, rew=rew, t=t, s=s_, prev=prev, with_s=with_s)
 print("wrote", DST, ob.shape, "student-stepped episodes:", np.where(with_s.all(1))[0])
+
+
+def make_reference_page(src="/root/reference/src/distilation/tests/data/dataset.json", dst=None, episodes=2):
+    """tests/golden/dataset_page_ref.json: the first `episodes` episodes of the reference's own page file, re-compressed unchanged
+    (gzip of the json_tricks primitives JSON) -- pins the on-disk page format (dataset.py:31-48)."""
+    import gzip
+    import json
+    import os
+    dst = dst or os.path.join(os.path.dirname(os.path.abspath(__file__)), "dataset_page_ref.json")
+    d = json.loads(gzip.decompress(open(src, "rb").read()))
+    open(dst, "wb").write(gzip.compress(json.dumps(d[:episodes]).encode()))

@@ -72,7 +72,39 @@ def test_single_env_reference_shape_and_errors():
     for k in range(38):
         ds.write(np.zeros((1, 11)))
     ds.flush()
-    with pytest.raises(NotImplementedError):
-        ds.dump()
+    with pytest.raises(ValueError):
+        ds.dump()                                             # no dir_path given
     assert ds.num_episodes() == 1
     ds.close()
+
+
+def test_page_store_round_trip_and_reference_page(tmp_path):
+    """Dataset.dump -> dataset_<k>.json pages (gzip JSON, MAX_CAPACITY episodes each) -> switch / load back; and a page written by
+    the REFERENCE itself (tests/golden/dataset_page_ref.json, 2 recorded MuJoCo episodes) loads into the device ring."""
+    import os
+    from reacherdistilation_b200.dataset import Dataset, DatasetStore
+    n = 25
+    dev, ref, _ = _fill(n, 2, 4, seed=5)
+    dev.dstore = DatasetStore(str(tmp_path))
+    pages = dev.dump()
+    assert [os.path.basename(p) for p in pages] == ["dataset_%d.json" % i for i in range(6)]          # 50 episodes / 10 per page, per generation 3
+    assert dev.dump() == []                                                                         # nothing new
+    eps = [ep for p in dev.pages() for ep in dev.switch(p)]
+    assert len(eps) == 2 * n and all(len(ep) == 50 for ep in eps)
+    for e, ep in enumerate(eps):
+        r = ref.data_in_memory[e]
+        for k in (0, 1, 17, 49):
+            assert np.array_equal(np.float32(ep[k]["ob"]), np.float32(r[k]["ob"])) and np.array_equal(np.float32(ep[k]["prev"]), np.float32(r[k]["prev"]))
+            assert ep[k]["with"] == r[k]["with"] and np.float32(np.ravel(ep[k]["rew"])[0]) == np.float32(r[k]["rew"])
+    dev.close()
+    # a page in the reference's own format
+    page = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "dataset_page_ref.json")
+    one = Dataset(num_envs=1, generations=4)
+    assert one.load_page_into_ring(page) == 2 and one.num_episodes() == 2
+    raw = DatasetStore.load(page)
+    ob, t, prev, prew, eps_idx, start = one.training_batch(4, 10, draw=0, with_indices=True)
+    s0 = int(start.item())
+    for b, e in enumerate(eps_idx.cpu().numpy()):
+        assert np.array_equal(ob[:, b].cpu().numpy(), np.float32([raw[e][k]["ob"] for k in range(s0, s0 + 10)]))
+        assert np.array_equal(prev[:, b].cpu().numpy(), np.float32([raw[e][k]["prev"] for k in range(s0, s0 + 10)]))   # recorded prev == t[k-1]
+    one.close()
