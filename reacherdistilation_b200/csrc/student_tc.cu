@@ -58,7 +58,13 @@ template <class S> struct Geo {
     __host__ __device__ static constexpr int dzslot(int l) { return l == S::L - 1 ? 0 : S::slot(l + 1); }
     __host__ __device__ static constexpr int wtile_off(int l) { return l == 0 ? 0 : wtile_off(l - 1) + N(l - 1) * K(l - 1) * 2; }   // bytes
     __host__ __device__ static constexpr int wtile_bytes() { return wtile_off(S::L); }
-    __host__ __device__ static constexpr int gcol(int l) { return l == 0 ? 128 : gcol(l - 1) + K(l - 1); }   // TMEM column of G_l
+    // weight-gradient accumulator G_l in TMEM.  "P": lanes = out features, columns = [in | 1] (K(l) columns).  "Q" (fewer columns when
+    // the layer narrows): lanes = [in | 1] (the window at X_l), columns = out (N(l)); if the ONES row falls outside the 128 lanes
+    // (in == 128) the bias gradient comes from one more small P-oriented product (16 columns).
+    __host__ __device__ static constexpr bool wq(int l) { return N(l) < K(l); }
+    __host__ __device__ static constexpr bool wq_extra(int l) { return wq(l) && ig(l) * 8 + 1 > 128; }
+    __host__ __device__ static constexpr int gcols(int l) { return wq(l) ? N(l) + (wq_extra(l) ? 16 : 0) : K(l); }
+    __host__ __device__ static constexpr int gcol(int l) { return l == 0 ? 128 : gcol(l - 1) + gcols(l - 1); }   // TMEM column of G_l
 };
 
 struct StudentTcArgs {
@@ -106,7 +112,8 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 }
 
 struct __align__(16) StudentTcCtl {
-    uint64_t mbar;
+    uint64_t mbar;                // forward layers / dgrad results
+    uint64_t mbar2;               // wgrad completion (X_l may be overwritten)
     uint32_t tmem_base;
     float red[ST_THREADS / 32];
 };
@@ -158,17 +165,36 @@ template <class S, int l> __device__ __forceinline__ void issue_dgrad(uint32_t t
              make_smem_desc(w_lo + bo, 128, N * 16), idesc, ks > 0);
     }
 }
-// G_l[128 (out features of the dZ window), K_l] += dZ_l^T [X_l | ONES | .] : both operands MN-major windows of ACT, K = samples
+// G_l += (see Geo::wq): both operands are MN-major windows of ACT, K = the 128 samples of the tile
 template <class S, int l> __device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t act_hi, uint32_t act_lo, uint32_t first) {
     using G = Geo<S>;
-    constexpr int K = G::K(l);
-    const uint32_t idesc = make_idesc_bf16_ex(128, K, 1, 1);
-    const uint32_t a0 = G::dzslot(l) * 2048, b0 = S::slot(l) * 2048, d = tmem + G::gcol(l);
+    const uint32_t xs = S::slot(l) * 2048, zs = G::dzslot(l) * 2048, d = tmem + G::gcol(l);
+    if constexpr (G::wq(l)) {
+        const uint32_t idesc = make_idesc_bf16_ex(128, G::N(l), 1, 1);                 // D[in|1, out] += [X_l | 1]^T dZ_l
 #pragma unroll
-    for (int ks = 0; ks < ST_TILE / 16; ++ks) {
-        const uint32_t ao = a0 + ks * 256, bo = b0 + ks * 256;
-        mma3(d, make_smem_desc(act_hi + ao, 128, 2048), make_smem_desc(act_lo + ao, 128, 2048), make_smem_desc(act_hi + bo, 128, 2048),
-             make_smem_desc(act_lo + bo, 128, 2048), idesc, (ks > 0) || !first);
+        for (int ks = 0; ks < ST_TILE / 16; ++ks) {
+            const uint32_t ao = xs + ks * 256, bo = zs + ks * 256;
+            mma3(d, make_smem_desc(act_hi + ao, 128, 2048), make_smem_desc(act_lo + ao, 128, 2048), make_smem_desc(act_hi + bo, 128, 2048),
+                 make_smem_desc(act_lo + bo, 128, 2048), idesc, (ks > 0) || !first);
+        }
+        if constexpr (G::wq_extra(l)) {                                                // D2[out, 16] += dZ_l^T [1 | .]  (column 0 = bias gradient)
+            const uint32_t idesc2 = make_idesc_bf16_ex(128, 16, 1, 1), os = (S::slot(l) + G::ig(l)) * 2048;
+#pragma unroll
+            for (int ks = 0; ks < ST_TILE / 16; ++ks) {
+                const uint32_t ao = zs + ks * 256, bo = os + ks * 256;
+                const uint64_t bh = make_smem_desc(act_hi + bo, 128, 2048);
+                mma_bf16(d + G::N(l), make_smem_desc(act_hi + ao, 128, 2048), bh, idesc2, (ks > 0) || !first);
+                mma_bf16(d + G::N(l), make_smem_desc(act_lo + ao, 128, 2048), bh, idesc2, 1);           // the lo half of ONES is zero
+            }
+        }
+    } else {
+        const uint32_t idesc = make_idesc_bf16_ex(128, G::K(l), 1, 1);                 // D[out, in|1] += dZ_l^T [X_l | 1 | .]
+#pragma unroll
+        for (int ks = 0; ks < ST_TILE / 16; ++ks) {
+            const uint32_t ao = zs + ks * 256, bo = xs + ks * 256;
+            mma3(d, make_smem_desc(act_hi + ao, 128, 2048), make_smem_desc(act_lo + ao, 128, 2048), make_smem_desc(act_hi + bo, 128, 2048),
+                 make_smem_desc(act_lo + bo, 128, 2048), idesc, (ks > 0) || !first);
+        }
     }
 }
 
@@ -201,32 +227,39 @@ template <class S, int l> __device__ __forceinline__ void epi_fwd(uint32_t tacc,
         }
     }
 }
-// backward epilogue: dX_l (ACC) * tanh'(X_l) -> dZ_{l-1}, in place over X_l
-template <class S, int l> __device__ __forceinline__ void epi_bwd(uint32_t tacc, uint8_t* act_hi, uint8_t* act_lo, int row, int part) {
-    constexpr int ig = S::in(l) / 8, gpp = (ig + 3) / 4;
+// backward epilogue in two halves so that the wgrad MMAs (which still read X_l) overlap the arithmetic:
+//   epi_bwd_compute: dX_l (ACC) * tanh'(X_l) -> registers        epi_bwd_store: registers -> dZ_{l-1}, in place over X_l
+template <class S, int l> struct EpiBwd {
+    static constexpr int ig = S::in(l) / 8, gpp = (ig + 3) / 4;
     static_assert(S::in(l) % 8 == 0, "hidden widths are multiples of 8");
     float v[gpp][8];
+    __device__ __forceinline__ void compute(uint32_t tacc, const uint8_t* act_hi, const uint8_t* act_lo, int row, int part) {
 #pragma unroll
-    for (int i = 0; i < gpp; ++i)
-        if (part * gpp + i < ig) tmem_ld_x8(tacc + (part * gpp + i) * 8, v[i]);
-    tmem_ld_wait();
+        for (int i = 0; i < gpp; ++i)
+            if (part * gpp + i < ig) tmem_ld_x8(tacc + (part * gpp + i) * 8, v[i]);
+        tmem_ld_wait();
 #pragma unroll
-    for (int i = 0; i < gpp; ++i) {
-        const int g = part * gpp + i;
-        if (g < ig) {
-            const uint4 hh = *reinterpret_cast<const uint4*>(act_hi + (S::slot(l) + g) * 2048 + row * 16);
-            const uint4 ll = *reinterpret_cast<const uint4*>(act_lo + (S::slot(l) + g) * 2048 + row * 16);
-            const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w}, lw[4] = {ll.x, ll.y, ll.z, ll.w};
+        for (int i = 0; i < gpp; ++i) {
+            const int g = part * gpp + i;
+            if (g < ig) {
+                const uint4 hh = *reinterpret_cast<const uint4*>(act_hi + (S::slot(l) + g) * 2048 + row * 16);
+                const uint4 ll = *reinterpret_cast<const uint4*>(act_lo + (S::slot(l) + g) * 2048 + row * 16);
+                const uint32_t hw[4] = {hh.x, hh.y, hh.z, hh.w}, lw[4] = {ll.x, ll.y, ll.z, ll.w};
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                const float h0 = bf16lo_to_f32(hw[q]) + bf16lo_to_f32(lw[q]), h1 = bf16hi_to_f32(hw[q]) + bf16hi_to_f32(lw[q]);
-                v[i][2 * q] *= fmaf(-h0, h0, 1.f);
-                v[i][2 * q + 1] *= fmaf(-h1, h1, 1.f);
+                for (int q = 0; q < 4; ++q) {
+                    const float h0 = bf16lo_to_f32(hw[q]) + bf16lo_to_f32(lw[q]), h1 = bf16hi_to_f32(hw[q]) + bf16hi_to_f32(lw[q]);
+                    v[i][2 * q] *= fmaf(-h0, h0, 1.f);
+                    v[i][2 * q + 1] *= fmaf(-h1, h1, 1.f);
+                }
             }
-            store_split8(act_hi, act_lo, S::slot(l) + g, row, v[i]);
         }
     }
-}
+    __device__ __forceinline__ void store(uint8_t* act_hi, uint8_t* act_lo, int row, int part) {
+#pragma unroll
+        for (int i = 0; i < gpp; ++i)
+            if (part * gpp + i < ig) store_split8(act_hi, act_lo, S::slot(l) + part * gpp + i, row, v[i]);
+    }
+};
 
 template <class S> struct LayerLoop {
     // weights -> global image of the K-major hi/lo tiles: element (n, k) = W[k][n] for k < in, b[n] at k == 8 * ig (the ONES
@@ -254,23 +287,52 @@ template <class S> struct LayerLoop {
         constexpr int total = Geo<S>::wtile_bytes() / 2;
         for (int e = gthreads - 1 - gtid; e < total; e += gthreads) image_element<0>(a, e);
     }
-    // G_l (TMEM) -> partial gradient vector: lane j = out feature, column i = in feature, column 8*ig = bias
+    // G_l (TMEM) -> partial gradient vector (layouts: Geo::wq)
     template <int l> __device__ static void dump_grads(const StudentTcArgs& a, uint32_t tmem, float* __restrict__ part_out, int sub, int part, int lane) {
         using G = Geo<S>;
-        constexpr int in = S::in(l), out = S::out(l), kb = G::ig(l) * 8, ncol8 = G::ig(l) + 1;      // 8-column chunks incl. the bias chunk
-        if (sub * 32 < out) {                                                                      // warp-uniform
-            const int j = sub * 32 + lane;
-            const uint32_t t0 = tmem + ((uint32_t)(sub * 32) << 16) + G::gcol(l);
-            for (int c = part; c < ncol8; c += 4) {
-                float v[8];
-                tmem_ld_x8(t0 + c * 8, v);
-                tmem_ld_wait();
-                if (j < out) {
+        constexpr int in = S::in(l), out = S::out(l), kb = G::ig(l) * 8;
+        const uint32_t t0 = tmem + ((uint32_t)(sub * 32) << 16) + G::gcol(l);
+        if constexpr (G::wq(l)) {                                                                  // lane i = in feature (kb: bias), column j = out
+            constexpr int rows = G::wq_extra(l) ? in : kb + 1;
+            if (sub * 32 < rows) {                                                                 // warp-uniform
+                const int i = sub * 32 + lane;
+                for (int c = part; c < G::N(l) / 8; c += 4) {
+                    float v[8];
+                    tmem_ld_x8(t0 + c * 8, v);
+                    tmem_ld_wait();
 #pragma unroll
                     for (int k = 0; k < 8; ++k) {
-                        const int i = c * 8 + k;
-                        if (i < in) part_out[a.pw[l] + i * out + j] = v[k];
-                        else if (i == kb) part_out[a.pb[l] + j] = v[k];
+                        const int j = c * 8 + k;
+                        if (j < out) {
+                            if (i < in) part_out[a.pw[l] + i * out + j] = v[k];
+                            else if (i == kb && !G::wq_extra(l)) part_out[a.pb[l] + j] = v[k];
+                        }
+                    }
+                }
+            }
+            if constexpr (G::wq_extra(l)) {                                                        // bias gradient: lane j = out feature, first extra column
+                if (part == 0 && sub * 32 < out) {
+                    float v[8];
+                    tmem_ld_x8(t0 + G::N(l), v);
+                    tmem_ld_wait();
+                    if (sub * 32 + lane < out) part_out[a.pb[l] + sub * 32 + lane] = v[0];
+                }
+            }
+        } else {                                                                                   // lane j = out feature, column i = in feature, kb = bias
+            constexpr int ncol8 = G::ig(l) + 1;                                                    // 8-column chunks incl. the bias chunk
+            if (sub * 32 < out) {                                                                  // warp-uniform
+                const int j = sub * 32 + lane;
+                for (int c = part; c < ncol8; c += 4) {
+                    float v[8];
+                    tmem_ld_x8(t0 + c * 8, v);
+                    tmem_ld_wait();
+                    if (j < out) {
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const int i = c * 8 + k;
+                            if (i < in) part_out[a.pw[l] + i * out + j] = v[k];
+                            else if (i == kb) part_out[a.pb[l] + j] = v[k];
+                        }
                     }
                 }
             }
@@ -370,7 +432,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
 
     // ---- phase 0: TMEM, barrier, zeroed activations + ONES groups; fold and split the weights once for the whole grid -----
     if (warp == 0) tmem_alloc<512>(&ctl.tmem_base);
-    if (tid == 0) { mbar_init(&ctl.mbar, 1); fence_mbar_init(); }
+    if (tid == 0) { mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); fence_mbar_init(); }
     for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     if constexpr (S::L == 4) fold_into_image(a.params, a.wimg, gtid, gthreads);       // SpecMLP: W34, b34
     LayerLoop<S>::build_image(a, gtid, gthreads);
@@ -387,7 +449,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     const uint32_t tmem = ctl.tmem_base;
     const uint32_t tacc = tmem + ((uint32_t)(sub * 32) << 16);
     const uint32_t ah = smem_u32(act_hi), al = smem_u32(act_lo), wh = smem_u32(w_hi), wl = smem_u32(w_lo);
-    uint32_t phase = 0;
+    uint32_t phase = 0, phase2 = 0;
     float loss_acc = 0.f;
     bool first = true;
 
@@ -486,15 +548,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         if constexpr (l < L) {                                                     \
             if (tid == 0) {                                                        \
                 fence_after_sync();                                                \
+                if constexpr (l > 0) {                                             \
+                    issue_dgrad<S, (l < L ? l : 0)>(tmem, ah, al, wh, wl);         \
+                    mma_commit(&ctl.mbar);                                         \
+                }                                                                  \
                 issue_wgrad<S, (l < L ? l : 0)>(tmem, ah, al, first ? 1u : 0u);    \
-                if constexpr (l > 0) issue_dgrad<S, (l < L ? l : 0)>(tmem, ah, al, wh, wl); \
-                mma_commit(&ctl.mbar);                                             \
+                mma_commit(&ctl.mbar2);                                            \
             }                                                                      \
-            mbar_wait(&ctl.mbar, phase); phase ^= 1u;                              \
-            fence_after_sync();                                                    \
             if constexpr (l > 0) {                                                 \
-                epi_bwd<S, (l > 0 && l < L ? l : 1)>(tacc, act_hi, act_lo, row, part); \
+                EpiBwd<S, (l > 0 && l < L ? l : 1)> eb;                            \
+                mbar_wait(&ctl.mbar, phase); phase ^= 1u;                          \
+                fence_after_sync();                                                \
+                eb.compute(tacc, act_hi, act_lo, row, part);                       \
+                mbar_wait(&ctl.mbar2, phase2); phase2 ^= 1u;                       \
+                eb.store(act_hi, act_lo, row, part);                               \
                 fence_async_smem();                                                \
+            } else {                                                               \
+                mbar_wait(&ctl.mbar2, phase2); phase2 ^= 1u;                       \
             }                                                                      \
             fence_before_sync();                                                   \
             __syncthreads();                                                       \
