@@ -186,6 +186,31 @@ int rb_dagger_invalidate_teacher(rb_dagger* d);
 int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
                   void* stream);
 
+/* ------------------------------------------------------------------------------------------------ LSTM student -
+ * student_lstm_graph  src/distilation/student_nn.py:21-49 (built at lstm_train.py:32-57): dropout(ob) (+) dense32(prev_pdflat) ->
+ * LSTMCell(200) -> per-unrolled-step heads 64-128-64-32-4, T = STEPS_UNROLLED = 10.  Window tensors are time-major [T,B,.].
+ * state = [2,B,200] (c, m) -- NULL means zeros (training windows, lstm_train.py:159); acting carries it (lstm_train.py:171-182).
+ * Flat parameters: rb_lstm_param_count() floats, layout W_e[4][32] b_e[32] W_l[243][800] b_l[800] then per step tau:
+ * W1[200][64] b1 W2[64][128] b2 W3[128][64] b3 W4[64][32] b4 W5[32][4] b5.   All GEMMs run on tcgen05 (bf16x3).              */
+int64_t rb_lstm_param_count(void);
+int rb_lstm_steps(void);
+int rb_lstm_units(void);
+int64_t rb_lstm_workspace_bytes(int64_t batch);
+/* sess.run((s_pdflat, final_state_batch))  lstm_train.py:171-182: forward only, keep_prob = 1 */
+int rb_lstm_fwd(const float* params_dev, const float* ob_dev, const float* prev_pdflat_dev, const float* init_state_dev, int64_t B,
+                float* s_pdflat_dev, float* final_state_dev, void* workspace_dev, void* stream);
+/* sess.run([loss, minimize_adam]) minus Adam  lstm_train.py:145-160: forward, KL loss (loss.py:3-13), back-propagation through time.
+ * gradloss_dev[P+1] = flat gradient | summed loss.  Dropout mask: Philox keyed (seed, sample_id0 + row, iteration).             */
+int rb_lstm_loss_grad(const float* params_dev, const float* ob_dev, const float* prev_pdflat_dev, const float* t_pdflat_dev,
+                      const float* init_state_dev, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0, uint32_t iteration,
+                      int loss_kind, float* s_pdflat_dev, float* final_state_dev, float* gradloss_dev, void* workspace_dev, void* stream);
+/* The tensor-core GEMM the LSTM is built from: C[M,N] (+)= epilogue(A[M,K] B[K,N]), fp32 in/out, bf16x3 inside.
+ * x_mn = 0: element (row, k) of the operand at X[row * ld + k]; 1: at X[k * ld + row].  epilogue: + bias[n], tanh (act = 1),
+ * * (1 - H[m,n]^2).  workspace (optional, floats) enables deterministic split-K.                                              */
+int rb_gemm_bf16x3(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
+                   const float* bias, int act, int accumulate, const float* H, int ldh, float* workspace, int64_t workspace_floats,
+                   void* stream);
+
 /* ------------------------------------------------------------------------------------------------ dataset -
  * Device-resident rollout buffer with the semantics of the reference Dataset (src/distilation/dataset.py:72-296) for N lock-step
  * envs: a ring of `generations` x 50 steps x N records {ob[11], rew, t[4], s[4], with}; prev / prew of record j are t / rew of

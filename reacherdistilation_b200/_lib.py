@@ -59,6 +59,14 @@ _SIGS = {
     "rb_dagger_observe": (C.c_int, [_vp, _fp, C.c_uint32, _fp, _fp, _fp, C.c_int, _vp]),
     "rb_dagger_invalidate_teacher": (C.c_int, [_vp]),
     "rb_dagger_act": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
+    "rb_lstm_param_count": (C.c_int64, []),
+    "rb_lstm_steps": (C.c_int, []),
+    "rb_lstm_units": (C.c_int, []),
+    "rb_lstm_workspace_bytes": (C.c_int64, [C.c_int64]),
+    "rb_lstm_fwd": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, _fp, _fp, _vp, _vp]),
+    "rb_lstm_loss_grad": (C.c_int, [_fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, _fp, _fp, _fp, _vp, _vp]),
+    "rb_gemm_bf16x3": (C.c_int, [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
+                                 C.c_int, _fp, C.c_int64, _vp]),
     "rb_dataset_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int]),
     "rb_dataset_destroy": (C.c_int, [_vp]),
     "rb_dataset_write": (C.c_int, [_vp, _fp, _fp, _fp, _fp, C.c_int, _vp]),

@@ -1,0 +1,296 @@
+// LSTM student (/root/reference src/distilation/student_nn.py:21-49, lstm_train.py:32-79): forward over a T = 10 step window, fused
+// KL loss (loss.py:3-13) and full back-propagation through time, as a sequence of tensor-core GEMMs (gemm_tc.cu) and small
+// element-wise kernels.  Graph, per window row (tau, b):
+//     e      = prev_pdflat W_e + b_e                          tf.layers.dense(prev_pdflat, 32), shared by all steps   (:27)
+//     x      = [dropout(ob, keep_prob) (11) | e (32)]                                                                 (:25,30)
+//     z      = [x | m_{tau-1}] W_l + b_l ;  i, j, f, o = split(z, 4)      tf.contrib.rnn.LSTMCell(200), forget_bias 1   (:23,41)
+//     c      = sigmoid(f + 1) c_{tau-1} + sigmoid(i) tanh(j) ;  m = sigmoid(o) tanh(c)
+//     s_tau  = head_tau(m): 200 -> 64 -> 128 -> 64 -> 32 (tanh) -> 4, weights NOT shared between the unrolled steps      (:42-46)
+// Flat parameter layout: W_e[4][32] b_e[32] W_l[243][800] b_l[800] then for tau = 0..9: W1[200][64] b1 W2[64][128] b2 W3[128][64] b3
+// W4[64][32] b4 W5[32][4] b5.
+#include "common.cuh"
+#include "dagger_input.cuh"
+#include "gemm_tc.cuh"
+
+namespace rb {
+
+constexpr int LT = 10, LU = 200, LG = 800, LX = 43, LE = 32, LXH = 243, LDXH = 256;
+constexpr int HD[6] = {200, 64, 128, 64, 32, 4};
+constexpr int L_WE = 0, L_BE = 128, L_WL = 160, L_BL = L_WL + LXH * LG, L_HEAD0 = L_BL + LG;
+constexpr int L_HEAD_SZ = 200 * 64 + 64 + 64 * 128 + 128 + 128 * 64 + 64 + 64 * 32 + 32 + 32 * 4 + 4;      // 31652
+constexpr int L_P = L_HEAD0 + LT * L_HEAD_SZ;                                                              // 511880
+static inline int head_w_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += HD[i] * HD[i + 1] + HD[i + 1]; return o; }
+
+// workspace layout (floats), R = T * B rows
+struct LstmWs {
+    float *xh, *z, *dz, *dxh, *c, *hh, *dh, *dc, *a[5], *da[5], *splitk;
+    size_t splitk_floats;
+};
+static size_t lstm_ws_floats(int64_t R, int64_t B, size_t* splitk) {
+    size_t per_row = LDXH + LG + LG + LDXH + LU + LU;
+    for (int l = 1; l <= 5; ++l) per_row += 2 * (size_t)HD[l];
+    const size_t sk = (size_t)32 * LDXH * LG;            // split-K partials of the largest wgrad (243 x 800, <= 32 slices)
+    if (splitk) *splitk = sk;
+    return per_row * R + (size_t)(LT + 1) * B * LU + (size_t)B * LU + sk + 1024;
+}
+static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
+    float* p = ws;
+    auto take = [&](size_t n) { float* q = p; p += (n + 3) & ~(size_t)3; return q; };
+    w.xh = take(R * LDXH); w.z = take(R * LG); w.dz = take(R * LG); w.dxh = take(R * LDXH);
+    w.c = take((size_t)(LT + 1) * B * LU); w.hh = take(R * LU); w.dh = take(R * LU); w.dc = take((size_t)B * LU);
+    for (int l = 1; l <= 5; ++l) { w.a[l - 1] = take(R * HD[l]); w.da[l - 1] = take(R * HD[l]); }
+    lstm_ws_floats(R, B, &w.splitk_floats);
+    w.splitk = take(w.splitk_floats);
+}
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// x rows: dropout(ob) -> xh[:, 0:11]; initial m state -> xh rows of step 0, columns 43..242; initial c -> c[0]
+__global__ void k_lstm_inputs(int64_t R, int64_t B, const float* __restrict__ ob, float keep_prob, uint32_t k0, uint32_t k1, uint32_t sample_id0,
+                              uint32_t iteration, const float* __restrict__ init_state, float* __restrict__ xh, float* __restrict__ c0) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < R) {
+        float o[11];
+#pragma unroll
+        for (int k = 0; k < 11; ++k) o[k] = __ldg(ob + i * 11 + k);
+        float4 r4[4];
+        mlp_input_row(o, keep_prob, k0, k1, sample_id0 + (uint32_t)i, iteration, make_float4(0.f, 0.f, 0.f, 0.f), 0.f, r4);
+        const float* r = reinterpret_cast<const float*>(r4);
+#pragma unroll
+        for (int k = 0; k < 11; ++k) xh[i * LDXH + k] = r[k];
+#pragma unroll
+        for (int k = LXH; k < LDXH; ++k) xh[i * LDXH + k] = 0.f;
+    }
+    if (i < B * LU) {
+        const int64_t b = i / LU, u = i - b * LU;
+        c0[i] = init_state ? __ldg(init_state + i) : 0.f;
+        xh[b * LDXH + LX + u] = init_state ? __ldg(init_state + B * LU + i) : 0.f;
+    }
+}
+
+// gates (pre-activation, [B,800]) -> activated in place; c, m; m also goes to the next step's xh rows and to hh
+__global__ void k_lstm_cell_fwd(int64_t B, float* __restrict__ z, const float* __restrict__ c_prev, float* __restrict__ c_out, float* __restrict__ hh,
+                                float* __restrict__ xh_next) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * LU) return;
+    const int64_t b = idx / LU, u = idx - b * LU;
+    float* zr = z + b * LG;
+    const float i = sigmoidf_(zr[u]), j = tanhf(zr[LU + u]), f = sigmoidf_(zr[2 * LU + u] + 1.0f), o = sigmoidf_(zr[3 * LU + u]);
+    const float c = fmaf(f, c_prev[idx], i * j), m = o * tanhf(c);
+    zr[u] = i; zr[LU + u] = j; zr[2 * LU + u] = f; zr[3 * LU + u] = o;
+    c_out[idx] = c;
+    hh[idx] = m;
+    if (xh_next) xh_next[b * LDXH + LX + u] = m;
+}
+
+// BPTT through one cell: dm (head part + recurrent part) and dc (running) -> dz (pre-activation gradients), dc for the previous step
+__global__ void k_lstm_cell_bwd(int64_t B, const float* __restrict__ gates, const float* __restrict__ c_prev, const float* __restrict__ c,
+                                const float* __restrict__ dh_head, const float* __restrict__ dxh_next, float* __restrict__ dc, float* __restrict__ dz) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= B * LU) return;
+    const int64_t b = idx / LU, u = idx - b * LU;
+    const float* g = gates + b * LG;
+    const float i = g[u], j = g[LU + u], f = g[2 * LU + u], o = g[3 * LU + u];
+    const float tc = tanhf(c[idx]);
+    const float dm = dh_head[idx] + (dxh_next ? dxh_next[b * LDXH + LX + u] : 0.f);
+    const float dct = dc[idx] + dm * o * (1.f - tc * tc);
+    float* d = dz + b * LG;
+    d[u] = dct * j * i * (1.f - i);
+    d[LU + u] = dct * i * (1.f - j * j);
+    d[2 * LU + u] = dct * c_prev[idx] * f * (1.f - f);
+    d[3 * LU + u] = dm * tc * o * (1.f - o);
+    dc[idx] = dct * f;
+}
+
+// KL(student || teacher) (or reverse) summed, and dL/ds, rows = T*B
+__global__ void k_lstm_kl(int64_t R, const float4* __restrict__ s, const float4* __restrict__ t, int loss_kind, float4* __restrict__ ds,
+                          float* __restrict__ loss_partial) {
+    __shared__ float red[8];
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (i < R) {
+        const float4 sv = s[i], tv = t[i];
+        const float vs0 = expf(2.f * sv.z), vs1 = expf(2.f * sv.w), vt0 = expf(2.f * tv.z), vt1 = expf(2.f * tv.w);
+        const float e0 = sv.x - tv.x, e1 = sv.y - tv.y;
+        float4 d;
+        if (loss_kind == RB_LOSS_KL_ST) {
+            l = (tv.z - sv.z + (vs0 + e0 * e0) / (2.f * vt0) - 0.5f) + (tv.w - sv.w + (vs1 + e1 * e1) / (2.f * vt1) - 0.5f);
+            d = make_float4(e0 / vt0, e1 / vt1, vs0 / vt0 - 1.f, vs1 / vt1 - 1.f);
+        } else {
+            l = (sv.z - tv.z + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (sv.w - tv.w + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
+            d = make_float4(e0 / vs0, e1 / vs1, 1.f - (vt0 + e0 * e0) / vs0, 1.f - (vt1 + e1 * e1) / vs1);
+        }
+        ds[i] = d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) l += __shfl_xor_sync(0xffffffffu, l, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = l;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float tot = 0.f;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) tot += red[w];
+        loss_partial[blockIdx.x] = tot;
+    }
+}
+__global__ void k_sum_serial(const float* __restrict__ x, int n, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < n; ++i) t += x[i];
+        *out = t;
+    }
+}
+
+// out[n] = sum over rows of X[rows, n] (ld) -- bias gradients; fixed order: 8 row-interleaved partial sums, then a tree
+__global__ void k_colsum(const float* __restrict__ X, int ld, int64_t rows, int n, float* __restrict__ out) {
+    __shared__ float red[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x;
+    float acc = 0.f;
+    if (col < n)
+        for (int64_t r = threadIdx.y; r < rows; r += 8) acc += X[r * ld + col];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        out[col] = t;
+    }
+}
+
+struct LstmCall {
+    const float* params; const float* ob; const float* prev_pd; const float* t_pd; const float* init_state;
+    float keep_prob; uint64_t seed; uint32_t sample_id0, iteration;
+    int64_t B; int loss_kind, fwd_only;
+    float* s_out; float* final_state; float* gradloss;
+};
+
+static int gemm(const float* A, int lda, int a_mn, const float* Bm, int ldb, int b_mn, float* C, int ldc, int M, int N, int K, const float* bias, int act,
+                int accumulate, const float* H, int ldh, LstmWs& w, int sms, cudaStream_t st, bool allow_split = false) {
+    GemmArgs g{};
+    g.A = A; g.lda = lda; g.a_mn = a_mn; g.B = Bm; g.ldb = ldb; g.b_mn = b_mn; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
+    g.bias = bias; g.act = act; g.accumulate = accumulate; g.H = H; g.ldh = ldh;
+    return gemm_bf16x3(g, allow_split ? w.splitk : nullptr, allow_split ? w.splitk_floats : 0, sms, st);
+}
+#define RB_TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
+
+static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
+    int device = 0, sms = 148;
+    RB_CUDA(cudaGetDevice(&device));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    const int64_t B = c.B, R = LT * B;
+    const int Bi = (int)B, Ri = (int)R;
+    LstmWs w;
+    lstm_ws_carve(ws, R, B, w);
+    const float* P = c.params;
+    // ---- inputs: dropout(ob), initial state, embedding of prev_pdflat --------------------------------------------------------
+    k_lstm_inputs<<<(unsigned)((max(R, B * LU) + 255) / 256), 256, 0, st>>>(R, B, c.ob, c.keep_prob, (uint32_t)c.seed, (uint32_t)(c.seed >> 32),
+                                                                           c.sample_id0, c.iteration, c.init_state, w.xh, w.c);
+    RB_CUDA(cudaGetLastError());
+    RB_TRY(gemm(c.prev_pd, 4, 0, P + L_WE, LE, 1, w.xh + 11, LDXH, Ri, LE, 4, P + L_BE, 0, 0, nullptr, 0, w, sms, st));
+    // ---- recurrence ------------------------------------------------------------------------------------------------------------
+    for (int t = 0; t < LT; ++t) {
+        float* xh_t = w.xh + (size_t)t * B * LDXH;
+        float* z_t = w.z + (size_t)t * B * LG;
+        RB_TRY(gemm(xh_t, LDXH, 0, P + L_WL, LG, 1, z_t, LG, Bi, LG, LXH, P + L_BL, 0, 0, nullptr, 0, w, sms, st));
+        k_lstm_cell_fwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, z_t, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
+                                                                           w.hh + (size_t)t * B * LU, t + 1 < LT ? xh_t + (size_t)B * LDXH : nullptr);
+        RB_CUDA(cudaGetLastError());
+    }
+    if (c.final_state) {
+        RB_CUDA(cudaMemcpyAsync(c.final_state, w.c + (size_t)LT * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
+        RB_CUDA(cudaMemcpyAsync(c.final_state + B * LU, w.hh + (size_t)(LT - 1) * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
+    }
+    // ---- per-step heads --------------------------------------------------------------------------------------------------------
+    for (int t = 0; t < LT; ++t) {
+        const float* hp = P + L_HEAD0 + (size_t)t * L_HEAD_SZ;
+        const float* in = w.hh + (size_t)t * B * LU;
+        for (int l = 0; l < 5; ++l) {
+            const float* W = hp + head_w_off(l);
+            float* out = l == 4 ? c.s_out + (size_t)t * B * 4 : w.a[l] + (size_t)t * B * HD[l + 1];
+            RB_TRY(gemm(in, HD[l], 0, W, HD[l + 1], 1, out, HD[l + 1], Bi, HD[l + 1], HD[l], W + HD[l] * HD[l + 1], l < 4 ? 1 : 0, 0, nullptr, 0, w, sms, st));
+            in = out;
+        }
+    }
+    if (c.fwd_only) return RB_OK;
+    // ---- loss and dL/ds --------------------------------------------------------------------------------------------------------
+    const unsigned kl_blocks = (unsigned)((R + 255) / 256);
+    RB_REQUIRE(kl_blocks <= 1024, "window batch too large for the loss reduction scratch");
+    float* loss_part = w.splitk + w.splitk_floats;       // 1024 spare floats behind the split-K area
+    k_lstm_kl<<<kl_blocks, 256, 0, st>>>(R, (const float4*)c.s_out, (const float4*)c.t_pd, c.loss_kind, (float4*)w.da[4], loss_part);
+    k_sum_serial<<<1, 32, 0, st>>>(loss_part, (int)kl_blocks, c.gradloss + L_P);
+    RB_CUDA(cudaGetLastError());
+    float* G = c.gradloss;
+    // ---- heads backward --------------------------------------------------------------------------------------------------------
+    for (int t = 0; t < LT; ++t) {
+        const float* hp = P + L_HEAD0 + (size_t)t * L_HEAD_SZ;
+        float* gp = G + L_HEAD0 + (size_t)t * L_HEAD_SZ;
+        for (int l = 4; l >= 0; --l) {
+            const float* W = hp + head_w_off(l);
+            const float* dout = w.da[l] + (size_t)t * B * HD[l + 1];
+            const float* in = l == 0 ? w.hh + (size_t)t * B * LU : w.a[l - 1] + (size_t)t * B * HD[l];
+            // dW = in^T dout, db = colsum(dout)
+            RB_TRY(gemm(in, HD[l], 1, dout, HD[l + 1], 1, gp + head_w_off(l), HD[l + 1], HD[l], HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
+            k_colsum<<<(HD[l + 1] + 31) / 32, dim3(32, 8), 0, st>>>(dout, HD[l + 1], B, HD[l + 1], gp + head_w_off(l) + HD[l] * HD[l + 1]);
+            RB_CUDA(cudaGetLastError());
+            // d(in) = dout W^T, times tanh' of the layer input (except for the LSTM output m)
+            float* din = l == 0 ? w.dh + (size_t)t * B * LU : w.da[l - 1] + (size_t)t * B * HD[l];
+            RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, HD[l], w, sms, st));
+        }
+    }
+    // ---- back-propagation through time -------------------------------------------------------------------------------------------
+    RB_CUDA(cudaMemsetAsync(w.dc, 0, sizeof(float) * B * LU, st));
+    for (int t = LT - 1; t >= 0; --t) {
+        float* dz_t = w.dz + (size_t)t * B * LG;
+        float* dxh_t = w.dxh + (size_t)t * B * LDXH;
+        k_lstm_cell_bwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, w.z + (size_t)t * B * LG, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
+                                                                           w.dh + (size_t)t * B * LU, t + 1 < LT ? dxh_t + (size_t)B * LDXH : nullptr, w.dc, dz_t);
+        RB_CUDA(cudaGetLastError());
+        RB_TRY(gemm(dz_t, LG, 0, P + L_WL, LG, 0, dxh_t, LDXH, Bi, LXH, LG, nullptr, 0, 0, nullptr, 0, w, sms, st));       // d[x | m_prev] = dz W_l^T
+    }
+    // ---- weight gradients of the shared parts, over all T*B rows ---------------------------------------------------------------------
+    RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
+    k_colsum<<<(LG + 31) / 32, dim3(32, 8), 0, st>>>(w.dz, LG, R, LG, G + L_BL);
+    RB_TRY(gemm(c.prev_pd, 4, 1, w.dxh + 11, LDXH, 1, G + L_WE, LE, 4, LE, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
+    k_colsum<<<(LE + 31) / 32, dim3(32, 8), 0, st>>>(w.dxh + 11, LDXH, R, LE, G + L_BE);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+}  // namespace rb
+
+using namespace rb;
+
+extern "C" {
+
+int64_t rb_lstm_param_count(void) { return L_P; }
+int rb_lstm_steps(void) { return LT; }
+int rb_lstm_units(void) { return LU; }
+int64_t rb_lstm_workspace_bytes(int64_t batch) { return batch > 0 ? (int64_t)(sizeof(float) * lstm_ws_floats(LT * batch, batch, nullptr)) : -1; }
+
+/* sess.run((s_pdflat_batch, final_state_batch))  lstm_train.py:171-182 -- forward over the T-step window from a given state */
+int rb_lstm_fwd(const float* params, const float* ob, const float* prev_pd, const float* init_state, int64_t B, float* s_out, float* final_state,
+                void* workspace, void* stream) {
+    RB_REQUIRE(params && ob && prev_pd && s_out && workspace, "NULL argument");
+    RB_REQUIRE(B > 0 && B * LT < ((int64_t)1 << 30), "bad batch");
+    LstmCall c{};
+    c.params = params; c.ob = ob; c.prev_pd = prev_pd; c.init_state = init_state; c.keep_prob = 1.f; c.B = B; c.fwd_only = 1;
+    c.s_out = s_out; c.final_state = final_state;
+    return lstm_run(c, (float*)workspace, (cudaStream_t)stream);
+}
+
+/* sess.run([loss, minimize_adam]) minus Adam  lstm_train.py:145-160 -- forward, KL loss, BPTT; gradloss[P+1] = flat gradient | loss */
+int rb_lstm_loss_grad(const float* params, const float* ob, const float* prev_pd, const float* t_pd, const float* init_state, int64_t B, float keep_prob,
+                      uint64_t seed, uint32_t sample_id0, uint32_t iteration, int loss_kind, float* s_out, float* final_state, float* gradloss,
+                      void* workspace, void* stream) {
+    RB_REQUIRE(params && ob && prev_pd && t_pd && s_out && gradloss && workspace, "NULL argument");
+    RB_REQUIRE(B > 0 && B * LT < ((int64_t)1 << 30), "bad batch");
+    RB_REQUIRE(keep_prob > 0.f, "keep_prob must be > 0");
+    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    LstmCall c{};
+    c.params = params; c.ob = ob; c.prev_pd = prev_pd; c.t_pd = t_pd; c.init_state = init_state; c.keep_prob = keep_prob; c.seed = seed;
+    c.sample_id0 = sample_id0; c.iteration = iteration; c.B = B; c.loss_kind = loss_kind; c.s_out = s_out; c.final_state = final_state;
+    c.gradloss = gradloss;
+    return lstm_run(c, (float*)workspace, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,8 +1,71 @@
-"""LSTM distillation entry point (/root/reference src/distilation/lstm_train.py:18-201).
+"""LSTM distillation loop -- drop-in for /root/reference src/distilation/lstm_train.py:18-201 (`train(train, restore)`), N envs wide.
 
-SURVEY 8(f) ranks the LSTM student as the first row AFTER the MLP hot path meets its bar; it is not built yet.  The entry
-point exists so `main.py -lt` fails loudly instead of silently doing something else."""
+phase A (:115-137)  the teacher acts, records go to the Dataset, flush on done, until more than 2 * LSTM_BATCH_SIZE episodes exist;
+phase B (:141-201)  per env step: one optimiser step per Dataset.training_batches() batch (windows [T,B,.], zero initial state, ob
+                    dropout keep_prob, teacher-forced prev_pdflat, KL loss, Adam lr 1e-3); teacher label for the current observation;
+                    student action = last row of the LSTM run over Dataset.test_batch(ob) from the CARRIED state (the reference feeds
+                    the previous final state back in, :171-182); record ('s'); step; flush on done.
+All tensor work is on the device (tcgen05 GEMMs); the checkpoint is a torch.save of the flat parameters + Adam moments (:199)."""
+import os
+
+import torch
+
+from .config import KEEP_PROB, LSTM_BATCH_SIZE, SEED, STEPS_UNROLLED, TOTAL_EPISODES, base_path
+from .dataset import Dataset
+from .env import VecReacher
+from .student_nn import StudentLSTM
+from .teacher import TeacherAgent
 
 
-def train(train, restore):
-    raise NotImplementedError("LSTM student (student_nn.py:21-49) is scheduled after the MLP hot path -- see DESIGN.md 'next'")
+def train(train=True, restore=False, num_envs=64, total_episodes=TOTAL_EPISODES, iterations=None, seed=SEED, device=0, keep_prob=KEEP_PROB,
+          batch_size=LSTM_BATCH_SIZE, generations=16, lr=1e-3, checkpoint=None, verbose=True):
+    from ._lib import MODE_TC
+    T = STEPS_UNROLLED
+    env = VecReacher(num_envs=num_envs, seed=seed, device=device)
+    teacher = TeacherAgent(env, restore=restore, mode=MODE_TC)
+    student = StudentLSTM(seed=1, device=env.device, lr=lr, max_batch=max(batch_size, num_envs))
+    ckpt = checkpoint or os.path.join(base_path, "student_lstm_b200.pt")
+    if restore and os.path.exists(ckpt):
+        student.load_state_dict(torch.load(ckpt))
+    dataset = Dataset(num_envs=num_envs, generations=generations, device=device, seed=seed)
+    ob = env.reset()
+    reward = torch.zeros(num_envs, device=env.device)
+    if not train:
+        return dict(env=env, teacher=teacher, student=student, dataset=dataset)
+    if verbose:
+        print("Begin Training! First Accumulate observation with teacher")
+    while dataset.num_episodes() <= 2 * LSTM_BATCH_SIZE:
+        t_pdflat = teacher.pdflat(ob)
+        dataset.write(ob, reward, t_pdflat, None, "t")
+        ob, reward, new, _ = env.step(t_pdflat[:, :2].contiguous())
+        if dataset.last_step() + 1 == 50:
+            dataset.flush()
+    if verbose:
+        print("Accumulated sufficient data points from teacher. now train")
+    state = student.zero_state(num_envs)                                   # curr_state_batch (:93-94)
+    losses, rewards, it = [], [], 0
+    max_it = iterations if iterations is not None else 50 * max(1, -(-total_episodes // num_envs))
+    total_loss = 0.0
+    while it < max_it:
+        for (ob_b, t_b, prev_b, _prew) in dataset.training_batches(batch_size, T):
+            student.loss_grad(ob_b, prev_b, t_b, None, keep_prob=keep_prob, seed=seed, iteration=it)
+            student.adam_step()
+            total_loss = student.gradloss[student.P]
+        t_pdflat = teacher.pdflat(ob)
+        tb = dataset.test_batch(ob, steps=T)
+        ob_w, prev_w = (tb[0], tb[1]) if num_envs > 1 else (tb[0][:, -1:, :].contiguous(), tb[1][:, -1:, :].contiguous())
+        s_win, state = student.forward(ob_w, prev_w, state)
+        s_pdflat = s_win[T - 1]
+        dataset.write(ob, reward, t_pdflat, s_pdflat, "s")
+        ob, reward, new, _ = env.step(s_pdflat[:, :2].contiguous())
+        it += 1
+        if dataset.last_step() + 1 == 50:
+            dataset.flush()
+            losses.append(float(total_loss)); rewards.append(float(reward.mean()))
+            if verbose:
+                print("************** Episode %d ****************" % dataset.num_episodes())
+                print("recent loss: %f " % losses[-1])
+            if checkpoint is not None:
+                os.makedirs(os.path.dirname(ckpt) or ".", exist_ok=True)
+                torch.save(student.state_dict(), ckpt)
+    return dict(losses=losses, rewards=rewards, iterations=it, env=env, teacher=teacher, student=student, dataset=dataset)

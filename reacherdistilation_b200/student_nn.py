@@ -144,3 +144,93 @@ def student_mlp_graph(training_input_batch, net):
     """Reference name (student_nn.py:51): forward of the 16-24-128-128-32-4 student on [.., 16] inputs -> [.., 4]."""
     shp = training_input_batch.shape[:-1]
     return net.forward(training_input_batch).reshape(*shp, 4)
+
+
+class StudentLSTM:
+    """student_lstm_graph (student_nn.py:21-49): owns the flat parameters, Adam moments and workspace of the LSTM student.
+    loss_grad / forward take time-major windows [T=10, B, .]; the carried acting state is [2, B, 200] (c, m)."""
+
+    def __init__(self, seed=0, device=0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, params=None, max_batch=None):
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.P, self.T, self.U = int(lib().rb_lstm_param_count()), int(lib().rb_lstm_steps()), int(lib().rb_lstm_units())
+        if params is None:
+            params = init_lstm_params(seed)
+        assert params.size == self.P
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps          # lstm_train.py:74-78
+        with torch.cuda.device(self.device):
+            self.params = torch.from_numpy(np.ascontiguousarray(params, np.float32)).to(self.device)
+            self.m, self.v = torch.zeros_like(self.params), torch.zeros_like(self.params)
+            self.gradloss = torch.zeros(self.P + 1, dtype=torch.float32, device=self.device)
+        self.t, self._ws, self._ws_batch = 0, None, 0
+        if max_batch:
+            self._workspace(max_batch)
+
+    def _workspace(self, B):
+        if B > self._ws_batch:
+            nbytes = int(lib().rb_lstm_workspace_bytes(B))
+            with torch.cuda.device(self.device):
+                self._ws = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            self._ws_batch = B
+        return self._ws
+
+    def zero_state(self, B):
+        return torch.zeros((2, B, self.U), dtype=torch.float32, device=self.device)
+
+    def forward(self, ob, prev_pdflat, state=None):
+        """Acting (lstm_train.py:171-182): -> (s_pdflat [T,B,4], final_state [2,B,200])."""
+        T, B = ob.shape[0], ob.shape[1]
+        assert T == self.T
+        ob, prev_pdflat = ob.contiguous(), prev_pdflat.contiguous()
+        s = torch.empty((T, B, 4), dtype=torch.float32, device=self.device)
+        fin = torch.empty((2, B, self.U), dtype=torch.float32, device=self.device)
+        check(lib().rb_lstm_fwd(ptr(self.params), ptr(ob), ptr(prev_pdflat), ptr(state.contiguous() if state is not None else None), B, ptr(s), ptr(fin),
+                                ptr(self._workspace(B)), stream_ptr()))
+        return s, fin
+
+    def loss_grad(self, ob, prev_pdflat, t_pdflat, state=None, keep_prob=1.0, seed=0, sample_id0=0, iteration=0, loss_kind=LOSS_KL_ST):
+        """Training window batch (lstm_train.py:145-160): fills self.gradloss = [flat grad | loss]; returns s_pdflat [T,B,4]."""
+        T, B = ob.shape[0], ob.shape[1]
+        assert T == self.T
+        ob, prev_pdflat, t_pdflat = ob.contiguous(), prev_pdflat.contiguous(), t_pdflat.contiguous()
+        s = torch.empty((T, B, 4), dtype=torch.float32, device=self.device)
+        check(lib().rb_lstm_loss_grad(ptr(self.params), ptr(ob), ptr(prev_pdflat), ptr(t_pdflat), ptr(state.contiguous() if state is not None else None), B,
+                                      float(keep_prob), int(seed), int(sample_id0), int(iteration), loss_kind, ptr(s), None, ptr(self.gradloss),
+                                      ptr(self._workspace(B)), stream_ptr()))
+        return s
+
+    def adam_step(self, grad_scale=1.0):
+        self.t += 1
+        check(lib().rb_adam_step(ptr(self.params), ptr(self.m), ptr(self.v), ptr(self.gradloss), self.P, self.t, self.lr, self.beta1, self.beta2,
+                                 self.eps, grad_scale, stream_ptr()))
+
+    def state_dict(self):
+        return dict(kind="lstm", params=self.params.cpu(), m=self.m.cpu(), v=self.v.cpu(), t=self.t)
+
+    def load_state_dict(self, sd):
+        assert sd["kind"] == "lstm"
+        self.params.copy_(sd["params"]); self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+
+
+LSTM_HEAD_DIMS = (200, 64, 128, 64, 32, 4)
+
+
+def init_lstm_params(seed=0):
+    """glorot-uniform kernels, zero biases (tf.layers.dense and LSTMCell defaults); layout: include/reacher_b200.h."""
+    rng = np.random.default_rng(seed)
+    parts = []
+    def glorot(fi, fo):
+        lim = np.sqrt(6.0 / (fi + fo))
+        parts.append(rng.uniform(-lim, lim, fi * fo).astype(np.float32)); parts.append(np.zeros(fo, np.float32))
+    glorot(4, 32)
+    glorot(243, 800)
+    for _ in range(10):
+        for l in range(5):
+            glorot(LSTM_HEAD_DIMS[l], LSTM_HEAD_DIMS[l + 1])
+    return np.concatenate(parts)
+
+
+def student_lstm_graph(ob_batch, keep_prob, prev_pdflat_batch, initial_state_batch, net, seed=0, iteration=0):
+    """Reference name (student_nn.py:21): forward of the LSTM student; keep_prob < 1 uses the Philox dropout mask."""
+    if keep_prob >= 1.0:
+        return net.forward(ob_batch, prev_pdflat_batch, initial_state_batch)
+    raise NotImplementedError("dropout forward is part of loss_grad (training); acting uses keep_prob = 1 (lstm_train.py:176)")

@@ -1,0 +1,19 @@
+"""Time of the cooperative student kernel (loss_grad) and of the fused step at the config-4 shard and at the full batch."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np, torch
+from reacherdistilation_b200 import MODE_TC, STUDENT_MLP, STUDENT_POLICY64
+from reacherdistilation_b200.student_nn import StudentNet
+for kind, name in ((STUDENT_MLP, "mlp"), (STUDENT_POLICY64, "policy64")):
+    for B in (32768, 262144):
+        net = StudentNet(kind=kind, seed=1, mode=MODE_TC)
+        x = torch.randn((B, net.in_dim), device="cuda"); t = torch.randn((B, 4), device="cuda") * 0.3
+        s = torch.empty((B, 4), device="cuda")
+        for fn, nm in ((lambda: net.loss_grad(x, t, s_out=s), "loss_grad"), (lambda: net.step(x, t, s_out=s), "step"), (lambda: net.forward(x, out=s), "forward")):
+            for _ in range(5): fn()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(50): fn()
+            e1.record(); torch.cuda.synchronize()
+            us = e0.elapsed_time(e1) * 1e3 / 50
+            print("%-9s B=%6d %-9s %7.1f us  %.3e samples/s" % (name, B, nm, us, B / us * 1e6), flush=True)

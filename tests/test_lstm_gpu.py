@@ -1,0 +1,65 @@
+"""LSTM student on the device (tcgen05 GEMMs + element-wise kernels) vs the float64 restatement: forward, carried state, KL loss,
+BPTT gradient of all 511 880 parameters, dropout mask, and the training loop entry point."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import lstm_np as L
+from oracle import nn_np as NN
+
+pytestmark = pytest.mark.gpu
+TOL = 2e-3      # stated tolerance of the tensor-core (bf16x3) student kernels, relative to max(1, |ref|)
+
+
+def _data(B, seed):
+    rng = np.random.default_rng(seed)
+    ob = rng.standard_normal((L.T, B, 11)).astype(np.float32)
+    pp = (rng.standard_normal((L.T, B, 4)) * 0.3).astype(np.float32)
+    tp = np.concatenate([rng.standard_normal((L.T, B, 2)) * 0.3, -1 + 0.2 * rng.standard_normal((L.T, B, 2))], -1).astype(np.float32)
+    st = (rng.standard_normal((2, B, 200)) * 0.1).astype(np.float32)
+    return ob, pp, tp, st
+
+
+@pytest.mark.parametrize("B", [1, 20, 150])
+def test_forward_and_state_match_oracle(B):
+    from reacherdistilation_b200.student_nn import StudentLSTM
+    net = StudentLSTM(seed=3)
+    p = net.params.cpu().numpy()
+    ob, pp, tp, st = _data(B, B)
+    for state in (None, st):
+        s, fin = net.forward(torch.from_numpy(ob).cuda(), torch.from_numpy(pp).cuda(), torch.from_numpy(state).cuda() if state is not None else None)
+        rs, rfin, _ = L.forward(p, ob, pp, state)
+        assert np.abs(s.cpu().numpy() - rs).max() <= 1e-4 and np.abs(fin.cpu().numpy() - rfin).max() <= 1e-4
+
+
+@pytest.mark.parametrize("B,keep_prob,loss_kind", [(20, 1.0, 0), (20, 0.5, 0), (7, 1.0, 1), (300, 0.8, 0)])
+def test_loss_and_bptt_gradient_match_oracle(B, keep_prob, loss_kind):
+    from reacherdistilation_b200.student_nn import StudentLSTM
+    net = StudentLSTM(seed=4)
+    p = net.params.cpu().numpy()
+    ob, pp, tp, st = _data(B, 10 * B)
+    seed, sid0, it = 9, 1000, 3
+    s = net.loss_grad(torch.from_numpy(ob).cuda(), torch.from_numpy(pp).cuda(), torch.from_numpy(tp).cuda(), torch.from_numpy(st).cuda(),
+                      keep_prob=keep_prob, seed=seed, sample_id0=sid0, iteration=it, loss_kind=loss_kind)
+    gl = net.gradloss.cpu().numpy().astype(np.float64)
+    ids = np.arange(L.T * B, dtype=np.uint32) + sid0
+    obd = NN.student_input(ob.reshape(-1, 11), np.zeros((L.T * B, 4)), np.zeros(L.T * B), keep_prob, seed, ids, it, dtype=np.float32)[:, :11]
+    rs, rl, rg = L.loss_grad(p, obd.reshape(L.T, B, 11), pp, tp, st, reverse=bool(loss_kind))
+    gs = max(1.0, np.abs(rg).max())
+    e_s, e_l, e_g = np.abs(s.cpu().numpy() - rs).max(), abs(gl[-1] - rl) / max(1.0, abs(rl)), np.abs(gl[:-1] - rg).max() / gs
+    print("lstm B=%d kp=%.1f loss=%d: s %.3g loss %.3g grad %.3g (|g|max %.3g)" % (B, keep_prob, loss_kind, e_s, e_l, e_g, gs))
+    assert e_s <= TOL and e_l <= TOL and e_g <= TOL
+    blocks = dict(We=(0, 128), be=(128, 160), Wl=(160, L.L_BL), bl=(L.L_BL, L.L_HEAD0), head0=(L.L_HEAD0, L.L_HEAD0 + L.L_HEAD_SZ),
+                  head9=(L.L_HEAD0 + 9 * L.L_HEAD_SZ, L.P))
+    for name, (a, b) in blocks.items():
+        assert np.abs(gl[a:b] - rg[a:b]).max() <= TOL * max(1.0, np.abs(rg[a:b]).max()), name
+    net.loss_grad(torch.from_numpy(ob).cuda(), torch.from_numpy(pp).cuda(), torch.from_numpy(tp).cuda(), torch.from_numpy(st).cuda(),
+                  keep_prob=keep_prob, seed=seed, sample_id0=sid0, iteration=it, loss_kind=loss_kind)
+    assert np.array_equal(gl, net.gradloss.cpu().numpy().astype(np.float64))            # deterministic
+
+
+def test_lstm_train_entry_point_learns():
+    from reacherdistilation_b200 import lstm_train
+    out = lstm_train.train(True, False, num_envs=48, iterations=100, verbose=False)
+    assert len(out["losses"]) == 2 and np.isfinite(out["losses"]).all() and out["losses"][-1] < out["losses"][0]
+    out["dataset"].close(); out["env"].close()
