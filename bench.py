@@ -32,9 +32,9 @@ CHUNK_T = 50
 DISTILL_ENVS_PER_GPU = 32768
 STEP_API_ENVS = 1 << 22
 ALG_BYTES_ROLLOUT = 65.0      # fused rollout writes one buffer row per env-step: ob 44 + pdflat 16 + rew 4 + done 1 B (17 scalars)
-ROLLOUT_TRAFFIC_NCU = 158.3e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
-                                # profiles/r01_ncu_full_k_rollout_policy_tc.csv; the rest of the 213 MB is still dirty in L2 at kernel end
-MUFU_PER_ENV_STEP = 265.0       # 128 tanh x (ex2 + rcp) + 8 rcp + 1 sqrt (profiles: MUFU instructions / warp-step)
+ROLLOUT_TRAFFIC_NCU = 159.6e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
+                                # profiles/r01_ncu_full_k_rollout_policy_tc_final.csv; the rest of the 213 MB is still dirty in L2 at kernel end
+MUFU_PER_ENV_STEP = 201.0       # 128 tanh x 1.5 (ex2 each, one rcp per pair) + 8 rcp + 1 sqrt; ncu source page: 201.1 MUFU / warp-step
 XU_LANES_PER_CLK_PER_SM = 16.0  # B200 MUFU rate
 ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -282,8 +282,8 @@ def main():
     line["pipes"] = dict(xu_mufu_per_env_step=MUFU_PER_ENV_STEP, xu_ceiling_env_steps_per_s=xu_ceiling, frac_of_xu_ceiling=value / world / xu_ceiling,
                          tensor_tflops_bf16x3=3 * 9856.0 * n * CHUNK_T / kernel_s / 1e12, tensor_peak_tflops=pk["bf16_burst"],
                          physics_flop_per_env_step=450.0, teacher_flop_per_env_step=9856.0,
-                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 265 MUFU per env-step; ncu (profiles/): XU pipe 45 % of active cycles, "
-                              "issue slots 47 %, tensor pipe 12 %")
+                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 201 MUFU per env-step; ncu (profiles/README.md): XU pipe 40 % of active "
+                              "cycles, issue slots 57 %, tensor pipe 18 %; only 13.8 warps/SM exist at 65 536 envs (latency-bound, see DESIGN.md 4.1)")
 
     if not args.quick:
         # ---- distill: DAgger iterations on the config-4 shard ---------------------------------------------------
@@ -348,6 +348,25 @@ def main():
                                                          kernel_ms=1e3 * lksec / 10, tensor_tflops=fl * nl / (lksec / 10) / 1e12,
                                                          frac_of_bf16_peak=fl * nl / (lksec / 10) / 1e12 / pk["bf16_burst"])
             trl.close()
+        if world == 1:
+            # ---- LSTM student (the reference's headline experiment): one optimiser step on a batch of 10-step windows ---------------
+            from reacherdistilation_b200.student_nn import StudentLSTM
+            Bw = 2048
+            lnet = StudentLSTM(seed=1, device=local, max_batch=Bw)
+            lob, lpp = torch.randn((10, Bw, 11), device=dev), torch.randn((10, Bw, 4), device=dev) * 0.3
+            ltp = torch.cat([torch.randn((10, Bw, 2), device=dev) * 0.3, -1 + 0.2 * torch.randn((10, Bw, 2), device=dev)], -1)
+            def lstep():
+                lnet.loss_grad(lob, lpp, ltp, None, keep_prob=0.5, seed=0, iteration=lnet.t)
+                lnet.adam_step()
+            for _ in range(3):
+                lstep()
+            lsec2, _ = timed(lstep, 10)
+            lflop = 6.0 * (243 * 800 + 31400 + 128) * 10 * Bw                       # 3 x 2 x MAC per window row, T = 10
+            line["lstm"] = dict(metric="lstm_window_rows_per_sec", value=10.0 * Bw * 10 / lsec2, unit="sample-steps/s", windows=Bw, steps_unrolled=10,
+                                ms_per_step=1e3 * lsec2 / 10, tensor_tflops=lflop / (lsec2 / 10) / 1e12, params=int(lnet.P),
+                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads; ~250 launches of k_gemm_bf16x3 and "
+                                     "element-wise kernels per step (launch-bound at this size; CUDA-graph capture is the next step)")
+            del lnet
         # ---- step API: HBM-bound single-step kernel at 4M envs ---------------------------------------------------
         ns = STEP_API_ENVS
         env2 = VecReacher(num_envs=ns, seed=0, device=local, env_offset=0)

@@ -24,7 +24,7 @@ def main(argv=None):
         sd = torch.load(path)
         print({k: (tuple(v.shape) if hasattr(v, "shape") else v) for k, v in sd.items()})
     elif args.lstm_train:
-        lstm_train.train(True, args.restore)
+        lstm_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob)
     elif args.mlp_train:
         mlp_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob)
 

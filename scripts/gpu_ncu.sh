@@ -7,4 +7,3 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file
 $CMD > gpurun_out/plain2.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k regex:k_rollout_policy_tc -s 3 -c 1 -f -o gpurun_out/prof_rollout_tc $CMD > gpurun_out/ncu2.log 2>&1
 tail -n 3 gpurun_out/ncu1.log gpurun_out/ncu2.log
-for nt in 4 5 6; do RB_ROLLOUT_NT=$nt python bench.py --steps 50 --warmup 5 --quick 2>&1 | grep -o '"value": [0-9.]*' | head -1; done
