@@ -9,10 +9,10 @@
 // latency.  One CTA per SM; envs are dealt to CTAs in units of one warp (32 envs) so every SM gets the same number of
 // warps +-1 whatever N is (65 536 envs = 2048 warp-units = 13.8 per SM; a 128-env granularity would leave a 15 % tail).
 //
-// Per policy evaluation a tile runs three dependent GEMMs [128 x K] * [K x N] (A, B in shared memory, D in TMEM):
+// Per policy evaluation a tile runs two dependent GEMMs [128 x K] * [K x N] (A, B in shared memory, D in TMEM) + a fused output layer:
 //     L1: K = 16 (11 obs + a ones column that carries b1 + zero pad), N = 64
 //     L2: K = 64 (+ one extra K = 16 step: a constant ones-tile times the b2 row), N = 64
-//     L3: K = 64, N = 16 (nout padded)
+//     L3: 64 -> nout on the CUDA cores, fused into the L2 epilogue (fp32 FMAs; no third GEMM round trip)
 // Operands are bf16 hi/lo splits of the fp32 values ("bf16x3": A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulate in
 // TMEM), which keeps the result within ~1e-5 of the fp32 network.  W1/b1/W2/b2 are pre-multiplied by 2*log2(e) when they
 // are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  : FADD, 2 MUFU, FFMA per element, then the bf16
@@ -44,9 +44,8 @@ struct __align__(128) TcShared {        // one per CTA: split weights + per-tile
     uint8_t B2b_lo[64 * 16 * 2];
     uint8_t B1_hi[64 * 16 * 2];
     uint8_t B1_lo[64 * 16 * 2];
-    uint8_t B3_hi[16 * 64 * 2];
-    uint8_t B3_lo[16 * 64 * 2];
     uint8_t ONES[128 * 16 * 2];         // A operand of the bias K-step: column 0 = 1.0, rest 0
+    float W3f[64 * 4];                  // output layer in fp32, [k][4] (zero columns for nout == 2): applied on the CUDA cores
     float b3[4];
     float mu[12];
     float inv_sd[12];
@@ -91,12 +90,9 @@ __device__ inline void policy_tc_load_weights(TcShared& S, const float* __restri
         *reinterpret_cast<uint16_t*>(S.B2_hi + tile_off(n, k, 64)) = h;
         *reinterpret_cast<uint16_t*>(S.B2_lo + tile_off(n, k, 64)) = l;
     }
-    for (int i = tid; i < 16 * 64; i += nt) {
-        const int n = i & 15, k = i >> 4;
-        uint16_t h, l;
-        split_scalar(n < nout ? __ldg(p + o.W3 + k * nout + n) : 0.f, h, l);
-        *reinterpret_cast<uint16_t*>(S.B3_hi + tile_off(n, k, 16)) = h;
-        *reinterpret_cast<uint16_t*>(S.B3_lo + tile_off(n, k, 16)) = l;
+    for (int i = tid; i < 64 * 4; i += nt) {
+        const int n = i & 3, k = i >> 2;
+        S.W3f[i] = n < nout ? __ldg(p + o.W3 + k * nout + n) : 0.f;
     }
     for (int i = tid; i < 128 * 16; i += nt) {
         const int r = i & 127, k = i >> 7;
@@ -175,6 +171,42 @@ __device__ __forceinline__ void hidden_epilogue(TcTile& T, uint32_t taddr, int r
     }
 }
 
+// epilogue of the LAST hidden layer fused with the output layer: out[j] += tanh(acc[k]) W3[k][j] in fp32 on the CUDA cores.  The
+// 64 -> nout layer is 128 (256) FMAs per row; running it here removes a third GEMM round trip (split + store of h2, tile barrier, MMA
+// issue / commit / wait, TMEM load) from the serial chain of every env step.
+template <int NOUT> __device__ __forceinline__ void final_chunk(const TcShared& S, const float* v, int cc, float* o) {
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+        float t0, t1;
+#if RB_TANH_VARIANT == 1
+        tanh_pair_from_scaled(v[2 * q], v[2 * q + 1], t0, t1);
+#else
+        t0 = tanh_from_scaled(v[2 * q]); t1 = tanh_from_scaled(v[2 * q + 1]);
+#endif
+        const int k = 16 * cc + 2 * q;
+        const float4 w0 = *reinterpret_cast<const float4*>(&S.W3f[4 * k]), w1 = *reinterpret_cast<const float4*>(&S.W3f[4 * k + 4]);
+        o[0] = fmaf(t0, w0.x, o[0]); o[1] = fmaf(t0, w0.y, o[1]);
+        o[0] = fmaf(t1, w1.x, o[0]); o[1] = fmaf(t1, w1.y, o[1]);
+        if (NOUT == 4) {
+            o[2] = fmaf(t0, w0.z, o[2]); o[3] = fmaf(t0, w0.w, o[3]);
+            o[2] = fmaf(t1, w1.z, o[2]); o[3] = fmaf(t1, w1.w, o[3]);
+        }
+    }
+}
+template <int NOUT> __device__ __forceinline__ void final_epilogue(const TcShared& S, uint32_t taddr, float* o) {
+    float va[16], vb[16];
+    tmem_ld_x16(taddr, va);
+#pragma unroll 1
+    for (int cc = 0; cc < 4; cc += 2) {
+        tmem_ld_wait();
+        tmem_ld_x16(taddr + 16 * (cc + 1), vb);
+        final_chunk<NOUT>(S, va, cc, o);
+        tmem_ld_wait();
+        if (cc + 2 < 4) tmem_ld_x16(taddr + 16 * (cc + 2), va);
+        final_chunk<NOUT>(S, vb, cc + 1, o);
+    }
+}
+
 // Full policy evaluation for one tile.  Every ACTIVE thread of the tile must call this (it contains the tile barrier,
 // `bar_threads` = 32 * active warps of the tile).  ob: this thread's 11-d observation.  pd: (mean0, mean1, logstd0,
 // logstd1) or the four raw outputs.  issuer: exactly one active thread of the tile.
@@ -200,8 +232,9 @@ __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile,
             *reinterpret_cast<uint4*>(T.A_lo + c * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
         }
     }
+    float o[4] = {S.b3[0], S.b3[1], S.b3[2], S.b3[3]};
 #pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {                     // the two 64-wide tanh layers share one copy of the epilogue code
+    for (int layer = 0; layer < 2; ++layer) {
         fence_async_smem();
         fence_before_sync();
         tile_sync(1 + tile, bar_threads);
@@ -220,24 +253,12 @@ __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile,
         }
         mbar_wait(mbar, phase); phase ^= 1u;
         fence_after_sync();
-        hidden_epilogue(T, tmem + lane_base, row);
+        if (layer == 0) hidden_epilogue(T, tmem + lane_base, row);   // h1 -> A tile of layer 2
+        else final_epilogue<NOUT>(S, tmem + lane_base, o);           // h2 and the output layer, registers only
     }
-    fence_async_smem();
-    fence_before_sync();
-    tile_sync(1 + tile, bar_threads);
-    if (issuer) {
-        fence_after_sync();
-        issue_bf16x3(tmem, ah, al, smem_u32(S.B3_hi), smem_u32(S.B3_lo), 4, 16, make_idesc_bf16(128, 16), 0);
-        mma_commit(mbar);
-    }
-    mbar_wait(mbar, phase); phase ^= 1u;
-    fence_after_sync();
-    float o[4];
-    tmem_ld_x4(tmem + lane_base, o);
-    tmem_ld_wait();
-    pd[0] = o[0] + S.b3[0];
-    pd[1] = o[1] + S.b3[1];
-    if (NOUT == 4) { pd[2] = o[2] + S.b3[2]; pd[3] = o[3] + S.b3[3]; } else { pd[2] = S.logstd[0]; pd[3] = S.logstd[1]; }
+    pd[0] = o[0];
+    pd[1] = o[1];
+    if (NOUT == 4) { pd[2] = o[2]; pd[3] = o[3]; } else { pd[2] = S.logstd[0]; pd[3] = S.logstd[1]; }
     fence_before_sync();       // orders this TMEM read before the next evaluation's MMA (issued after the next tile barrier)
 }
 
