@@ -171,8 +171,9 @@ def run_reference(args):
     sample = "%d of %d envs per step x %d steps/chunk, float64 C restatement of the MuJoCo+TF CPU path, OpenMP %d threads" % (n, ENVS_PER_GPU, CHUNK_T, cores)
     line = dict(impl="reference", metric="reacher_env_steps_per_sec", value=val, unit="env-steps/s", n_gpus=args.gpus, steps=steps, warmup=warm,
                 ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="config3: fused teacher (11-64-64-2 tanh) rollout, 50-step chunks, rollout buffer recorded",
-                            envs_per_step=n, chunk_steps=CHUNK_T),
+                config=dict(workload="config3: %d envs/GPU, fused teacher MLP (11-64-64-2 tanh) in the loop, 50-step chunk per step, "
+                                     "rollout buffer device-resident" % ENVS_PER_GPU, envs_per_gpu=ENVS_PER_GPU, chunk_steps=CHUNK_T,
+                            reference_sample="each step = %d of the %d envs x %d steps on the host cores (bounded sample)" % (n, ENVS_PER_GPU, CHUNK_T)),
                 cpu_baseline=dict(value=val, unit="env-steps/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
@@ -313,7 +314,8 @@ def main():
         fl = FLOP_PER_SAMPLE[args.student]
         line["distill"] = dict(metric="distill_samples_per_sec", value=float(nd) * Kd * world / dsec, unit="samples/s", steps=Kd,
                                ms_per_step=1e3 * dsec / Kd, workload="config4 shard: %d envs/GPU, student %s, KL(s||t), TF-Adam, %s"
-                               % (nd, args.student, "NCCL all-reduce of flat grad" if world > 1 else "single GPU"),
+                               % (nd, args.student, ("gradient all-reduce fused into the student kernel (NVLink peer memory)" if tr.fused_allreduce
+                                                     else "NCCL all-reduce of flat grad") if world > 1 else "single GPU"),
                                e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=4),
                                gpu_launches_per_step=(3 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
                                last_loss=float(tr.last_loss()),
@@ -322,6 +324,11 @@ def main():
                                              kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
                                                      else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
                                              note="tile GEMMs run bf16x3 (3 MMAs per product): tensor-pipe work is 3x the algorithmic FLOP"))
+        if world > 1:                                                   # every rank must hold bit-identical student parameters
+            chk = torch.stack([tr.student.params.double().sum(), tr.student.params.double().abs().sum()]).to(dev)
+            allc = [torch.empty_like(chk) for _ in range(world)]
+            torch.distributed.all_gather(allc, chk)
+            line["distill"]["ranks_bit_identical"] = bool(all(torch.equal(a, allc[0]) for a in allc))
         line["distill"]["exchange"] = ("none (single rank)" if world == 1 else
                                        "one-shot all-reduce over NVLink peer memory fused into k_student_tc" if tr.fused_allreduce else "NCCL all-reduce")
         tr.close()
