@@ -245,23 +245,33 @@ def main():
     clocks = sampler.window(*win) if sampler else None
     mean_rew = float(buf["rew"].mean())
 
-    # ---- e2e: host-buffer C-ABI call, H2D params + D2H whole rollout buffer every step -----------------------
+    # ---- e2e: the host-buffer C-ABI call (rb_env_rollout_policy_host), synchronous, copies inside the timed region -------------
+    #   e2e             : H2D of the teacher parameters, the rollout (buffer stays device-resident for the distillation loop, north_star (3)),
+    #                     D2H of the step's RESULT: reward and done of every env-step (what the reference prints / extract_reward.py consumes)
+    #   e2e_full_buffer : same call returning the WHOLE rollout buffer (obs, pdflat, reward, done = 65 B/env-step) to the host -- PCIe-bound
     Ke = max(3, min(K, 20))
     hbuf = dict(obs=torch.empty((CHUNK_T, n, 11)).pin_memory(), pdflat=torch.empty((CHUNK_T, n, 4)).pin_memory(),
                 rew=torch.empty((CHUNK_T, n)).pin_memory(), done=torch.empty((CHUNK_T, n), dtype=torch.uint8).pin_memory())
+    hres = dict(obs=None, pdflat=None, rew=hbuf["rew"], done=hbuf["done"])
     tparams_host = torch.from_numpy(init_policy_params(seed=0)).pin_memory()
-    e2e_fn = lambda: env.rollout_policy_host(tparams_host, CHUNK_T, nout=2, mode=mode, out=hbuf)
-    for _ in range(2):
-        e2e_fn()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(Ke):
-        e2e_fn()                                                       # synchronous call (copies + sync inside)
-    barrier()
-    e2e_sec = max_over_ranks(time.perf_counter() - t0, dev)
+
+    def e2e_time(out):
+        fn = lambda: env.rollout_policy_host(tparams_host, CHUNK_T, nout=2, mode=mode, out=out)
+        for _ in range(2):
+            fn()
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(Ke):
+            fn()                                                       # synchronous call (copies + sync inside)
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0, dev)
+    e2e_sec, e2e_full_sec = e2e_time(hres), e2e_time(hbuf)
     e2e = dict(value=float(n) * CHUNK_T * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
-               d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke,
-               api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host)")
+               d2h_bytes_per_step=int(n * CHUNK_T * (4 + 1)), steps=Ke, api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host)",
+               result="reward[T,N] f32 + done[T,N] u8 to pinned host memory; obs / pdflat stay in the device-resident rollout buffer",
+               mean_reward_host=float(hbuf["rew"].mean()))
+    e2e_full = dict(value=float(n) * CHUNK_T * Ke * world / e2e_full_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
+                    d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke, note="whole rollout buffer to the host: PCIe-bound")
     env.close()
     del buf, hbuf
 
@@ -271,7 +281,7 @@ def main():
                                      "rollout buffer device-resident" % n, envs_per_gpu=n, chunk_steps=CHUNK_T, policy_mode=mode_name,
                             l2="no flush: each step writes a fresh %.0f MB rollout buffer (> 126 MB L2); state 2.6 MB stays in registers"
                                % (n * CHUNK_T * 68 / 1e6), seed=0, mean_teacher_reward=mean_rew),
-                e2e=e2e, gpu_launches=K, clocks=clocks)
+                e2e=e2e, e2e_full_buffer=e2e_full, gpu_launches=K, clocks=clocks)
     line["roofline"] = dict(bound="hbm", achieved=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9, peak=pk["hbm"], unit="GB/s",
                             frac=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9 / pk["hbm"],
                             traffic=(ROLLOUT_TRAFFIC_NCU if (mode == MODE_TC and n == 65536) else None), peak_source=pk["src"],

@@ -20,6 +20,8 @@ struct rb_env {
     float* d_buf_obs = nullptr; float* d_buf_pd = nullptr; float* d_buf_rew = nullptr; uint8_t* d_buf_done = nullptr;
     int64_t buf_T = 0;
     cudaStream_t host_stream = nullptr;
+    cudaStream_t copy_stream = nullptr;      // D2H of finished time slabs overlaps the next slab's kernel
+    cudaEvent_t slab_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int sm_count = 148;
 };
 

@@ -233,6 +233,8 @@ int rb_env_destroy(rb_env* e) {
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
+    if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
+    for (int i = 0; i < 8; ++i) if (e->slab_done[i]) cudaEventDestroy(e->slab_done[i]);
     delete e;
     return RB_OK;
 }
@@ -266,6 +268,8 @@ static int ensure_host_staging(rb_env* e) {
     if (e->d_act) return RB_OK;
     RB_CUDA(cudaSetDevice(e->device));
     RB_CUDA(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
+    RB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 8; ++i) RB_CUDA(cudaEventCreateWithFlags(&e->slab_done[i], cudaEventDisableTiming));
     RB_CUDA(cudaMalloc(&e->d_act, sizeof(float) * 2 * e->n));
     RB_CUDA(cudaMalloc(&e->d_obs, sizeof(float) * OBS * e->n));
     RB_CUDA(cudaMalloc(&e->d_rew, sizeof(float) * e->n));
@@ -397,16 +401,27 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
         RB_CUDA(cudaMalloc(&e->d_buf_done, rows));
         e->buf_T = T;
     }
-    cudaStream_t s = e->host_stream;
-    const int64_t rows = (int64_t)T * e->n;
+    cudaStream_t s = e->host_stream, sc = e->copy_stream;
     RB_CUDA(cudaMemcpyAsync(e->d_params, params_host, sizeof(float) * rb_policy_param_count(nout), cudaMemcpyHostToDevice, s));
-    rc = rb_env_rollout_policy(e, e->d_params, nout, T, obs_host ? e->d_buf_obs : nullptr, pd_host ? e->d_buf_pd : nullptr,
-                               rew_host ? e->d_buf_rew : nullptr, done_host ? e->d_buf_done : nullptr, mode, s);
-    if (rc) return rc;
-    if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host, e->d_buf_obs, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, s));
-    if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host, e->d_buf_pd, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, s));
-    if (rew_host) RB_CUDA(cudaMemcpyAsync(rew_host, e->d_buf_rew, sizeof(float) * rows, cudaMemcpyDeviceToHost, s));
-    if (done_host) RB_CUDA(cudaMemcpyAsync(done_host, e->d_buf_done, rows, cudaMemcpyDeviceToHost, s));
+    // The T steps run as up to 5 time slabs (same trajectories: the state round-trips through HBM exactly); the device->host copy of
+    // slab i (copy stream) overlaps the kernel of slab i+1 (compute stream).
+    const int nslab = T < 5 ? T : 5;
+    int t0 = 0;
+    for (int i = 0; i < nslab; ++i) {
+        const int tn = (T * (i + 1)) / nslab - t0;
+        const int64_t r0 = (int64_t)t0 * e->n, rows = (int64_t)tn * e->n;
+        rc = rb_env_rollout_policy(e, e->d_params, nout, tn, obs_host ? e->d_buf_obs + OBS * r0 : nullptr, pd_host ? e->d_buf_pd + 4 * r0 : nullptr,
+                                   rew_host ? e->d_buf_rew + r0 : nullptr, done_host ? e->d_buf_done + r0 : nullptr, mode, s);
+        if (rc) return rc;
+        RB_CUDA(cudaEventRecord(e->slab_done[i], s));
+        RB_CUDA(cudaStreamWaitEvent(sc, e->slab_done[i], 0));
+        if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host + OBS * r0, e->d_buf_obs + OBS * r0, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, sc));
+        if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host + 4 * r0, e->d_buf_pd + 4 * r0, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, sc));
+        if (rew_host) RB_CUDA(cudaMemcpyAsync(rew_host + r0, e->d_buf_rew + r0, sizeof(float) * rows, cudaMemcpyDeviceToHost, sc));
+        if (done_host) RB_CUDA(cudaMemcpyAsync(done_host + r0, e->d_buf_done + r0, rows, cudaMemcpyDeviceToHost, sc));
+        t0 += tn;
+    }
+    RB_CUDA(cudaStreamSynchronize(sc));
     RB_CUDA(cudaStreamSynchronize(s));
     return RB_OK;
 }

@@ -133,8 +133,8 @@ class VecReacher:
         if out is None:
             out = dict(obs=torch.empty((T, n, 11)).pin_memory(), pdflat=torch.empty((T, n, 4)).pin_memory(),
                        rew=torch.empty((T, n)).pin_memory(), done=torch.empty((T, n), dtype=torch.uint8).pin_memory())
-        check(lib().rb_env_rollout_policy_host(self._h, ptr(params_host), nout, T, ptr(out["obs"]), ptr(out["pdflat"]), ptr(out["rew"]),
-                                               ptr(out["done"]), mode))
+        check(lib().rb_env_rollout_policy_host(self._h, ptr(params_host), nout, T, ptr(out.get("obs")), ptr(out.get("pdflat")), ptr(out.get("rew")),
+                                               ptr(out.get("done")), mode))                  # None entries: that field is not copied to the host
         return out
 
 
