@@ -169,6 +169,10 @@ int rb_student_step_dp(int kind, float* params_dev, float* m_dev, float* v_dev, 
                        float beta2, float eps, float grad_scale, int rank, int world, const uint64_t* peer_grad_slots,
                        const uint64_t* peer_flags, uint32_t epoch, void* stream);
 
+/* Debug aid: globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last RB_MODE_TC student launch (16 values; see
+ * student_tc.cu).  Synchronises the device.                                                                            */
+int rb_debug_student_timers(unsigned long long* host_out16);
+
 /* ------------------------------------------------------------------------------------------------ DAgger --
  * One lock-step DAgger iteration pieces (src/distilation/mlp_train.py:143-204 batched):
  * rb_dagger_observe: for every env write ob[N,11], teacher label t_pdflat[N,4] and the student input x[N,in]

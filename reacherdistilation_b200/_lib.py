@@ -53,6 +53,7 @@ _SIGS = {
                                   C.c_float, C.c_float, C.c_int, _vp]),
     "rb_student_step_dp": (C.c_int, [C.c_int, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_int, _fp, _fp, _vp, C.c_int64, C.c_float, C.c_float, C.c_float,
                                      C.c_float, C.c_float, C.c_int, C.c_int, _vp, _vp, C.c_uint32, _vp]),
+    "rb_debug_student_timers": (C.c_int, [_vp]),
     "rb_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "rb_dagger_create": (C.c_int, [C.POINTER(C.c_void_p), _vp, C.c_int, C.c_float]),
     "rb_dagger_destroy": (C.c_int, [_vp]),

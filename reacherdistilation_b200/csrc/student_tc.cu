@@ -99,6 +99,10 @@ struct StudentTcArgs {
     uint32_t* peer_flag[8];
 };
 
+// Plain (weak) global load.  Data produced earlier in the SAME launch by other CTAs is read only after a grid barrier and is never
+// touched by this SM before that barrier, so no stale L1 line can exist; unlike ld.global.cg / volatile these loads may be batched.
+template <typename T> __device__ __forceinline__ T ldw(const T* p) { return *p; }
+
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
     uint32_t v;
@@ -263,7 +267,7 @@ template <class S> struct LayerLoop {
             float v = 0.f;
             if (S::L == 4 && l == 2) {                       // SpecMLP folded layer: its non-zero elements come from fold_into_image()
                 if (n < out && (k < in || k == kb)) return;
-            } else if (n < out) v = k < in ? __ldcg(a.w[l] + k * out + n) : (k == kb ? __ldcg(a.b[l] + n) : 0.f);
+            } else if (n < out) v = k < in ? ldw(a.w[l] + k * out + n) : (k == kb ? ldw(a.b[l] + n) : 0.f);
             uint16_t h, lo;
             split_scalar(v, h, lo);
             const uint32_t off = G::wtile_off(l) + tile_off(n, k, N);
@@ -287,16 +291,30 @@ template <class S> struct LayerLoop {
             constexpr int rows = G::wq_extra(l) ? in : kb + 1;
             if (sub * 32 < rows) {                                                                 // warp-uniform
                 const int i = sub * 32 + lane;
-                for (int c = part; c < G::N(l) / 8; c += 4) {
-                    float v[8];
-                    tmem_ld_x8(t0 + c * 8, v);
-                    tmem_ld_wait();
+                constexpr int NC = G::N(l) / 8, PER = (NC + 3) / 4;
+                float v[PER][8];
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {
-                        const int j = c * 8 + k;
-                        if (j < out) {
-                            if (i < in) part_out[a.pw[l] + i * out + j] = v[k];
-                            else if (i == kb && !G::wq_extra(l)) part_out[a.pb[l] + j] = v[k];
+                for (int u = 0; u < PER; ++u)
+                    if (part + 4 * u < NC) tmem_ld_x8(t0 + (part + 4 * u) * 8, v[u]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int c = part + 4 * u;
+                    if (c < NC) {
+                        if (out % 4 == 0 && i < in && (reinterpret_cast<uintptr_t>(part_out + a.pw[l] + i * out) & 15) == 0) {   // lane's row of dW
+#pragma unroll
+                            for (int k = 0; k < 8; k += 4)
+                                if (c * 8 + k < out)
+                                    *reinterpret_cast<float4*>(part_out + a.pw[l] + i * out + c * 8 + k) = make_float4(v[u][k], v[u][k + 1], v[u][k + 2], v[u][k + 3]);
+                        } else {
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {
+                                const int j = c * 8 + k;
+                                if (j < out) {
+                                    if (i < in) part_out[a.pw[l] + i * out + j] = v[u][k];
+                                    else if (i == kb && !G::wq_extra(l)) part_out[a.pb[l] + j] = v[u][k];
+                                }
+                            }
                         }
                     }
                 }
@@ -313,16 +331,21 @@ template <class S> struct LayerLoop {
             constexpr int ncol8 = G::ig(l) + 1;                                                    // 8-column chunks incl. the bias chunk
             if (sub * 32 < out) {                                                                  // warp-uniform
                 const int j = sub * 32 + lane;
-                for (int c = part; c < ncol8; c += 4) {
-                    float v[8];
-                    tmem_ld_x8(t0 + c * 8, v);
-                    tmem_ld_wait();
-                    if (j < out) {
+                constexpr int PER = (ncol8 + 3) / 4;
+                float v[PER][8];
+#pragma unroll
+                for (int u = 0; u < PER; ++u)
+                    if (part + 4 * u < ncol8) tmem_ld_x8(t0 + (part + 4 * u) * 8, v[u]);
+                tmem_ld_wait();
+#pragma unroll
+                for (int u = 0; u < PER; ++u) {
+                    const int c = part + 4 * u;
+                    if (c < ncol8 && j < out) {
 #pragma unroll
                         for (int k = 0; k < 8; ++k) {
                             const int i = c * 8 + k;
-                            if (i < in) part_out[a.pw[l] + i * out + j] = v[k];
-                            else if (i == kb) part_out[a.pb[l] + j] = v[k];
+                            if (i < in) part_out[a.pw[l] + i * out + j] = v[u][k];
+                            else if (i == kb) part_out[a.pb[l] + j] = v[u][k];
                         }
                     }
                 }
@@ -349,11 +372,11 @@ __device__ __forceinline__ void fold_into_image(const float* p, uint8_t* img, in
         const int i = idx < 4096 ? idx >> 5 : 128, j = idx & 31;
         const float* lhs = idx < 4096 ? p + M_W3 + i * 128 : p + M_B3;
 #pragma unroll
-        for (int m = 0; m < 8; ++m) { const int k = sub + 16 * m; acc = fmaf(__ldcg(lhs + k), __ldcg(p + M_W4 + k * 32 + j), acc); }
+        for (int m = 0; m < 8; ++m) { const int k = sub + 16 * m; acc = fmaf(ldw(lhs + k), ldw(p + M_W4 + k * 32 + j), acc); }
 #pragma unroll
         for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (sub == 0) {
-            if (idx >= 4096) acc += __ldcg(p + M_B4 + j);
+            if (idx >= 4096) acc += ldw(p + M_B4 + j);
             uint16_t h, lo;
             split_scalar(acc, h, lo);
             const uint32_t off = G::wtile_off(2) + tile_off(j, i, G::N(2));
@@ -372,8 +395,8 @@ __device__ __forceinline__ void finish_mlp(const float* p, const float* red, flo
             float acc = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 g = __ldcg(reinterpret_cast<const float4*>(red + R_G34 + r * 32) + j4);
-                const float4 w = __ldcg(reinterpret_cast<const float4*>(p + M_W4 + tid * 32) + j4);
+                const float4 g = ldw(reinterpret_cast<const float4*>(red + R_G34 + r * 32) + j4);
+                const float4 w = ldw(reinterpret_cast<const float4*>(p + M_W4 + tid * 32) + j4);
                 acc = fmaf(g.x, w.x, acc); acc = fmaf(g.y, w.y, acc); acc = fmaf(g.z, w.z, acc); acc = fmaf(g.w, w.w, acc);
             }
             gradloss[M_W3 + r * 128 + tid] = acc;
@@ -382,25 +405,35 @@ __device__ __forceinline__ void finish_mlp(const float* p, const float* red, flo
             const int j = tid >> 4, sub = tid & 15;
             float acc = 0.f;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) { const int aa = sub + 16 * m; acc = fmaf(__ldcg(p + M_W3 + aa * 128 + r), __ldcg(red + R_G34 + aa * 32 + j), acc); }
+            for (int m = 0; m < 8; ++m) { const int aa = sub + 16 * m; acc = fmaf(ldw(p + M_W3 + aa * 128 + r), ldw(red + R_G34 + aa * 32 + j), acc); }
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (sub == 0) gradloss[M_W4 + r * 32 + j] = fmaf(__ldcg(p + M_B3 + r), __ldcg(red + R_g34 + j), acc);
+            if (sub == 0) gradloss[M_W4 + r * 32 + j] = fmaf(ldw(p + M_B3 + r), ldw(red + R_g34 + j), acc);
         }
     }
     constexpr int n_a = M_W3, n_b = M_W4 - M_B3, n_c = M_P + 1 - M_B4;       // [0, W3) | db3 | [db4 .. loss]
     for (int q = gthreads - 1 - gtid; q < n_a + n_b + n_c; q += gthreads) {
-        if (q < n_a) gradloss[q] = __ldcg(red + q);                  // dW1 db1 dW2 db2 share offsets
+        if (q < n_a) gradloss[q] = ldw(red + q);                  // dW1 db1 dW2 db2 share offsets
         else if (q < n_a + n_b) {                                    // db3[k] = sum_j W4[k][j] g34[j]
             const int k = q - n_a;
             float acc = 0.f;
 #pragma unroll 8
-            for (int j = 0; j < 32; ++j) acc = fmaf(__ldcg(p + M_W4 + k * 32 + j), __ldcg(red + R_g34 + j), acc);
+            for (int j = 0; j < 32; ++j) acc = fmaf(ldw(p + M_W4 + k * 32 + j), ldw(red + R_g34 + j), acc);
             gradloss[M_B3 + k] = acc;
         } else {
             const int i = M_B4 + (q - n_a - n_b);
-            gradloss[i] = i == M_P ? __ldcg(red + R_LOSS) : (i < M_W5 ? __ldcg(red + R_g34 + (i - M_B4)) : __ldcg(red + R_W5 + (i - M_W5)));
+            gradloss[i] = i == M_P ? ldw(red + R_LOSS) : (i < M_W5 ? ldw(red + R_g34 + (i - M_B4)) : ldw(red + R_W5 + (i - M_W5)));
         }
+    }
+}
+
+// phase timestamps of CTA 0 (globaltimer, ns) of the last launch -- read back with rb_debug_student_timers()
+__device__ unsigned long long g_st_timers[16];
+__device__ __forceinline__ void st_stamp(int i) {
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        g_st_timers[i] = t;
     }
 }
 
@@ -422,17 +455,20 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     const int gtid = blockIdx.x * ST_THREADS + tid, gthreads = gridDim.x * ST_THREADS;
 
     // ---- phase 0: TMEM, barrier, zeroed activations + ONES groups; fold and split the weights once for the whole grid -----
+    st_stamp(0);
     if (warp == 0) tmem_alloc<512>(&ctl.tmem_base);
     if (tid == 0) { mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); fence_mbar_init(); }
     for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     if constexpr (S::L == 4) fold_into_image(a.params, a.wimg, gtid, gthreads);       // SpecMLP: W34, b34
     LayerLoop<S>::build_image(a, gtid, gthreads);
+    st_stamp(1);
     grid.sync();
+    st_stamp(2);
     if (tid < ST_TILE) {
 #pragma unroll
         for (int l = 0; l < L; ++l) *reinterpret_cast<uint16_t*>(act_hi + (S::slot(l) + G::ig(l)) * 2048 + tid * 16) = (uint16_t)0x3F80u;
     }
-    for (int i = tid; i < 2 * G::wtile_bytes() / 16; i += ST_THREADS) reinterpret_cast<uint4*>(w_hi)[i] = __ldcg(reinterpret_cast<const uint4*>(a.wimg) + i);
+    for (int i = tid; i < 2 * G::wtile_bytes() / 16; i += ST_THREADS) reinterpret_cast<uint4*>(w_hi)[i] = ldw(reinterpret_cast<const uint4*>(a.wimg) + i);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -444,6 +480,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     float loss_acc = 0.f;
     bool first = true;
 
+    st_stamp(3);
     const int64_t ntiles = (a.B + ST_TILE - 1) / ST_TILE;
     // software prefetch of the next tile's inputs (SpecMLP: one float4 of x per thread) while the current tile computes
     float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -565,6 +602,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         first = false;
     }
 
+    st_stamp(4);
     if (!a.fwd_only) {
         // ---- this CTA's partial gradient + loss -> global ---------------------------------------------------------------------
         float* part_out = a.partials + (size_t)blockIdx.x * a.pstride;
@@ -576,26 +614,37 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         if (lane == 0) ctl.red[warp] = v;
         __syncthreads();
         if (tid == 0) part_out[a.ploss] = (ctl.red[0] + ctl.red[1]) + (ctl.red[2] + ctl.red[3]);     // part 0 = warps 0..3
+        st_stamp(5);
         grid.sync();
-        // ---- grid-wide reduction of the partial vectors: 8 lanes per element, CTA order, fixed tree => bit-reproducible -----------
+        st_stamp(6);
+        // ---- grid-wide reduction of the partial vectors in CTA order with a fixed tree => bit-reproducible.  A warp owns 32
+        // consecutive elements (coalesced 128-byte reads of every partial); 8 warps split the partials, shared memory combines them.
         {
-            const int nparts = (int)min((int64_t)gridDim.x, ntiles), l8 = gtid & 7;
-            for (int i = gtid >> 3; i < ((a.pstride + 3) & ~3); i += gthreads >> 3) {
+            float* red2 = reinterpret_cast<float*>(act_hi);                 // 16 x 32 floats of scratch (activations are dead here)
+            const int nparts = (int)min((int64_t)gridDim.x, ntiles), sl = warp & 7;
+            const int nblk = (a.pstride + 31) / 32;
+            for (int eb0 = blockIdx.x * 2; eb0 < nblk; eb0 += gridDim.x * 2) {
+                const int i = (eb0 + (warp >> 3)) * 32 + lane;
                 float acc = 0.f;
                 if (i < a.pstride)
-                    for (int b = l8; b < nparts; b += 8) acc += __ldcg(a.partials + (size_t)b * a.pstride + i);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 4);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 2);
-                acc += __shfl_xor_sync(0xffffffffu, acc, 1);
-                if (l8 == 0 && i < a.pstride) a.red[i] = acc;
+                    for (int b = sl; b < nparts; b += 8) acc += ldw(a.partials + (size_t)b * a.pstride + i);
+                red2[warp * 32 + lane] = acc;
+                __syncthreads();
+                if (sl == 0 && i < a.pstride) {
+                    const float* r = red2 + (warp >> 3) * 256 + lane;
+                    a.red[i] = ((r[0] + r[32]) + (r[64] + r[96])) + ((r[128] + r[160]) + (r[192] + r[224]));
+                }
+                __syncthreads();
             }
         }
+        st_stamp(7);
         grid.sync();
+        st_stamp(8);
         // ---- gradient of the un-folded parameters ---------------------------------------------------------------------------------
         float* gl = a.world > 1 ? a.peer_gl[a.rank] : a.gradloss;          // data parallel: this rank's slot of the symmetric buffer
         if constexpr (S::L == 4) finish_mlp(a.params, a.red, gl, gtid, gthreads);
         else
-            for (int i = gtid; i <= a.P; i += gthreads) gl[i] = __ldcg(a.red + i);
+            for (int i = gtid; i <= a.P; i += gthreads) gl[i] = ldw(a.red + i);
         if (a.world > 1) {
             // ---- one-shot all-reduce over NVLink peer memory (MpiAdam.update's Allreduce, backup/student_rollout.py:709) ----------
             grid.sync();                                                   // the whole local gradient is written (gpu scope)
@@ -611,32 +660,38 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
                 a.gradloss[i] = tot;
             }
         }
+        st_stamp(9);
         if (a.do_adam) {                   // TF1 Adam, same arithmetic as k_adam (student.cu)
             if (a.world <= 1) grid.sync(); // every read of the old parameters (finish) is done, every gradloss entry written
             else __syncthreads();          // (the exchange above already separated finish from here; own-thread gradloss entries)
             for (int i = gtid; i < a.P; i += gthreads) {
                 float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
-                adam_update(pi, mi, vi, a.world > 1 ? a.gradloss[i] : __ldcg(a.gradloss + i), a.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                adam_update(pi, mi, vi, a.world > 1 ? a.gradloss[i] : ldw(a.gradloss + i), a.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
                 a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
             }
         }
     }
+    st_stamp(10);
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<512>(tmem);
+    st_stamp(11);
 }
 
 template <class S> static size_t student_tc_smem() { return 2 * (size_t)ST_ACT_BYTES + 2 * (size_t)Geo<S>::wtile_bytes() + sizeof(StudentTcCtl); }
 
+constexpr int ST_MAX_GRID = 160;
 static int tc_grid(int64_t B, int* grid) {
     int device = 0, sms = 148;
     RB_CUDA(cudaGetDevice(&device));
     RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    *grid = (int)min((int64_t)min(sms, 160), (B + ST_TILE - 1) / ST_TILE);
+    // always one CTA per SM: CTAs without a tile still share the grid-wide phases (fold, weight image, reduction, un-fold, Adam),
+    // which would otherwise run on a handful of CTAs for small batches (a 128-sample step took 630 us on a single CTA)
+    (void)B;
+    *grid = min(sms, ST_MAX_GRID);
     return RB_OK;
 }
 
-constexpr int ST_MAX_GRID = 160;
 // workspace (floats): [fold 4160][reduced 8192][weight image 12288 (48 KB)][partials ST_MAX_GRID * 8192]
 constexpr size_t WS_FOLD = 0, WS_RED = 4160, WS_IMG = WS_RED + 8192, WS_PART = WS_IMG + 12288, WS_PSTRIDE_MAX = 8192;
 
@@ -680,7 +735,7 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
         a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
         a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
         a.pw[0] = R_W1; a.pb[0] = R_B1; a.pw[1] = R_W2; a.pb[1] = R_B2; a.pw[2] = R_G34; a.pb[2] = R_g34; a.pw[3] = R_W5; a.pb[3] = R_B5;
-        a.ploss = R_LOSS; a.pstride = R_LOSS + 1; a.P = M_P;
+        a.ploss = R_LOSS; a.pstride = R_N; a.P = M_P;            // R_N: multiple of 4 floats, keeps every CTA's partial 16-byte aligned
         return launch_student_tc<SpecMLP>(a, grid, st);
     }
     const PolicyOffsets o = policy_offsets(4);
@@ -694,6 +749,15 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
 }
 
 }  // namespace rb
+
+// debug: phase timestamps (ns) of CTA 0 of the last k_student_tc launch: 0 start, 1 image built, 2 after sync, 3 image loaded, 4 tiles done,
+// 5 partials written, 6 after sync, 7 reduced, 8 after sync, 9 un-folded, 10 Adam done, 11 end
+extern "C" int rb_debug_student_timers(unsigned long long* host_out16) {
+    RB_REQUIRE(host_out16 != nullptr, "NULL argument");
+    RB_CUDA(cudaDeviceSynchronize());
+    RB_CUDA(cudaMemcpyFromSymbol(host_out16, rb::g_st_timers, sizeof(unsigned long long) * 16));
+    return RB_OK;
+}
 
 extern "C" int rb_student_mode_available(int mode) { return mode == RB_MODE_FP32 || mode == RB_MODE_TC; }
 extern "C" int rb_mode_available(int mode) { return mode == RB_MODE_FP32 || mode == RB_MODE_TC; }

@@ -17,3 +17,16 @@ for kind, name in ((STUDENT_MLP, "mlp"), (STUDENT_POLICY64, "policy64")):
             e1.record(); torch.cuda.synchronize()
             us = e0.elapsed_time(e1) * 1e3 / 50
             print("%-9s B=%6d %-9s %7.1f us  %.3e samples/s" % (name, B, nm, us, B / us * 1e6), flush=True)
+
+# phase breakdown of the cooperative kernel (CTA 0, globaltimer)
+import ctypes
+from reacherdistilation_b200._lib import lib
+names = ["fold+image", "sync", "image load", "tiles", "dump", "sync", "reduce", "sync", "un-fold", "sync+adam", "teardown"]
+for B in (128, 32768, 262144):
+    net = StudentNet(kind=STUDENT_MLP, seed=1, mode=MODE_TC)
+    x = torch.randn((B, 16), device="cuda"); t = torch.randn((B, 4), device="cuda") * 0.3
+    for _ in range(5): net.step(x, t)
+    buf = (ctypes.c_ulonglong * 16)()
+    lib().rb_debug_student_timers(buf)
+    ts = [buf[i] for i in range(12)]
+    print("B=%d phases (us): " % B + ", ".join("%s %.1f" % (n, (ts[i + 1] - ts[i]) / 1e3) for i, n in enumerate(names)) + "  total %.1f" % ((ts[11] - ts[0]) / 1e3))
