@@ -169,8 +169,8 @@ int rb_student_step_dp(int kind, float* params_dev, float* m_dev, float* v_dev, 
                        float beta2, float eps, float grad_scale, int rank, int world, const uint64_t* peer_grad_slots,
                        const uint64_t* peer_flags, uint32_t epoch, void* stream);
 
-/* Debug aid: globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last RB_MODE_TC student launch (16 values; see
- * student_tc.cu).  Synchronises the device.                                                                            */
+/* Debug aid: globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last RB_MODE_TC student launch (48 values: [0,12) launch phases, [16,31) phases of
+ * CTA 0's first tile; see student_tc.cu).  Synchronises the device.                                                                            */
 int rb_debug_student_timers(unsigned long long* host_out16);
 
 /* ------------------------------------------------------------------------------------------------ DAgger --

@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
-        if (tid == 0) {
+        if (warp == 0 && elect_one_sync()) {
             fence_after_sync();
             const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll

@@ -112,14 +112,15 @@ __device__ inline void policy_tc_load_weights(TcShared& S, const float* __restri
 __device__ __forceinline__ void issue_bf16x3(uint32_t tmem_d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int ksteps, int n_rows_b,
                                              uint32_t idesc, uint32_t acc) {
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)n_rows_b * 16;
+    uint64_t dah = make_smem_desc(ah, a_lbo, 128), dal = make_smem_desc(al, a_lbo, 128);
+    uint64_t dbh = make_smem_desc(bh, b_lbo, 128), dbl = make_smem_desc(bl, b_lbo, 128);
 #pragma unroll
     for (int ks = 0; ks < ksteps; ++ks) {
-        const uint64_t dah = make_smem_desc(ah + ks * 2 * a_lbo, a_lbo, 128), dal = make_smem_desc(al + ks * 2 * a_lbo, a_lbo, 128);
-        const uint64_t dbh = make_smem_desc(bh + ks * 2 * b_lbo, b_lbo, 128), dbl = make_smem_desc(bl + ks * 2 * b_lbo, b_lbo, 128);
         mma_bf16(tmem_d, dah, dbh, idesc, acc);
         mma_bf16(tmem_d, dal, dbh, idesc, 1);
         mma_bf16(tmem_d, dah, dbl, idesc, 1);
         acc = 1;
+        dah = desc_advance(dah, 2 * a_lbo); dal = desc_advance(dal, 2 * a_lbo); dbh = desc_advance(dbh, 2 * b_lbo); dbl = desc_advance(dbl, 2 * b_lbo);
     }
 }
 
@@ -209,7 +210,7 @@ template <int NOUT> __device__ __forceinline__ void final_epilogue(const TcShare
 
 // Full policy evaluation for one tile.  Every ACTIVE thread of the tile must call this (it contains the tile barrier,
 // `bar_threads` = 32 * active warps of the tile).  ob: this thread's 11-d observation.  pd: (mean0, mean1, logstd0,
-// logstd1) or the four raw outputs.  issuer: exactly one active thread of the tile.
+// logstd1) or the four raw outputs.  issuer: true for exactly one (whole, active) warp of the tile; one elected lane issues the MMAs.
 template <int NOUT>
 __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile, int row, int bar_threads, bool issuer, const float* ob,
                                                float* pd, uint32_t& phase) {
@@ -238,7 +239,7 @@ __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile,
         fence_async_smem();
         fence_before_sync();
         tile_sync(1 + tile, bar_threads);
-        if (issuer) {
+        if (issuer && elect_one_sync()) {                           // `issuer` is warp-uniform: one whole warp of the tile
             fence_after_sync();
             const uint32_t idesc = make_idesc_bf16(128, 64);
             if (layer == 0) {
@@ -318,7 +319,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_policy_fwd_tc(const float* __re
         float ob[OBS], pd[4];
         warp_load_rows<OBS>(obs, row0, nvalid, ob, strip, lane);
         __syncwarp();
-        policy_tc_eval<NOUT>(S, T, tile, row, TILE, row == 0, ob, pd, phase);
+        policy_tc_eval<NOUT>(S, T, tile, row, TILE, row < 32, ob, pd, phase);
         if (i < n) pd_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
     }
     policy_tc_teardown<NT>(S);
@@ -364,7 +365,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, co
             if (KIND == RB_STUDENT_POLICY64 && x_out != obs_out) warp_store_rows<OBS>(x_out, row0, nvalid, ob, strip, lane);
         }
         __syncwarp();
-        policy_tc_eval<2>(S, T, tile, row, TILE, row == 0, ob, pd, phase);
+        policy_tc_eval<2>(S, T, tile, row, TILE, row < 32, ob, pd, phase);
         if (valid) {
             t_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
             if (KIND == RB_STUDENT_MLP) {
@@ -417,7 +418,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
             observe(e, ob);
             if (obs_buf) warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strip, lane);
             __syncwarp();
-            policy_tc_eval<NOUT>(S, Tl, tile, row, bar_threads, row == 0, ob, pd, phase);
+            policy_tc_eval<NOUT>(S, Tl, tile, row, bar_threads, row < 32, ob, pd, phase);
             bool d;
             const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
             const int64_t r = (int64_t)t * n + i;

@@ -140,11 +140,13 @@ template <class S, int l> __device__ __forceinline__ void issue_fwd(uint32_t tme
     constexpr int K = G::K(l), N = G::N(l);
     const uint32_t idesc = make_idesc_bf16_ex(128, N, 0, 0);
     const uint32_t a0 = S::slot(l) * 2048, b0 = G::wtile_off(l);
+    uint64_t dah = make_smem_desc(act_hi + a0, 2048, 128), dal = make_smem_desc(act_lo + a0, 2048, 128);
+    uint64_t dbh = make_smem_desc(w_hi + b0, N * 16, 128), dbl = make_smem_desc(w_lo + b0, N * 16, 128);
 #pragma unroll
     for (int ks = 0; ks < K / 16; ++ks) {
-        const uint32_t ao = a0 + ks * 2 * 2048, bo = b0 + ks * 2 * (N * 16);
-        mma3(tmem, make_smem_desc(act_hi + ao, 2048, 128), make_smem_desc(act_lo + ao, 2048, 128), make_smem_desc(w_hi + bo, N * 16, 128),
-             make_smem_desc(w_lo + bo, N * 16, 128), idesc, ks > 0);
+        mma3(tmem, dah, dal, dbh, dbl, idesc, ks > 0);
+        dah = desc_advance(dah, 2 * 2048); dal = desc_advance(dal, 2 * 2048);
+        dbh = desc_advance(dbh, 2 * N * 16); dbl = desc_advance(dbl, 2 * N * 16);
     }
 }
 // dX_l[128, inpad] = dZ_l[128, N_l] * W_l^T : A = dZ window (K-major), B = weight tile through an MN-major descriptor
@@ -153,42 +155,47 @@ template <class S, int l> __device__ __forceinline__ void issue_dgrad(uint32_t t
     constexpr int N = G::N(l), NP = G::inpad(l);
     const uint32_t idesc = make_idesc_bf16_ex(128, NP, 0, 1);
     const uint32_t a0 = G::dzslot(l) * 2048, b0 = G::wtile_off(l);
+    uint64_t dah = make_smem_desc(act_hi + a0, 2048, 128), dal = make_smem_desc(act_lo + a0, 2048, 128);
+    uint64_t dbh = make_smem_desc(w_hi + b0, 128, N * 16), dbl = make_smem_desc(w_lo + b0, 128, N * 16);
 #pragma unroll
     for (int ks = 0; ks < N / 16; ++ks) {
-        const uint32_t ao = a0 + ks * 2 * 2048, bo = b0 + ks * 2 * 128;
-        mma3(tmem, make_smem_desc(act_hi + ao, 2048, 128), make_smem_desc(act_lo + ao, 2048, 128), make_smem_desc(w_hi + bo, 128, N * 16),
-             make_smem_desc(w_lo + bo, 128, N * 16), idesc, ks > 0);
+        mma3(tmem, dah, dal, dbh, dbl, idesc, ks > 0);
+        dah = desc_advance(dah, 2 * 2048); dal = desc_advance(dal, 2 * 2048);
+        dbh = desc_advance(dbh, 2 * 128); dbl = desc_advance(dbl, 2 * 128);
     }
 }
 // G_l += (see Geo::wq): both operands are MN-major windows of ACT, K = the 128 samples of the tile
 template <class S, int l> __device__ __forceinline__ void issue_wgrad(uint32_t tmem, uint32_t act_hi, uint32_t act_lo, uint32_t first) {
     using G = Geo<S>;
     const uint32_t xs = S::slot(l) * 2048, zs = G::dzslot(l) * 2048, d = tmem + G::gcol(l);
+    const uint32_t acc0 = first ? 0u : 1u;
     if constexpr (G::wq(l)) {
         const uint32_t idesc = make_idesc_bf16_ex(128, G::N(l), 1, 1);                 // D[in|1, out] += [X_l | 1]^T dZ_l
+        uint64_t dah = make_smem_desc(act_hi + xs, 128, 2048), dal = make_smem_desc(act_lo + xs, 128, 2048);
+        uint64_t dbh = make_smem_desc(act_hi + zs, 128, 2048), dbl = make_smem_desc(act_lo + zs, 128, 2048);
 #pragma unroll
         for (int ks = 0; ks < ST_TILE / 16; ++ks) {
-            const uint32_t ao = xs + ks * 256, bo = zs + ks * 256;
-            mma3(d, make_smem_desc(act_hi + ao, 128, 2048), make_smem_desc(act_lo + ao, 128, 2048), make_smem_desc(act_hi + bo, 128, 2048),
-                 make_smem_desc(act_lo + bo, 128, 2048), idesc, (ks > 0) || !first);
+            mma3(d, dah, dal, dbh, dbl, idesc, ks > 0 ? 1u : acc0);
+            dah = desc_advance(dah, 256); dal = desc_advance(dal, 256); dbh = desc_advance(dbh, 256); dbl = desc_advance(dbl, 256);
         }
         if constexpr (G::wq_extra(l)) {                                                // D2[out, 16] += dZ_l^T [1 | .]  (column 0 = bias gradient)
             const uint32_t idesc2 = make_idesc_bf16_ex(128, 16, 1, 1), os = (S::slot(l) + G::ig(l)) * 2048;
+            uint64_t eah = make_smem_desc(act_hi + zs, 128, 2048), eal = make_smem_desc(act_lo + zs, 128, 2048), ebh = make_smem_desc(act_hi + os, 128, 2048);
 #pragma unroll
             for (int ks = 0; ks < ST_TILE / 16; ++ks) {
-                const uint32_t ao = zs + ks * 256, bo = os + ks * 256;
-                const uint64_t bh = make_smem_desc(act_hi + bo, 128, 2048);
-                mma_bf16(d + G::N(l), make_smem_desc(act_hi + ao, 128, 2048), bh, idesc2, (ks > 0) || !first);
-                mma_bf16(d + G::N(l), make_smem_desc(act_lo + ao, 128, 2048), bh, idesc2, 1);           // the lo half of ONES is zero
+                mma_bf16(d + G::N(l), eah, ebh, idesc2, ks > 0 ? 1u : acc0);
+                mma_bf16(d + G::N(l), eal, ebh, idesc2, 1);                                          // the lo half of ONES is zero
+                eah = desc_advance(eah, 256); eal = desc_advance(eal, 256); ebh = desc_advance(ebh, 256);
             }
         }
     } else {
         const uint32_t idesc = make_idesc_bf16_ex(128, G::K(l), 1, 1);                 // D[out, in|1] += dZ_l^T [X_l | 1 | .]
+        uint64_t dah = make_smem_desc(act_hi + zs, 128, 2048), dal = make_smem_desc(act_lo + zs, 128, 2048);
+        uint64_t dbh = make_smem_desc(act_hi + xs, 128, 2048), dbl = make_smem_desc(act_lo + xs, 128, 2048);
 #pragma unroll
         for (int ks = 0; ks < ST_TILE / 16; ++ks) {
-            const uint32_t ao = zs + ks * 256, bo = xs + ks * 256;
-            mma3(d, make_smem_desc(act_hi + ao, 128, 2048), make_smem_desc(act_lo + ao, 128, 2048), make_smem_desc(act_hi + bo, 128, 2048),
-                 make_smem_desc(act_lo + bo, 128, 2048), idesc, (ks > 0) || !first);
+            mma3(d, dah, dal, dbh, dbl, idesc, ks > 0 ? 1u : acc0);
+            dah = desc_advance(dah, 256); dal = desc_advance(dal, 256); dbh = desc_advance(dbh, 256); dbl = desc_advance(dbl, 256);
         }
     }
 }
@@ -428,7 +435,7 @@ __device__ __forceinline__ void finish_mlp(const float* p, const float* red, flo
 }
 
 // phase timestamps of CTA 0 (globaltimer, ns) of the last launch -- read back with rb_debug_student_timers()
-__device__ unsigned long long g_st_timers[16];
+__device__ unsigned long long g_st_timers[48];
 __device__ __forceinline__ void st_stamp(int i) {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         unsigned long long t;
@@ -491,6 +498,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * ST_TILE;
         const int nvalid = (int)min((int64_t)ST_TILE, a.B - base);
+        const bool prof = tile == blockIdx.x;
+#define RB_TS(i) do { if (prof) st_stamp(16 + (i)); } while (0)
+        RB_TS(0);
         // ---- X0: global fp32 -> (obfilter) -> bf16 hi/lo rows ---------------------------------------------------------------
         if constexpr (S::IN0 == 16) {
             const int r = tid >> 2, q = tid & 3;                       // 4 threads per sample row, 4 features each
@@ -523,22 +533,25 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        RB_TS(1);
 
         // ---- forward ----------------------------------------------------------------------------------------------------
 #define RB_ST_FWD(l)                                                               \
         if constexpr (l < L) {                                                     \
-            if (tid == 0) {                                                        \
+            if (warp == 0 && elect_one_sync()) {                                   \
                 fence_after_sync();                                                \
                 issue_fwd<S, (l < L ? l : 0)>(tmem, ah, al, wh, wl);               \
                 mma_commit(&ctl.mbar);                                             \
             }                                                                      \
             mbar_wait(&ctl.mbar, phase); phase ^= 1u;                              \
             fence_after_sync();                                                    \
+            RB_TS(2 + 2 * l);                                                      \
             if constexpr (l < L - 1) {                                             \
                 epi_fwd<S, (l < L - 1 ? l : 0)>(tacc, act_hi, act_lo, row, part);  \
                 fence_async_smem();                                                \
                 fence_before_sync();                                               \
                 __syncthreads();                                                   \
+                RB_TS(3 + 2 * l);                                                  \
             }                                                                      \
         }
         RB_ST_FWD(0) RB_ST_FWD(1) RB_ST_FWD(2) RB_ST_FWD(3)
@@ -569,12 +582,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        RB_TS(10);
         if (a.fwd_only) continue;
 
         // ---- backward: wgrad_l (accumulates in TMEM) + dgrad_l, then dZ_{l-1} in place over X_l ------------------------------
 #define RB_ST_BWD(l)                                                               \
         if constexpr (l < L) {                                                     \
-            if (tid == 0) {                                                        \
+            if (warp == 0 && elect_one_sync()) {                                   \
                 fence_after_sync();                                                \
                 if constexpr (l > 0) {                                             \
                     issue_dgrad<S, (l < L ? l : 0)>(tmem, ah, al, wh, wl);         \
@@ -596,6 +610,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             }                                                                      \
             fence_before_sync();                                                   \
             __syncthreads();                                                       \
+            RB_TS(14 - l);                                                         \
         }
         RB_ST_BWD(3) RB_ST_BWD(2) RB_ST_BWD(1) RB_ST_BWD(0)
 #undef RB_ST_BWD
@@ -752,10 +767,10 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
 
 // debug: phase timestamps (ns) of CTA 0 of the last k_student_tc launch: 0 start, 1 image built, 2 after sync, 3 image loaded, 4 tiles done,
 // 5 partials written, 6 after sync, 7 reduced, 8 after sync, 9 un-folded, 10 Adam done, 11 end
-extern "C" int rb_debug_student_timers(unsigned long long* host_out16) {
+extern "C" int rb_debug_student_timers(unsigned long long* host_out16) {   // 48 values: [0,12) launch phases, [16,31) first tile of CTA 0
     RB_REQUIRE(host_out16 != nullptr, "NULL argument");
     RB_CUDA(cudaDeviceSynchronize());
-    RB_CUDA(cudaMemcpyFromSymbol(host_out16, rb::g_st_timers, sizeof(unsigned long long) * 16));
+    RB_CUDA(cudaMemcpyFromSymbol(host_out16, rb::g_st_timers, sizeof(unsigned long long) * 48));
     return RB_OK;
 }
 

@@ -26,6 +26,23 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t saddr, uint32_t lbo_
     return d;
 }
 
+// advance a descriptor's start address by `bytes` (multiple of 16; the 14-bit field cannot overflow for shared-memory addresses)
+__device__ __forceinline__ uint64_t desc_advance(uint64_t d, uint32_t bytes) { return d + (uint64_t)(bytes >> 4); }
+
+// One lane of a converged warp (elect.sync).  tcgen05.mma / commit issued under this predicate compile to a single UTCHMMA; under a
+// per-thread condition such as `threadIdx.x == 0` ptxas wraps every MMA in an ELECT / BRA.U.ANY waterfall loop (~50 cycles each).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "elect.sync _|P, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(pred));
+    return pred != 0;
+}
+
 // instruction descriptor, kind::f16: D fp32, A/B bf16, both K-major, dense
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);

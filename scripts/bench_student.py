@@ -26,7 +26,10 @@ for B in (128, 32768, 262144):
     net = StudentNet(kind=STUDENT_MLP, seed=1, mode=MODE_TC)
     x = torch.randn((B, 16), device="cuda"); t = torch.randn((B, 4), device="cuda") * 0.3
     for _ in range(5): net.step(x, t)
-    buf = (ctypes.c_ulonglong * 16)()
+    buf = (ctypes.c_ulonglong * 48)()
     lib().rb_debug_student_timers(buf)
     ts = [buf[i] for i in range(12)]
     print("B=%d phases (us): " % B + ", ".join("%s %.1f" % (n, (ts[i + 1] - ts[i]) / 1e3) for i, n in enumerate(names)) + "  total %.1f" % ((ts[11] - ts[0]) / 1e3))
+    tn = ["x0+sync", "L0 mma", "L0 epi", "L1 mma", "L1 epi", "L2 mma", "L2 epi", "L3 mma", "(skip)", "out epi", "bwd3", "bwd2", "bwd1", "bwd0"]
+    tt = [buf[16 + i] for i in range(15)]
+    print("   first tile (us): " + ", ".join("%s %.2f" % (n, (tt[i + 1] - tt[i]) / 1e3) for i, n in enumerate(tn) if n != "(skip)" and tt[i + 1] >= tt[i]))
