@@ -717,6 +717,9 @@ template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cuda
     const size_t smem = student_tc_smem<S>();
     static bool attr = false;
     if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static int occ = -1;                           // a cooperative grid must be co-resident: check once that one CTA per SM fits
+    if (occ < 0) RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_student_tc<S>, ST_THREADS, smem));
+    RB_REQUIRE(occ >= 1, "k_student_tc does not fit on this device (shared memory / registers)");
     void* args[] = {(void*)&a};
     RB_CUDA(cudaLaunchCooperativeKernel((const void*)k_student_tc<S>, dim3(grid), dim3(ST_THREADS), args, smem, st));
     return RB_OK;
