@@ -187,6 +187,15 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params_dev, uint32_t it
 /* RB_MODE_TC observe caches the split-weight image of the (frozen, teacher.py:17-20) teacher keyed by the parameter POINTER;
  * call this after modifying the teacher parameters in place.                                                                */
 int rb_dagger_invalidate_teacher(rb_dagger* d);
+/* One whole DAgger iteration (RB_MODE_TC): rb_dagger_observe + rb_student_step[_dp] + rb_dagger_act, with every per-step quantity
+ * (dropout iteration, Adam step, exchange epoch / slot parity) read from a device-side clock set once by rb_dagger_set_clock and
+ * advanced by the last kernel -- so the three launches are captured ONCE in a CUDA graph (use_graph != 0) and replayed with a single
+ * cudaGraphLaunch per iteration.  world > 1: slots_even / slots_odd / flags as in rb_student_step_dp (the two slot sets alternate). */
+int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_step, uint32_t epoch, void* stream);
+int rb_dagger_step(rb_dagger* d, const float* teacher_params_dev, float* params_dev, float* m_dev, float* v_dev, float* gradloss_dev,
+                   void* workspace_dev, float* obs_dev, float* t_pdflat_dev, float* x_dev, float* s_pdflat_dev, float* rew_dev, uint8_t* done_dev,
+                   int loss_kind, float lr, float beta1, float beta2, float eps, float grad_scale, int rank, int world,
+                   const uint64_t* slots_even, const uint64_t* slots_odd, const uint64_t* flags, int use_graph, void* stream);
 int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
                   void* stream);
 

@@ -1,6 +1,8 @@
 // Lock-step DAgger iteration pieces: observe (ob, teacher label, student input) and act (step with the student mean).
 // Replaces the per-env-step body of /root/reference src/distilation/mlp_train.py:143-204 (teacher label :165-167, record
 // :188-193 with dataset.py:118-143 `prev` / `prew` semantics, env.step(s_ac) :196) for N envs at once.
+#include <cstring>
+
 #include "common.cuh"
 #include "dagger_input.cuh"
 #include "physics.cuh"
@@ -15,6 +17,11 @@ struct rb_dagger {
     float4* prev_t = nullptr;      // teacher pdflat of the previous record of the current episode
     float* prev_rec_rew = nullptr; // 'rew' field of the previous record
     float* last_reward = nullptr;  // reward returned by the last env.step (not cleared at reset, mlp_train.py:114,196)
+    // rb_dagger_step: device-side step clock {iteration, adam step, exchange epoch} and the captured CUDA graph of one iteration
+    uint32_t* clock = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t gkey = 0;
+    cudaStream_t cap_stream = nullptr;   // capture happens here (the legacy default stream cannot be captured); replay on the caller's stream
 };
 
 namespace rb {
@@ -38,8 +45,9 @@ __global__ void k_dagger_input(int64_t n, const uint2* __restrict__ ctr, const f
 __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint2* ctr, const float4* __restrict__ s_pd,
                                                     const float4* __restrict__ t_pd, float4* prev_t, float* prev_rec_rew, float* last_reward,
                                                     float* __restrict__ rew, uint8_t* __restrict__ done, uint32_t k0, uint32_t k1,
-                                                    uint32_t offset) {
+                                                    uint32_t offset, uint32_t* clock) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (clock && i == 0) { clock[0] += 1u; clock[1] += 1u; clock[2] += 1u; }      // end of the iteration: advance the device-side step clock
     if (i >= n) return;
     EnvState e = load_state(qv, tp, ctr, i);
     const float4 sp = __ldg(s_pd + i);
@@ -53,11 +61,22 @@ __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float
     if (done) done[i] = d ? 1 : 0;
 }
 
+__global__ void k_set_clock(uint32_t* clock, uint32_t iteration, uint32_t adam_t, uint32_t epoch) {
+    clock[0] = iteration; clock[1] = adam_t; clock[2] = epoch; clock[3] = 0u;
+}
+
+// implemented in student_tc.cu
+struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
+struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
+struct StepClock { const uint32_t* clock; float lr; };
+int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
+                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, cudaStream_t st);
+
 // implemented in policy_tc.cu
 size_t policy_tc_image_bytes();
 int policy_tc_build_image(const float* params, int nout, void* img, cudaStream_t s);
 int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, float keep_prob, const float4* prev_t, const float* prev_rec_rew,
-                      uint32_t iteration, float* obs, float* t_pd, float* x, cudaStream_t s);
+                      uint32_t iteration, const uint32_t* clock, float* obs, float* t_pd, float* x, cudaStream_t s);
 
 }  // namespace rb
 
@@ -85,7 +104,9 @@ int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_
 
 int rb_dagger_destroy(rb_dagger* d) {
     if (!d) return RB_OK;
-    cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward); cudaFree(d->teacher_img);
+    cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward); cudaFree(d->teacher_img); cudaFree(d->clock);
+    if (d->gexec) cudaGraphExecDestroy(d->gexec);
+    if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
     delete d;
     return RB_OK;
 }
@@ -100,7 +121,7 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iterat
             if (rc0) return rc0;
             d->teacher_img_src = teacher_params;
         }
-        return dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, iteration, obs, t_pd, x,
+        return dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, iteration, nullptr, obs, t_pd, x,
                                  (cudaStream_t)stream);
     }
     int rc = rb_env_observe(e, obs, stream);
@@ -129,8 +150,76 @@ int rb_dagger_act(rb_dagger* d, const float* s_pd, const float* t_pd, float* rew
     rb_env* e = d->env;
     k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd,
                                                                                   d->prev_t, d->prev_rec_rew, d->last_reward, rew, done,
-                                                                                  (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset);
+                                                                                  (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset, nullptr);
     RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_t, uint32_t epoch, void* stream) {
+    RB_REQUIRE(d != nullptr, "NULL argument");
+    if (!d->clock) RB_CUDA(cudaMalloc(&d->clock, 4 * sizeof(uint32_t)));
+    k_set_clock<<<1, 1, 0, (cudaStream_t)stream>>>(d->clock, iteration, adam_t, epoch);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+// One whole DAgger iteration (observe + teacher label + student input | student loss, gradient [, peer all-reduce], Adam | env step) as
+// three launches that take every per-step quantity from the device-side clock, so the sequence is captured once in a CUDA graph and
+// replayed with a single cudaGraphLaunch.
+int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, float* m, float* v, float* gradloss, void* ws, float* obs, float* t_pd,
+                   float* x, float* s_pd, float* rew, uint8_t* done, int loss_kind, float lr, float b1, float b2, float eps, float gscale, int rank,
+                   int world, const uint64_t* slots_even, const uint64_t* slots_odd, const uint64_t* flags, int use_graph, void* stream) {
+    RB_REQUIRE(d && teacher_params && params && m && v && gradloss && ws && obs && t_pd && x && s_pd, "NULL argument");
+    RB_REQUIRE(d->clock != nullptr, "call rb_dagger_set_clock first");
+    RB_REQUIRE(world == 1 || (world >= 2 && world <= 8 && slots_even && slots_odd && flags), "data parallel: 2..8 ranks with peer slots and flags");
+    rb_env* e = d->env;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (!d->teacher_img) RB_CUDA(cudaMalloc(&d->teacher_img, policy_tc_image_bytes()));
+    if (d->teacher_img_src != teacher_params) {
+        int rc0 = policy_tc_build_image(teacher_params, 2, d->teacher_img, st);
+        if (rc0) return rc0;
+        d->teacher_img_src = teacher_params;
+    }
+    auto issue = [&](cudaStream_t st) -> int {
+        int rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, st);
+        if (rc) return rc;
+        const AdamFuse af{params, m, v, 0.f, b1, b2, eps, gscale};
+        const PeerExchange px{world, rank, 0u, slots_even, flags, slots_odd};
+        const StepClock clk{d->clock, lr};
+        rc = student_tc_run(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, st);
+        if (rc) return rc;
+        k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, st>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd, d->prev_t,
+                                                                      d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed,
+                                                                      (uint32_t)(e->seed >> 32), e->offset, d->clock);
+        RB_CUDA(cudaGetLastError());
+        return RB_OK;
+    };
+    if (!use_graph) return issue(st);
+    // graph key: everything the captured launches bake in
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t vv) { key = (key ^ vv) * 1099511628211ull; };
+    const void* ptrs[] = {teacher_params, params, m, v, gradloss, ws, obs, t_pd, x, s_pd, rew, done, stream, slots_even, slots_odd, flags};
+    for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+    const float fl[] = {lr, b1, b2, eps, gscale};
+    for (float f : fl) { uint32_t u; memcpy(&u, &f, 4); mix(u); }
+    mix((uint64_t)loss_kind); mix((uint64_t)rank); mix((uint64_t)world);
+    if (world > 1) for (int r = 0; r < world; ++r) { mix(slots_even[r]); mix(slots_odd[r]); mix(flags[r]); }
+    if (!d->gexec || d->gkey != key) {
+        if (d->gexec) { cudaGraphExecDestroy(d->gexec); d->gexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        if (!d->cap_stream) RB_CUDA(cudaStreamCreateWithFlags(&d->cap_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaStreamSynchronize(st));                            // e.g. the teacher image build above
+        RB_CUDA(cudaStreamBeginCapture(d->cap_stream, cudaStreamCaptureModeRelaxed));
+        const int rc = issue(d->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(d->cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        const cudaError_t ci = cudaGraphInstantiate(&d->gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) { d->gexec = nullptr; return cuda_fail(ci, "cudaGraphInstantiate"); }
+        d->gkey = key;
+    }
+    RB_CUDA(cudaGraphLaunch(d->gexec, st));
     return RB_OK;
 }
 

@@ -335,8 +335,10 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, co
                                                                     const uint2* __restrict__ ctr, const void* __restrict__ teacher_img,
                                                                     const float4* __restrict__ prev_t, const float* __restrict__ prev_rec_rew,
                                                                     float keep_prob, uint32_t k0, uint32_t k1, uint32_t offset, uint32_t iteration,
-                                                                    float* __restrict__ obs_out, float4* __restrict__ t_out, float* __restrict__ x_out) {
+                                                                    const uint32_t* __restrict__ clock, float* __restrict__ obs_out,
+                                                                    float4* __restrict__ t_out, float* __restrict__ x_out) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
+    if (clock) iteration = clock[0];          // device-side step clock (CUDA-graph replay)
     TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
     TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
     policy_tc_setup_from_image<NT>(S, teacher_img);
@@ -478,7 +480,7 @@ int policy_tc_build_image(const float* params, int nout, void* img, cudaStream_t
 }
 
 int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, float keep_prob, const float4* prev_t, const float* prev_rec_rew,
-                      uint32_t iteration, float* obs, float* t_pd, float* x, cudaStream_t s) {
+                      uint32_t iteration, const uint32_t* clock, float* obs, float* t_pd, float* x, cudaStream_t s) {
     constexpr int NT = FWD_NT;
     const int64_t ngroups = (e->n + NT * TILE - 1) / (NT * TILE);
     const unsigned grid = (unsigned)min((int64_t)e->sm_count * 2, ngroups);
@@ -488,12 +490,12 @@ int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, floa
         int rc = set_smem_attr(k_dagger_observe_tc<RB_STUDENT_MLP, NT>, smem);
         if (rc) return rc;
         k_dagger_observe_tc<RB_STUDENT_MLP, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, teacher_img, prev_t, prev_rec_rew, keep_prob, k0,
-                                                                            k1, e->offset, iteration, obs, (float4*)t_pd, x);
+                                                                            k1, e->offset, iteration, clock, obs, (float4*)t_pd, x);
     } else {
         int rc = set_smem_attr(k_dagger_observe_tc<RB_STUDENT_POLICY64, NT>, smem);
         if (rc) return rc;
         k_dagger_observe_tc<RB_STUDENT_POLICY64, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, teacher_img, prev_t, prev_rec_rew,
-                                                                                 keep_prob, k0, k1, e->offset, iteration, obs, (float4*)t_pd, x);
+                                                                                 keep_prob, k0, k1, e->offset, iteration, clock, obs, (float4*)t_pd, x);
     }
     RB_CUDA(cudaGetLastError());
     return RB_OK;

@@ -316,9 +316,10 @@ static int launch_student(const NetSpec& S, const float* params, const float* x,
 
 // implemented in student_tc.cu (tcgen05 path)
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
-struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; };
+struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
+struct StepClock { const uint32_t* clock; float lr; };
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
-                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, cudaStream_t st);
+                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, cudaStream_t st);
 size_t student_tc_workspace_floats();
 
 }  // namespace rb
@@ -365,7 +366,7 @@ int rb_student_fwd_ws(int kind, const float* params, const float* x, int64_t B, 
     RB_REQUIRE(params && x && s_pd, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
     if (B <= 0) return RB_OK;
-    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, ws, nullptr, nullptr, (cudaStream_t)stream);
+    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, ws, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
     return student_dispatch(kind, params, x, nullptr, B, 0, 1, s_pd, nullptr, nullptr, (cudaStream_t)stream);
 }
@@ -384,7 +385,7 @@ int rb_student_loss_grad(int kind, const float* params, const float* x, const fl
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
     RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
     RB_REQUIRE(B > 0, "empty batch");
-    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, nullptr, nullptr, (cudaStream_t)stream);
+    if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
     return student_dispatch(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, (cudaStream_t)stream);
 }
@@ -401,7 +402,7 @@ int rb_student_step(int kind, float* params, float* m, float* v, const float* x,
     RB_REQUIRE(B > 0 && t >= 1, "empty batch / bad step");
     if (mode == RB_MODE_TC) {
         const AdamFuse af{params, m, v, adam_lr_t(lr, b1, b2, t), b1, b2, eps, gscale};
-        return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, &af, nullptr, (cudaStream_t)stream);
+        return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, &af, nullptr, nullptr, (cudaStream_t)stream);
     }
     int rc = rb_student_loss_grad(kind, params, x, tpd, B, loss_kind, s_pd, gradloss, ws, mode, stream);
     if (rc) return rc;
@@ -417,8 +418,8 @@ int rb_student_step_dp(int kind, float* params, float* m, float* v, const float*
     RB_REQUIRE(B > 0 && t >= 1 && epoch >= 1, "empty batch / bad step / epoch must start at 1");
     RB_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, "2..8 ranks");
     const AdamFuse af{params, m, v, adam_lr_t(lr, b1, b2, t), b1, b2, eps, gscale};
-    const PeerExchange px{world, rank, epoch, peer_grad_slots, peer_flags};
-    return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, &af, &px, (cudaStream_t)stream);
+    const PeerExchange px{world, rank, epoch, peer_grad_slots, peer_flags, nullptr};
+    return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, &af, &px, nullptr, (cudaStream_t)stream);
 }
 
 int rb_adam_step(float* p, float* m, float* v, const float* g, int64_t P, int64_t t, float lr, float b1, float b2, float eps,

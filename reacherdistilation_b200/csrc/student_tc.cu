@@ -97,6 +97,11 @@ struct StudentTcArgs {
     uint32_t epoch;
     float* peer_gl[8];
     uint32_t* peer_flag[8];
+    // optional device-side step clock {iteration, adam step, exchange epoch} (CUDA-graph replay: no per-step host arguments).
+    // When set, adam step = clock[1] + 1 (lr_t computed in-kernel from `lr`), epoch = clock[2] + 1, slots = peer_gl2[epoch & 1].
+    const uint32_t* clock;
+    float lr;
+    float* peer_gl2[2][8];
 };
 
 // Plain (weak) global load.  Data produced earlier in the SAME launch by other CTAs is read only after a grid barrier and is never
@@ -116,6 +121,8 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 }
 
 struct __align__(16) StudentTcCtl {
+    float lr_t;                   // Adam step size of this launch (from the host, or from the device clock)
+    uint32_t epoch;
     uint64_t mbar;                // forward layers / dgrad results
     uint64_t mbar2;               // wgrad completion (X_l may be overwritten)
     uint32_t tmem_base;
@@ -464,7 +471,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     // ---- phase 0: TMEM, barrier, zeroed activations + ONES groups; fold and split the weights once for the whole grid -----
     st_stamp(0);
     if (warp == 0) tmem_alloc<512>(&ctl.tmem_base);
-    if (tid == 0) { mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); fence_mbar_init(); }
+    if (tid == 0) {
+        mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); fence_mbar_init();
+        ctl.lr_t = a.lr_t; ctl.epoch = a.epoch;
+        if (a.clock) {                             // same formula as the host (student.cu: adam_lr_t), in double
+            const double t = (double)(a.clock[1] + 1u);
+            ctl.lr_t = (float)((double)a.lr * sqrt(1.0 - pow((double)a.beta2, t)) / (1.0 - pow((double)a.beta1, t)));
+            ctl.epoch = a.clock[2] + 1u;
+        }
+    }
     for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
     if constexpr (S::L == 4) fold_into_image(a.params, a.wimg, gtid, gthreads);       // SpecMLP: W34, b34
     LayerLoop<S>::build_image(a, gtid, gthreads);
@@ -656,7 +671,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         grid.sync();
         st_stamp(8);
         // ---- gradient of the un-folded parameters ---------------------------------------------------------------------------------
-        float* gl = a.world > 1 ? a.peer_gl[a.rank] : a.gradloss;          // data parallel: this rank's slot of the symmetric buffer
+        const uint32_t epoch = ctl.epoch;
+        float* const* pgl = a.clock ? a.peer_gl2[epoch & 1u] : a.peer_gl;     // slots of this step (double buffered by epoch parity)
+        float* gl = a.world > 1 ? pgl[a.rank] : a.gradloss;                   // data parallel: this rank's slot of the symmetric buffer
         if constexpr (S::L == 4) finish_mlp(a.params, a.red, gl, gtid, gthreads);
         else
             for (int i = gtid; i <= a.P; i += gthreads) gl[i] = ldw(a.red + i);
@@ -665,13 +682,13 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             grid.sync();                                                   // the whole local gradient is written (gpu scope)
             if (blockIdx.x == 0 && tid < a.world) {                        // fence.sys + release.sys are cumulative over what the barrier ordered
                 __threadfence_system();
-                st_release_sys(a.peer_flag[tid] + a.rank, a.epoch);        // tell rank `tid` that this rank's slot is ready
-                while (ld_acquire_sys(a.peer_flag[a.rank] + tid) < a.epoch) { }     // ... and wait for rank `tid`'s slot
+                st_release_sys(a.peer_flag[tid] + a.rank, epoch);          // tell rank `tid` that this rank's slot is ready
+                while (ld_acquire_sys(a.peer_flag[a.rank] + tid) < epoch) { }       // ... and wait for rank `tid`'s slot
             }
             grid.sync();
             for (int i = gtid; i <= a.P; i += gthreads) {                  // every rank adds the slots in rank order: identical sums
                 float tot = 0.f;
-                for (int r = 0; r < a.world; ++r) tot += ld_relaxed_sys(a.peer_gl[r] + i);
+                for (int r = 0; r < a.world; ++r) tot += ld_relaxed_sys(pgl[r] + i);
                 a.gradloss[i] = tot;
             }
         }
@@ -681,7 +698,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             else __syncthreads();          // (the exchange above already separated finish from here; own-thread gradloss entries)
             for (int i = gtid; i < a.P; i += gthreads) {
                 float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
-                adam_update(pi, mi, vi, a.world > 1 ? a.gradloss[i] : ldw(a.gradloss + i), a.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                adam_update(pi, mi, vi, a.world > 1 ? a.gradloss[i] : ldw(a.gradloss + i), ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
                 a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
             }
         }
@@ -726,10 +743,11 @@ template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cuda
 }
 
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
-struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; };
+struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
+struct StepClock { const uint32_t* clock; float lr; };
 
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
-                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, cudaStream_t st) {
+                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, cudaStream_t st) {
     RB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(params) & 3) == 0, "x must be 16-byte aligned");
     RB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     float* ws = (float*)workspace;
@@ -747,8 +765,13 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
     if (px && !fwd_only && px->world > 1) {
         RB_REQUIRE(px->world <= 8 && px->rank >= 0 && px->rank < px->world, "peer exchange supports 2..8 ranks");
         a.world = px->world; a.rank = px->rank; a.epoch = px->epoch;
-        for (int r = 0; r < px->world; ++r) { a.peer_gl[r] = (float*)px->gl_ptrs[r]; a.peer_flag[r] = (uint32_t*)px->flag_ptrs[r]; }
+        for (int r = 0; r < px->world; ++r) {
+            a.peer_gl[r] = (float*)px->gl_ptrs[r]; a.peer_flag[r] = (uint32_t*)px->flag_ptrs[r];
+            a.peer_gl2[0][r] = (float*)px->gl_ptrs[r];                                  // slots of even epochs
+            a.peer_gl2[1][r] = (float*)(px->gl_ptrs_alt ? px->gl_ptrs_alt[r] : px->gl_ptrs[r]);   // slots of odd epochs
+        }
     }
+    if (clk && clk->clock) { a.clock = clk->clock; a.lr = clk->lr; }
     if (kind == RB_STUDENT_MLP) {
         a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
         a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;

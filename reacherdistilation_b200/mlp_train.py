@@ -26,7 +26,7 @@ from .teacher import TeacherAgent
 class DaggerTrainer:
     def __init__(self, num_envs=NUM_ENVS, seed=SEED, device=0, student_kind=STUDENT_MLP, keep_prob=KEEP_PROB, mode=MODE_FP32,
                  teacher_params=None, teacher_seed=0, student_seed=1, env_offset=0, loss_kind=LOSS_KL_ST, lr=None, eps=None,
-                 process_group=None, average_grads=False, student_params=None, student_mode=None, fused_allreduce=None):
+                 process_group=None, average_grads=False, student_params=None, student_mode=None, fused_allreduce=None, use_graph=None):
         import ctypes as C
         self.env = VecReacher(num_envs=num_envs, seed=seed, device=device, env_offset=env_offset)
         self.device = self.env.device
@@ -56,6 +56,10 @@ class DaggerTrainer:
         self.fused_allreduce = (self.world > 1 and self.student_mode == _lib.MODE_TC) if fused_allreduce is None else bool(fused_allreduce)
         if self.fused_allreduce:
             self.student.enable_peer_exchange(process_group)
+        # one CUDA-graph launch per iteration (device-side step clock) whenever the whole iteration is on the tensor-core path
+        graph_ok = self.mode == _lib.MODE_TC and self.student_mode == _lib.MODE_TC and (self.world == 1 or self.fused_allreduce)
+        self.use_graph = graph_ok if use_graph is None else (bool(use_graph) and graph_ok)
+        self._clock_synced = False
         self.iteration = 0
         self.env.reset()
 
@@ -67,6 +71,9 @@ class DaggerTrainer:
     def step(self):
         """One DAgger iteration over all envs.  Asynchronous; returns nothing (loss: self.last_loss())."""
         L, st = lib(), stream_ptr()
+        if self.use_graph:
+            return self._step_graph(L, st)
+        self._clock_synced = False
         check(L.rb_dagger_observe(self._h, ptr(self.teacher.params), self.iteration, ptr(self.obs), ptr(self.t_pd), ptr(self.x), self.mode, st))
         if self.fused_allreduce:
             self.student.step_dp(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd, grad_scale=self.grad_scale)
@@ -78,6 +85,26 @@ class DaggerTrainer:
             self.student.step(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd, grad_scale=self.grad_scale)
         check(L.rb_dagger_act(self._h, ptr(self.s_pd), ptr(self.t_pd), ptr(self.rew), ptr(self.done), st))
         self.iteration += 1
+
+    def _step_graph(self, L, st):
+        """rb_dagger_step: the iteration as one captured CUDA graph; per-step values come from the device-side clock."""
+        stu = self.student
+        if not self._clock_synced:         # (re)load the device clock from the host counters after any non-graph step
+            check(L.rb_dagger_set_clock(self._h, self.iteration, stu.t, getattr(stu, "_px_epoch", 0), st))
+            self._clock_synced = True
+        if self.fused_allreduce:
+            se, so, fl = stu._px_slots[0].ctypes.data, stu._px_slots[1].ctypes.data, stu._px_flags.ctypes.data
+            rank, world = stu._px_rank, stu._px_world
+        else:
+            se = so = fl = None
+            rank, world = 0, 1
+        check(L.rb_dagger_step(self._h, ptr(self.teacher.params), ptr(stu.params), ptr(stu.m), ptr(stu.v), ptr(stu.gradloss), ptr(stu.workspace),
+                               ptr(self.obs), ptr(self.t_pd), ptr(self.x), ptr(self.s_pd), ptr(self.rew), ptr(self.done), self.loss_kind,
+                               stu.lr, stu.beta1, stu.beta2, stu.eps, self.grad_scale, rank, world, se, so, fl, 1, st))
+        self.iteration += 1
+        stu.t += 1
+        if self.fused_allreduce:
+            stu._px_epoch += 1
 
     def last_loss(self):
         return self.student.gradloss[self.student.P]

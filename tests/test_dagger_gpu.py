@@ -92,3 +92,29 @@ def test_reference_shaped_replay_loop(num_envs):
     if num_envs > 1:
         assert out["losses"][-1] < out["losses"][0]
     ds.close(); out["env"].close()
+
+
+@pytest.mark.parametrize("kind_name", ["mlp", "policy64"])
+def test_graph_step_equals_three_launch_step(kind_name):
+    """rb_dagger_step (one CUDA-graph launch, per-step values from the device-side clock) vs the three separate calls with host-side
+    counters: same kernels, same arguments => identical losses, rewards and parameters (lr_t comes from a device pow(): 1e-6)."""
+    from reacherdistilation_b200 import MODE_TC, STUDENT_MLP, STUDENT_POLICY64
+    from reacherdistilation_b200.mlp_train import DaggerTrainer
+    kind = STUDENT_MLP if kind_name == "mlp" else STUDENT_POLICY64
+    a = DaggerTrainer(num_envs=700, seed=2, student_kind=kind, mode=MODE_TC, lr=1e-3, use_graph=True)
+    b = DaggerTrainer(num_envs=700, seed=2, student_kind=kind, mode=MODE_TC, lr=1e-3, use_graph=False)
+    assert a.use_graph and not b.use_graph
+    for it in range(60):
+        a.step(); b.step()
+        if it % 10 == 9:
+            la, lb = float(a.last_loss()), float(b.last_loss())
+            assert abs(la - lb) <= 1e-5 * max(1.0, abs(lb)), (it, la, lb)
+            assert torch.equal(a.done, b.done) and (a.rew - b.rew).abs().max().item() <= 1e-5
+    assert (a.student.params - b.student.params).abs().max().item() <= 1e-5
+    assert a.iteration == b.iteration == 60 and a.student.t == b.student.t == 60
+    a.use_graph = False                                    # mixed use: host counters stay authoritative
+    a.step(); b.step()
+    a.use_graph = True
+    a.step(); b.step()
+    assert abs(float(a.last_loss()) - float(b.last_loss())) <= 1e-5 * max(1.0, abs(float(b.last_loss())))
+    a.close(); b.close()
