@@ -327,7 +327,8 @@ def main():
                                % (nd, args.student, ("gradient all-reduce fused into the student kernel (NVLink peer memory)" if tr.fused_allreduce
                                                      else "NCCL all-reduce of flat grad") if world > 1 else "single GPU"),
                                e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=4),
-                               gpu_launches_per_step=(3 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
+                               gpu_launches_per_step=(3 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8),
+                               cuda_graph=bool(tr.use_graph), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
                                last_loss=float(tr.last_loss()),
                                roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",
                                              frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"], traffic=None, peak_source=pk["src"],
@@ -373,16 +374,15 @@ def main():
             lob, lpp = torch.randn((10, Bw, 11), device=dev), torch.randn((10, Bw, 4), device=dev) * 0.3
             ltp = torch.cat([torch.randn((10, Bw, 2), device=dev) * 0.3, -1 + 0.2 * torch.randn((10, Bw, 2), device=dev)], -1)
             def lstep():
-                lnet.loss_grad(lob, lpp, ltp, None, keep_prob=0.5, seed=0, iteration=lnet.t)
-                lnet.adam_step()
+                lnet.step(lob, lpp, ltp, None, keep_prob=0.5, seed=0)      # one CUDA-graph launch (~250 kernels)
             for _ in range(3):
                 lstep()
             lsec2, _ = timed(lstep, 10)
             lflop = 6.0 * (243 * 800 + 31400 + 128) * 10 * Bw                       # 3 x 2 x MAC per window row, T = 10
             line["lstm"] = dict(metric="lstm_window_rows_per_sec", value=10.0 * Bw * 10 / lsec2, unit="sample-steps/s", windows=Bw, steps_unrolled=10,
                                 ms_per_step=1e3 * lsec2 / 10, tensor_tflops=lflop / (lsec2 / 10) / 1e12, params=int(lnet.P),
-                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads; ~250 launches of k_gemm_bf16x3 and "
-                                     "element-wise kernels per step (launch-bound at this size; CUDA-graph capture is the next step)")
+                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads: ~250 launches of k_gemm_bf16x3 and "
+                                     "element-wise kernels captured once in a CUDA graph (rb_lstm_step, device-side step clock)")
             del lnet
         # ---- step API: HBM-bound single-step kernel at 4M envs ---------------------------------------------------
         ns = STEP_API_ENVS

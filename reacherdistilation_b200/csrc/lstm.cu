@@ -8,6 +8,8 @@
 //     s_tau  = head_tau(m): 200 -> 64 -> 128 -> 64 -> 32 (tanh) -> 4, weights NOT shared between the unrolled steps      (:42-46)
 // Flat parameter layout: W_e[4][32] b_e[32] W_l[243][800] b_l[800] then for tau = 0..9: W1[200][64] b1 W2[64][128] b2 W3[128][64] b3
 // W4[64][32] b4 W5[32][4] b5.
+#include <cstring>
+
 #include "common.cuh"
 #include "dagger_input.cuh"
 #include "gemm_tc.cuh"
@@ -47,8 +49,10 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 
 // x rows: dropout(ob) -> xh[:, 0:11]; initial m state -> xh rows of step 0, columns 43..242; initial c -> c[0]
 __global__ void k_lstm_inputs(int64_t R, int64_t B, const float* __restrict__ ob, float keep_prob, uint32_t k0, uint32_t k1, uint32_t sample_id0,
-                              uint32_t iteration, const float* __restrict__ init_state, float* __restrict__ xh, float* __restrict__ c0) {
+                              uint32_t iteration, const uint32_t* __restrict__ clock, const float* __restrict__ init_state, float* __restrict__ xh,
+                              float* __restrict__ c0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (clock) iteration = clock[0];                 // device-side step clock (CUDA-graph replay)
     if (i < R) {
         float o[11];
 #pragma unroll
@@ -162,6 +166,7 @@ struct LstmCall {
     float keep_prob; uint64_t seed; uint32_t sample_id0, iteration;
     int64_t B; int loss_kind, fwd_only;
     float* s_out; float* final_state; float* gradloss;
+    const uint32_t* clock;
 };
 
 static int gemm(const float* A, int lda, int a_mn, const float* Bm, int ldb, int b_mn, float* C, int ldc, int M, int N, int K, const float* bias, int act,
@@ -184,7 +189,7 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     const float* P = c.params;
     // ---- inputs: dropout(ob), initial state, embedding of prev_pdflat --------------------------------------------------------
     k_lstm_inputs<<<(unsigned)((max(R, B * LU) + 255) / 256), 256, 0, st>>>(R, B, c.ob, c.keep_prob, (uint32_t)c.seed, (uint32_t)(c.seed >> 32),
-                                                                           c.sample_id0, c.iteration, c.init_state, w.xh, w.c);
+                                                                           c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c);
     RB_CUDA(cudaGetLastError());
     RB_TRY(gemm(c.prev_pd, 4, 0, P + L_WE, LE, 1, w.xh + 11, LDXH, Ri, LE, 4, P + L_BE, 0, 0, nullptr, 0, w, sms, st));
     // ---- recurrence ------------------------------------------------------------------------------------------------------------
@@ -256,7 +261,32 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     return RB_OK;
 }
 
+// step clock helpers: lr_t of this step from clock[1] + 1 (same formula as the host, in double); advance after the update
+__global__ void k_lstm_clock_prep(const uint32_t* clock, float lr, float b1, float b2, float* lr_t) {
+    const double t = (double)(clock[1] + 1u);
+    *lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, t)) / (1.0 - pow((double)b1, t)));
+}
+__global__ void k_lstm_clock_advance(uint32_t* clock) { clock[0] += 1u; clock[1] += 1u; }
+__global__ void k_lstm_clock_set(uint32_t* clock, uint32_t iteration, uint32_t adam_t) { clock[0] = iteration; clock[1] = adam_t; }
+__global__ void k_adam_dev_lr(float* __restrict__ p, float* __restrict__ m, float* __restrict__ v, const float* __restrict__ g, int64_t n,
+                              const float* __restrict__ lr_t, float b1, float b2, float eps, float gscale) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    float pi = p[i], mi = m[i], vi = v[i];
+    adam_update(pi, mi, vi, g[i], *lr_t, b1, b2, eps, gscale);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+}
+
 }  // namespace rb
+
+struct rb_lstm_ctx {
+    int device = 0;
+    uint32_t* clock = nullptr;       // {dropout iteration, adam step}
+    float* lr_t = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    uint64_t gkey = 0;
+    cudaStream_t cap_stream = nullptr;
+};
 
 using namespace rb;
 
@@ -291,6 +321,81 @@ int rb_lstm_loss_grad(const float* params, const float* ob, const float* prev_pd
     c.sample_id0 = sample_id0; c.iteration = iteration; c.B = B; c.loss_kind = loss_kind; c.s_out = s_out; c.final_state = final_state;
     c.gradloss = gradloss;
     return lstm_run(c, (float*)workspace, (cudaStream_t)stream);
+}
+
+/* One optimiser step of the LSTM student (loss_grad + TF-form Adam) with the per-step values (dropout iteration, Adam step) taken from a
+ * device-side clock, so the ~250 launches are captured ONCE in a CUDA graph and replayed with one cudaGraphLaunch.               */
+int rb_lstm_ctx_destroy(rb_lstm_ctx* c) {
+    if (!c) return RB_OK;
+    cudaSetDevice(c->device);
+    cudaFree(c->clock); cudaFree(c->lr_t);
+    if (c->gexec) cudaGraphExecDestroy(c->gexec);
+    if (c->cap_stream) cudaStreamDestroy(c->cap_stream);
+    delete c;
+    return RB_OK;
+}
+int rb_lstm_ctx_create(rb_lstm_ctx** out, int device) {
+    RB_REQUIRE(out != nullptr, "out is NULL");
+    RB_CUDA(cudaSetDevice(device));
+    rb_lstm_ctx* c = new rb_lstm_ctx();
+    c->device = device;
+    cudaError_t err = cudaMalloc(&c->clock, 4 * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaMalloc(&c->lr_t, sizeof(float));
+    if (err == cudaSuccess) err = cudaMemset(c->clock, 0, 4 * sizeof(uint32_t));
+    if (err == cudaSuccess) err = cudaStreamCreateWithFlags(&c->cap_stream, cudaStreamNonBlocking);
+    if (err != cudaSuccess) { rb_lstm_ctx_destroy(c); return cuda_fail(err, "rb_lstm_ctx_create"); }
+    *out = c;
+    return RB_OK;
+}
+int rb_lstm_ctx_set_clock(rb_lstm_ctx* c, uint32_t iteration, uint32_t adam_step, void* stream) {
+    RB_REQUIRE(c != nullptr, "NULL argument");
+    k_lstm_clock_set<<<1, 1, 0, (cudaStream_t)stream>>>(c->clock, iteration, adam_step);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+int rb_lstm_step(rb_lstm_ctx* ctx, float* params, float* m, float* v, const float* ob, const float* prev_pd, const float* t_pd, const float* init_state,
+                 int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0, int loss_kind, float* s_out, float* gradloss, void* workspace,
+                 float lr, float b1, float b2, float eps, float gscale, int use_graph, void* stream) {
+    RB_REQUIRE(ctx && params && m && v && ob && prev_pd && t_pd && s_out && gradloss && workspace, "NULL argument");
+    RB_REQUIRE(B > 0 && B * LT < ((int64_t)1 << 30) && keep_prob > 0.f, "bad batch / keep_prob");
+    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    cudaStream_t st = (cudaStream_t)stream;
+    auto issue = [&](cudaStream_t s) -> int {
+        k_lstm_clock_prep<<<1, 1, 0, s>>>(ctx->clock, lr, b1, b2, ctx->lr_t);
+        LstmCall c{};
+        c.params = params; c.ob = ob; c.prev_pd = prev_pd; c.t_pd = t_pd; c.init_state = init_state; c.keep_prob = keep_prob; c.seed = seed;
+        c.sample_id0 = sample_id0; c.B = B; c.loss_kind = loss_kind; c.s_out = s_out; c.gradloss = gradloss; c.clock = ctx->clock;
+        int rc = lstm_run(c, (float*)workspace, s);
+        if (rc) return rc;
+        k_adam_dev_lr<<<(unsigned)((L_P + 255) / 256), 256, 0, s>>>(params, m, v, gradloss, L_P, ctx->lr_t, b1, b2, eps, gscale);
+        k_lstm_clock_advance<<<1, 1, 0, s>>>(ctx->clock);
+        RB_CUDA(cudaGetLastError());
+        return RB_OK;
+    };
+    if (!use_graph) return issue(st);
+    uint64_t key = 1469598103934665603ull;
+    auto mix = [&](uint64_t vv) { key = (key ^ vv) * 1099511628211ull; };
+    const void* ptrs[] = {params, m, v, ob, prev_pd, t_pd, init_state, s_out, gradloss, workspace};
+    for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+    const float fl[] = {keep_prob, lr, b1, b2, eps, gscale};
+    for (float f : fl) { uint32_t u; memcpy(&u, &f, 4); mix(u); }
+    mix((uint64_t)B); mix(seed); mix(sample_id0); mix((uint64_t)loss_kind);
+    if (!ctx->gexec || ctx->gkey != key) {
+        if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        RB_CUDA(cudaStreamSynchronize(st));
+        RB_CUDA(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeRelaxed));
+        const int rc = issue(ctx->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        const cudaError_t ci = cudaGraphInstantiate(&ctx->gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) { ctx->gexec = nullptr; return cuda_fail(ci, "cudaGraphInstantiate"); }
+        ctx->gkey = key;
+    }
+    RB_CUDA(cudaGraphLaunch(ctx->gexec, st));
+    return RB_OK;
 }
 
 }  // extern "C"

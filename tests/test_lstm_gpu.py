@@ -63,3 +63,21 @@ def test_lstm_train_entry_point_learns():
     out = lstm_train.train(True, False, num_envs=48, iterations=100, verbose=False)
     assert len(out["losses"]) == 2 and np.isfinite(out["losses"]).all() and out["losses"][-1] < out["losses"][0]
     out["dataset"].close(); out["env"].close()
+
+
+def test_graph_step_equals_loss_grad_then_adam():
+    """rb_lstm_step (one CUDA-graph launch, device-side clock) vs rb_lstm_loss_grad + rb_adam_step with host counters."""
+    from reacherdistilation_b200.student_nn import StudentLSTM
+    a, b = StudentLSTM(seed=5), StudentLSTM(seed=5)
+    B = 40
+    ob, pp, tp, st = _data(B, 77)
+    dob, dpp, dtp = torch.from_numpy(ob).cuda(), torch.from_numpy(pp).cuda(), torch.from_numpy(tp).cuda()
+    for it in range(6):
+        a.step(dob, dpp, dtp, None, keep_prob=0.5, seed=3)
+        b.loss_grad(dob, dpp, dtp, None, keep_prob=0.5, seed=3, iteration=it)
+        b.adam_step()
+        if it == 0:
+            assert torch.equal(a.gradloss, b.gradloss)                 # same kernels, same dropout mask (iteration from the device clock)
+        assert torch.allclose(a.gradloss, b.gradloss, rtol=1e-3, atol=1e-3 * float(b.gradloss[:-1].abs().max())), it
+        assert (a.params - b.params).abs().max().item() <= 1e-6
+    assert a.t == b.t == 6
