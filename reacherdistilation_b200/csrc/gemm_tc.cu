@@ -87,7 +87,10 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
     GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(smem + GM_STAGES * STAGE_BYTES);
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * BN;
-    const int kbeg = blockIdx.z * g.ksplit, kend = min(g.K, kbeg + g.ksplit);
+    const int bz = blockIdx.z / g.nsplit, sz = blockIdx.z - bz * g.nsplit;          // batch index, K slice
+    const float* __restrict__ Ab = g.A + (size_t)bz * g.sA;
+    const float* __restrict__ Bb = g.B + (size_t)bz * g.sB;
+    const int kbeg = sz * g.ksplit, kend = min(g.K, kbeg + g.ksplit);
     const int ktiles = (kend - kbeg + GM_BK - 1) / GM_BK;
 
     if (warp == 0) tmem_alloc<TCOLS>(&ctl.tmem_base);
@@ -111,14 +114,14 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
             const int c = tid + i * GM_THREADS;
             int row, k; uint32_t off;
             TA::map(c, g.a_mn, row, k, off);
-            if (c < TA::CHUNKS) load_chunk(g.A, g.lda, g.a_mn, m0 + row, k0 + k, g.M, kend, va[i]);
+            if (c < TA::CHUNKS) load_chunk(Ab, g.lda, g.a_mn, m0 + row, k0 + k, g.M, kend, va[i]);
         }
 #pragma unroll
         for (int i = 0; i < TB::PER_THREAD; ++i) {
             const int c = tid + i * GM_THREADS;
             int row, k; uint32_t off;
             TB::map(c, g.b_mn, row, k, off);
-            if (c < TB::CHUNKS) load_chunk(g.B, g.ldb, g.b_mn, n0 + row, k0 + k, g.N, kend, vb[i]);
+            if (c < TB::CHUNKS) load_chunk(Bb, g.ldb, g.b_mn, n0 + row, k0 + k, g.N, kend, vb[i]);
         }
     };
     uint32_t stage_phase = 0;           // bit s = parity to wait for on stage_bar[s]
@@ -175,8 +178,11 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
     constexpr int CHUNKS8 = BN / 8, HALF = (CHUNKS8 + 1) / 2;
     const int c_beg = (warp >> 2) * HALF, c_end = min(CHUNKS8, c_beg + HALF);
     const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-    float* out = gridDim.z > 1 ? g.partial + (size_t)blockIdx.z * g.M * g.N : g.C;
-    const int ldo = gridDim.z > 1 ? g.N : g.ldc;
+    const bool split = g.nsplit > 1;
+    float* out = split ? g.partial + (size_t)blockIdx.z * g.M * g.N : g.C + (size_t)bz * g.sC;
+    const int ldo = split ? g.N : g.ldc;
+    const float* bias = g.bias ? g.bias + (size_t)bz * g.sBias : nullptr;
+    const float* Hb = g.H ? g.H + (size_t)bz * g.sH : nullptr;
     for (int c = c_beg; c < c_end; ++c) {
         float v[8];
         if (ktiles > 0) { tmem_ld_x8(tacc + c * 8, v); tmem_ld_wait(); }
@@ -190,10 +196,10 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
                 const int n = n0 + c * 8 + i;
                 if (n < g.N) {
                     float x = v[i];
-                    if (gridDim.z == 1) {
-                        if (g.bias) x += __ldg(g.bias + n);
+                    if (!split) {
+                        if (bias) x += __ldg(bias + n);
                         if (g.act == 1) x = tanhf(x);
-                        if (g.H) { const float h = __ldg(g.H + (size_t)m * g.ldh + n); x *= fmaf(-h, h, 1.f); }
+                        if (Hb) { const float h = __ldg(Hb + (size_t)m * g.ldh + n); x *= fmaf(-h, h, 1.f); }
                         if (g.accumulate) x += out[(size_t)m * ldo + n];
                     }
                     out[(size_t)m * ldo + n] = x;
@@ -206,18 +212,21 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
     if (warp == 0) tmem_dealloc<TCOLS>(tmem);
 }
 
-// C (+)= epilogue(sum over the split-K partial tiles, in slice order)
-__global__ void k_gemm_splitk_reduce(const GemmArgs g, int nsplit) {
-    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= (int64_t)g.M * g.N) return;
-    const int m = (int)(idx / g.N), n = (int)(idx - (int64_t)m * g.N);
+// C (+)= epilogue(sum over the split-K partial tiles, in slice order), for every batch entry
+__global__ void k_gemm_splitk_reduce(const GemmArgs g, int nsplit, int batch) {
+    const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, mn = (int64_t)g.M * g.N;
+    if (idx >= mn * batch) return;
+    const int bz = (int)(idx / mn);
+    const int64_t r = idx - (int64_t)bz * mn;
+    const int m = (int)(r / g.N), n = (int)(r - (int64_t)m * g.N);
     float x = 0.f;
-    for (int z = 0; z < nsplit; ++z) x += g.partial[(size_t)z * g.M * g.N + idx];
-    if (g.bias) x += __ldg(g.bias + n);
+    for (int z = 0; z < nsplit; ++z) x += g.partial[((size_t)bz * nsplit + z) * mn + r];
+    if (g.bias) x += __ldg(g.bias + (size_t)bz * g.sBias + n);
     if (g.act == 1) x = tanhf(x);
-    if (g.H) { const float h = __ldg(g.H + (size_t)m * g.ldh + n); x *= fmaf(-h, h, 1.f); }
-    if (g.accumulate) x += g.C[(size_t)m * g.ldc + n];
-    g.C[(size_t)m * g.ldc + n] = x;
+    if (g.H) { const float h = __ldg(g.H + (size_t)bz * g.sH + (size_t)m * g.ldh + n); x *= fmaf(-h, h, 1.f); }
+    float* c = g.C + (size_t)bz * g.sC + (size_t)m * g.ldc + n;
+    if (g.accumulate) x += *c;
+    *c = x;
 }
 
 template <int BN> static int launch_gemm(const GemmArgs& g, dim3 grid, cudaStream_t st) {
@@ -229,25 +238,23 @@ template <int BN> static int launch_gemm(const GemmArgs& g, dim3 grid, cudaStrea
     return RB_OK;
 }
 
-// workspace floats needed for the split-K partials of an (M, N, K) product on `sms` SMs
-int gemm_pick_split(int M, int N, int K, int sms) {
-    const int bn = N > 64 ? 128 : (N > 32 ? 64 : (N > 16 ? 32 : 16));
-    const int tiles = ((M + GM_BM - 1) / GM_BM) * ((N + bn - 1) / bn);
-    int split = 1;
-    if (tiles < sms && K >= 8 * GM_BK) split = min(min(32, (2 * sms + tiles - 1) / tiles), K / (4 * GM_BK));
-    return max(1, split);
-}
-
 int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, cudaStream_t st) {
     RB_REQUIRE(g.M > 0 && g.N > 0 && g.K >= 0, "bad GEMM shape");
+    if (g.batch <= 0) g.batch = 1;
     const int bn = g.N > 64 ? 128 : (g.N > 32 ? 64 : (g.N > 16 ? 32 : 16));
-    int split = splitk_ws ? gemm_pick_split(g.M, g.N, g.K, sms) : 1;
-    while (split > 1 && (size_t)split * g.M * g.N > splitk_ws_floats) --split;
+    const int tiles = ((g.M + GM_BM - 1) / GM_BM) * ((g.N + bn - 1) / bn) * g.batch;
+    int split = 1;
+    if (splitk_ws) {
+        if (g.force_split > 0) split = g.force_split;
+        else if (tiles < sms && g.K >= 8 * GM_BK) split = min(min(32, (2 * sms + tiles - 1) / tiles), g.K / (4 * GM_BK));
+    }
+    split = max(1, split);
+    while (split > 1 && (size_t)split * g.batch * g.M * g.N > splitk_ws_floats) --split;
     int ks = ((g.K + split - 1) / split + GM_BK - 1) / GM_BK * GM_BK;
     if (ks == 0) ks = GM_BK;
     split = g.K > 0 ? (g.K + ks - 1) / ks : 1;
-    g.ksplit = ks; g.partial = splitk_ws;
-    const dim3 grid((g.M + GM_BM - 1) / GM_BM, (g.N + bn - 1) / bn, split);
+    g.ksplit = ks; g.nsplit = split; g.partial = splitk_ws;
+    const dim3 grid((g.M + GM_BM - 1) / GM_BM, (g.N + bn - 1) / bn, split * g.batch);
     int rc;
     switch (bn) {
         case 128: rc = launch_gemm<128>(g, grid, st); break;
@@ -257,8 +264,8 @@ int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, 
     }
     if (rc) return rc;
     if (split > 1) {
-        const int64_t total = (int64_t)g.M * g.N;
-        k_gemm_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, split);
+        const int64_t total = (int64_t)g.M * g.N * g.batch;
+        k_gemm_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, split, g.batch);
         RB_CUDA(cudaGetLastError());
     }
     return RB_OK;

@@ -13,10 +13,12 @@ struct GemmArgs {
     const float* bias;               // [N] or NULL
     int act, accumulate;             // act: 0 none, 1 tanh;  accumulate: C += result
     const float* H; int ldh;         // optional: result *= 1 - H[m][n]^2   (tanh backward)
-    int ksplit;                      // set by gemm_bf16x3
+    int batch;                       // >= 1: independent products, operand b of batch i at X + i * stride (elements); 0 is treated as 1
+    long long sA, sB, sC, sBias, sH;
+    int force_split;                 // > 0: use this many K slices (when a workspace is given)
+    int ksplit, nsplit;              // set by gemm_bf16x3
     float* partial;                  // set by gemm_bf16x3
 };
-int gemm_pick_split(int M, int N, int K, int sms);
 int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, cudaStream_t st);
 
 }  // namespace rb

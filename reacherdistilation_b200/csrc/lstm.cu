@@ -23,9 +23,11 @@ constexpr int L_HEAD_SZ = 200 * 64 + 64 + 64 * 128 + 128 + 128 * 64 + 64 + 64 * 
 constexpr int L_P = L_HEAD0 + LT * L_HEAD_SZ;                                                              // 511880
 static inline int head_w_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += HD[i] * HD[i + 1] + HD[i + 1]; return o; }
 
+constexpr size_t COLPART_FLOATS = 64 * 1024;     // partial column sums: <= 64 row blocks x (n x batch <= 1024)
+
 // workspace layout (floats), R = T * B rows
 struct LstmWs {
-    float *xh, *z, *dz, *dxh, *c, *hh, *dh, *dc, *a[5], *da[5], *splitk;
+    float *xh, *z, *dz, *dxh, *c, *hh, *dh, *dc, *a[5], *da[5], *splitk, *colpart;
     size_t splitk_floats;
 };
 static size_t lstm_ws_floats(int64_t R, int64_t B, size_t* splitk) {
@@ -33,7 +35,7 @@ static size_t lstm_ws_floats(int64_t R, int64_t B, size_t* splitk) {
     for (int l = 1; l <= 5; ++l) per_row += 2 * (size_t)HD[l];
     const size_t sk = (size_t)32 * LDXH * LG;            // split-K partials of the largest wgrad (243 x 800, <= 32 slices)
     if (splitk) *splitk = sk;
-    return per_row * R + (size_t)(LT + 1) * B * LU + (size_t)B * LU + sk + 1024;
+    return per_row * R + (size_t)(LT + 1) * B * LU + (size_t)B * LU + sk + 1024 + COLPART_FLOATS + 64;
 }
 static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
     float* p = ws;
@@ -42,7 +44,8 @@ static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
     w.c = take((size_t)(LT + 1) * B * LU); w.hh = take(R * LU); w.dh = take(R * LU); w.dc = take((size_t)B * LU);
     for (int l = 1; l <= 5; ++l) { w.a[l - 1] = take(R * HD[l]); w.da[l - 1] = take(R * HD[l]); }
     lstm_ws_floats(R, B, &w.splitk_floats);
-    w.splitk = take(w.splitk_floats);
+    w.splitk = take(w.splitk_floats + 1024);
+    w.colpart = take(COLPART_FLOATS);
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -144,21 +147,39 @@ __global__ void k_sum_serial(const float* __restrict__ x, int n, float* __restri
     }
 }
 
-// out[n] = sum over rows of X[rows, n] (ld) -- bias gradients; fixed order: 8 row-interleaved partial sums, then a tree
-__global__ void k_colsum(const float* __restrict__ X, int ld, int64_t rows, int n, float* __restrict__ out) {
+// column sums (bias gradients) in two fixed-order stages: partial[bz][rb][col] over row blocks, then the sum over rb
+__global__ void k_colsum_partial(const float* __restrict__ X, int ld, int64_t rows, int n, long long sX, int RB, float* __restrict__ partial) {
     __shared__ float red[8][33];
-    const int col = blockIdx.x * 32 + threadIdx.x;
+    const int col = blockIdx.x * 32 + threadIdx.x, rb = blockIdx.y, bz = blockIdx.z;
+    const int64_t chunk = (rows + RB - 1) / RB, r0 = rb * chunk, r1 = min(rows, r0 + chunk);
+    const float* Xb = X + (size_t)bz * sX;
     float acc = 0.f;
     if (col < n)
-        for (int64_t r = threadIdx.y; r < rows; r += 8) acc += X[r * ld + col];
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += Xb[r * ld + col];
     red[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && col < n) {
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-        out[col] = t;
+        partial[((size_t)bz * RB + rb) * n + col] = t;
     }
+}
+__global__ void k_colsum_final(const float* __restrict__ partial, int RB, int n, int batch, float* __restrict__ out, long long sOut) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * batch) return;
+    const int bz = idx / n, col = idx - bz * n;
+    float t = 0.f;
+    for (int rb = 0; rb < RB; ++rb) t += partial[((size_t)bz * RB + rb) * n + col];
+    out[(size_t)bz * sOut + col] = t;
+}
+static int colsum(const float* X, int ld, int64_t rows, int n, int batch, long long sX, float* out, long long sOut, float* colpart, cudaStream_t st) {
+    int RB = (int)min((int64_t)64, (rows + 63) / 64);
+    while (RB > 1 && (size_t)RB * n * batch > COLPART_FLOATS) --RB;
+    k_colsum_partial<<<dim3((n + 31) / 32, RB, batch), dim3(32, 8), 0, st>>>(X, ld, rows, n, sX, RB, colpart);
+    k_colsum_final<<<(n * batch + 255) / 256, 256, 0, st>>>(colpart, RB, n, batch, out, sOut);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
 }
 
 struct LstmCall {
@@ -169,11 +190,13 @@ struct LstmCall {
     const uint32_t* clock;
 };
 
+struct Bat { int n = 1; long long sA = 0, sB = 0, sC = 0, sBias = 0, sH = 0; };
 static int gemm(const float* A, int lda, int a_mn, const float* Bm, int ldb, int b_mn, float* C, int ldc, int M, int N, int K, const float* bias, int act,
-                int accumulate, const float* H, int ldh, LstmWs& w, int sms, cudaStream_t st, bool allow_split = false) {
+                int accumulate, const float* H, int ldh, LstmWs& w, int sms, cudaStream_t st, bool allow_split = false, const Bat& bt = Bat()) {
     GemmArgs g{};
     g.A = A; g.lda = lda; g.a_mn = a_mn; g.B = Bm; g.ldb = ldb; g.b_mn = b_mn; g.C = C; g.ldc = ldc; g.M = M; g.N = N; g.K = K;
     g.bias = bias; g.act = act; g.accumulate = accumulate; g.H = H; g.ldh = ldh;
+    g.batch = bt.n; g.sA = bt.sA; g.sB = bt.sB; g.sC = bt.sC; g.sBias = bt.sBias; g.sH = bt.sH;
     return gemm_bf16x3(g, allow_split ? w.splitk : nullptr, allow_split ? w.splitk_floats : 0, sms, st);
 }
 #define RB_TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
@@ -205,14 +228,15 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         RB_CUDA(cudaMemcpyAsync(c.final_state, w.c + (size_t)LT * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
         RB_CUDA(cudaMemcpyAsync(c.final_state + B * LU, w.hh + (size_t)(LT - 1) * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
     }
-    // ---- per-step heads --------------------------------------------------------------------------------------------------------
-    for (int t = 0; t < LT; ++t) {
-        const float* hp = P + L_HEAD0 + (size_t)t * L_HEAD_SZ;
-        const float* in = w.hh + (size_t)t * B * LU;
+    // ---- per-step heads: the T heads have their own weights (student_nn.py:42-46) => one BATCHED GEMM per layer (batch = T) ------
+    {
+        const float* in = w.hh;
         for (int l = 0; l < 5; ++l) {
-            const float* W = hp + head_w_off(l);
-            float* out = l == 4 ? c.s_out + (size_t)t * B * 4 : w.a[l] + (size_t)t * B * HD[l + 1];
-            RB_TRY(gemm(in, HD[l], 0, W, HD[l + 1], 1, out, HD[l + 1], Bi, HD[l + 1], HD[l], W + HD[l] * HD[l + 1], l < 4 ? 1 : 0, 0, nullptr, 0, w, sms, st));
+            const float* W = P + L_HEAD0 + head_w_off(l);
+            float* out = l == 4 ? c.s_out : w.a[l];
+            Bat bt; bt.n = LT; bt.sA = B * HD[l]; bt.sB = L_HEAD_SZ; bt.sC = B * HD[l + 1]; bt.sBias = L_HEAD_SZ;
+            RB_TRY(gemm(in, HD[l], 0, W, HD[l + 1], 1, out, HD[l + 1], Bi, HD[l + 1], HD[l], W + HD[l] * HD[l + 1], l < 4 ? 1 : 0, 0, nullptr, 0, w, sms, st,
+                        false, bt));
             in = out;
         }
     }
@@ -220,27 +244,23 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     // ---- loss and dL/ds --------------------------------------------------------------------------------------------------------
     const unsigned kl_blocks = (unsigned)((R + 255) / 256);
     RB_REQUIRE(kl_blocks <= 1024, "window batch too large for the loss reduction scratch");
-    float* loss_part = w.splitk + w.splitk_floats;       // 1024 spare floats behind the split-K area
+    float* loss_part = w.splitk + w.splitk_floats;       // 1024 spare floats behind the split-K area (lstm_ws_carve)
     k_lstm_kl<<<kl_blocks, 256, 0, st>>>(R, (const float4*)c.s_out, (const float4*)c.t_pd, c.loss_kind, (float4*)w.da[4], loss_part);
     k_sum_serial<<<1, 32, 0, st>>>(loss_part, (int)kl_blocks, c.gradloss + L_P);
     RB_CUDA(cudaGetLastError());
     float* G = c.gradloss;
-    // ---- heads backward --------------------------------------------------------------------------------------------------------
-    for (int t = 0; t < LT; ++t) {
-        const float* hp = P + L_HEAD0 + (size_t)t * L_HEAD_SZ;
-        float* gp = G + L_HEAD0 + (size_t)t * L_HEAD_SZ;
-        for (int l = 4; l >= 0; --l) {
-            const float* W = hp + head_w_off(l);
-            const float* dout = w.da[l] + (size_t)t * B * HD[l + 1];
-            const float* in = l == 0 ? w.hh + (size_t)t * B * LU : w.a[l - 1] + (size_t)t * B * HD[l];
-            // dW = in^T dout, db = colsum(dout)
-            RB_TRY(gemm(in, HD[l], 1, dout, HD[l + 1], 1, gp + head_w_off(l), HD[l + 1], HD[l], HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
-            k_colsum<<<(HD[l + 1] + 31) / 32, dim3(32, 8), 0, st>>>(dout, HD[l + 1], B, HD[l + 1], gp + head_w_off(l) + HD[l] * HD[l + 1]);
-            RB_CUDA(cudaGetLastError());
-            // d(in) = dout W^T, times tanh' of the layer input (except for the LSTM output m)
-            float* din = l == 0 ? w.dh + (size_t)t * B * LU : w.da[l - 1] + (size_t)t * B * HD[l];
-            RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, HD[l], w, sms, st));
-        }
+    // ---- heads backward, batched over the T steps ----------------------------------------------------------------------------------
+    for (int l = 4; l >= 0; --l) {
+        const float* W = P + L_HEAD0 + head_w_off(l);
+        float* gW = G + L_HEAD0 + head_w_off(l);
+        const float* dout = w.da[l];
+        const float* in = l == 0 ? w.hh : w.a[l - 1];
+        Bat bw; bw.n = LT; bw.sA = B * HD[l]; bw.sB = B * HD[l + 1]; bw.sC = L_HEAD_SZ;                 // dW = in^T dout
+        RB_TRY(gemm(in, HD[l], 1, dout, HD[l + 1], 1, gW, HD[l + 1], HD[l], HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, st, true, bw));
+        RB_TRY(colsum(dout, HD[l + 1], B, HD[l + 1], LT, B * HD[l + 1], gW + HD[l] * HD[l + 1], L_HEAD_SZ, w.colpart, st));      // db = colsum(dout)
+        float* din = l == 0 ? w.dh : w.da[l - 1];                                                     // d(in) = dout W^T (* tanh' of the layer input)
+        Bat bd; bd.n = LT; bd.sA = B * HD[l + 1]; bd.sB = L_HEAD_SZ; bd.sC = B * HD[l]; bd.sH = B * HD[l];
+        RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, HD[l], w, sms, st, false, bd));
     }
     // ---- back-propagation through time -------------------------------------------------------------------------------------------
     RB_CUDA(cudaMemsetAsync(w.dc, 0, sizeof(float) * B * LU, st));
@@ -250,13 +270,13 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         k_lstm_cell_bwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, w.z + (size_t)t * B * LG, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
                                                                            w.dh + (size_t)t * B * LU, t + 1 < LT ? dxh_t + (size_t)B * LDXH : nullptr, w.dc, dz_t);
         RB_CUDA(cudaGetLastError());
-        RB_TRY(gemm(dz_t, LG, 0, P + L_WL, LG, 0, dxh_t, LDXH, Bi, LXH, LG, nullptr, 0, 0, nullptr, 0, w, sms, st));       // d[x | m_prev] = dz W_l^T
+        RB_TRY(gemm(dz_t, LG, 0, P + L_WL, LG, 0, dxh_t, LDXH, Bi, LXH, LG, nullptr, 0, 0, nullptr, 0, w, sms, st, true));  // d[x | m_prev] = dz W_l^T
     }
     // ---- weight gradients of the shared parts, over all T*B rows ---------------------------------------------------------------------
     RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
-    k_colsum<<<(LG + 31) / 32, dim3(32, 8), 0, st>>>(w.dz, LG, R, LG, G + L_BL);
+    RB_TRY(colsum(w.dz, LG, R, LG, 1, 0, G + L_BL, 0, w.colpart, st));
     RB_TRY(gemm(c.prev_pd, 4, 1, w.dxh + 11, LDXH, 1, G + L_WE, LE, 4, LE, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
-    k_colsum<<<(LE + 31) / 32, dim3(32, 8), 0, st>>>(w.dxh + 11, LDXH, R, LE, G + L_BE);
+    RB_TRY(colsum(w.dxh + 11, LDXH, R, LE, 1, 0, G + L_BE, 0, w.colpart, st));
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
