@@ -34,7 +34,7 @@ STEP_API_ENVS = 1 << 22
 ALG_BYTES_ROLLOUT = 65.0      # fused rollout writes one buffer row per env-step: ob 44 + pdflat 16 + rew 4 + done 1 B (17 scalars)
 ROLLOUT_TRAFFIC_NCU = 159.6e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
                                 # profiles/r01_ncu_full_k_rollout_policy_tc_final.csv; the rest of the 213 MB is still dirty in L2 at kernel end
-MUFU_PER_ENV_STEP = 201.0       # 128 tanh x 1.5 (ex2 each, one rcp per pair) + 8 rcp + 1 sqrt; ncu source page: 201.1 MUFU / warp-step
+MUFU_PER_ENV_STEP = 169.0       # 128 tanh x 1.25 (ex2 each, one rcp per four) + 8 rcp + 1 sqrt
 XU_LANES_PER_CLK_PER_SM = 16.0  # B200 MUFU rate
 ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
@@ -293,7 +293,7 @@ def main():
     line["pipes"] = dict(xu_mufu_per_env_step=MUFU_PER_ENV_STEP, xu_ceiling_env_steps_per_s=xu_ceiling, frac_of_xu_ceiling=value / world / xu_ceiling,
                          tensor_tflops_bf16x3=3 * 9856.0 * n * CHUNK_T / kernel_s / 1e12, tensor_peak_tflops=pk["bf16_burst"],
                          physics_flop_per_env_step=450.0, teacher_flop_per_env_step=9856.0,
-                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 201 MUFU per env-step; ncu (profiles/README.md): XU pipe 40 % of active "
+                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 169 MUFU per env-step; ncu (profiles/README.md): XU pipe 40 % of active "
                               "cycles, issue slots 57 %, tensor pipe 18 %; only 13.8 warps/SM exist at 65 536 envs (latency-bound, see DESIGN.md 4.1)")
 
     if not args.quick:

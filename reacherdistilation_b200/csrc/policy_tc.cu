@@ -15,8 +15,9 @@
 //     L3: 64 -> nout on the CUDA cores, fused into the L2 epilogue (fp32 FMAs; no third GEMM round trip)
 // Operands are bf16 hi/lo splits of the fp32 values ("bf16x3": A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulate in
 // TMEM), which keeps the result within ~1e-5 of the fp32 network.  W1/b1/W2/b2 are pre-multiplied by 2*log2(e) when they
-// are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  : FADD, 2 MUFU, FFMA per element, then the bf16
-// hi/lo split written straight into the next layer's A tile (no-swizzle K-major layout, see tc_common.cuh).
+// are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  with ONE reciprocal per four elements (1.25 MUFU per
+// element: the XU pipe sits inside the serial chain of every env step) and packed FADD2 / FMUL2 / FFMA2 arithmetic, then the
+// bf16 hi/lo split written straight into the next layer's A tile (no-swizzle K-major layout, see tc_common.cuh).
 #include <cstddef>
 #include <cstdlib>
 
@@ -26,7 +27,8 @@
 #include "tc_common.cuh"
 
 #ifndef RB_TANH_VARIANT
-#define RB_TANH_VARIANT 1
+#define RB_TANH_VARIANT 5       // 5: four values per reciprocal, packed FADD2 / FMUL2 / FFMA2 (default); 4: pair per reciprocal, packed;
+                                // 1: pair, scalar ops; 0 / 2 / 3: experiments
 #endif
 
 namespace rb {
@@ -45,7 +47,7 @@ struct __align__(128) TcShared {        // one per CTA: split weights + per-tile
     uint8_t B1_hi[64 * 16 * 2];
     uint8_t B1_lo[64 * 16 * 2];
     uint8_t ONES[128 * 16 * 2];         // A operand of the bias K-step: column 0 = 1.0, rest 0
-    float W3f[64 * 4];                  // output layer in fp32, [k][4] (zero columns for nout == 2): applied on the CUDA cores
+    float W3f[64 * 4];                  // output layer in fp32, [k][nout]: applied on the CUDA cores
     float b3[4];
     float mu[12];
     float inv_sd[12];
@@ -90,10 +92,7 @@ __device__ inline void policy_tc_load_weights(TcShared& S, const float* __restri
         *reinterpret_cast<uint16_t*>(S.B2_hi + tile_off(n, k, 64)) = h;
         *reinterpret_cast<uint16_t*>(S.B2_lo + tile_off(n, k, 64)) = l;
     }
-    for (int i = tid; i < 64 * 4; i += nt) {
-        const int n = i & 3, k = i >> 2;
-        S.W3f[i] = n < nout ? __ldg(p + o.W3 + k * nout + n) : 0.f;
-    }
+    for (int i = tid; i < 64 * 4; i += nt) S.W3f[i] = i < 64 * nout ? __ldg(p + o.W3 + i) : 0.f;     // [k][nout], as in the parameter vector
     for (int i = tid; i < 128 * 16; i += nt) {
         const int r = i & 127, k = i >> 7;
         *reinterpret_cast<uint16_t*>(S.ONES + tile_off(r, k, 128)) = k == 0 ? (uint16_t)0x3F80u : (uint16_t)0u;
@@ -129,7 +128,15 @@ __device__ __forceinline__ void hidden_chunk(TcTile& T, const float* v, int cc, 
 #pragma unroll
     for (int q8 = 0; q8 < 2; ++q8) {
         uint32_t h[4], l[4];
-#if RB_TANH_VARIANT == 3
+#if RB_TANH_VARIANT == 5
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            f32x2 t10, t32;
+            tanh_quad_packed(v + 8 * q8 + 4 * q, t10, t32);
+            split_packed_swapped(t10, h[2 * q], l[2 * q]);
+            split_packed_swapped(t32, h[2 * q + 1], l[2 * q + 1]);
+        }
+#elif RB_TANH_VARIANT == 3
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
             float t[4];
@@ -140,6 +147,9 @@ __device__ __forceinline__ void hidden_chunk(TcTile& T, const float* v, int cc, 
 #else
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
+#if RB_TANH_VARIANT == 4
+            tanh_split_pair_packed(v[8 * q8 + 2 * q], v[8 * q8 + 2 * q + 1], h[q], l[q]);
+#else
             float t0, t1;
 #if RB_TANH_VARIANT == 1
             tanh_pair_from_scaled(v[8 * q8 + 2 * q], v[8 * q8 + 2 * q + 1], t0, t1);
@@ -149,6 +159,7 @@ __device__ __forceinline__ void hidden_chunk(TcTile& T, const float* v, int cc, 
             t0 = tanh_from_scaled(v[8 * q8 + 2 * q]); t1 = tanh_from_scaled(v[8 * q8 + 2 * q + 1]);
 #endif
             split_pair(t0, t1, h[q], l[q]);
+#endif
         }
 #endif
         *reinterpret_cast<uint4*>(T.A_hi + (2 * cc + q8) * 2048 + row * 16) = make_uint4(h[0], h[1], h[2], h[3]);
@@ -175,26 +186,48 @@ __device__ __forceinline__ void hidden_epilogue(TcTile& T, uint32_t taddr, int r
 // epilogue of the LAST hidden layer fused with the output layer: out[j] += tanh(acc[k]) W3[k][j] in fp32 on the CUDA cores.  The
 // 64 -> nout layer is 128 (256) FMAs per row; running it here removes a third GEMM round trip (split + store of h2, tile barrier, MMA
 // issue / commit / wait, TMEM load) from the serial chain of every env step.
-template <int NOUT> __device__ __forceinline__ void final_chunk(const TcShared& S, const float* v, int cc, float* o) {
+// W3f layout: [k][NOUT] (nout == 2: one 128-bit load brings the weight pairs of k and k + 1)
+template <int NOUT> __device__ __forceinline__ void final_pair(const TcShared& S, int k, float t0, float t1, f32x2* o) {
+    // (o0, o1) += t (w[k][0], w[k][1]): one FFMA2 per k (and one more for (o2, o3) when NOUT == 4); same order of additions as a scalar loop over k
+    if (NOUT == 2) {
+        const ulonglong2 w = *reinterpret_cast<const ulonglong2*>(&S.W3f[2 * k]);
+        o[0] = fma2(w.x, pk2(t0, t0), o[0]);
+        o[0] = fma2(w.y, pk2(t1, t1), o[0]);
+    } else {
+        const ulonglong2 w0 = *reinterpret_cast<const ulonglong2*>(&S.W3f[4 * k]), w1 = *reinterpret_cast<const ulonglong2*>(&S.W3f[4 * k + 4]);
+        o[0] = fma2(w0.x, pk2(t0, t0), o[0]);
+        o[1] = fma2(w0.y, pk2(t0, t0), o[1]);
+        o[0] = fma2(w1.x, pk2(t1, t1), o[0]);
+        o[1] = fma2(w1.y, pk2(t1, t1), o[1]);
+    }
+}
+template <int NOUT> __device__ __forceinline__ void final_chunk(const TcShared& S, const float* v, int cc, f32x2* o) {
+#if RB_TANH_VARIANT == 5
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        f32x2 t10, t32;
+        float t0, t1, t2, t3;
+        tanh_quad_packed(v + 4 * q, t10, t32);
+        upk2(t10, t1, t0); upk2(t32, t3, t2);
+        final_pair<NOUT>(S, 16 * cc + 4 * q, t0, t1, o);
+        final_pair<NOUT>(S, 16 * cc + 4 * q + 2, t2, t3, o);
+    }
+#else
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
         float t0, t1;
-#if RB_TANH_VARIANT == 1
+#if RB_TANH_VARIANT == 4
+        upk2(tanh_pair_packed(v[2 * q], v[2 * q + 1]), t1, t0);
+#elif RB_TANH_VARIANT == 1
         tanh_pair_from_scaled(v[2 * q], v[2 * q + 1], t0, t1);
 #else
         t0 = tanh_from_scaled(v[2 * q]); t1 = tanh_from_scaled(v[2 * q + 1]);
 #endif
-        const int k = 16 * cc + 2 * q;
-        const float4 w0 = *reinterpret_cast<const float4*>(&S.W3f[4 * k]), w1 = *reinterpret_cast<const float4*>(&S.W3f[4 * k + 4]);
-        o[0] = fmaf(t0, w0.x, o[0]); o[1] = fmaf(t0, w0.y, o[1]);
-        o[0] = fmaf(t1, w1.x, o[0]); o[1] = fmaf(t1, w1.y, o[1]);
-        if (NOUT == 4) {
-            o[2] = fmaf(t0, w0.z, o[2]); o[3] = fmaf(t0, w0.w, o[3]);
-            o[2] = fmaf(t1, w1.z, o[2]); o[3] = fmaf(t1, w1.w, o[3]);
-        }
+        final_pair<NOUT>(S, 16 * cc + 2 * q, t0, t1, o);
     }
+#endif
 }
-template <int NOUT> __device__ __forceinline__ void final_epilogue(const TcShared& S, uint32_t taddr, float* o) {
+template <int NOUT> __device__ __forceinline__ void final_epilogue(const TcShared& S, uint32_t taddr, f32x2* o) {
     float va[16], vb[16];
     tmem_ld_x16(taddr, va);
 #pragma unroll 1
@@ -233,7 +266,7 @@ __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile,
             *reinterpret_cast<uint4*>(T.A_lo + c * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
         }
     }
-    float o[4] = {S.b3[0], S.b3[1], S.b3[2], S.b3[3]};
+    f32x2 o[2] = {pk2(S.b3[0], S.b3[1]), pk2(S.b3[2], S.b3[3])};
 #pragma unroll 1
     for (int layer = 0; layer < 2; ++layer) {
         fence_async_smem();
@@ -257,9 +290,8 @@ __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile,
         if (layer == 0) hidden_epilogue(T, tmem + lane_base, row);   // h1 -> A tile of layer 2
         else final_epilogue<NOUT>(S, tmem + lane_base, o);           // h2 and the output layer, registers only
     }
-    pd[0] = o[0];
-    pd[1] = o[1];
-    if (NOUT == 4) { pd[2] = o[2]; pd[3] = o[3]; } else { pd[2] = S.logstd[0]; pd[3] = S.logstd[1]; }
+    upk2(o[0], pd[0], pd[1]);
+    if (NOUT == 4) upk2(o[1], pd[2], pd[3]); else { pd[2] = S.logstd[0]; pd[3] = S.logstd[1]; }
     fence_before_sync();       // orders this TMEM read before the next evaluation's MMA (issued after the next tile barrier)
 }
 

@@ -135,6 +135,15 @@ __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float* v) {
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
+// ---- packed fp32 pairs (Blackwell FFMA2 / FADD2 / FMUL2: ONE issue slot for two IEEE-rn fp32 operations).  A pair lives in a 64-bit
+// register (slot 0 = low word).  ptxas folds scalar broadcasts ({x, x}), swapped halves ({hi, lo}) and negations into operand modifiers.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float s0, float s1) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(s0), "f"(s1)); return r; }
+__device__ __forceinline__ void upk2(f32x2 r, float& s0, float& s1) { asm("mov.b64 {%0,%1}, %2;" : "=f"(s0), "=f"(s1) : "l"(r)); }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+
 // ---- bf16 hi/lo split (bf16x3 scheme): x ~= hi + lo, each bf16; two values packed per 32-bit word (first -> low half)
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo_half, float hi_half) {
     uint32_t d;
@@ -179,6 +188,48 @@ __device__ __forceinline__ void tanh_pair_from_scaled(float y0, float y1, float&
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
     t0 = fmaf(-2.0f * a1, r, 1.0f);
     t1 = fmaf(-2.0f * a0, r, 1.0f);
+}
+// Packed form of tanh_pair_from_scaled: the +1 and the final 1 - 2 a r are one FADD2 / FFMA2 for the pair (same roundings, same
+// bits).  Returns the pair as (tanh(y1'), tanh(y0')) i.e. SLOT 0 = t1, SLOT 1 = t0 (that is how 1 - 2 a_other r falls out of (a0, a1)).
+__device__ __forceinline__ f32x2 tanh_pair_packed(float y0, float y1) {
+    float e0, e1, r, a0, a1;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e0) : "f"(fminf(y0, 60.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e1) : "f"(fminf(y1, 60.f)));
+    const f32x2 a = add2(pk2(e0, e1), pk2(1.0f, 1.0f));
+    upk2(a, a0, a1);
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a0 * a1));
+    const float rr = -2.0f * r;
+    return fma2(a, pk2(rr, rr), pk2(1.0f, 1.0f));
+}
+__device__ __forceinline__ void split_packed_swapped(f32x2 t, uint32_t& hi2, uint32_t& lo2);
+// tanh pair + bf16 hi/lo split: 14 issue slots per pair (19 with scalar FADD / FFMA)
+__device__ __forceinline__ void tanh_split_pair_packed(float y0, float y1, uint32_t& hi2, uint32_t& lo2) {
+    split_packed_swapped(tanh_pair_packed(y0, y1), hi2, lo2);
+}
+// FOUR values with one reciprocal, packed: 5 MUFU and 18 issue slots per 4 elements (pair form: 6 MUFU, 18 slots).  y clamped to 30
+// (tanh(30 / (2 log2 e)) rounds to 1.0f; the product of four (e + 1) <= 2^121 stays finite).  Returns (t1, t0) and (t3, t2).
+__device__ __forceinline__ void tanh_quad_packed(const float* y, f32x2& t10, f32x2& t32) {
+    float e[4], a0, a1, a2, a3, r;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e[i]) : "f"(fminf(y[i], 30.f)));
+    const f32x2 a01 = add2(pk2(e[0], e[1]), pk2(1.0f, 1.0f)), a23 = add2(pk2(e[2], e[3]), pk2(1.0f, 1.0f));
+    upk2(a01, a0, a1); upk2(a23, a2, a3);
+    const float p01 = a0 * a1, p23 = a2 * a3;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(p01 * p23));
+    const float rr = -2.0f * r;
+    float r01, r23;
+    upk2(mul2(pk2(p23, p01), pk2(rr, rr)), r01, r23);      // -2 / (a0 a1), -2 / (a2 a3)
+    t10 = fma2(a01, pk2(r01, r01), pk2(1.0f, 1.0f));
+    t32 = fma2(a23, pk2(r23, r23), pk2(1.0f, 1.0f));
+}
+// bf16 hi/lo split of a packed pair given as (x1, x0): hi2 / lo2 hold element 0 in the low half
+__device__ __forceinline__ void split_packed_swapped(f32x2 t, uint32_t& hi2, uint32_t& lo2) {
+    float t1, t0, l1, l0;
+    upk2(t, t1, t0);
+    hi2 = pack_bf16x2(t0, t1);
+    const float ah = __uint_as_float(hi2 << 16), bh = __uint_as_float(hi2 & 0xFFFF0000u);
+    upk2(add2(t, pk2(-bh, -ah)), l1, l0);
+    lo2 = pack_bf16x2(l0, l1);
 }
 // same for FOUR values with one reciprocal (5 MUFU per 4 elements); y clamped to 30: tanh(30 / (2 log2 e)) rounds to 1.0f exactly and
 // the product of four (e + 1) <= 2^121 stays finite.
