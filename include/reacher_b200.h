@@ -48,6 +48,7 @@ typedef enum {
 /* loss kinds */
 #define RB_LOSS_KL_ST 0 /* loss.py:3-13  KL(student || teacher), summed                       */
 #define RB_LOSS_KL_TS 1 /* backup/student_rollout.py:639-640  KL(teacher || student), summed  */
+#define RB_LOSS_MSE 2   /* backup/student_rollout_mlp_vf.py:276, student_rollout.py:328  sum of squared errors (dense stacks only) */
 
 const char* rb_last_error(void);
 int rb_version(void);
@@ -233,6 +234,27 @@ int rb_lstm_step(rb_lstm_ctx* ctx, float* params_dev, float* m_dev, float* v_dev
 int rb_gemm_bf16x3(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
                    const float* bias, int act, int accumulate, const float* H, int ldh, float* workspace, int64_t workspace_floats,
                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------ dense stacks -
+ * The auxiliary objectives of the reference's backup experiments, as a generic dense stack on rb_gemm_bf16x3:
+ *   value-function regressor   src/distilation/backup/student_rollout_mlp_vf.py:251-276 ([prev_ob | next_ac] -> 64 linear -> 10 x tanh(100) -> 1,
+ *                              v_loss = sum (vpred - vtarg)^2 :276, Adam lr 1e-2 :290-295), targets by add_vtarg :608-616
+ *   reward-prediction head     src/distilation/backup/student_rollout.py:161-164 (64 tanh -> 1), loss += sum (reward - target)^2 :328
+ *   KL-trained dense students of other widths (loss.py:3-13, backup/student_rollout.py:639-642)
+ * dims[0..n_layers] are the widths (input first); acts[l] = 0 linear / 1 tanh for layer l (NULL: tanh everywhere but the last layer; the
+ * output layer must be linear for rb_dense_loss_grad).  Flat parameters: for every layer W[d_in][d_out] (row-major) then b[d_out].
+ * x [B, dims[0]], target / out [B, dims[n_layers]] row-major.  gradloss = rb_dense_param_count() + 1 floats: flat gradient | loss.
+ * Results are bit-reproducible (fixed-order reductions).  Adam: rb_adam_step on the flat vectors.                                   */
+#define RB_DENSE_MAX_LAYERS 16
+int64_t rb_dense_param_count(int n_layers, const int* dims);
+int64_t rb_dense_workspace_bytes(int n_layers, const int* dims, int64_t batch);
+int rb_dense_fwd(const float* params_dev, int n_layers, const int* dims, const int* acts, const float* x_dev, int64_t B, float* out_dev,
+                 void* workspace_dev, void* stream);
+int rb_dense_loss_grad(const float* params_dev, int n_layers, const int* dims, const int* acts, const float* x_dev, const float* target_dev, int64_t B,
+                       int loss_kind, float* out_dev /* may be NULL */, float* gradloss_dev, void* workspace_dev, void* stream);
+/* add_vtarg  backup/student_rollout_mlp_vf.py:608-616 for `episodes` reward rows [episodes, steps]: vtarg[e][steps-1] = gamma^steps r[steps-1],
+ * vtarg[e][i] = gamma^i r[i] + vtarg[e][i+1] (the reference's absolute-time discount, exponent quirk of the last step included).         */
+int rb_vf_targets(const float* rew_dev, int64_t episodes, int steps, float gamma, float* vtarg_dev, void* stream);
 
 /* ------------------------------------------------------------------------------------------------ dataset -
  * Device-resident rollout buffer with the semantics of the reference Dataset (src/distilation/dataset.py:72-296) for N lock-step

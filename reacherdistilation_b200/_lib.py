@@ -76,6 +76,11 @@ _SIGS = {
                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp]),
     "rb_gemm_bf16x3": (C.c_int, [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
                                  C.c_int, _fp, C.c_int64, _vp]),
+    "rb_dense_param_count": (C.c_int64, [C.c_int, C.POINTER(C.c_int)]),
+    "rb_dense_workspace_bytes": (C.c_int64, [C.c_int, C.POINTER(C.c_int), C.c_int64]),
+    "rb_dense_fwd": (C.c_int, [_fp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _fp, C.c_int64, _fp, _vp, _vp]),
+    "rb_dense_loss_grad": (C.c_int, [_fp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _fp, _fp, C.c_int64, C.c_int, _fp, _fp, _vp, _vp]),
+    "rb_vf_targets": (C.c_int, [_fp, C.c_int64, C.c_int, C.c_float, _fp, _vp]),
     "rb_dataset_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int64, C.c_int64, C.c_int]),
     "rb_dataset_destroy": (C.c_int, [_vp]),
     "rb_dataset_write": (C.c_int, [_vp, _fp, _fp, _fp, _fp, C.c_int, _vp]),
@@ -91,7 +96,7 @@ _SIGS = {
 
 MODE_FP32, MODE_TC = 0, 1
 STUDENT_POLICY64, STUDENT_MLP = 0, 1
-LOSS_KL_ST, LOSS_KL_TS = 0, 1
+LOSS_KL_ST, LOSS_KL_TS, LOSS_MSE = 0, 1, 2
 
 
 def header_symbols():

@@ -8,8 +8,11 @@
 //     MN-contiguous (x_mn = 1): element (row, k) at X[k * ld + row]   -> UMMA MN-major tile (no transpose pass needed)
 // The loader threads read 8 contiguous floats (one 32 B sector), split them into bf16 hi / lo and write one 16-byte chunk into the
 // no-swizzle canonical layout of that orientation, so A^T B (wgrad), A B^T (dgrad) and A B (forward) all run at the same speed.
-// 128 x BN output tile per CTA, BK = 32 per stage, 3 stages; accumulator in TMEM; MMAs issued by one thread, stage reuse gated by
-// tcgen05.commit -> mbarrier.  Split-K (grid.z) writes partial tiles that a second kernel adds in a fixed order (deterministic).
+// 128 x BN output tile per CTA, BK = 32 per k-tile.  Pipeline: cp.async (LDGSTS) streams the raw fp32 k-tiles into 3-4 shared-memory
+// stages (deep enough to cover the L2 / HBM latency without holding registers); each k-tile is then split into bf16 hi / lo
+// operand stages (2, reuse gated by tcgen05.commit -> mbarrier) and consumed by MMAs issued by one elected thread; accumulator in
+// TMEM; the epilogue goes through a padded shared-memory tile so every global access is a coalesced 128-bit one.
+// Split-K (grid.z) writes partial tiles that a second kernel adds in a fixed order (deterministic).
 #include "common.cuh"
 #include "gemm_tc.cuh"
 #include "tc_common.cuh"
@@ -21,41 +24,82 @@ using namespace tc;
 constexpr int GM_THREADS = 256;
 constexpr int GM_BM = 128;
 constexpr int GM_BK = 32;
-constexpr int GM_STAGES = 3;
+constexpr int GM_BF_STAGES = 2;          // bf16 hi/lo operand stages (consumed by the MMAs)
 
 struct __align__(16) GemmCtl {
-    uint64_t stage_bar[GM_STAGES];
+    uint64_t stage_bar[GM_BF_STAGES];
     uint64_t done_bar;
     uint32_t tmem_base;
 };
 
-// one 8-float chunk of an operand tile: rows [row0, row0+R), k in [k0, k0+32); returns zeros outside [nrows) x [kend)
-__device__ __forceinline__ void load_chunk(const float* __restrict__ X, int ld, int mn, int row, int k, int nrows, int kend, float* v) {
-    const bool vec_ok = (ld & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
-    if (mn == 0) {                                   // 8 consecutive k of one row
-        const float* p = X + (size_t)row * ld + k;
-        if (row < nrows && k + 8 <= kend && vec_ok && (k & 3) == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+// ---- global -> shared, asynchronously (LDGSTS).  A chunk = 8 consecutive fp32 of the operand's contiguous dimension; its two 16-byte
+// halves go to two planes of the raw stage (plane[h][chunk]: 16-byte stride, conflict-free both ways).  Elements outside the
+// operand are zero-filled by the copy itself (src-size < cp-size).
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_4(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Per-thread descriptor of one chunk of an operand tile, set up ONCE before the k-loop: where it comes from (pointer at k-tile 0, advanced
+// by a constant step per k-tile), how many of its 8 elements exist along the row dimension, and where it goes (raw plane slot, bf16 slot).
+struct ChunkPlan {
+    const float* p;       // source of the chunk in k-tile 0 (advanced by `step` floats per k-tile)
+    int kofs;             // k of the chunk inside the k-tile
+    int rows_ok;          // K-major: 1 if the row exists; MN-major: how many of the 8 rows exist (0..8)
+    uint32_t raw, off;    // byte offsets: raw plane slot (c * 16), bf16 tile slot
+    bool aligned, active;
+};
+template <int R>
+__device__ __forceinline__ void plan_chunk(ChunkPlan& cp, int c, const float* __restrict__ X, int ld, int mn, int row0, int nrows, int kbeg, bool active) {
+    // Lane -> chunk mapping inside a warp's block of 32 chunks (lane = 8 q + j): the 8 lanes of a quarter-warp take 8 consecutive rows
+    // (K-major) / k (MN-major) of the SAME 16-byte column group => conflict-free 128-bit stores into the UMMA layout, and the four
+    // quarters take the four 32-byte pieces of the same 128-byte global lines => 8 lines per warp request instead of 32.
+    int row, k;
+    const int blk = c >> 5, j = c & 7, q = (c >> 3) & 3;
+    if (mn == 0) { row = blk * 8 + j; k = q * 8; cp.off = q * (R * 16) + row * 16; active = active && row < R; }
+    else {
+        k = (blk & 3) * 8 + j;
+        const int rg = (blk >> 2) * 4 + q;
+        row = rg * 8; cp.off = rg * 512 + (k >> 3) * 128 + (k & 7) * 16;
+        active = active && rg < R / 8;
+    }
+    cp.kofs = k; cp.raw = c * 16; cp.active = active;
+    const int gr = row0 + row;
+    if (mn == 0) { cp.rows_ok = gr < nrows ? 1 : 0; cp.p = X + (size_t)min(gr, nrows - 1) * ld + kbeg + k; }
+    else { cp.rows_ok = min(8, max(0, nrows - gr)); cp.p = X + (size_t)(kbeg + k) * ld + min(gr, nrows - 1); }
+    cp.aligned = (reinterpret_cast<uintptr_t>(cp.p) & 15) == 0;        // the per-k-tile step (128 B or 128 * ld B) keeps it
+}
+// copy the chunk of k-tile starting at k0 (absolute) into its raw slots; elements at k >= kend or beyond the rows are zero-filled by the copy
+__device__ __forceinline__ void copy_planned(const ChunkPlan& cp, const float* X, int mn, int k0, int kend, uint32_t plane0, uint32_t plane1) {
+    int cnt;
+    if (mn == 0) cnt = cp.rows_ok ? min(8, max(0, kend - (k0 + cp.kofs))) : 0;
+    else cnt = (k0 + cp.kofs < kend) ? cp.rows_ok : 0;
+    const uint32_t d0 = plane0 + cp.raw, d1 = plane1 + cp.raw;
+    if (cnt == 0) {                                                 // nothing is read (src-size 0): any 16-byte aligned address inside the allocation
+        const float* z = reinterpret_cast<const float*>(reinterpret_cast<uintptr_t>(X) & ~(uintptr_t)15);
+        cp_async_16(d0, z, 0);
+        cp_async_16(d1, z, 0);
+        return;
+    }
+    const float* p = cp.p;
+    if (cp.aligned) {
+        cp_async_16(d0, p, min(16, 4 * cnt));
+        cp_async_16(d1, cnt > 4 ? p + 4 : p, max(0, min(16, 4 * (cnt - 4))));
+    } else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (row < nrows && k + i < kend) ? __ldg(p + i) : 0.f;
-        }
-    } else {                                         // 8 consecutive rows of one k
-        const float* p = X + (size_t)k * ld + row;
-        if (k < kend && row + 8 <= nrows && vec_ok && (row & 3) == 0) {
-            const float4 a = __ldg(reinterpret_cast<const float4*>(p)), b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-        } else {
+        for (int i = 0; i < 4; ++i) cp_async_4(d0 + 4 * i, i < cnt ? p + i : p, i < cnt ? 4 : 0);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = (k < kend && row + i < nrows) ? __ldg(p + i) : 0.f;
-        }
+        for (int i = 4; i < 8; ++i) cp_async_4(d1 + 4 * (i - 4), i < cnt ? p + i : p, i < cnt ? 4 : 0);
     }
 }
-__device__ __forceinline__ void store_chunk(uint8_t* hi, uint8_t* lo, uint32_t off, const float* v) {
+__device__ __forceinline__ void store_chunk(uint8_t* hi, uint8_t* lo, uint32_t off, const float4& a, const float4& b) {
     uint32_t h[4], l[4];
-#pragma unroll
-    for (int q = 0; q < 4; ++q) split_pair(v[2 * q], v[2 * q + 1], h[q], l[q]);
+    split_pair(a.x, a.y, h[0], l[0]); split_pair(a.z, a.w, h[1], l[1]);
+    split_pair(b.x, b.y, h[2], l[2]); split_pair(b.z, b.w, h[3], l[3]);
     *reinterpret_cast<uint4*>(hi + off) = make_uint4(h[0], h[1], h[2], h[3]);
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
@@ -64,27 +108,37 @@ __device__ __forceinline__ void store_chunk(uint8_t* hi, uint8_t* lo, uint32_t o
 //   K-major : chunk (row r, k-group kg)  at kg * (R*16) + r*16          LBO = R*16, SBO = 128, K-step advance = 2 * LBO
 //   MN-major: chunk (k, row-group rg)    at rg * 512 + (k/8)*128 + (k%8)*16     LBO = 128, SBO = 512, K-step advance = 256
 template <int R> struct OperandTile {
-    static constexpr int CHUNKS = R * GM_BK / 8;
-    static constexpr int PER_THREAD = (CHUNKS + GM_THREADS - 1) / GM_THREADS;
-    static constexpr int BYTES = R * GM_BK * 2;
-    // chunk index c -> (row, k) of its first element and byte offset in the tile
-    __device__ static __forceinline__ void map(int c, int mn, int& row, int& k, uint32_t& off) {
-        if (mn == 0) { row = c % R; const int kg = c / R; k = kg * 8; off = kg * (R * 16) + row * 16; }
-        else { k = c % GM_BK; const int rg = c / GM_BK; row = rg * 8; off = rg * 512 + (k >> 3) * 128 + (k & 7) * 16; }
-    }
+    static constexpr int CHUNKS = R * GM_BK / 8;                                 // 8-float chunks per k-tile
+    static constexpr int SLOTS = CHUNKS < 128 ? 128 : CHUNKS;                    // thread slots (the MN-major mapping needs 4 warps at least)
+    static constexpr int PER_THREAD = (SLOTS + GM_THREADS - 1) / GM_THREADS;
+    static constexpr int BYTES = R * GM_BK * 2;          // one bf16 half
+    static constexpr int RAW_BYTES = SLOTS * 32;         // fp32 staging: two planes of SLOTS x 16 bytes
     __device__ static __forceinline__ uint64_t desc(uint32_t base, int mn, int ks) {
         return mn == 0 ? make_smem_desc(base + ks * 2 * (R * 16), R * 16, 128) : make_smem_desc(base + ks * 256, 128, 512);
     }
 };
 
+// raw (fp32) stages in flight: the 128-wide tile runs one CTA per SM with a deep pipeline, the narrower ones two CTAs per SM
+template <int BN> struct GemmCfg {
+    static constexpr int RAW_STAGES = BN >= 128 ? 4 : (BN == 64 ? 2 : 3);       // BN <= 64: <= 113 KB so that two CTAs share an SM
+    static constexpr int BF_STAGE_BYTES = 2 * OperandTile<GM_BM>::BYTES + 2 * OperandTile<BN>::BYTES;
+    static constexpr int RAW_STAGE_BYTES = OperandTile<GM_BM>::RAW_BYTES + OperandTile<BN>::RAW_BYTES;
+    static constexpr int PIPE_BYTES = GM_BF_STAGES * BF_STAGE_BYTES + RAW_STAGES * RAW_STAGE_BYTES;
+    static constexpr int CT_LD = BN + 4;                                 // fp32 C staging tile, padded rows (conflict-free 128-bit accesses)
+    static constexpr int CT_BYTES = GM_BM * CT_LD * 4;
+    static constexpr int SMEM = (PIPE_BYTES > CT_BYTES ? PIPE_BYTES : CT_BYTES) + (int)sizeof(GemmCtl);
+};
+
 template <int BN>
-__global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g) {
+__global__ void __launch_bounds__(GM_THREADS, BN >= 128 ? 1 : 2) k_gemm_bf16x3(const GemmArgs g) {
     using TA = OperandTile<GM_BM>;
     using TB = OperandTile<BN>;
-    constexpr int STAGE_BYTES = 2 * TA::BYTES + 2 * TB::BYTES;
+    using CF = GemmCfg<BN>;
+    constexpr int RS = CF::RAW_STAGES;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
     extern __shared__ __align__(128) uint8_t smem[];
-    GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(smem + GM_STAGES * STAGE_BYTES);
+    uint8_t* raw_base = smem + GM_BF_STAGES * CF::BF_STAGE_BYTES;
+    GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(smem + CF::SMEM - sizeof(GemmCtl));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * BN;
     const int bz = blockIdx.z / g.nsplit, sz = blockIdx.z - bz * g.nsplit;          // batch index, K slice
@@ -96,9 +150,31 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
     if (warp == 0) tmem_alloc<TCOLS>(&ctl.tmem_base);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GM_STAGES; ++s) mbar_init(&ctl.stage_bar[s], 1);
+        for (int s = 0; s < GM_BF_STAGES; ++s) mbar_init(&ctl.stage_bar[s], 1);
         mbar_init(&ctl.done_bar, 1);
         fence_mbar_init();
+    }
+    // every thread copies / converts the same chunks of every k-tile, so it only ever waits for its own cp.async groups
+    ChunkPlan pa[TA::PER_THREAD], pb[TB::PER_THREAD];
+#pragma unroll
+    for (int i = 0; i < TA::PER_THREAD; ++i) plan_chunk<GM_BM>(pa[i], tid + i * GM_THREADS, Ab, g.lda, g.a_mn, m0, g.M, kbeg, tid + i * GM_THREADS < TA::SLOTS);
+#pragma unroll
+    for (int i = 0; i < TB::PER_THREAD; ++i) plan_chunk<BN>(pb[i], tid + i * GM_THREADS, Bb, g.ldb, g.b_mn, n0, g.N, kbeg, tid + i * GM_THREADS < TB::SLOTS);
+    const size_t step_a = g.a_mn == 0 ? (size_t)GM_BK : (size_t)GM_BK * g.lda, step_b = g.b_mn == 0 ? (size_t)GM_BK : (size_t)GM_BK * g.ldb;
+    auto issue_copies = [&](int kt) {                                // must be called for kt = 0, 1, 2, ... in order (the plans advance)
+        const int k0 = kbeg + kt * GM_BK;
+        const uint32_t ra = smem_u32(raw_base + (kt % RS) * CF::RAW_STAGE_BYTES), rb_ = ra + TA::RAW_BYTES;
+#pragma unroll
+        for (int i = 0; i < TA::PER_THREAD; ++i)
+            if (pa[i].active) { copy_planned(pa[i], Ab, g.a_mn, k0, kend, ra, ra + TA::SLOTS * 16); pa[i].p += step_a; }
+#pragma unroll
+        for (int i = 0; i < TB::PER_THREAD; ++i)
+            if (pb[i].active) { copy_planned(pb[i], Bb, g.b_mn, k0, kend, rb_, rb_ + TB::SLOTS * 16); pb[i].p += step_b; }
+    };
+#pragma unroll
+    for (int p = 0; p < RS - 1; ++p) {                 // prologue: RS - 1 tiles in flight (empty groups keep the group count uniform)
+        if (p < ktiles) issue_copies(p);
+        cp_async_commit();
     }
     fence_before_sync();
     __syncthreads();
@@ -106,51 +182,30 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
     const uint32_t tmem = ctl.tmem_base;
     const uint32_t idesc = make_idesc_bf16(GM_BM, BN) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16);
 
-    float va[TA::PER_THREAD][8], vb[TB::PER_THREAD][8];
-    auto gload = [&](int kt) {
-        const int k0 = kbeg + kt * GM_BK;
-#pragma unroll
-        for (int i = 0; i < TA::PER_THREAD; ++i) {
-            const int c = tid + i * GM_THREADS;
-            int row, k; uint32_t off;
-            TA::map(c, g.a_mn, row, k, off);
-            if (c < TA::CHUNKS) load_chunk(Ab, g.lda, g.a_mn, m0 + row, k0 + k, g.M, kend, va[i]);
-        }
-#pragma unroll
-        for (int i = 0; i < TB::PER_THREAD; ++i) {
-            const int c = tid + i * GM_THREADS;
-            int row, k; uint32_t off;
-            TB::map(c, g.b_mn, row, k, off);
-            if (c < TB::CHUNKS) load_chunk(Bb, g.ldb, g.b_mn, n0 + row, k0 + k, g.N, kend, vb[i]);
-        }
-    };
     uint32_t stage_phase = 0;           // bit s = parity to wait for on stage_bar[s]
-    if (ktiles > 0) gload(0);
     for (int kt = 0; kt < ktiles; ++kt) {
-        const int s = kt % GM_STAGES;
-        uint8_t* a_hi = smem + s * STAGE_BYTES;
+        if (kt + RS - 1 < ktiles) issue_copies(kt + RS - 1);          // its raw stage was converted by this same thread in iteration kt - 1
+        cp_async_commit();
+        cp_async_wait<RS - 1>();                                      // this thread's copies of tile kt have landed
+        const int s = kt % GM_BF_STAGES;
+        uint8_t* a_hi = smem + s * CF::BF_STAGE_BYTES;
         uint8_t* a_lo = a_hi + TA::BYTES;
         uint8_t* b_hi = a_lo + TA::BYTES;
         uint8_t* b_lo = b_hi + TB::BYTES;
-        if (kt >= GM_STAGES) {                                        // the MMAs that read this stage (tile kt - STAGES) are done
+        if (kt >= GM_BF_STAGES) {                                     // the MMAs that read this bf16 stage (tile kt - 2) are done
             mbar_wait(&ctl.stage_bar[s], (stage_phase >> s) & 1u);
             stage_phase ^= 1u << s;
         }
+        const uint8_t* ra = raw_base + (kt % RS) * CF::RAW_STAGE_BYTES;
+        const uint8_t* rb_ = ra + TA::RAW_BYTES;
 #pragma unroll
-        for (int i = 0; i < TA::PER_THREAD; ++i) {
-            const int c = tid + i * GM_THREADS;
-            int row, k; uint32_t off;
-            TA::map(c, g.a_mn, row, k, off);
-            if (c < TA::CHUNKS) store_chunk(a_hi, a_lo, off, va[i]);
-        }
+        for (int i = 0; i < TA::PER_THREAD; ++i)
+            if (pa[i].active)
+                store_chunk(a_hi, a_lo, pa[i].off, *reinterpret_cast<const float4*>(ra + pa[i].raw), *reinterpret_cast<const float4*>(ra + TA::SLOTS * 16 + pa[i].raw));
 #pragma unroll
-        for (int i = 0; i < TB::PER_THREAD; ++i) {
-            const int c = tid + i * GM_THREADS;
-            int row, k; uint32_t off;
-            TB::map(c, g.b_mn, row, k, off);
-            if (c < TB::CHUNKS) store_chunk(b_hi, b_lo, off, vb[i]);
-        }
-        if (kt + 1 < ktiles) gload(kt + 1);                           // next tile's global loads fly while this tile's MMAs are issued
+        for (int i = 0; i < TB::PER_THREAD; ++i)
+            if (pb[i].active)
+                store_chunk(b_hi, b_lo, pb[i].off, *reinterpret_cast<const float4*>(rb_ + pb[i].raw), *reinterpret_cast<const float4*>(rb_ + TB::SLOTS * 16 + pb[i].raw));
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -169,42 +224,83 @@ __global__ void __launch_bounds__(GM_THREADS, 2) k_gemm_bf16x3(const GemmArgs g)
             if (kt == ktiles - 1) mma_commit(&ctl.done_bar);
         }
     }
-    // ---- epilogue: warps w and w+4 share TMEM lane quadrant w & 3 and split the columns ---------------------------------------
+    // ---- epilogue: TMEM -> padded fp32 tile in shared memory (the pipeline stages are dead) -> coalesced 128-bit global accesses ------
+    cp_async_wait<0>();
     if (ktiles > 0) {
         mbar_wait(&ctl.done_bar, 0);
         fence_after_sync();
     }
-    const int row = (warp & 3) * 32 + lane, m = m0 + row;
-    constexpr int CHUNKS8 = BN / 8, HALF = (CHUNKS8 + 1) / 2;
-    const int c_beg = (warp >> 2) * HALF, c_end = min(CHUNKS8, c_beg + HALF);
-    const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    float* ct = reinterpret_cast<float*>(smem);
+    {
+        const int row = (warp & 3) * 32 + lane;                      // warps w and w + 4 share TMEM lane quadrant w & 3 and split the columns
+        constexpr int CHUNKS8 = BN / 8, HALF = (CHUNKS8 + 1) / 2;
+        const int c_beg = (warp >> 2) * HALF, c_end = min(CHUNKS8, c_beg + HALF);
+        const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+        for (int c = c_beg; c < c_end; ++c) {
+            float v[8];
+            if (ktiles > 0) { tmem_ld_x8(tacc + c * 8, v); tmem_ld_wait(); }
+            else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            }
+            float4* d = reinterpret_cast<float4*>(ct + row * CF::CT_LD + c * 8);
+            d[0] = make_float4(v[0], v[1], v[2], v[3]);
+            d[1] = make_float4(v[4], v[5], v[6], v[7]);
+        }
+    }
+    fence_before_sync();
+    __syncthreads();
     const bool split = g.nsplit > 1;
     float* out = split ? g.partial + (size_t)blockIdx.z * g.M * g.N : g.C + (size_t)bz * g.sC;
     const int ldo = split ? g.N : g.ldc;
-    const float* bias = g.bias ? g.bias + (size_t)bz * g.sBias : nullptr;
-    const float* Hb = g.H ? g.H + (size_t)bz * g.sH : nullptr;
-    for (int c = c_beg; c < c_end; ++c) {
-        float v[8];
-        if (ktiles > 0) { tmem_ld_x8(tacc + c * 8, v); tmem_ld_wait(); }
-        else {
+    const float* bias = (!split && g.bias) ? g.bias + (size_t)bz * g.sBias : nullptr;
+    const float* Hb = (!split && g.H) ? g.H + (size_t)bz * g.sH : nullptr;
+    const int act = split ? 0 : g.act, accumulate = split ? 0 : g.accumulate;
+    constexpr int Q = BN / 4;                                        // float4 groups per tile row
+    // CTA-uniform: may rows of this output / bias / H be accessed as aligned float4 (n0 and the group offsets are multiples of 4)?
+    const bool vec_o = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo & 3) == 0;
+    const bool vec_b = bias && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    const bool vec_h = Hb && (reinterpret_cast<uintptr_t>(Hb) & 15) == 0 && (g.ldh & 3) == 0;
+    for (int idx = tid; idx < GM_BM * Q; idx += GM_THREADS) {
+        const int r = idx / Q, q = idx - r * Q, m = m0 + r, n = n0 + q * 4;
+        if (m >= g.M || n >= g.N) continue;
+        const float4 cv = *reinterpret_cast<const float4*>(ct + r * CF::CT_LD + q * 4);
+        float x[4] = {cv.x, cv.y, cv.z, cv.w};
+        float* o = out + (size_t)m * ldo + n;
+        const float* hp = Hb ? Hb + (size_t)m * g.ldh + n : nullptr;
+        const int nv = min(4, g.N - n);
+        const bool full = nv == 4;
+        if (bias) {
+            float b[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full && vec_b) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n)); b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
+            else {
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = 0.f;
-        }
-        if (m < g.M) {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const int n = n0 + c * 8 + i;
-                if (n < g.N) {
-                    float x = v[i];
-                    if (!split) {
-                        if (bias) x += __ldg(bias + n);
-                        if (g.act == 1) x = tanhf(x);
-                        if (Hb) { const float h = __ldg(Hb + (size_t)m * g.ldh + n); x *= fmaf(-h, h, 1.f); }
-                        if (g.accumulate) x += out[(size_t)m * ldo + n];
-                    }
-                    out[(size_t)m * ldo + n] = x;
-                }
+                for (int i = 0; i < 4; ++i) if (i < nv) b[i] = __ldg(bias + n + i);
             }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] += b[i];
+        }
+        if (act == 1) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] = tanhf(x[i]);
+        }
+        if (hp) {
+            float h[4] = {0.f, 0.f, 0.f, 0.f};
+            if (full && vec_h) { const float4 t = __ldg(reinterpret_cast<const float4*>(hp)); h[0] = t.x; h[1] = t.y; h[2] = t.z; h[3] = t.w; }
+            else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) if (i < nv) h[i] = __ldg(hp + i);
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i) x[i] *= fmaf(-h[i], h[i], 1.f);
+        }
+        if (full && vec_o) {
+            if (accumulate) { const float4 t = *reinterpret_cast<const float4*>(o); x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w; }
+            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (i < nv) o[i] = accumulate ? o[i] + x[i] : x[i];
         }
     }
     fence_before_sync();
@@ -230,7 +326,7 @@ __global__ void k_gemm_splitk_reduce(const GemmArgs g, int nsplit, int batch) {
 }
 
 template <int BN> static int launch_gemm(const GemmArgs& g, dim3 grid, cudaStream_t st) {
-    constexpr size_t smem = GM_STAGES * (2 * OperandTile<GM_BM>::BYTES + 2 * OperandTile<BN>::BYTES) + sizeof(GemmCtl);
+    constexpr size_t smem = GemmCfg<BN>::SMEM;
     static bool attr = false;
     if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
     k_gemm_bf16x3<BN><<<grid, GM_THREADS, smem, st>>>(g);
@@ -268,6 +364,55 @@ int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, 
         k_gemm_splitk_reduce<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(g, split, g.batch);
         RB_CUDA(cudaGetLastError());
     }
+    return RB_OK;
+}
+
+__global__ void k_sum_serial(const float* __restrict__ x, int n, float* __restrict__ out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < n; ++i) t += x[i];
+        *out = t;
+    }
+}
+
+// column sums (bias gradients) in two fixed-order stages: partial[bz][rb][col] over row blocks, then the sum over rb
+__global__ void k_colsum_partial(const float* __restrict__ X, int ld, int64_t rows, int n, long long sX, int RB, float* __restrict__ partial) {
+    __shared__ float red[8][33];
+    const int col = blockIdx.x * 32 + threadIdx.x, rb = blockIdx.y, bz = blockIdx.z;
+    const int64_t chunk = (rows + RB - 1) / RB, r0 = rb * chunk, r1 = min(rows, r0 + chunk);
+    const float* Xb = X + (size_t)bz * sX;
+    float acc = 0.f;
+    if (col < n)
+        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += Xb[r * ld + col];
+    red[threadIdx.y][threadIdx.x] = acc;
+    __syncthreads();
+    if (threadIdx.y == 0 && col < n) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
+        partial[((size_t)bz * RB + rb) * n + col] = t;
+    }
+}
+__global__ void k_colsum_final(const float* __restrict__ partial, int RB, int n, int batch, float* __restrict__ out, long long sOut) {
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * batch) return;
+    const int bz = idx / n, col = idx - bz * n;
+    float t = 0.f;
+    for (int rb = 0; rb < RB; ++rb) t += partial[((size_t)bz * RB + rb) * n + col];
+    out[(size_t)bz * sOut + col] = t;
+}
+int colsum(const float* X, int ld, int64_t rows, int n, int batch, long long sX, float* out, long long sOut, float* colpart, cudaStream_t st) {
+    int RB = (int)min((int64_t)64, (rows + 63) / 64);
+    while (RB > 1 && (size_t)RB * n * batch > COLPART_FLOATS) --RB;
+    k_colsum_partial<<<dim3((n + 31) / 32, RB, batch), dim3(32, 8), 0, st>>>(X, ld, rows, n, sX, RB, colpart);
+    k_colsum_final<<<(n * batch + 255) / 256, 256, 0, st>>>(colpart, RB, n, batch, out, sOut);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+
+int sum_serial(const float* x, int n, float* out, cudaStream_t st) {
+    k_sum_serial<<<1, 32, 0, st>>>(x, n, out);
+    RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
 

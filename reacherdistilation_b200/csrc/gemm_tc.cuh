@@ -21,4 +21,11 @@ struct GemmArgs {
 };
 int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, cudaStream_t st);
 
+// column sums (bias gradients) of `batch` row-major blocks X[b] (rows x n, leading dimension ld) in two fixed-order stages;
+// colpart = COLPART_FLOATS floats of scratch
+constexpr size_t COLPART_FLOATS = 64 * 1024;     // <= 64 row blocks x (n x batch <= 1024)
+int colsum(const float* X, int ld, int64_t rows, int n, int batch, long long sX, float* out, long long sOut, float* colpart, cudaStream_t st);
+// out[0] = x[0] + x[1] + ... in index order (one thread: the deterministic tail of the loss reductions)
+int sum_serial(const float* x, int n, float* out, cudaStream_t st);
+
 }  // namespace rb

@@ -1,0 +1,20 @@
+// KL between diagonal Gaussians given as pdflat rows (mean0, mean1, logstd0, logstd1), summed over the two dimensions, and its
+// gradient with respect to the student row: /root/reference src/distilation/loss.py:8-13 (KL(student || teacher)) and
+// backup/student_rollout.py:639-640 (KL(teacher || student)).
+#pragma once
+#include "../../include/reacher_b200.h"
+
+namespace rb {
+
+__device__ __forceinline__ float kl_row(const float4 sv, const float4 tv, int loss_kind, float4& d) {
+    const float vs0 = expf(2.f * sv.z), vs1 = expf(2.f * sv.w), vt0 = expf(2.f * tv.z), vt1 = expf(2.f * tv.w);
+    const float e0 = sv.x - tv.x, e1 = sv.y - tv.y;
+    if (loss_kind == RB_LOSS_KL_ST) {
+        d = make_float4(e0 / vt0, e1 / vt1, vs0 / vt0 - 1.f, vs1 / vt1 - 1.f);
+        return (tv.z - sv.z + (vs0 + e0 * e0) / (2.f * vt0) - 0.5f) + (tv.w - sv.w + (vs1 + e1 * e1) / (2.f * vt1) - 0.5f);
+    }
+    d = make_float4(e0 / vs0, e1 / vs1, 1.f - (vt0 + e0 * e0) / vs0, 1.f - (vt1 + e1 * e1) / vs1);
+    return (sv.z - tv.z + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (sv.w - tv.w + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
+}
+
+}  // namespace rb

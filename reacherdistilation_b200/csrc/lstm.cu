@@ -13,6 +13,7 @@
 #include "common.cuh"
 #include "dagger_input.cuh"
 #include "gemm_tc.cuh"
+#include "loss.cuh"
 
 namespace rb {
 
@@ -22,8 +23,6 @@ constexpr int L_WE = 0, L_BE = 128, L_WL = 160, L_BL = L_WL + LXH * LG, L_HEAD0 
 constexpr int L_HEAD_SZ = 200 * 64 + 64 + 64 * 128 + 128 + 128 * 64 + 64 + 64 * 32 + 32 + 32 * 4 + 4;      // 31652
 constexpr int L_P = L_HEAD0 + LT * L_HEAD_SZ;                                                              // 511880
 static inline int head_w_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o += HD[i] * HD[i + 1] + HD[i + 1]; return o; }
-
-constexpr size_t COLPART_FLOATS = 64 * 1024;     // partial column sums: <= 64 row blocks x (n x batch <= 1024)
 
 // workspace layout (floats), R = T * B rows
 struct LstmWs {
@@ -116,17 +115,8 @@ __global__ void k_lstm_kl(int64_t R, const float4* __restrict__ s, const float4*
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     float l = 0.f;
     if (i < R) {
-        const float4 sv = s[i], tv = t[i];
-        const float vs0 = expf(2.f * sv.z), vs1 = expf(2.f * sv.w), vt0 = expf(2.f * tv.z), vt1 = expf(2.f * tv.w);
-        const float e0 = sv.x - tv.x, e1 = sv.y - tv.y;
         float4 d;
-        if (loss_kind == RB_LOSS_KL_ST) {
-            l = (tv.z - sv.z + (vs0 + e0 * e0) / (2.f * vt0) - 0.5f) + (tv.w - sv.w + (vs1 + e1 * e1) / (2.f * vt1) - 0.5f);
-            d = make_float4(e0 / vt0, e1 / vt1, vs0 / vt0 - 1.f, vs1 / vt1 - 1.f);
-        } else {
-            l = (sv.z - tv.z + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (sv.w - tv.w + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
-            d = make_float4(e0 / vs0, e1 / vs1, 1.f - (vt0 + e0 * e0) / vs0, 1.f - (vt1 + e1 * e1) / vs1);
-        }
+        l = kl_row(s[i], t[i], loss_kind, d);
         ds[i] = d;
     }
 #pragma unroll
@@ -139,49 +129,6 @@ __global__ void k_lstm_kl(int64_t R, const float4* __restrict__ s, const float4*
         loss_partial[blockIdx.x] = tot;
     }
 }
-__global__ void k_sum_serial(const float* __restrict__ x, int n, float* __restrict__ out) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        float t = 0.f;
-        for (int i = 0; i < n; ++i) t += x[i];
-        *out = t;
-    }
-}
-
-// column sums (bias gradients) in two fixed-order stages: partial[bz][rb][col] over row blocks, then the sum over rb
-__global__ void k_colsum_partial(const float* __restrict__ X, int ld, int64_t rows, int n, long long sX, int RB, float* __restrict__ partial) {
-    __shared__ float red[8][33];
-    const int col = blockIdx.x * 32 + threadIdx.x, rb = blockIdx.y, bz = blockIdx.z;
-    const int64_t chunk = (rows + RB - 1) / RB, r0 = rb * chunk, r1 = min(rows, r0 + chunk);
-    const float* Xb = X + (size_t)bz * sX;
-    float acc = 0.f;
-    if (col < n)
-        for (int64_t r = r0 + threadIdx.y; r < r1; r += 8) acc += Xb[r * ld + col];
-    red[threadIdx.y][threadIdx.x] = acc;
-    __syncthreads();
-    if (threadIdx.y == 0 && col < n) {
-        float t = 0.f;
-#pragma unroll
-        for (int k = 0; k < 8; ++k) t += red[k][threadIdx.x];
-        partial[((size_t)bz * RB + rb) * n + col] = t;
-    }
-}
-__global__ void k_colsum_final(const float* __restrict__ partial, int RB, int n, int batch, float* __restrict__ out, long long sOut) {
-    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= n * batch) return;
-    const int bz = idx / n, col = idx - bz * n;
-    float t = 0.f;
-    for (int rb = 0; rb < RB; ++rb) t += partial[((size_t)bz * RB + rb) * n + col];
-    out[(size_t)bz * sOut + col] = t;
-}
-static int colsum(const float* X, int ld, int64_t rows, int n, int batch, long long sX, float* out, long long sOut, float* colpart, cudaStream_t st) {
-    int RB = (int)min((int64_t)64, (rows + 63) / 64);
-    while (RB > 1 && (size_t)RB * n * batch > COLPART_FLOATS) --RB;
-    k_colsum_partial<<<dim3((n + 31) / 32, RB, batch), dim3(32, 8), 0, st>>>(X, ld, rows, n, sX, RB, colpart);
-    k_colsum_final<<<(n * batch + 255) / 256, 256, 0, st>>>(colpart, RB, n, batch, out, sOut);
-    RB_CUDA(cudaGetLastError());
-    return RB_OK;
-}
-
 struct LstmCall {
     const float* params; const float* ob; const float* prev_pd; const float* t_pd; const float* init_state;
     float keep_prob; uint64_t seed; uint32_t sample_id0, iteration;
@@ -246,8 +193,8 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     RB_REQUIRE(kl_blocks <= 1024, "window batch too large for the loss reduction scratch");
     float* loss_part = w.splitk + w.splitk_floats;       // 1024 spare floats behind the split-K area (lstm_ws_carve)
     k_lstm_kl<<<kl_blocks, 256, 0, st>>>(R, (const float4*)c.s_out, (const float4*)c.t_pd, c.loss_kind, (float4*)w.da[4], loss_part);
-    k_sum_serial<<<1, 32, 0, st>>>(loss_part, (int)kl_blocks, c.gradloss + L_P);
     RB_CUDA(cudaGetLastError());
+    RB_TRY(sum_serial(loss_part, (int)kl_blocks, c.gradloss + L_P, st));
     float* G = c.gradloss;
     // ---- heads backward, batched over the T steps ----------------------------------------------------------------------------------
     for (int l = 4; l >= 0; --l) {
