@@ -4,7 +4,7 @@
 //
 // Work decomposition.  A *tile* = 128 envs/samples = the 128 TMEM lanes of one M=128 accumulator = 4 warps; thread r of a
 // tile owns row r end to end (env state in its registers, accumulator row through tcgen05.ld 32x32b).  A CTA holds NT tiles
-// that share ONE shared-memory copy of the split weights; each tile has its own A-operand buffers, its own 64 TMEM
+// that share ONE shared-memory copy of the split weights; each tile has its own A-operand buffers, its own TMEM
 // columns, its own mbarrier and its own named barrier, so tiles run unsynchronised and hide each other's MMA / MUFU
 // latency.  One CTA per SM; envs are dealt to CTAs in units of one warp (32 envs) so every SM gets the same number of
 // warps +-1 whatever N is (65 536 envs = 2048 warp-units = 13.8 per SM; a 128-env granularity would leave a 15 % tail).
@@ -13,6 +13,9 @@
 //     L1: K = 16 (11 obs + a ones column that carries b1 + zero pad), N = 64
 //     L2: K = 64 (+ one extra K = 16 step: a constant ones-tile times the b2 row), N = 64
 //     L3: 64 -> nout on the CUDA cores, fused into the L2 epilogue (fp32 FMAs; no third GEMM round trip)
+// Each tile owns two 64-column TMEM accumulators (when 128 columns per tile fit, i.e. up to 4 tiles per CTA): the L2 MMAs of K-steps
+// 0-1 are issued as soon as the first half of the L1 epilogue has written them, so most of the L2 GEMM runs under the second half of
+// the L1 epilogue instead of after it (the MMA round trip sits in the serial chain of every env step).
 // Operands are bf16 hi/lo splits of the fp32 values ("bf16x3": A_hi*B_hi + A_lo*B_hi + A_hi*B_lo, fp32 accumulate in
 // TMEM), which keeps the result within ~1e-5 of the fp32 network.  W1/b1/W2/b2 are pre-multiplied by 2*log2(e) when they
 // are split, so the hidden epilogue is  tanh = 1 - 2 / (ex2(acc) + 1)  with ONE reciprocal per four elements (1.25 MUFU per
@@ -64,7 +67,12 @@ struct __align__(128) TcTile {
 };
 constexpr uint32_t STRIP_OFF = 8192;    // obs staging strips live in A_hi[8192 .. 8192 + 4*1408)
 
-template <int NT> __host__ __device__ constexpr int tmem_cols() { return NT * 64 <= 64 ? 64 : (NT * 64 <= 128 ? 128 : (NT * 64 <= 256 ? 256 : 512)); }
+// TMEM columns per tile: 128 (layer-1 accumulator in [0,64), layer-2 accumulator in [64,128): lets the layer-2 MMAs start while the layer-1
+// epilogue is still reading) when NT tiles fit the 512 columns, else one shared 64-column accumulator
+template <int NT> __host__ __device__ constexpr int tile_cols() { return NT * 128 <= 512 ? 128 : 64; }
+template <int NT> __host__ __device__ constexpr int tmem_cols() {
+    return NT * tile_cols<NT>() <= 64 ? 64 : (NT * tile_cols<NT>() <= 128 ? 128 : (NT * tile_cols<NT>() <= 256 ? 256 : 512));
+}
 template <int NT> constexpr size_t tc_smem_bytes() { return sizeof(TcShared) + (size_t)NT * sizeof(TcTile); }
 
 __device__ __forceinline__ void tile_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
@@ -109,10 +117,10 @@ __device__ inline void policy_tc_load_weights(TcShared& S, const float* __restri
 
 // D[tmem_d] (+)= sum over k-steps and hi/lo terms of A * B^T.  Called by ONE thread.  A tiles have 128 rows, B tiles n_rows_b.
 __device__ __forceinline__ void issue_bf16x3(uint32_t tmem_d, uint32_t ah, uint32_t al, uint32_t bh, uint32_t bl, int ksteps, int n_rows_b,
-                                             uint32_t idesc, uint32_t acc) {
+                                             uint32_t idesc, uint32_t acc, int ks0 = 0) {
     const uint32_t a_lbo = 128 * 16, b_lbo = (uint32_t)n_rows_b * 16;
-    uint64_t dah = make_smem_desc(ah, a_lbo, 128), dal = make_smem_desc(al, a_lbo, 128);
-    uint64_t dbh = make_smem_desc(bh, b_lbo, 128), dbl = make_smem_desc(bl, b_lbo, 128);
+    uint64_t dah = make_smem_desc(ah + ks0 * 2 * a_lbo, a_lbo, 128), dal = make_smem_desc(al + ks0 * 2 * a_lbo, a_lbo, 128);
+    uint64_t dbh = make_smem_desc(bh + ks0 * 2 * b_lbo, b_lbo, 128), dbl = make_smem_desc(bl + ks0 * 2 * b_lbo, b_lbo, 128);
 #pragma unroll
     for (int ks = 0; ks < ksteps; ++ks) {
         mma_bf16(tmem_d, dah, dbh, idesc, acc);
@@ -167,25 +175,6 @@ __device__ __forceinline__ void hidden_chunk(TcTile& T, const float* v, int cc, 
     }
 }
 
-// epilogue of a 64-wide hidden layer: TMEM row -> tanh -> split -> this thread's row of the next A tile; TMEM loads of
-// the next 16 columns are in flight while the current 16 are processed
-__device__ __forceinline__ void hidden_epilogue(TcTile& T, uint32_t taddr, int row) {
-    float va[16], vb[16];
-    tmem_ld_x16(taddr, va);
-#pragma unroll 1
-    for (int cc = 0; cc < 4; cc += 2) {
-        tmem_ld_wait();
-        tmem_ld_x16(taddr + 16 * (cc + 1), vb);
-        hidden_chunk(T, va, cc, row);
-        tmem_ld_wait();
-        if (cc + 2 < 4) tmem_ld_x16(taddr + 16 * (cc + 2), va);
-        hidden_chunk(T, vb, cc + 1, row);
-    }
-}
-
-// epilogue of the LAST hidden layer fused with the output layer: out[j] += tanh(acc[k]) W3[k][j] in fp32 on the CUDA cores.  The
-// 64 -> nout layer is 128 (256) FMAs per row; running it here removes a third GEMM round trip (split + store of h2, tile barrier, MMA
-// issue / commit / wait, TMEM load) from the serial chain of every env step.
 // W3f layout: [k][NOUT] (nout == 2: one 128-bit load brings the weight pairs of k and k + 1)
 template <int NOUT> __device__ __forceinline__ void final_pair(const TcShared& S, int k, float t0, float t1, f32x2* o) {
     // (o0, o1) += t (w[k][0], w[k][1]): one FFMA2 per k (and one more for (o2, o3) when NOUT == 4); same order of additions as a scalar loop over k
@@ -244,13 +233,15 @@ template <int NOUT> __device__ __forceinline__ void final_epilogue(const TcShare
 // Full policy evaluation for one tile.  Every ACTIVE thread of the tile must call this (it contains the tile barrier,
 // `bar_threads` = 32 * active warps of the tile).  ob: this thread's 11-d observation.  pd: (mean0, mean1, logstd0,
 // logstd1) or the four raw outputs.  issuer: true for exactly one (whole, active) warp of the tile; one elected lane issues the MMAs.
-template <int NOUT>
+template <int NOUT, int TCOLS>
 __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile, int row, int bar_threads, bool issuer, const float* ob,
                                                float* pd, uint32_t& phase) {
-    const uint32_t tmem = S.tmem_base + (uint32_t)tile * 64u;
+    const uint32_t tmem1 = S.tmem_base + (uint32_t)tile * (uint32_t)TCOLS;       // layer-1 accumulator
+    const uint32_t tmem2 = TCOLS >= 128 ? tmem1 + 64u : tmem1;                   // layer-2 accumulator (its own columns when they exist)
     const uint32_t lane_base = (uint32_t)(row & ~31) << 16;     // this warp's 32-lane TMEM window
     uint64_t* mbar = &S.mbar[tile];
     const uint32_t ah = smem_u32(T.A_hi), al = smem_u32(T.A_lo);
+    const uint32_t idesc = make_idesc_bf16(128, 64);
     // ---- A1 = [clip((ob - mu) * inv_sd), 1, 0...] --------------------------------------------------------------
     {
         float z[16];
@@ -266,30 +257,56 @@ __device__ __forceinline__ void policy_tc_eval(TcShared& S, TcTile& T, int tile,
             *reinterpret_cast<uint4*>(T.A_lo + c * 2048 + row * 16) = make_uint4(l[0], l[1], l[2], l[3]);
         }
     }
-    f32x2 o[2] = {pk2(S.b3[0], S.b3[1]), pk2(S.b3[2], S.b3[3])};
-#pragma unroll 1
-    for (int layer = 0; layer < 2; ++layer) {
-        fence_async_smem();
-        fence_before_sync();
-        tile_sync(1 + tile, bar_threads);
-        if (issuer && elect_one_sync()) {                           // `issuer` is warp-uniform: one whole warp of the tile
-            fence_after_sync();
-            const uint32_t idesc = make_idesc_bf16(128, 64);
-            if (layer == 0) {
-                issue_bf16x3(tmem, ah, al, smem_u32(S.B1_hi), smem_u32(S.B1_lo), 1, 64, idesc, 0);     // b1 rides in the ones column
-            } else {
-                const uint64_t ones = make_smem_desc(smem_u32(S.ONES), 128 * 16, 128);
-                mma_bf16(tmem, ones, make_smem_desc(smem_u32(S.B2b_hi), 64 * 16, 128), idesc, 0);     // D = 1 * b2 (hi + lo)
-                mma_bf16(tmem, ones, make_smem_desc(smem_u32(S.B2b_lo), 64 * 16, 128), idesc, 1);
-                issue_bf16x3(tmem, ah, al, smem_u32(S.B2_hi), smem_u32(S.B2_lo), 4, 64, idesc, 1);
-            }
-            mma_commit(mbar);
-        }
-        mbar_wait(mbar, phase); phase ^= 1u;
+    // ---- layer 1: one K = 16 step (b1 rides in the ones column) ---------------------------------------------------
+    fence_async_smem();
+    fence_before_sync();
+    tile_sync(1 + tile, bar_threads);
+    if (issuer && elect_one_sync()) {                               // `issuer` is warp-uniform: one whole warp of the tile
         fence_after_sync();
-        if (layer == 0) hidden_epilogue(T, tmem + lane_base, row);   // h1 -> A tile of layer 2
-        else final_epilogue<NOUT>(S, tmem + lane_base, o);           // h2 and the output layer, registers only
+        issue_bf16x3(tmem1, ah, al, smem_u32(S.B1_hi), smem_u32(S.B1_lo), 1, 64, idesc, 0);
+        mma_commit(mbar);
     }
+    mbar_wait(mbar, phase); phase ^= 1u;
+    fence_after_sync();
+    // ---- layer-1 epilogue (h1 -> A tile of layer 2) with the layer-2 MMAs issued as soon as their K-steps are written ---------------
+    auto issue_l2 = [&](int ks0, int ksteps, bool first, bool last) {
+        if (issuer && elect_one_sync()) {
+            fence_after_sync();
+            if (first) {
+                const uint64_t ones = make_smem_desc(smem_u32(S.ONES), 128 * 16, 128);
+                mma_bf16(tmem2, ones, make_smem_desc(smem_u32(S.B2b_hi), 64 * 16, 128), idesc, 0);     // D = 1 * b2 (hi + lo)
+                mma_bf16(tmem2, ones, make_smem_desc(smem_u32(S.B2b_lo), 64 * 16, 128), idesc, 1);
+            }
+            issue_bf16x3(tmem2, ah, al, smem_u32(S.B2_hi), smem_u32(S.B2_lo), ksteps, 64, idesc, 1, ks0);
+            if (last) mma_commit(mbar);
+        }
+    };
+    {
+        const uint32_t taddr = tmem1 + lane_base;
+        float va[16], vb[16];
+        tmem_ld_x16(taddr, va);
+#pragma unroll 1
+        for (int cc = 0; cc < 4; cc += 2) {
+            tmem_ld_wait();
+            tmem_ld_x16(taddr + 16 * (cc + 1), vb);
+            hidden_chunk(T, va, cc, row);
+            tmem_ld_wait();
+            if (cc + 2 < 4) tmem_ld_x16(taddr + 16 * (cc + 2), va);
+            hidden_chunk(T, vb, cc + 1, row);
+            if (TCOLS >= 128 || cc == 2) {                          // K-steps cc, cc + 1 of the layer-2 A tile are complete for this thread
+                fence_async_smem();
+                fence_before_sync();
+                tile_sync(1 + tile, bar_threads);
+                if (TCOLS >= 128) issue_l2(cc, 2, cc == 0, cc == 2);
+                else issue_l2(0, 4, true, true);                     // shared accumulator: only after the whole layer-1 row has been read
+            }
+        }
+    }
+    mbar_wait(mbar, phase); phase ^= 1u;
+    fence_after_sync();
+    // ---- layer-2 epilogue + output layer, registers only -------------------------------------------------------------------------
+    f32x2 o[2] = {pk2(S.b3[0], S.b3[1]), pk2(S.b3[2], S.b3[3])};
+    final_epilogue<NOUT>(S, tmem2 + lane_base, o);
     upk2(o[0], pd[0], pd[1]);
     if (NOUT == 4) upk2(o[1], pd[2], pd[3]); else { pd[2] = S.logstd[0]; pd[3] = S.logstd[1]; }
     fence_before_sync();       // orders this TMEM read before the next evaluation's MMA (issued after the next tile barrier)
@@ -351,7 +368,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_policy_fwd_tc(const float* __re
         float ob[OBS], pd[4];
         warp_load_rows<OBS>(obs, row0, nvalid, ob, strip, lane);
         __syncwarp();
-        policy_tc_eval<NOUT>(S, T, tile, row, TILE, row < 32, ob, pd, phase);
+        policy_tc_eval<NOUT, tile_cols<NT>()>(S, T, tile, row, TILE, row < 32, ob, pd, phase);
         if (i < n) pd_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
     }
     policy_tc_teardown<NT>(S);
@@ -399,7 +416,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, co
             if (KIND == RB_STUDENT_POLICY64 && x_out != obs_out) warp_store_rows<OBS>(x_out, row0, nvalid, ob, strip, lane);
         }
         __syncwarp();
-        policy_tc_eval<2>(S, T, tile, row, TILE, row < 32, ob, pd, phase);
+        policy_tc_eval<2, tile_cols<NT>()>(S, T, tile, row, TILE, row < 32, ob, pd, phase);
         if (valid) {
             t_out[i] = make_float4(pd[0], pd[1], pd[2], pd[3]);
             if (KIND == RB_STUDENT_MLP) {
@@ -452,7 +469,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
             observe(e, ob);
             if (obs_buf) warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strip, lane);
             __syncwarp();
-            policy_tc_eval<NOUT>(S, Tl, tile, row, bar_threads, row < 32, ob, pd, phase);
+            policy_tc_eval<NOUT, tile_cols<NT>()>(S, Tl, tile, row, bar_threads, row < 32, ob, pd, phase);
             bool d;
             const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
             const int64_t r = (int64_t)t * n + i;
