@@ -335,6 +335,16 @@ def main():
                                              kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
                                                      else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
                                              note="tile GEMMs run bf16x3 (3 MMAs per product): tensor-pipe work is 3x the algorithmic FLOP"))
+        if tr.student_mode == MODE_TC:                                  # phase stamps (CTA 0, globaltimer) of the last cooperative launch on rank 0
+            import ctypes
+            tb = (ctypes.c_ulonglong * 48)()
+            L.rb_debug_student_timers(tb)
+            us = lambda i, j: round((tb[j] - tb[i]) / 1e3, 2)
+            ph = dict(fold_image=us(0, 1), sync=us(1, 2), image_load=us(2, 3), tiles=us(3, 4), dump=us(4, 5), sync2=us(5, 6), reduce=us(6, 7), sync3=us(7, 8),
+                      unfold=us(8, 32), sync_adam_teardown=us(9, 11), total=us(0, 11))
+            if world > 1:
+                ph.update(exch_sync=us(32, 33), exch_push=us(33, 34), exch_recv_sum_adam=us(34, 9))
+            line["distill"]["student_kernel_phases_us"] = ph
         if world > 1:                                                   # every rank must hold bit-identical student parameters
             chk = torch.stack([tr.student.params.double().sum(), tr.student.params.double().abs().sum()]).to(dev)
             allc = [torch.empty_like(chk) for _ in range(world)]
@@ -381,8 +391,8 @@ def main():
             lflop = 6.0 * (243 * 800 + 31400 + 128) * 10 * Bw                       # 3 x 2 x MAC per window row, T = 10
             line["lstm"] = dict(metric="lstm_window_rows_per_sec", value=10.0 * Bw * 10 / lsec2, unit="sample-steps/s", windows=Bw, steps_unrolled=10,
                                 ms_per_step=1e3 * lsec2 / 10, tensor_tflops=lflop / (lsec2 / 10) / 1e12, params=int(lnet.P),
-                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads: ~250 launches of k_gemm_bf16x3 and "
-                                     "element-wise kernels captured once in a CUDA graph (rb_lstm_step, device-side step clock)")
+                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads: 97 launches (batched k_gemm_bf16x3 over the "
+                                     "un-shared heads, element-wise kernels) captured once in a CUDA graph (rb_lstm_step, device-side step clock)")
             del lnet
         # ---- step API: HBM-bound single-step kernel at 4M envs ---------------------------------------------------
         ns = STEP_API_ENVS

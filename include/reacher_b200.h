@@ -159,10 +159,13 @@ int rb_student_step(int kind, float* params_dev, float* m_dev, float* v_dev, con
 
 /* Data-parallel form of rb_student_step (MpiAdam.update = Allreduce + Adam, backup/student_rollout.py:658,709), RB_MODE_TC only:
  * ONE cooperative kernel per rank computes the local [grad | loss], exchanges it with a one-shot all-reduce over NVLink peer
- * memory (every rank adds all ranks' slots in rank order => bit-identical sums everywhere) and applies Adam.
- *   peer_grad_slots[world]: device address, valid on THIS rank, of every rank's slot of rb_student_param_count+1 floats for this
- *                           step (symmetric / IPC-mapped memory; the caller alternates two slots per rank from step to step),
- *   peer_flags[world]     : device address of every rank's flag array (uint32[world], zero before the first step),
+ * memory and applies Adam.  The exchange is a low-latency push: every rank stores {value, epoch} pairs (8 bytes, delivered atomically)
+ * into every rank's receive area and sums its own area in rank order as the pairs arrive => bit-identical sums everywhere, no flag
+ * round trip, no remote loads.
+ *   peer_grad_slots[world]: device address, valid on THIS rank, of every rank's receive area for this step: uint64 [world][SL] with
+ *                           SL = rb_student_param_count + 1 rounded up to 64 (symmetric / IPC-mapped memory, zero before the first
+ *                           step; the caller alternates two areas per rank from step to step),
+ *   peer_flags[world]     : reserved (may be NULL),
  *   epoch                 : 1, 2, 3, ... identical on all ranks.  gradloss_dev receives the all-reduced [grad | loss].
  * All ranks must launch the same step; the kernels wait for one another.                                               */
 int rb_student_step_dp(int kind, float* params_dev, float* m_dev, float* v_dev, const float* x_dev, const float* t_pdflat_dev, int64_t B,
@@ -171,7 +174,7 @@ int rb_student_step_dp(int kind, float* params_dev, float* m_dev, float* v_dev, 
                        const uint64_t* peer_flags, uint32_t epoch, void* stream);
 
 /* Debug aid: globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last RB_MODE_TC student launch (48 values: [0,12) launch phases, [16,31) phases of
- * CTA 0's first tile; see student_tc.cu).  Synchronises the device.                                                                            */
+ * CTA 0's first tile, [32,35) un-fold done / local gradient visible / pushed to the peers; see student_tc.cu).  Synchronises the device.                                                                            */
 int rb_debug_student_timers(unsigned long long* host_out16);
 
 /* ------------------------------------------------------------------------------------------------ DAgger --
@@ -191,7 +194,7 @@ int rb_dagger_invalidate_teacher(rb_dagger* d);
 /* One whole DAgger iteration (RB_MODE_TC): rb_dagger_observe + rb_student_step[_dp] + rb_dagger_act, with every per-step quantity
  * (dropout iteration, Adam step, exchange epoch / slot parity) read from a device-side clock set once by rb_dagger_set_clock and
  * advanced by the last kernel -- so the three launches are captured ONCE in a CUDA graph (use_graph != 0) and replayed with a single
- * cudaGraphLaunch per iteration.  world > 1: slots_even / slots_odd / flags as in rb_student_step_dp (the two slot sets alternate). */
+ * cudaGraphLaunch per iteration.  world > 1: slots_even / slots_odd / flags as in rb_student_step_dp (the two receive-area sets alternate). */
 int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_step, uint32_t epoch, void* stream);
 int rb_dagger_step(rb_dagger* d, const float* teacher_params_dev, float* params_dev, float* m_dev, float* v_dev, float* gradloss_dev,
                    void* workspace_dev, float* obs_dev, float* t_pdflat_dev, float* x_dev, float* s_pdflat_dev, float* rew_dev, uint8_t* done_dev,

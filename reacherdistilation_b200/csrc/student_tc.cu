@@ -91,28 +91,29 @@ struct StudentTcArgs {
     float* adam_p; float* adam_m; float* adam_v;
     float lr_t, beta1, beta2, eps, gscale;
     // optional data-parallel exchange fused in front of the update: one-shot all-reduce over NVLink peer memory.
-    // peer_gl[r] = rank r's [P+1] gradient slot of this step (symmetric allocation, double buffered by the caller),
-    // peer_flag[r] = rank r's flag array (uint32[world]); this rank writes `epoch` into peer_flag[r][rank].
+    // peer_ll[r] = rank r's receive area of this step: uint2 {value bits, epoch} [world][SL], SL = round_up(P + 1, 64); this rank writes
+    // row `rank` of every area (symmetric allocation, double buffered by the caller: peer_ll2[epoch & 1] when the step clock is used)
     int world, rank;
     uint32_t epoch;
-    float* peer_gl[8];
-    uint32_t* peer_flag[8];
-    // optional device-side step clock {iteration, adam step, exchange epoch} (CUDA-graph replay: no per-step host arguments).
-    // When set, adam step = clock[1] + 1 (lr_t computed in-kernel from `lr`), epoch = clock[2] + 1, slots = peer_gl2[epoch & 1].
+    uint2* peer_ll[8];
+    // When set, adam step = clock[1] + 1 (lr_t computed in-kernel from `lr`), epoch = clock[2] + 1, areas = peer_ll2[epoch & 1].
     const uint32_t* clock;
     float lr;
-    float* peer_gl2[2][8];
+    uint2* peer_ll2[2][8];
 };
 
 // Plain (weak) global load.  Data produced earlier in the SAME launch by other CTAs is read only after a grid barrier and is never
 // touched by this SM before that barrier, so no stale L1 line can exist; unlike ld.global.cg / volatile these loads may be batched.
 template <typename T> __device__ __forceinline__ T ldw(const T* p) { return *p; }
 
-__device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
-__device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-    return v;
+// {value, epoch} pair as ONE 8-byte store / load at system scope (peer memory over NVLink; bypasses L1 on the polling side)
+__device__ __forceinline__ void st_ll(uint2* p, uint32_t v, uint32_t e) {
+    asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(v), "r"(e) : "memory");
+}
+__device__ __forceinline__ uint2 ld_ll(const uint2* p) {
+    uint2 w;
+    asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(w.x), "=r"(w.y) : "l"(p) : "memory");
+    return w;
 }
 __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
     float v;
@@ -672,33 +673,48 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         st_stamp(8);
         // ---- gradient of the un-folded parameters ---------------------------------------------------------------------------------
         const uint32_t epoch = ctl.epoch;
-        float* const* pgl = a.clock ? a.peer_gl2[epoch & 1u] : a.peer_gl;     // slots of this step (double buffered by epoch parity)
-        float* gl = a.world > 1 ? pgl[a.rank] : a.gradloss;                   // data parallel: this rank's slot of the symmetric buffer
+        float* gl = a.gradloss;
         if constexpr (S::L == 4) finish_mlp(a.params, a.red, gl, gtid, gthreads);
         else
             for (int i = gtid; i <= a.P; i += gthreads) gl[i] = ldw(a.red + i);
+        st_stamp(32);
         if (a.world > 1) {
-            // ---- one-shot all-reduce over NVLink peer memory (MpiAdam.update's Allreduce, backup/student_rollout.py:709) ----------
-            grid.sync();                                                   // the whole local gradient is written (gpu scope)
-            if (blockIdx.x == 0 && tid < a.world) {                        // fence.sys + release.sys are cumulative over what the barrier ordered
-                __threadfence_system();
-                st_release_sys(a.peer_flag[tid] + a.rank, epoch);          // tell rank `tid` that this rank's slot is ready
-                while (ld_acquire_sys(a.peer_flag[a.rank] + tid) < epoch) { }       // ... and wait for rank `tid`'s slot
+            // ---- one-shot all-reduce over NVLink peer memory (MpiAdam.update's Allreduce, backup/student_rollout.py:709), low-latency form:
+            // every rank PUSHES {value, epoch} pairs (one 8-byte store each, delivered atomically) into every rank's receive area, then sums
+            // its own area in rank order as the pairs of this epoch arrive -- no flag round trip, no remote loads, no extra grid barrier; the
+            // one-way NVLink latency overlaps the pushes still in flight.  Areas are double buffered by epoch parity (a fast rank may push
+            // step k + 1 while a slow one still reads step k).
+            grid.sync();                       // the local gradient is complete, and every read of the old parameters (finish) is done
+            st_stamp(33);
+            const int SL = (a.P + 1 + 63) / 64 * 64;                               // slot stride (elements) inside a receive area
+            uint2* const* ll = a.clock ? a.peer_ll2[epoch & 1u] : a.peer_ll;
+            for (int i = gtid; i <= a.P; i += gthreads) {
+                const uint32_t v = __float_as_uint(ldw(gl + i));
+                for (int q = 0; q < a.world; ++q) st_ll(ll[q] + (size_t)a.rank * SL + i, v, epoch);
             }
-            grid.sync();
-            for (int i = gtid; i <= a.P; i += gthreads) {                  // every rank adds the slots in rank order: identical sums
+            st_stamp(34);
+            const uint2* mine = ll[a.rank];
+            for (int i = gtid; i <= a.P; i += gthreads) {                           // rank order: bit-identical sums on every rank
                 float tot = 0.f;
-                for (int r = 0; r < a.world; ++r) tot += ld_relaxed_sys(pgl[r] + i);
-                a.gradloss[i] = tot;
+                for (int r = 0; r < a.world; ++r) {
+                    uint2 w;
+                    do { w = ld_ll(mine + (size_t)r * SL + i); } while (w.y != epoch);
+                    tot += __uint_as_float(w.x);
+                }
+                gl[i] = tot;
+                if (a.do_adam && i < a.P) {    // TF1 Adam, same arithmetic as k_adam (student.cu); element i only needs gradient i
+                    float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
+                    adam_update(pi, mi, vi, tot, ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                    a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
+                }
             }
         }
         st_stamp(9);
-        if (a.do_adam) {                   // TF1 Adam, same arithmetic as k_adam (student.cu)
-            if (a.world <= 1) grid.sync(); // every read of the old parameters (finish) is done, every gradloss entry written
-            else __syncthreads();          // (the exchange above already separated finish from here; own-thread gradloss entries)
+        if (a.do_adam && a.world <= 1) {
+            grid.sync();                       // every read of the old parameters (finish) is done, every gradloss entry written
             for (int i = gtid; i < a.P; i += gthreads) {
                 float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
-                adam_update(pi, mi, vi, a.world > 1 ? a.gradloss[i] : ldw(a.gradloss + i), ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                adam_update(pi, mi, vi, ldw(a.gradloss + i), ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
                 a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
             }
         }
@@ -766,9 +782,9 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
         RB_REQUIRE(px->world <= 8 && px->rank >= 0 && px->rank < px->world, "peer exchange supports 2..8 ranks");
         a.world = px->world; a.rank = px->rank; a.epoch = px->epoch;
         for (int r = 0; r < px->world; ++r) {
-            a.peer_gl[r] = (float*)px->gl_ptrs[r]; a.peer_flag[r] = (uint32_t*)px->flag_ptrs[r];
-            a.peer_gl2[0][r] = (float*)px->gl_ptrs[r];                                  // slots of even epochs
-            a.peer_gl2[1][r] = (float*)(px->gl_ptrs_alt ? px->gl_ptrs_alt[r] : px->gl_ptrs[r]);   // slots of odd epochs
+            a.peer_ll[r] = (uint2*)px->gl_ptrs[r];
+            a.peer_ll2[0][r] = (uint2*)px->gl_ptrs[r];                                  // receive areas of even epochs
+            a.peer_ll2[1][r] = (uint2*)(px->gl_ptrs_alt ? px->gl_ptrs_alt[r] : px->gl_ptrs[r]);   // ... of odd epochs
         }
     }
     if (clk && clk->clock) { a.clock = clk->clock; a.lr = clk->lr; }

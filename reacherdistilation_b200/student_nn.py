@@ -79,8 +79,9 @@ class StudentNet:
 
     # ---- data parallel: one-shot all-reduce over NVLink peer memory fused into the step kernel -------------------------
     def enable_peer_exchange(self, group=None):
-        """Allocate this rank's symmetric buffer [flags(64 u32) | slot 0 | slot 1] and exchange the peer mappings
-        (torch.distributed._symmetric_memory: CUDA VMM handles over the process group's store).  RB_MODE_TC only."""
+        """Allocate this rank's symmetric buffer [reserved(64 u32) | receive area 0 | receive area 1] (an area = {value, epoch} pairs
+        [world][slot], see rb_student_step_dp) and exchange the peer mappings (torch.distributed._symmetric_memory: CUDA VMM handles over
+        the process group's store).  RB_MODE_TC only."""
         import torch.distributed as dist
         import torch.distributed._symmetric_memory as symm
         assert self.mode == _lib.MODE_TC, "the fused exchange lives in the tcgen05 student kernel"
@@ -88,18 +89,19 @@ class StudentNet:
         self._px_world, self._px_rank = dist.get_world_size(group), dist.get_rank(group)
         assert 2 <= self._px_world <= 8
         slot = (self.P + 1 + 63) // 64 * 64
+        area = 2 * self._px_world * slot                # floats: 8-byte pairs, one row per sending rank
         with torch.cuda.device(self.device):
-            self._px_buf = symm.empty(64 + 2 * slot, dtype=torch.float32, device=self.device)
+            self._px_buf = symm.empty(64 + 2 * area, dtype=torch.float32, device=self.device)
         self._px_buf.zero_()
         hdl = symm.rendezvous(self._px_buf, group.group_name)
         self._px_hdl = hdl
         base = [int(p) for p in hdl.buffer_ptrs]
         mk = lambda vals: torch.tensor(vals, dtype=torch.int64).numpy().astype(np.uint64)
         self._px_flags = mk(base)
-        self._px_slots = [mk([b + 4 * (64 + k * slot) for b in base]) for k in (0, 1)]
+        self._px_slots = [mk([b + 4 * (64 + k * area) for b in base]) for k in (0, 1)]
         self._px_epoch = 0
         torch.cuda.synchronize(self.device)
-        hdl.barrier()                                   # every rank's flags are zero before anyone steps
+        hdl.barrier()                                   # every rank's receive areas are zero before anyone steps
         torch.cuda.synchronize(self.device)
 
     def step_dp(self, x, t_pdflat, loss_kind=LOSS_KL_ST, s_out=None, grad_scale=1.0):
