@@ -8,12 +8,14 @@
 //     s_tau  = head_tau(m): 200 -> 64 -> 128 -> 64 -> 32 (tanh) -> 4, weights NOT shared between the unrolled steps      (:42-46)
 // Flat parameter layout: W_e[4][32] b_e[32] W_l[243][800] b_l[800] then for tau = 0..9: W1[200][64] b1 W2[64][128] b2 W3[128][64] b3
 // W4[64][32] b4 W5[32][4] b5.
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
 #include "dagger_input.cuh"
 #include "gemm_tc.cuh"
 #include "loss.cuh"
+#include "lstm_recur.cuh"
 
 namespace rb {
 
@@ -26,7 +28,7 @@ static inline int head_w_off(int l) { int o = 0; for (int i = 0; i < l; ++i) o +
 
 // workspace layout (floats), R = T * B rows
 struct LstmWs {
-    float *xh, *z, *dz, *dxh, *c, *hh, *dh, *dc, *a[5], *da[5], *splitk, *colpart;
+    float *xh, *z, *dz, *dxh, *c, *hh, *dh, *dc, *a[5], *da[5], *splitk, *colpart, *recur;
     size_t splitk_floats;
 };
 static size_t lstm_ws_floats(int64_t R, int64_t B, size_t* splitk) {
@@ -34,7 +36,7 @@ static size_t lstm_ws_floats(int64_t R, int64_t B, size_t* splitk) {
     for (int l = 1; l <= 5; ++l) per_row += 2 * (size_t)HD[l];
     const size_t sk = (size_t)32 * LDXH * LG;            // split-K partials of the largest wgrad (243 x 800, <= 32 slices)
     if (splitk) *splitk = sk;
-    return per_row * R + (size_t)(LT + 1) * B * LU + (size_t)B * LU + sk + 1024 + COLPART_FLOATS + 64;
+    return per_row * R + (size_t)(LT + 1) * B * LU + (size_t)B * LU + sk + 1024 + COLPART_FLOATS + lstm_recur_ws_floats(B) + 128;
 }
 static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
     float* p = ws;
@@ -45,6 +47,7 @@ static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
     lstm_ws_floats(R, B, &w.splitk_floats);
     w.splitk = take(w.splitk_floats + 1024);
     w.colpart = take(COLPART_FLOATS);
+    w.recur = take(lstm_recur_ws_floats(B));
 }
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
@@ -162,14 +165,24 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
                                                                            c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c);
     RB_CUDA(cudaGetLastError());
     RB_TRY(gemm(c.prev_pd, 4, 0, P + L_WE, LE, 1, w.xh + 11, LDXH, Ri, LE, 4, P + L_BE, 0, 0, nullptr, 0, w, sms, st));
-    // ---- recurrence ------------------------------------------------------------------------------------------------------------
-    for (int t = 0; t < LT; ++t) {
-        float* xh_t = w.xh + (size_t)t * B * LDXH;
-        float* z_t = w.z + (size_t)t * B * LG;
-        RB_TRY(gemm(xh_t, LDXH, 0, P + L_WL, LG, 1, z_t, LG, Bi, LG, LXH, P + L_BL, 0, 0, nullptr, 0, w, sms, st));
-        k_lstm_cell_fwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, z_t, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
-                                                                           w.hh + (size_t)t * B * LU, t + 1 < LT ? xh_t + (size_t)B * LDXH : nullptr);
-        RB_CUDA(cudaGetLastError());
+    // ---- recurrence: one persistent cluster launch (lstm_recur.cu); RB_LSTM_RECUR=0 keeps the GEMM + cell launch sequence ------------
+    static int use_recur = -1;
+    if (use_recur < 0) { const char* v = getenv("RB_LSTM_RECUR"); use_recur = v ? atoi(v) : 1; }
+    LstmRecurArgs ra{};
+    ra.W_l = P + L_WL; ra.b_l = P + L_BL; ra.B = B; ra.xh = w.xh; ra.hh = w.hh; ra.c0 = w.c; ra.c_last = w.c + (size_t)LT * B * LU;
+    ra.dh = w.dh; ra.dz = w.dz; ra.dxh = w.dxh; ra.scratch = w.recur;
+    if (use_recur) {
+        RB_TRY(lstm_recur_build_images(ra, st));
+        RB_TRY(lstm_recur_forward(ra, st));
+    } else {
+        for (int t = 0; t < LT; ++t) {
+            float* xh_t = w.xh + (size_t)t * B * LDXH;
+            float* z_t = w.z + (size_t)t * B * LG;
+            RB_TRY(gemm(xh_t, LDXH, 0, P + L_WL, LG, 1, z_t, LG, Bi, LG, LXH, P + L_BL, 0, 0, nullptr, 0, w, sms, st));
+            k_lstm_cell_fwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, z_t, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
+                                                                               w.hh + (size_t)t * B * LU, t + 1 < LT ? xh_t + (size_t)B * LDXH : nullptr);
+            RB_CUDA(cudaGetLastError());
+        }
     }
     if (c.final_state) {
         RB_CUDA(cudaMemcpyAsync(c.final_state, w.c + (size_t)LT * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
@@ -210,14 +223,18 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, HD[l], w, sms, st, false, bd));
     }
     // ---- back-propagation through time -------------------------------------------------------------------------------------------
-    RB_CUDA(cudaMemsetAsync(w.dc, 0, sizeof(float) * B * LU, st));
-    for (int t = LT - 1; t >= 0; --t) {
-        float* dz_t = w.dz + (size_t)t * B * LG;
-        float* dxh_t = w.dxh + (size_t)t * B * LDXH;
-        k_lstm_cell_bwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, w.z + (size_t)t * B * LG, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
-                                                                           w.dh + (size_t)t * B * LU, t + 1 < LT ? dxh_t + (size_t)B * LDXH : nullptr, w.dc, dz_t);
-        RB_CUDA(cudaGetLastError());
-        RB_TRY(gemm(dz_t, LG, 0, P + L_WL, LG, 0, dxh_t, LDXH, Bi, LXH, LG, nullptr, 0, 0, nullptr, 0, w, sms, st, true));  // d[x | m_prev] = dz W_l^T
+    if (use_recur) {
+        RB_TRY(lstm_recur_backward(ra, st));
+    } else {
+        RB_CUDA(cudaMemsetAsync(w.dc, 0, sizeof(float) * B * LU, st));
+        for (int t = LT - 1; t >= 0; --t) {
+            float* dz_t = w.dz + (size_t)t * B * LG;
+            float* dxh_t = w.dxh + (size_t)t * B * LDXH;
+            k_lstm_cell_bwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, w.z + (size_t)t * B * LG, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
+                                                                               w.dh + (size_t)t * B * LU, t + 1 < LT ? dxh_t + (size_t)B * LDXH : nullptr, w.dc, dz_t);
+            RB_CUDA(cudaGetLastError());
+            RB_TRY(gemm(dz_t, LG, 0, P + L_WL, LG, 0, dxh_t, LDXH, Bi, LXH, LG, nullptr, 0, 0, nullptr, 0, w, sms, st, true));  // d[x | m_prev] = dz W_l^T
+        }
     }
     // ---- weight gradients of the shared parts, over all T*B rows ---------------------------------------------------------------------
     RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
