@@ -53,19 +53,37 @@ struct ChunkPlan {
     uint32_t raw, off;    // byte offsets: raw plane slot (c * 16), bf16 tile slot
     bool aligned, active;
 };
+// bf16 tile geometry (one half, hi or lo) of an operand with R rows, BK = 32, no-swizzle canonical layouts with PADDED strides:
+//   K-major : chunk (row r, k-group kg)  at kg * LBO_K + r * 16,                    LBO_K = R*16 + 32, SBO = 128
+//   MN-major: chunk (k, row-group rg)    at rg * SBO_MN + (k/8)*128 + (k%8)*16,     LBO = 128, SBO_MN = 512 + 16
+// The pads let a quarter-warp whose 8 lanes read ONE or TWO contiguous global lines (see plan_chunk) store its 8 chunks into 8 distinct
+// 16-byte bank groups.
+template <int R> struct TileGeo {
+    static constexpr int LBO_K = R * 16 + 32;
+    static constexpr int SBO_MN = 512 + 16;
+    static constexpr int BYTES_RAW = (4 * LBO_K > (R / 8) * SBO_MN) ? 4 * LBO_K : (R / 8) * SBO_MN;
+    static constexpr int BYTES = (BYTES_RAW + 127) / 128 * 128;
+};
 template <int R>
 __device__ __forceinline__ void plan_chunk(ChunkPlan& cp, int c, const float* __restrict__ X, int ld, int mn, int row0, int nrows, int kbeg, bool active) {
-    // Lane -> chunk mapping inside a warp's block of 32 chunks (lane = 8 q + j): the 8 lanes of a quarter-warp take 8 consecutive rows
-    // (K-major) / k (MN-major) of the SAME 16-byte column group => conflict-free 128-bit stores into the UMMA layout, and the four
-    // quarters take the four 32-byte pieces of the same 128-byte global lines => 8 lines per warp request instead of 32.
+    // Chunk -> lane mapping.  The L1 handles a 128-bit-per-lane request one QUARTER-warp (8 lanes) at a time and pays one tag look-up per
+    // distinct 128-byte line in it: a row-per-lane mapping (8 lines per quarter-warp) made the copies of a k-tile cost ~2000 cycles.  Here
+    // a quarter-warp (task) takes chunks that lie in one or two contiguous lines:
+    //   K-major : 2 consecutive rows x their 4 k-groups (two 128-byte lines)
+    //   MN-major: 8 consecutive row-groups at one k (256 contiguous bytes); narrower tiles: R/8 row-groups x 8/(R/8) values of k
     int row, k;
-    const int blk = c >> 5, j = c & 7, q = (c >> 3) & 3;
-    if (mn == 0) { row = blk * 8 + j; k = q * 8; cp.off = q * (R * 16) + row * 16; active = active && row < R; }
-    else {
-        k = (blk & 3) * 8 + j;
-        const int rg = (blk >> 2) * 4 + q;
-        row = rg * 8; cp.off = rg * 512 + (k >> 3) * 128 + (k & 7) * 16;
-        active = active && rg < R / 8;
+    const int l8 = c & 7, task = c >> 3;
+    active = active && task < R / 2;
+    if (mn == 0) {
+        row = 2 * task + (l8 >> 2); k = (l8 & 3) * 8;
+        cp.off = (l8 & 3) * TileGeo<R>::LBO_K + row * 16;
+    } else {
+        constexpr int RGn = R / 8, LPK = RGn < 8 ? RGn : 8, KS = LPK;          // lanes per k; k stride inside a task = 8 / (8 / LPK)
+        int rg;
+        if (RGn >= 8) { k = task & 31; rg = (task >> 5) * 8 + l8; }
+        else { k = (task % KS) + 8 * (task / KS) + KS * (l8 / LPK); rg = l8 % LPK; }
+        row = rg * 8;
+        cp.off = rg * TileGeo<R>::SBO_MN + (k >> 3) * 128 + (k & 7) * 16;
     }
     cp.kofs = k; cp.raw = c * 16; cp.active = active;
     const int gr = row0 + row;
@@ -104,17 +122,15 @@ __device__ __forceinline__ void store_chunk(uint8_t* hi, uint8_t* lo, uint32_t o
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
-// Tile geometry of an operand with R rows (R = 128 for A, BN for B), BK = 32:
-//   K-major : chunk (row r, k-group kg)  at kg * (R*16) + r*16          LBO = R*16, SBO = 128, K-step advance = 2 * LBO
-//   MN-major: chunk (k, row-group rg)    at rg * 512 + (k/8)*128 + (k%8)*16     LBO = 128, SBO = 512, K-step advance = 256
 template <int R> struct OperandTile {
     static constexpr int CHUNKS = R * GM_BK / 8;                                 // 8-float chunks per k-tile
     static constexpr int SLOTS = CHUNKS < 128 ? 128 : CHUNKS;                    // thread slots (the MN-major mapping needs 4 warps at least)
     static constexpr int PER_THREAD = (SLOTS + GM_THREADS - 1) / GM_THREADS;
-    static constexpr int BYTES = R * GM_BK * 2;          // one bf16 half
+    static constexpr int BYTES = TileGeo<R>::BYTES;      // one bf16 half
     static constexpr int RAW_BYTES = SLOTS * 32;         // fp32 staging: two planes of SLOTS x 16 bytes
-    __device__ static __forceinline__ uint64_t desc(uint32_t base, int mn, int ks) {
-        return mn == 0 ? make_smem_desc(base + ks * 2 * (R * 16), R * 16, 128) : make_smem_desc(base + ks * 256, 128, 512);
+    __device__ static __forceinline__ uint64_t desc(uint32_t base, int mn, int ks) {       // K-step ks (16 values of k) of the tile
+        return mn == 0 ? make_smem_desc(base + ks * 2 * TileGeo<R>::LBO_K, TileGeo<R>::LBO_K, 128)
+                       : make_smem_desc(base + ks * 256, 128, TileGeo<R>::SBO_MN);
     }
 };
 
