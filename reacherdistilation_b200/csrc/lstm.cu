@@ -20,7 +20,16 @@
 namespace rb {
 
 constexpr int LT = 10, LU = 200, LG = 800, LX = 43, LE = 32, LXH = 243, LDXH = 256;
+// Activation buffers carry a constant ONES column right behind their last feature (hh: column 200 of 204, head layer outputs: column HD[l]
+// of HD[l] + 4, xh: column 243 of 256).  The forward / dgrad GEMMs never read it (K = the feature count); the weight-gradient GEMM takes one
+// more row of its transposed operand, and since every bias sits right behind its weight matrix in the parameter vector, that extra output
+// row IS the bias gradient: no column-sum launches.
+constexpr int LDHH = LU + 4;
+
 constexpr int HD[6] = {200, 64, 128, 64, 32, 4};
+#define HD_PAD(l) (HD[l] + 4)
+static_assert(HD[1] == 64 && HD[2] == 128 && HD[3] == 64 && HD[4] == 32, "k_lstm_inputs spells the ones-column offsets out");
+static inline int act_ld(int l) { return l == 0 ? LDHH : HD_PAD(l); }       // leading dimension of the input of head layer l
 constexpr int L_WE = 0, L_BE = 128, L_WL = 160, L_BL = L_WL + LXH * LG, L_HEAD0 = L_BL + LG;
 constexpr int L_HEAD_SZ = 200 * 64 + 64 + 64 * 128 + 128 + 128 * 64 + 64 + 64 * 32 + 32 + 32 * 4 + 4;      // 31652
 constexpr int L_P = L_HEAD0 + LT * L_HEAD_SZ;                                                              // 511880
@@ -32,8 +41,8 @@ struct LstmWs {
     size_t splitk_floats;
 };
 static size_t lstm_ws_floats(int64_t R, int64_t B, size_t* splitk) {
-    size_t per_row = LDXH + LG + LG + LDXH + LU + LU;
-    for (int l = 1; l <= 5; ++l) per_row += 2 * (size_t)HD[l];
+    size_t per_row = LDXH + LG + LG + LDXH + LDHH + LU;
+    for (int l = 1; l <= 5; ++l) per_row += 2 * (size_t)HD[l] + 4;
     const size_t sk = (size_t)32 * LDXH * LG;            // split-K partials of the largest wgrad (243 x 800, <= 32 slices)
     if (splitk) *splitk = sk;
     return per_row * R + (size_t)(LT + 1) * B * LU + (size_t)B * LU + sk + 1024 + COLPART_FLOATS + lstm_recur_ws_floats(B) + 128;
@@ -42,8 +51,8 @@ static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
     float* p = ws;
     auto take = [&](size_t n) { float* q = p; p += (n + 3) & ~(size_t)3; return q; };
     w.xh = take(R * LDXH); w.z = take(R * LG); w.dz = take(R * LG); w.dxh = take(R * LDXH);
-    w.c = take((size_t)(LT + 1) * B * LU); w.hh = take(R * LU); w.dh = take(R * LU); w.dc = take((size_t)B * LU);
-    for (int l = 1; l <= 5; ++l) { w.a[l - 1] = take(R * HD[l]); w.da[l - 1] = take(R * HD[l]); }
+    w.c = take((size_t)(LT + 1) * B * LU); w.hh = take(R * LDHH); w.dh = take(R * LU); w.dc = take((size_t)B * LU);
+    for (int l = 1; l <= 5; ++l) { w.a[l - 1] = take(R * HD_PAD(l)); w.da[l - 1] = take(R * HD[l]); }
     lstm_ws_floats(R, B, &w.splitk_floats);
     w.splitk = take(w.splitk_floats + 1024);
     w.colpart = take(COLPART_FLOATS);
@@ -55,7 +64,8 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-
 // x rows: dropout(ob) -> xh[:, 0:11]; initial m state -> xh rows of step 0, columns 43..242; initial c -> c[0]
 __global__ void k_lstm_inputs(int64_t R, int64_t B, const float* __restrict__ ob, float keep_prob, uint32_t k0, uint32_t k1, uint32_t sample_id0,
                               uint32_t iteration, const uint32_t* __restrict__ clock, const float* __restrict__ init_state, float* __restrict__ xh,
-                              float* __restrict__ c0) {
+                              float* __restrict__ c0, float* __restrict__ hh, float* __restrict__ a1, float* __restrict__ a2, float* __restrict__ a3,
+                              float* __restrict__ a4) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (clock) iteration = clock[0];                 // device-side step clock (CUDA-graph replay)
     if (i < R) {
@@ -68,7 +78,9 @@ __global__ void k_lstm_inputs(int64_t R, int64_t B, const float* __restrict__ ob
 #pragma unroll
         for (int k = 0; k < 11; ++k) xh[i * LDXH + k] = r[k];
 #pragma unroll
-        for (int k = LXH; k < LDXH; ++k) xh[i * LDXH + k] = 0.f;
+        for (int k = LXH; k < LDXH; ++k) xh[i * LDXH + k] = k == LXH ? 1.f : 0.f;       // ones column -> b_l gradient
+        hh[i * LDHH + LU] = 1.f;                                                         // ones columns of the head inputs -> bias gradients
+        a1[i * 68 + 64] = 1.f; a2[i * 132 + 128] = 1.f; a3[i * 68 + 64] = 1.f; a4[i * 36 + 32] = 1.f;       // HD_PAD(l) / HD[l], l = 1..4
     }
     if (i < B * LU) {
         const int64_t b = i / LU, u = i - b * LU;
@@ -79,7 +91,7 @@ __global__ void k_lstm_inputs(int64_t R, int64_t B, const float* __restrict__ ob
 
 // gates (pre-activation, [B,800]) -> activated in place; c, m; m also goes to the next step's xh rows and to hh
 __global__ void k_lstm_cell_fwd(int64_t B, float* __restrict__ z, const float* __restrict__ c_prev, float* __restrict__ c_out, float* __restrict__ hh,
-                                float* __restrict__ xh_next) {
+                                float* __restrict__ xh_next) {       // hh rows have LDHH floats
     const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (idx >= B * LU) return;
     const int64_t b = idx / LU, u = idx - b * LU;
@@ -88,7 +100,7 @@ __global__ void k_lstm_cell_fwd(int64_t B, float* __restrict__ z, const float* _
     const float c = fmaf(f, c_prev[idx], i * j), m = o * tanhf(c);
     zr[u] = i; zr[LU + u] = j; zr[2 * LU + u] = f; zr[3 * LU + u] = o;
     c_out[idx] = c;
-    hh[idx] = m;
+    hh[b * LDHH + u] = m;
     if (xh_next) xh_next[b * LDXH + LX + u] = m;
 }
 
@@ -162,14 +174,14 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     const float* P = c.params;
     // ---- inputs: dropout(ob), initial state, embedding of prev_pdflat --------------------------------------------------------
     k_lstm_inputs<<<(unsigned)((max(R, B * LU) + 255) / 256), 256, 0, st>>>(R, B, c.ob, c.keep_prob, (uint32_t)c.seed, (uint32_t)(c.seed >> 32),
-                                                                           c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c);
+                                                                           c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c, w.hh, w.a[0], w.a[1], w.a[2], w.a[3]);
     RB_CUDA(cudaGetLastError());
     RB_TRY(gemm(c.prev_pd, 4, 0, P + L_WE, LE, 1, w.xh + 11, LDXH, Ri, LE, 4, P + L_BE, 0, 0, nullptr, 0, w, sms, st));
     // ---- recurrence: one persistent cluster launch (lstm_recur.cu); RB_LSTM_RECUR=0 keeps the GEMM + cell launch sequence ------------
     static int use_recur = -1;
     if (use_recur < 0) { const char* v = getenv("RB_LSTM_RECUR"); use_recur = v ? atoi(v) : 1; }
     LstmRecurArgs ra{};
-    ra.W_l = P + L_WL; ra.b_l = P + L_BL; ra.B = B; ra.xh = w.xh; ra.hh = w.hh; ra.c0 = w.c; ra.c_last = w.c + (size_t)LT * B * LU;
+    ra.W_l = P + L_WL; ra.b_l = P + L_BL; ra.B = B; ra.xh = w.xh; ra.hh = w.hh; ra.hh_ld = LDHH; ra.c0 = w.c; ra.c_last = w.c + (size_t)LT * B * LU;
     ra.dh = w.dh; ra.dz = w.dz; ra.dxh = w.dxh; ra.scratch = w.recur;
     if (use_recur) {
         RB_TRY(lstm_recur_build_images(ra, st));
@@ -180,13 +192,14 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
             float* z_t = w.z + (size_t)t * B * LG;
             RB_TRY(gemm(xh_t, LDXH, 0, P + L_WL, LG, 1, z_t, LG, Bi, LG, LXH, P + L_BL, 0, 0, nullptr, 0, w, sms, st));
             k_lstm_cell_fwd<<<(unsigned)((B * LU + 255) / 256), 256, 0, st>>>(B, z_t, w.c + (size_t)t * B * LU, w.c + (size_t)(t + 1) * B * LU,
-                                                                               w.hh + (size_t)t * B * LU, t + 1 < LT ? xh_t + (size_t)B * LDXH : nullptr);
+                                                                               w.hh + (size_t)t * B * LDHH, t + 1 < LT ? xh_t + (size_t)B * LDXH : nullptr);
             RB_CUDA(cudaGetLastError());
         }
     }
     if (c.final_state) {
         RB_CUDA(cudaMemcpyAsync(c.final_state, w.c + (size_t)LT * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
-        RB_CUDA(cudaMemcpyAsync(c.final_state + B * LU, w.hh + (size_t)(LT - 1) * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
+        RB_CUDA(cudaMemcpy2DAsync(c.final_state + B * LU, sizeof(float) * LU, w.hh + (size_t)(LT - 1) * B * LDHH, sizeof(float) * LDHH, sizeof(float) * LU,
+                                  (size_t)B, cudaMemcpyDeviceToDevice, st));
     }
     // ---- per-step heads: the T heads have their own weights (student_nn.py:42-46) => one BATCHED GEMM per layer (batch = T) ------
     {
@@ -194,8 +207,9 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         for (int l = 0; l < 5; ++l) {
             const float* W = P + L_HEAD0 + head_w_off(l);
             float* out = l == 4 ? c.s_out : w.a[l];
-            Bat bt; bt.n = LT; bt.sA = B * HD[l]; bt.sB = L_HEAD_SZ; bt.sC = B * HD[l + 1]; bt.sBias = L_HEAD_SZ;
-            RB_TRY(gemm(in, HD[l], 0, W, HD[l + 1], 1, out, HD[l + 1], Bi, HD[l + 1], HD[l], W + HD[l] * HD[l + 1], l < 4 ? 1 : 0, 0, nullptr, 0, w, sms, st,
+            const int ld_in = act_ld(l), ld_out = l == 4 ? HD[5] : act_ld(l + 1);
+            Bat bt; bt.n = LT; bt.sA = B * ld_in; bt.sB = L_HEAD_SZ; bt.sC = B * ld_out; bt.sBias = L_HEAD_SZ;
+            RB_TRY(gemm(in, ld_in, 0, W, HD[l + 1], 1, out, ld_out, Bi, HD[l + 1], HD[l], W + HD[l] * HD[l + 1], l < 4 ? 1 : 0, 0, nullptr, 0, w, sms, st,
                         false, bt));
             in = out;
         }
@@ -215,12 +229,13 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         float* gW = G + L_HEAD0 + head_w_off(l);
         const float* dout = w.da[l];
         const float* in = l == 0 ? w.hh : w.a[l - 1];
-        Bat bw; bw.n = LT; bw.sA = B * HD[l]; bw.sB = B * HD[l + 1]; bw.sC = L_HEAD_SZ;                 // dW = in^T dout
-        RB_TRY(gemm(in, HD[l], 1, dout, HD[l + 1], 1, gW, HD[l + 1], HD[l], HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, st, true, bw));
-        RB_TRY(colsum(dout, HD[l + 1], B, HD[l + 1], LT, B * HD[l + 1], gW + HD[l] * HD[l + 1], L_HEAD_SZ, w.colpart, st));      // db = colsum(dout)
+        const int ld_in = act_ld(l);
+        // [dW ; db] = [in | 1]^T dout : HD[l] + 1 output rows, the last one lands on the bias gradient (b follows W in the parameter vector)
+        Bat bw; bw.n = LT; bw.sA = B * ld_in; bw.sB = B * HD[l + 1]; bw.sC = L_HEAD_SZ;
+        RB_TRY(gemm(in, ld_in, 1, dout, HD[l + 1], 1, gW, HD[l + 1], HD[l] + 1, HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, st, true, bw));
         float* din = l == 0 ? w.dh : w.da[l - 1];                                                     // d(in) = dout W^T (* tanh' of the layer input)
-        Bat bd; bd.n = LT; bd.sA = B * HD[l + 1]; bd.sB = L_HEAD_SZ; bd.sC = B * HD[l]; bd.sH = B * HD[l];
-        RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, HD[l], w, sms, st, false, bd));
+        Bat bd; bd.n = LT; bd.sA = B * HD[l + 1]; bd.sB = L_HEAD_SZ; bd.sC = B * HD[l]; bd.sH = B * ld_in;
+        RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, ld_in, w, sms, st, false, bd));
     }
     // ---- back-propagation through time -------------------------------------------------------------------------------------------
     if (use_recur) {
@@ -237,8 +252,7 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         }
     }
     // ---- weight gradients of the shared parts, over all T*B rows ---------------------------------------------------------------------
-    RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
-    RB_TRY(colsum(w.dz, LG, R, LG, 1, 0, G + L_BL, 0, w.colpart, st));
+    RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH + 1, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));   // row 243 (ones column) = db_l
     RB_TRY(gemm(c.prev_pd, 4, 1, w.dxh + 11, LDXH, 1, G + L_WE, LE, 4, LE, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
     RB_TRY(colsum(w.dxh + 11, LDXH, R, LE, 1, 0, G + L_BE, 0, w.colpart, st));
     RB_CUDA(cudaGetLastError());

@@ -101,7 +101,7 @@ __device__ __forceinline__ void rc_stamp(int k, int t, int i) {
 struct RecurDev {
     const float* b_l; const uint8_t* img;
     int64_t B; int nrb;
-    float* xh; float* hh; const float* c0; float* c_last;
+    float* xh; float* hh; int hh_ld; const float* c0; float* c_last;
     const float* dh; float* dz; float* dxh;
     float4* gates; float* cst; float* part;
     unsigned int* bar;       // one counter per group (zeroed by lstm_recur_build_images)
@@ -255,13 +255,13 @@ __global__ void __launch_bounds__(RC_THREADS, 1) k_lstm_recur_fwd(const RecurDev
             __syncthreads();
             rc_stamp(0, t, 6);
             if (lane < RC_UN) {       // warp w stores rows w, w + 16, ...: one 100-byte segment per row and destination
-                float* hh_t = a.hh + ((size_t)t * B + row0) * RU + RC_UN * j + lane;
+                float* hh_t = a.hh + ((size_t)t * B + row0) * a.hh_ld + RC_UN * j + lane;
                 float* xh_n = a.xh + ((size_t)(t + 1) * B + row0) * RLD + RX + RC_UN * j + lane;
 #pragma unroll
                 for (int r = warp; r < 128; r += RC_THREADS / 32) {
                     if (row0 + r < B) {
                         const float m = S.mst[r * RC_UN + lane];
-                        hh_t[(size_t)r * RU] = m;
+                        hh_t[(size_t)r * a.hh_ld] = m;
                         if (t + 1 < RT) xh_n[(size_t)r * RLD] = m;
                     }
                 }
@@ -500,7 +500,7 @@ int make_dev(const LstmRecurArgs& a, bool backward, RecurDev& d) {
     const Carve c = carve(a.scratch, a.B);
     d = RecurDev{};
     d.b_l = a.b_l; d.img = backward ? c.img_b : c.img_f; d.B = a.B; d.nrb = (int)row_blocks(a.B);
-    d.xh = a.xh; d.hh = a.hh; d.c0 = a.c0; d.c_last = a.c_last; d.dh = a.dh; d.dz = a.dz; d.dxh = a.dxh;
+    d.xh = a.xh; d.hh = a.hh; d.hh_ld = a.hh_ld; d.c0 = a.c0; d.c_last = a.c_last; d.dh = a.dh; d.dz = a.dz; d.dxh = a.dxh;
     d.gates = c.gates; d.cst = c.cst; d.part = c.part; d.bar = c.bar;
     return group_count(d.nrb, &d.ngroups);
 }

@@ -15,7 +15,7 @@ struct LstmRecurArgs {
     const float* b_l;        // [800]
     int64_t B;               // window rows
     float* xh;               // [T*B][256]  in: x columns 0..42 of every step and m_0 in columns 43..242 of step 0; out: m_{t-1} of steps 1..T-1
-    float* hh;               // [T*B][200]  out: m_t (input of the per-step heads)
+    float* hh; int hh_ld;    // [T*B][hh_ld >= 200]  out: m_t (input of the per-step heads); columns >= 200 are left alone
     const float* c0;         // [B][200]    initial cell state
     float* c_last;           // [B][200]    out: c_T
     const float* dh;         // [T*B][200]  in (backward): dL/dm_t from the heads
