@@ -268,7 +268,8 @@ def main():
     e2e_sec, e2e_full_sec = e2e_time(hres), e2e_time(hbuf)
     e2e = dict(value=float(n) * CHUNK_T * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
                d2h_bytes_per_step=int(n * CHUNK_T * (4 + 1)), steps=Ke, api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host)",
-               result="reward[T,N] f32 + done[T,N] u8 to pinned host memory; obs / pdflat stay in the device-resident rollout buffer",
+               result="reward[T,N] f32 + done[T,N] u8 to pinned host memory (reward written by the kernel into the mapped buffer, done "
+                      "copied after it); obs / pdflat are written to the device-resident rollout buffer (rb_env_rollout_buffer) and stay there",
                mean_reward_host=float(hbuf["rew"].mean()))
     e2e_full = dict(value=float(n) * CHUNK_T * Ke * world / e2e_full_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
                     d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke, note="whole rollout buffer to the host: PCIe-bound")

@@ -114,9 +114,16 @@ int rb_policy_fwd_host(const float* params_host, int nout, const float* obs_host
  *   rew_buf_dev[T,N]     reward returned by that step              done_buf_dev[T,N]  1 when that step ended the episode */
 int rb_env_rollout_policy(rb_env* env, const float* params_dev, int nout, int T, float* obs_buf_dev, float* pd_buf_dev,
                           float* rew_buf_dev, uint8_t* done_buf_dev, int mode, void* stream);
-/* host-buffer variant: params_host in, the four buffers out (pinned or pageable host memory), synchronises */
+/* host-buffer variant: params_host in, the four buffers out (pinned or pageable host memory), synchronises.
+ * The whole rollout buffer is always written on the device (it stays resident for the distillation loop, see
+ * rb_env_rollout_buffer); a NULL host pointer only means that field is not brought to the host.  Page-locked (mapped) reward /
+ * done buffers are written by the kernel directly; everything else is copied in time slabs that overlap the next slab's kernel. */
 int rb_env_rollout_policy_host(rb_env* env, const float* params_host, int nout, int T, float* obs_buf_host, float* pd_buf_host,
                                float* rew_buf_host, uint8_t* done_buf_host, int mode);
+/* device pointers of the resident rollout buffer the last rb_env_rollout_policy_host call filled ([T,N,11], [T,N,4], [T,N], [T,N]);
+ * any out pointer may be NULL.  Owned by the env, valid until the next host rollout or rb_env_destroy.  (reward / done are only
+ * present on the device when the host buffers of that call were pageable or NULL.) */
+int rb_env_rollout_buffer(rb_env* env, float** obs_buf_dev, float** pd_buf_dev, float** rew_buf_dev, uint8_t** done_buf_dev, int* T);
 
 /* ------------------------------------------------------------------------------------------------ student -
  * Flat parameter layout: POLICY64 = the nout=4 policy layout above; MLP = for each layer W[in][out] then b[out],

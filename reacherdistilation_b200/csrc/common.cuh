@@ -18,10 +18,10 @@ struct rb_env {
     float* d_act = nullptr; float* d_obs = nullptr; float* d_rew = nullptr; uint8_t* d_done = nullptr;
     float* d_params = nullptr;
     float* d_buf_obs = nullptr; float* d_buf_pd = nullptr; float* d_buf_rew = nullptr; uint8_t* d_buf_done = nullptr;
-    int64_t buf_T = 0;
+    int64_t buf_T = 0, buf_last_T = 0;       // allocated / last used number of time steps of the resident rollout buffer
     cudaStream_t host_stream = nullptr;
     cudaStream_t copy_stream = nullptr;      // D2H of finished time slabs overlaps the next slab's kernel
-    cudaEvent_t slab_done[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t slab_done[16] = {};
     int sm_count = 148;
 };
 

@@ -234,7 +234,7 @@ int rb_env_destroy(rb_env* e) {
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
-    for (int i = 0; i < 8; ++i) if (e->slab_done[i]) cudaEventDestroy(e->slab_done[i]);
+    for (int i = 0; i < 16; ++i) if (e->slab_done[i]) cudaEventDestroy(e->slab_done[i]);
     delete e;
     return RB_OK;
 }
@@ -269,7 +269,7 @@ static int ensure_host_staging(rb_env* e) {
     RB_CUDA(cudaSetDevice(e->device));
     RB_CUDA(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
     RB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 8; ++i) RB_CUDA(cudaEventCreateWithFlags(&e->slab_done[i], cudaEventDisableTiming));
+    for (int i = 0; i < 16; ++i) RB_CUDA(cudaEventCreateWithFlags(&e->slab_done[i], cudaEventDisableTiming));
     RB_CUDA(cudaMalloc(&e->d_act, sizeof(float) * 2 * e->n));
     RB_CUDA(cudaMalloc(&e->d_obs, sizeof(float) * OBS * e->n));
     RB_CUDA(cudaMalloc(&e->d_rew, sizeof(float) * e->n));
@@ -385,6 +385,19 @@ int rb_env_rollout_policy(rb_env* e, const float* params, int nout, int T, float
     return RB_OK;
 }
 
+// device-visible alias of a HOST pointer when the memory is page-locked and mapped (cudaHostAlloc / cudaHostRegister under UVA), else NULL
+static void* mapped_alias(const void* host) {
+    if (!host) return nullptr;
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
+}
+static int env_knob(const char* name, int dflt, int lo, int hi) {
+    const char* v = getenv(name);
+    const int x = v ? atoi(v) : dflt;
+    return x < lo ? lo : (x > hi ? hi : x);
+}
+
 int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
                                uint8_t* done_host, int mode) {
     RB_REQUIRE(e != nullptr && params_host != nullptr && T > 0, "bad argument");
@@ -401,28 +414,70 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
         RB_CUDA(cudaMalloc(&e->d_buf_done, rows));
         e->buf_T = T;
     }
+    e->buf_last_T = T;
     cudaStream_t s = e->host_stream, sc = e->copy_stream;
     RB_CUDA(cudaMemcpyAsync(e->d_params, params_host, sizeof(float) * rb_policy_param_count(nout), cudaMemcpyHostToDevice, s));
-    // The T steps run as up to 5 time slabs (same trajectories: the state round-trips through HBM exactly); the device->host copy of
-    // slab i (copy stream) overlaps the kernel of slab i+1 (compute stream).
-    const int nslab = T < 5 ? T : 5;
+    // The kernel ALWAYS fills the device-resident rollout buffer (obs, pdflat: rb_env_rollout_buffer() hands it to the distillation loop);
+    // a NULL host pointer only means "do not bring that field to the host".  How the fields reach the host:
+    //  * reward, when the host buffer is page-locked and mapped: the kernel stores it straight into host memory (one posted 128-byte PCIe
+    //    write per warp-step, issued while the rollout runs -- 13 MB at config 3, hidden under the kernel).  RB_HOST_ZEROCOPY (bit 0: reward,
+    //    bit 1: done; default 1) selects this; `done` is 32 bytes per warp-step, which makes poor PCIe packets, so by default it takes
+    //    the copy path;
+    //  * everything else goes through the device buffer and the copy engine in TIME SLABS (same trajectories: the state round-trips
+    //    through HBM exactly): the device->host copy of slab i (copy stream) overlaps the kernel of slab i+1 (compute stream).  A slab
+    //    boundary costs ~10 us of kernel time and its copy competes with the kernel's own PCIe writes, so when only small fields are
+    //    left to copy they go in RB_HOST_SLABS_SMALL (1) slab(s) after the kernel; obs / pdflat / pageable reward (PCIe-bound bulk) use
+    //    RB_HOST_SLABS (6) slabs with a short first one (RB_HOST_SLAB_FIRST, 2 steps) so that the copy engine starts early.
+    //  Measured on B200, 65 536 envs x 50 steps, result = reward + done (scripts/e2e_sweep.py): 0.403 ms per call with the defaults;
+    //  0.419 with 2 small slabs; 0.428 with both fields kernel-written; 0.448 with everything copied in 5 equal slabs (kernel alone 0.307,
+    //  the 16.4 MB result alone 0.30 at the 55 GB/s this box copies at).
+    static const int zc = env_knob("RB_HOST_ZEROCOPY", 1, 0, 3), nslab_bulk = env_knob("RB_HOST_SLABS", 6, 1, 16),
+                     first_steps = env_knob("RB_HOST_SLAB_FIRST", 2, 1, 1 << 20), nslab_small = env_knob("RB_HOST_SLABS_SMALL", 1, 1, 16);
+    float* rew_zc = (zc & 1) ? (float*)mapped_alias(rew_host) : nullptr;
+    uint8_t* done_zc = (zc & 2) ? (uint8_t*)mapped_alias(done_host) : nullptr;
+    const bool copy_rew = rew_host && !rew_zc, copy_done = done_host && !done_zc;
+    const bool bulk = obs_host || pd_host || copy_rew, any_copy = bulk || copy_done;
+    int ends[16];                                                                    // cumulative slab ends
+    int nslab = !any_copy ? 1 : (bulk ? nslab_bulk : nslab_small);
+    if (nslab > T) nslab = T;
+    if (bulk) {
+        const int first = (nslab > 1 && first_steps < T / nslab) ? first_steps : 0;  // 0: equal slabs
+        for (int i = 0; i < nslab; ++i) ends[i] = first ? first + (int)(((int64_t)(T - first) * i) / (nslab - 1)) : (int)(((int64_t)T * (i + 1)) / nslab);
+    } else {
+        for (int i = 0; i < nslab; ++i) ends[i] = T - (T >> (2 * (i + 1)));          // 3/4, 15/16, ... of T
+    }
+    ends[nslab - 1] = T;
     int t0 = 0;
     for (int i = 0; i < nslab; ++i) {
-        const int tn = (T * (i + 1)) / nslab - t0;
+        const int tn = ends[i] - t0;
+        if (tn <= 0) continue;
         const int64_t r0 = (int64_t)t0 * e->n, rows = (int64_t)tn * e->n;
-        rc = rb_env_rollout_policy(e, e->d_params, nout, tn, obs_host ? e->d_buf_obs + OBS * r0 : nullptr, pd_host ? e->d_buf_pd + 4 * r0 : nullptr,
-                                   rew_host ? e->d_buf_rew + r0 : nullptr, done_host ? e->d_buf_done + r0 : nullptr, mode, s);
+        rc = rb_env_rollout_policy(e, e->d_params, nout, tn, e->d_buf_obs + OBS * r0, e->d_buf_pd + 4 * r0, rew_zc ? rew_zc + r0 : e->d_buf_rew + r0,
+                                   done_zc ? done_zc + r0 : e->d_buf_done + r0, mode, s);
         if (rc) return rc;
-        RB_CUDA(cudaEventRecord(e->slab_done[i], s));
-        RB_CUDA(cudaStreamWaitEvent(sc, e->slab_done[i], 0));
-        if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host + OBS * r0, e->d_buf_obs + OBS * r0, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, sc));
-        if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host + 4 * r0, e->d_buf_pd + 4 * r0, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, sc));
-        if (rew_host) RB_CUDA(cudaMemcpyAsync(rew_host + r0, e->d_buf_rew + r0, sizeof(float) * rows, cudaMemcpyDeviceToHost, sc));
-        if (done_host) RB_CUDA(cudaMemcpyAsync(done_host + r0, e->d_buf_done + r0, rows, cudaMemcpyDeviceToHost, sc));
+        if (any_copy) {
+            RB_CUDA(cudaEventRecord(e->slab_done[i], s));
+            RB_CUDA(cudaStreamWaitEvent(sc, e->slab_done[i], 0));
+            if (copy_done) RB_CUDA(cudaMemcpyAsync(done_host + r0, e->d_buf_done + r0, rows, cudaMemcpyDeviceToHost, sc));
+            if (copy_rew) RB_CUDA(cudaMemcpyAsync(rew_host + r0, e->d_buf_rew + r0, sizeof(float) * rows, cudaMemcpyDeviceToHost, sc));
+            if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host + OBS * r0, e->d_buf_obs + OBS * r0, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, sc));
+            if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host + 4 * r0, e->d_buf_pd + 4 * r0, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, sc));
+        }
         t0 += tn;
     }
-    RB_CUDA(cudaStreamSynchronize(sc));
+    if (any_copy) RB_CUDA(cudaStreamSynchronize(sc));
     RB_CUDA(cudaStreamSynchronize(s));
+    return RB_OK;
+}
+
+int rb_env_rollout_buffer(rb_env* e, float** obs_dev, float** pd_dev, float** rew_dev, uint8_t** done_dev, int* T) {
+    RB_REQUIRE(e != nullptr, "env is NULL");
+    RB_REQUIRE(e->buf_last_T > 0, "no host rollout has run on this env yet");
+    if (obs_dev) *obs_dev = e->d_buf_obs;
+    if (pd_dev) *pd_dev = e->d_buf_pd;
+    if (rew_dev) *rew_dev = e->d_buf_rew;
+    if (done_dev) *done_dev = e->d_buf_done;
+    if (T) *T = (int)e->buf_last_T;
     return RB_OK;
 }
 

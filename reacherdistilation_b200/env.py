@@ -128,7 +128,8 @@ class VecReacher:
         return out
 
     def rollout_policy_host(self, params_host, T, nout=2, mode=_lib.MODE_FP32, out=None):
-        """Same through HOST buffers (H2D of the parameters, D2H of the whole rollout buffer inside the call)."""
+        """Same through HOST buffers (H2D of the parameters, D2H inside the call).  The rollout buffer is always written on the device
+        (rollout_buffer()); `out` entries that are None are not brought to the host."""
         n = self.num_envs
         if out is None:
             out = dict(obs=torch.empty((T, n, 11)).pin_memory(), pdflat=torch.empty((T, n, 4)).pin_memory(),
@@ -136,6 +137,24 @@ class VecReacher:
         check(lib().rb_env_rollout_policy_host(self._h, ptr(params_host), nout, T, ptr(out.get("obs")), ptr(out.get("pdflat")), ptr(out.get("rew")),
                                                ptr(out.get("done")), mode))                  # None entries: that field is not copied to the host
         return out
+
+    def rollout_buffer(self):
+        """Device views (no copy) of the resident rollout buffer the last rollout_policy_host() filled: dict(obs [T,N,11], pdflat [T,N,4],
+        rew [T,N], done [T,N]).  rew / done only hold data when that call's host buffers were pageable or absent (page-locked ones are
+        written by the kernel directly).  Valid until the next host rollout or close()."""
+        import ctypes as C
+        po, pp, pr, pdn, T = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int()
+        check(lib().rb_env_rollout_buffer(self._h, C.byref(po), C.byref(pp), C.byref(pr), C.byref(pdn), C.byref(T)))
+        n, T = self.num_envs, T.value
+
+        class _View:
+            def __init__(self, addr, shape, typestr):
+                self.__cuda_array_interface__ = dict(shape=shape, typestr=typestr, data=(addr, False), version=2, strides=None)
+        with torch.cuda.device(self.device):
+            return dict(obs=torch.as_tensor(_View(po.value, (T, n, 11), "<f4"), device=self.device),
+                        pdflat=torch.as_tensor(_View(pp.value, (T, n, 4), "<f4"), device=self.device),
+                        rew=torch.as_tensor(_View(pr.value, (T, n), "<f4"), device=self.device),
+                        done=torch.as_tensor(_View(pdn.value, (T, n), "|u1"), device=self.device))
 
 
 def make_mujoco_env(env_id, seed, num_envs=1, device=0, rank=0, host=None):
