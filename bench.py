@@ -9,7 +9,8 @@ loop, device-resident rollout buffer; one bench "step" = one 50-step chunk (one 
 per GPU.  Weak scaling: every rank owns 65 536 envs (global env ids rank*65536 ..), no data-path collective.
 `value`   env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks.
 `e2e`     same metric through the host-buffer C-ABI call (rb_env_rollout_policy_host): H2D of the teacher parameters and D2H of
-          the whole rollout buffer (obs, pdflat, reward, done) inside the timed region.
+          the step's result (reward + done of every env-step) inside the timed region; the rollout buffer (obs, pdflat) is written
+          and stays on the device.  `e2e_full_buffer`: the same call bringing the whole buffer to the host (PCIe-bound).
 `distill` BASELINE.json config 4 shard (32 768 envs per GPU): DAgger iterations = env step + teacher label + student
           forward/backward + KL + [NCCL all-reduce of the flat gradient] + Adam; samples/s == env-steps/s of that loop.
 `step_api` the gym-style single-step kernel (HBM-bound) at 4 194 304 envs.
