@@ -38,6 +38,9 @@ ROLLOUT_TRAFFIC_NCU = 159.6e6   # dram__bytes_read.sum + dram__bytes_write.sum o
 MUFU_PER_ENV_STEP = 169.0       # 128 tanh x 1.25 (ex2 each, one rcp per four) + 8 rcp + 1 sqrt
 XU_LANES_PER_CLK_PER_SM = 16.0  # B200 MUFU rate
 ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
+STEP_TRAFFIC_NCU = 515.4e6    # dram read + write of one k_step launch at 4 194 304 envs (profiles/r01_ncu_full_k_step.csv) = 122.9 B per env-step
+STUDENT_TRAFFIC_NCU = 3.0e6   # dram read + write of one k_student_tc<SpecMLP> launch at 32 768 samples (profiles/r01_ncu_full_k_student_tc_final.csv);
+                              # the 2.6 MB of inputs are read once, everything else stays in L2
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 FLOP_PER_ENV_STEP = 450.0 + 9856.0          # physics + teacher MLP
 FLOP_PER_SAMPLE = {"mlp": 144.4e3, "policy64": 30.3e3}
@@ -333,7 +336,9 @@ def main():
                                cuda_graph=bool(tr.use_graph), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
                                last_loss=float(tr.last_loss()),
                                roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",
-                                             frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"], traffic=None, peak_source=pk["src"],
+                                             frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"],
+                                             traffic=(STUDENT_TRAFFIC_NCU if (tr.student_mode == MODE_TC and nd == 32768 and args.student == "mlp") else None),
+                                             peak_source=pk["src"],
                                              kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
                                                      else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
                                              note="tile GEMMs run bf16x3 (3 MMAs per product): tensor-pipe work is 3x the algorithmic FLOP"))
@@ -407,8 +412,10 @@ def main():
         ssec, _ = timed(sfn, 50)
         line["step_api"] = dict(metric="reacher_env_steps_per_sec", value=float(ns) * 50 * world / ssec, unit="env-steps/s", envs_per_gpu=ns,
                                 roofline=dict(bound="hbm", achieved=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9, peak=pk["hbm"], unit="GB/s",
-                                              frac=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9 / pk["hbm"], traffic=None, peak_source=pk["src"], kernel="k_step",
-                                              note="working set %.0f MB > L2; actual bytes moved 137 B/env-step" % (ns * 137 / 1e6)))
+                                              frac=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9 / pk["hbm"], traffic=(STEP_TRAFFIC_NCU if ns == (1 << 22) else None),
+                                              peak_source=pk["src"], kernel="k_step",
+                                              note="working set %.0f MB > L2; ncu: 122.9 B of DRAM traffic per env-step (algorithmic 113), issue slots 82 %% "
+                                                   "active: the RK4 physics (~750 warp-instructions per step) bounds this kernel before HBM does" % (ns * 97 / 1e6)))
         env2.close()
         if rank == 0 and world == 1:
             cb, _, _ = cpu_reference_leg()

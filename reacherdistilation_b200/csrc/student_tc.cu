@@ -35,6 +35,7 @@ constexpr int ST_TILE = 128;
 constexpr int ST_GROUPS = 32;                         // groups per ACT half
 constexpr int ST_ACT_BYTES = ST_GROUPS * 2048;        // 64 KB
 constexpr int ST_MAXL = 4;
+constexpr int ST_MAX_GRID = 160;                      // cooperative grid = one CTA per SM, at most this many
 
 // ---- network specs (the folded MLP and the 2x64 policy student) ---------------------------------------------------------
 struct SpecMLP {   // 16 -> 24 tanh -> 128 tanh -> [128 lin -> ] 32 tanh -> 4
@@ -231,8 +232,12 @@ template <class S, int l> __device__ __forceinline__ void epi_fwd(uint32_t tacc,
         const int g = part * gpp + i;
         if (g < og) {
 #pragma unroll
-            for (int k = 0; k < 8; k += 2)                   // one reciprocal per pair: 3 MUFU instead of 4
-                tanh_pair_from_scaled(v[i][k] * 2.8853900817779268f, v[i][k + 1] * 2.8853900817779268f, v[i][k], v[i][k + 1]);
+            for (int k = 0; k < 8; k += 4) {                 // one reciprocal per four values: 5 MUFU instead of 8 (L1 epilogue is XU-bound)
+                float y[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) y[u] = v[i][k + u] * 2.8853900817779268f;
+                tanh_quad_from_scaled(y, &v[i][k]);
+            }
             store_split8(act_hi, act_lo, S::slot(l + 1) + g, row, v[i]);
         }
     }
@@ -406,24 +411,35 @@ __device__ __forceinline__ void fold_into_image(const float* p, uint8_t* img, in
 __device__ __forceinline__ void finish_mlp(const float* p, const float* red, float* gradloss, int gtid, int gthreads) {
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < 128; r += gridDim.x) {
+        // all loads of both products are issued before the first use: one L2 round trip instead of two
+        float4 g[8], w[8];
+        if (tid < 128) {
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                g[j4] = ldw(reinterpret_cast<const float4*>(red + R_G34 + r * 32) + j4);
+                w[j4] = ldw(reinterpret_cast<const float4*>(p + M_W4 + tid * 32) + j4);
+            }
+        }
+        const int j = tid >> 4, sub = tid & 15;
+        float w3[8], g4[8];
+#pragma unroll
+        for (int m = 0; m < 8; ++m) { const int aa = sub + 16 * m; w3[m] = ldw(p + M_W3 + aa * 128 + r); g4[m] = ldw(red + R_G34 + aa * 32 + j); }
+        const float b3r = ldw(p + M_B3 + r), g34j = ldw(red + R_g34 + j);
         if (tid < 128) {                                             // dW3[r][k] = sum_j G34[r][j] W4[k][j],  k = tid
             float acc = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                const float4 g = ldw(reinterpret_cast<const float4*>(red + R_G34 + r * 32) + j4);
-                const float4 w = ldw(reinterpret_cast<const float4*>(p + M_W4 + tid * 32) + j4);
-                acc = fmaf(g.x, w.x, acc); acc = fmaf(g.y, w.y, acc); acc = fmaf(g.z, w.z, acc); acc = fmaf(g.w, w.w, acc);
+                acc = fmaf(g[j4].x, w[j4].x, acc); acc = fmaf(g[j4].y, w[j4].y, acc); acc = fmaf(g[j4].z, w[j4].z, acc); acc = fmaf(g[j4].w, w[j4].w, acc);
             }
             gradloss[M_W3 + r * 128 + tid] = acc;
         }
         {                                                            // dW4[r][j] = sum_a W3[a][r] G34[a][j] + b3[r] g34[j],  16 lanes per j
-            const int j = tid >> 4, sub = tid & 15;
             float acc = 0.f;
 #pragma unroll
-            for (int m = 0; m < 8; ++m) { const int aa = sub + 16 * m; acc = fmaf(ldw(p + M_W3 + aa * 128 + r), ldw(red + R_G34 + aa * 32 + j), acc); }
+            for (int m = 0; m < 8; ++m) acc = fmaf(w3[m], g4[m], acc);
 #pragma unroll
             for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (sub == 0) gradloss[M_W4 + r * 32 + j] = fmaf(ldw(p + M_B3 + r), ldw(red + R_g34 + j), acc);
+            if (sub == 0) gradloss[M_W4 + r * 32 + j] = fmaf(b3r, g34j, acc);
         }
     }
     constexpr int n_a = M_W3, n_b = M_W4 - M_B3, n_c = M_P + 1 - M_B4;       // [0, W3) | db3 | [db4 .. loss]
@@ -431,9 +447,17 @@ __device__ __forceinline__ void finish_mlp(const float* p, const float* red, flo
         if (q < n_a) gradloss[q] = ldw(red + q);                  // dW1 db1 dW2 db2 share offsets
         else if (q < n_a + n_b) {                                    // db3[k] = sum_j W4[k][j] g34[j]
             const int k = q - n_a;
+            float4 wv[8], gv[8];                                      // row k of W4 and g34 as 16 vector loads, all in flight together
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                wv[j4] = ldw(reinterpret_cast<const float4*>(p + M_W4 + k * 32) + j4);
+                gv[j4] = ldw(reinterpret_cast<const float4*>(red + R_g34) + j4);
+            }
             float acc = 0.f;
-#pragma unroll 8
-            for (int j = 0; j < 32; ++j) acc = fmaf(ldw(p + M_W4 + k * 32 + j), ldw(red + R_g34 + j), acc);
+#pragma unroll
+            for (int j4 = 0; j4 < 8; ++j4) {
+                acc = fmaf(wv[j4].x, gv[j4].x, acc); acc = fmaf(wv[j4].y, gv[j4].y, acc); acc = fmaf(wv[j4].z, gv[j4].z, acc); acc = fmaf(wv[j4].w, gv[j4].w, acc);
+            }
             gradloss[M_B3 + k] = acc;
         } else {
             const int i = M_B4 + (q - n_a - n_b);
@@ -657,8 +681,16 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             for (int eb0 = blockIdx.x * 2; eb0 < nblk; eb0 += gridDim.x * 2) {
                 const int i = (eb0 + (warp >> 3)) * 32 + lane;
                 float acc = 0.f;
-                if (i < a.pstride)
-                    for (int b = sl; b < nparts; b += 8) acc += ldw(a.partials + (size_t)b * a.pstride + i);
+                if (i < a.pstride) {
+                    float pv[ST_MAX_GRID / 8];                         // all partials of this slot in flight together (one L2 round trip)
+#pragma unroll
+                    for (int u = 0; u < ST_MAX_GRID / 8; ++u) {
+                        const int b = sl + 8 * u;
+                        pv[u] = b < nparts ? ldw(a.partials + (size_t)b * a.pstride + i) : 0.f;
+                    }
+#pragma unroll
+                    for (int u = 0; u < ST_MAX_GRID / 8; ++u) acc += pv[u];      // CTA order, absent partials add 0
+                }
                 red2[warp * 32 + lane] = acc;
                 __syncthreads();
                 if (sl == 0 && i < a.pstride) {
@@ -728,7 +760,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
 
 template <class S> static size_t student_tc_smem() { return 2 * (size_t)ST_ACT_BYTES + 2 * (size_t)Geo<S>::wtile_bytes() + sizeof(StudentTcCtl); }
 
-constexpr int ST_MAX_GRID = 160;
 static int tc_grid(int64_t B, int* grid) {
     int device = 0, sms = 148;
     RB_CUDA(cudaGetDevice(&device));
