@@ -317,10 +317,9 @@ def main():
             lg()
         ksec, _ = timed(lg, 20)
         # e2e: the loss comes back to the host every iteration
-        loss_host = torch.empty(1).pin_memory()
         def dstep_e2e():
             tr.step()
-            loss_host.copy_(tr.last_loss().reshape(1), non_blocking=False)
+            tr.wait_loss()        # graph path: the iteration's last kernel posts {loss, iteration} into mapped host memory, the host polls it
         barrier(); t0 = time.perf_counter()
         for _ in range(Kd):
             dstep_e2e()
@@ -331,7 +330,8 @@ def main():
                                ms_per_step=1e3 * dsec / Kd, workload="config4 shard: %d envs/GPU, student %s, KL(s||t), TF-Adam, %s"
                                % (nd, args.student, ("gradient all-reduce fused into the student kernel (NVLink peer memory)" if tr.fused_allreduce
                                                      else "NCCL all-reduce of flat grad") if world > 1 else "single GPU"),
-                               e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=4),
+                               e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=8,
+                                        api="DaggerTrainer.step + wait_loss (rb_dagger_step, rb_dagger_wait_loss: {loss, iteration} posted into mapped host memory)"),
                                gpu_launches_per_step=(3 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8),
                                cuda_graph=bool(tr.use_graph), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
                                last_loss=float(tr.last_loss()),

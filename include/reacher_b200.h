@@ -209,6 +209,11 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params_dev, float* params_
                    const uint64_t* slots_even, const uint64_t* slots_odd, const uint64_t* flags, int use_graph, void* stream);
 int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
                   void* stream);
+/* The per-iteration loss the reference prints (src/distilation/mlp_train.py:148-161, 199-201) without a stream synchronise: the last
+ * kernel of rb_dagger_step stores {loss, iterations done} as one 8-byte word into page-locked mapped host memory; this call polls it
+ * until the device clock has reached `iteration` (= the value given to rb_dagger_set_clock + the number of rb_dagger_step calls since)
+ * and returns that iteration's loss (summed over ranks when world > 1).  Fails if a later iteration has already overwritten it. */
+int rb_dagger_wait_loss(rb_dagger* d, uint32_t iteration, float* loss_host_out);
 
 /* ------------------------------------------------------------------------------------------------ LSTM student -
  * student_lstm_graph  src/distilation/student_nn.py:21-49 (built at lstm_train.py:32-57): dropout(ob) (+) dense32(prev_pdflat) ->

@@ -65,6 +65,7 @@ _SIGS = {
     "rb_dagger_step": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _u8p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "rb_dagger_act": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
+    "rb_dagger_wait_loss": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float)]),
     "rb_lstm_param_count": (C.c_int64, []),
     "rb_lstm_steps": (C.c_int, []),
     "rb_lstm_units": (C.c_int, []),

@@ -1,6 +1,7 @@
 // Lock-step DAgger iteration pieces: observe (ob, teacher label, student input) and act (step with the student mean).
 // Replaces the per-env-step body of /root/reference src/distilation/mlp_train.py:143-204 (teacher label :165-167, record
 // :188-193 with dataset.py:118-143 `prev` / `prew` semantics, env.step(s_ac) :196) for N envs at once.
+#include <chrono>
 #include <cstring>
 
 #include "common.cuh"
@@ -22,6 +23,11 @@ struct rb_dagger {
     cudaGraphExec_t gexec = nullptr;
     uint64_t gkey = 0;
     cudaStream_t cap_stream = nullptr;   // capture happens here (the legacy default stream cannot be captured); replay on the caller's stream
+    // result mailbox in page-locked mapped HOST memory: {loss bits, iteration count} stored by the last kernel of rb_dagger_step as one 8-byte
+    // word; rb_dagger_wait_loss polls it, so the per-iteration loss read-back (mlp_train.py:148-161 prints it) needs no stream synchronise
+    // and no copy-engine transfer
+    volatile uint2* mailbox_host = nullptr;
+    uint2* mailbox_dev = nullptr;
 };
 
 namespace rb {
@@ -45,9 +51,14 @@ __global__ void k_dagger_input(int64_t n, const uint2* __restrict__ ctr, const f
 __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint2* ctr, const float4* __restrict__ s_pd,
                                                     const float4* __restrict__ t_pd, float4* prev_t, float* prev_rec_rew, float* last_reward,
                                                     float* __restrict__ rew, uint8_t* __restrict__ done, uint32_t k0, uint32_t k1,
-                                                    uint32_t offset, uint32_t* clock) {
+                                                    uint32_t offset, uint32_t* clock, const float* __restrict__ loss_src, uint2* mailbox) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (clock && i == 0) { clock[0] += 1u; clock[1] += 1u; clock[2] += 1u; }      // end of the iteration: advance the device-side step clock
+    if (clock && i == 0) {                                                        // end of the iteration: advance the device-side step clock
+        const uint32_t it = clock[0] + 1u;
+        clock[0] = it; clock[1] += 1u; clock[2] += 1u;
+        if (mailbox)                                                              // {loss, iterations done} -> host memory, one 8-byte posted write
+            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(mailbox), "r"(__float_as_uint(*loss_src)), "r"(it) : "memory");
+    }
     if (i >= n) return;
     EnvState e = load_state(qv, tp, ctr, i);
     const float4 sp = __ldg(s_pd + i);
@@ -105,6 +116,7 @@ int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_
 int rb_dagger_destroy(rb_dagger* d) {
     if (!d) return RB_OK;
     cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward); cudaFree(d->teacher_img); cudaFree(d->clock);
+    if (d->mailbox_host) cudaFreeHost((void*)d->mailbox_host);
     if (d->gexec) cudaGraphExecDestroy(d->gexec);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
     delete d;
@@ -150,7 +162,7 @@ int rb_dagger_act(rb_dagger* d, const float* s_pd, const float* t_pd, float* rew
     rb_env* e = d->env;
     k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd,
                                                                                   d->prev_t, d->prev_rec_rew, d->last_reward, rew, done,
-                                                                                  (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset, nullptr);
+                                                                                  (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset, nullptr, nullptr, nullptr);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
@@ -174,6 +186,15 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
     RB_REQUIRE(world == 1 || (world >= 2 && world <= 8 && slots_even && slots_odd && flags), "data parallel: 2..8 ranks with peer slots and flags");
     rb_env* e = d->env;
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t loss_index = rb_student_param_count(d->kind);          // gradloss = [grad P | loss]
+    if (!d->mailbox_host) {
+        void* h = nullptr;
+        RB_CUDA(cudaHostAlloc(&h, sizeof(uint2), cudaHostAllocMapped));
+        memset(h, 0, sizeof(uint2));
+        void* dv = nullptr;
+        RB_CUDA(cudaHostGetDevicePointer(&dv, h, 0));
+        d->mailbox_host = (volatile uint2*)h; d->mailbox_dev = (uint2*)dv;
+    }
     if (!d->teacher_img) RB_CUDA(cudaMalloc(&d->teacher_img, policy_tc_image_bytes()));
     if (d->teacher_img_src != teacher_params) {
         int rc0 = policy_tc_build_image(teacher_params, 2, d->teacher_img, st);
@@ -190,7 +211,7 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
         if (rc) return rc;
         k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, st>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd, d->prev_t,
                                                                       d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed,
-                                                                      (uint32_t)(e->seed >> 32), e->offset, d->clock);
+                                                                      (uint32_t)(e->seed >> 32), e->offset, d->clock, gradloss + loss_index, d->mailbox_dev);
         RB_CUDA(cudaGetLastError());
         return RB_OK;
     };
@@ -221,6 +242,30 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
     }
     RB_CUDA(cudaGraphLaunch(d->gexec, st));
     return RB_OK;
+}
+
+// Blocks until the rb_dagger_step iteration that brought the device clock's iteration count to `iteration` has finished and returns its
+// loss (summed over ranks in the data-parallel case).  Polls the mapped host mailbox: no stream synchronise, no copy.
+int rb_dagger_wait_loss(rb_dagger* d, uint32_t iteration, float* loss_out) {
+    RB_REQUIRE(d && loss_out, "NULL argument");
+    RB_REQUIRE(d->mailbox_host != nullptr, "rb_dagger_step has not run yet");
+    const auto t0 = std::chrono::steady_clock::now();
+    uint64_t spins = 0;
+    for (;;) {
+        const uint64_t w = *reinterpret_cast<volatile uint64_t*>(d->mailbox_host);      // one aligned 8-byte read: {loss, iteration} are consistent
+        const uint32_t it = (uint32_t)(w >> 32);
+        if ((int32_t)(it - iteration) >= 0) {
+            RB_REQUIRE(it == iteration, "rb_dagger_wait_loss: that iteration has already been overwritten by a later one");
+            const uint32_t bits = (uint32_t)w;
+            memcpy(loss_out, &bits, 4);
+            return RB_OK;
+        }
+        if ((++spins & 0xFFFu) == 0) {
+            const cudaError_t err = cudaPeekAtLastError();
+            if (err != cudaSuccess) return cuda_fail(err, "rb_dagger_wait_loss");
+            if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) { set_error("rb_dagger_wait_loss: timed out"); return RB_ERR_CUDA; }
+        }
+    }
 }
 
 }  // extern "C"

@@ -109,6 +109,17 @@ class DaggerTrainer:
     def last_loss(self):
         return self.student.gradloss[self.student.P]
 
+    def wait_loss(self):
+        """Loss of the iteration the last step() issued, as a host float.  On the CUDA-graph path the last kernel of the iteration posts it
+        into page-locked host memory and this call polls for it (rb_dagger_wait_loss: no stream synchronise, no copy); otherwise it is a
+        plain device read."""
+        if self.use_graph:
+            import ctypes as C
+            out = C.c_float()
+            check(lib().rb_dagger_wait_loss(self._h, self.iteration, C.byref(out)))
+            return out.value
+        return float(self.last_loss())
+
     def close(self):
         if self._h:
             lib().rb_dagger_destroy(self._h)

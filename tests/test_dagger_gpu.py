@@ -118,3 +118,29 @@ def test_graph_step_equals_three_launch_step(kind_name):
     a.step(); b.step()
     assert abs(float(a.last_loss()) - float(b.last_loss())) <= 1e-5 * max(1.0, abs(float(b.last_loss())))
     a.close(); b.close()
+
+
+def test_wait_loss_mailbox_matches_device_loss():
+    """rb_dagger_wait_loss: the {loss, iteration} word the last kernel of the graph posts into mapped host memory is exactly the
+    device-side loss of that iteration, every iteration, with no stream synchronise in between; an iteration that has already been
+    overwritten is refused."""
+    import ctypes as C
+    from reacherdistilation_b200 import MODE_TC
+    from reacherdistilation_b200._lib import ReacherB200Error, check, lib
+    from reacherdistilation_b200.mlp_train import DaggerTrainer
+    tr = DaggerTrainer(num_envs=900, seed=5, mode=MODE_TC, lr=1e-3, use_graph=True)
+    for it in range(25):
+        tr.step()
+        host = tr.wait_loss()                                  # polls; the stream is NOT synchronised here
+        dev = float(tr.last_loss())                            # device read (synchronises)
+        assert np.float32(host) == np.float32(dev), (it, host, dev)
+    tr.step(); tr.step()
+    torch.cuda.synchronize()
+    out = C.c_float()
+    with pytest.raises(ReacherB200Error):
+        check(lib().rb_dagger_wait_loss(tr._h, tr.iteration - 1, C.byref(out)))
+    assert np.float32(tr.wait_loss()) == np.float32(float(tr.last_loss()))
+    tr.use_graph = False                                       # three-launch path: plain device read
+    tr.step()
+    assert np.isfinite(tr.wait_loss())
+    tr.close()
