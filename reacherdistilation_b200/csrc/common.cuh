@@ -23,6 +23,14 @@ struct rb_env {
     cudaStream_t copy_stream = nullptr;      // D2H of finished time slabs overlaps the next slab's kernel
     cudaEvent_t slab_done[16] = {};
     int sm_count = 148;
+    // In-kernel slab progress of the fused tensor-core rollout (rb_env_rollout_policy_host): every warp bumps prog_counters[slab] when it has
+    // written the last step of a time slab; the warp that completes the count posts the call's epoch into prog_flags_host[slab] (page-locked
+    // mapped host memory), and the host, polling it, starts the device->host copy of that slab while the SAME launch computes the next one.
+    uint32_t* prog_counters = nullptr;            // device, [16], zeroed by the host call before the launch
+    volatile uint32_t* prog_flags_host = nullptr; // mapped host memory, [16]
+    uint32_t* prog_flags_dev = nullptr;           // device alias of prog_flags_host
+    uint32_t prog_epoch = 0;
+    int prog_slab_len = 0;                        // > 0 only while the host call launches its kernel
 };
 
 namespace rb {

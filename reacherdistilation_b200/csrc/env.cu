@@ -6,6 +6,9 @@
 //   qv  float4[N] = (q0, q1, v0, v1)       tp  float4[N] = (tx, ty, px, py)      ctr uint2[N] = (step, episode)
 // Observation rows ([N,11] fp32, 44 B) are staged through a warp-private shared-memory strip so that the global
 // stores are 128-bit and contiguous.
+#include <chrono>
+#include <cstring>
+
 #include "common.cuh"
 #include "physics.cuh"
 #include "policy_simt.cuh"
@@ -232,6 +235,8 @@ int rb_env_destroy(rb_env* e) {
     cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
+    cudaFree(e->prog_counters);
+    if (e->prog_flags_host) cudaFreeHost((void*)e->prog_flags_host);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
     for (int i = 0; i < 16; ++i) if (e->slab_done[i]) cudaEventDestroy(e->slab_done[i]);
@@ -275,6 +280,13 @@ static int ensure_host_staging(rb_env* e) {
     RB_CUDA(cudaMalloc(&e->d_rew, sizeof(float) * e->n));
     RB_CUDA(cudaMalloc(&e->d_done, e->n));
     RB_CUDA(cudaMalloc(&e->d_params, sizeof(float) * rb_policy_param_count(4)));
+    RB_CUDA(cudaMalloc(&e->prog_counters, 16 * sizeof(uint32_t)));
+    void* h = nullptr;
+    RB_CUDA(cudaHostAlloc(&h, 16 * sizeof(uint32_t), cudaHostAllocMapped));
+    memset(h, 0, 16 * sizeof(uint32_t));
+    void* dv = nullptr;
+    RB_CUDA(cudaHostGetDevicePointer(&dv, h, 0));
+    e->prog_flags_host = (volatile uint32_t*)h; e->prog_flags_dev = (uint32_t*)dv;
     return RB_OK;
 }
 
@@ -428,15 +440,51 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
     //    boundary costs ~10 us of kernel time and its copy competes with the kernel's own PCIe writes, so when only small fields are
     //    left to copy they go in RB_HOST_SLABS_SMALL (1) slab(s) after the kernel; obs / pdflat / pageable reward (PCIe-bound bulk) use
     //    RB_HOST_SLABS (6) slabs with a short first one (RB_HOST_SLAB_FIRST, 2 steps) so that the copy engine starts early.
-    //  Measured on B200, 65 536 envs x 50 steps, result = reward + done (scripts/e2e_sweep.py): 0.403 ms per call with the defaults;
-    //  0.419 with 2 small slabs; 0.428 with both fields kernel-written; 0.448 with everything copied in 5 equal slabs (kernel alone 0.307,
-    //  the 16.4 MB result alone 0.30 at the 55 GB/s this box copies at).
+    //  Tensor-core mode does not cut the launch at all: see the in-kernel progress path below.
+    //  Measured on B200, 65 536 envs x 50 steps, result = reward + done, ms per call (scripts/e2e_sweep.py; kernel alone 0.307, the 16.4 MB
+    //  result alone 0.30 at the 55 GB/s this box copies at): 0.362 progress path with the defaults (reward kernel-written, done copied per
+    //  progress slab); 0.435 progress path with everything on the copy engine; 0.403 reward kernel-written + done copied after the kernel;
+    //  0.419 the same with 2 kernel slabs; 0.428 both fields kernel-written; 0.448 everything copied in 5 equal kernel slabs.
     static const int zc = env_knob("RB_HOST_ZEROCOPY", 1, 0, 3), nslab_bulk = env_knob("RB_HOST_SLABS", 6, 1, 16),
                      first_steps = env_knob("RB_HOST_SLAB_FIRST", 2, 1, 1 << 20), nslab_small = env_knob("RB_HOST_SLABS_SMALL", 1, 1, 16);
     float* rew_zc = (zc & 1) ? (float*)mapped_alias(rew_host) : nullptr;
     uint8_t* done_zc = (zc & 2) ? (uint8_t*)mapped_alias(done_host) : nullptr;
     const bool copy_rew = rew_host && !rew_zc, copy_done = done_host && !done_zc;
     const bool bulk = obs_host || pd_host || copy_rew, any_copy = bulk || copy_done;
+    if (mode == RB_MODE_TC && any_copy && env_knob("RB_HOST_PROGRESS", 1, 0, 1)) {
+        // Tensor-core rollout: ONE launch for all T steps; the kernel posts per-slab completion flags into mapped host memory (common.cuh:
+        // rb_env::prog_*) and this thread, polling them, queues the copy of slab i on the copy stream while the launch computes slab i+1.
+        // No slab boundaries in the kernel (each costs ~10 us), only the last slab's copy is left after it.
+        static const int nprog = env_knob("RB_HOST_PROGRESS_SLABS", 5, 1, 16);
+        const int slab_len = (T + nprog - 1) / nprog, nsl = (T + slab_len - 1) / slab_len;
+        e->prog_epoch += 1u;
+        RB_CUDA(cudaMemsetAsync(e->prog_counters, 0, 16 * sizeof(uint32_t), s));
+        e->prog_slab_len = slab_len;
+        rc = rb_env_rollout_policy(e, e->d_params, nout, T, e->d_buf_obs, e->d_buf_pd, rew_zc ? rew_zc : e->d_buf_rew, done_zc ? done_zc : e->d_buf_done, mode, s);
+        e->prog_slab_len = 0;
+        if (rc) return rc;
+        const auto t_start = std::chrono::steady_clock::now();
+        for (int i = 0; i < nsl; ++i) {
+            uint64_t spins = 0;
+            while (e->prog_flags_host[i] != e->prog_epoch) {
+                if ((++spins & 0x3FFu) == 0) {
+                    const cudaError_t q = cudaStreamQuery(s);
+                    if (q == cudaSuccess) break;                                   // the launch is over: everything is written
+                    if (q != cudaErrorNotReady) return cuda_fail(q, "rb_env_rollout_policy_host");
+                    if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(60)) { set_error("rb_env_rollout_policy_host: timed out"); return RB_ERR_CUDA; }
+                }
+            }
+            const int t0 = i * slab_len, tn = (t0 + slab_len <= T ? slab_len : T - t0);
+            const int64_t r0 = (int64_t)t0 * e->n, rows = (int64_t)tn * e->n;
+            if (copy_done) RB_CUDA(cudaMemcpyAsync(done_host + r0, e->d_buf_done + r0, rows, cudaMemcpyDeviceToHost, sc));
+            if (copy_rew) RB_CUDA(cudaMemcpyAsync(rew_host + r0, e->d_buf_rew + r0, sizeof(float) * rows, cudaMemcpyDeviceToHost, sc));
+            if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host + OBS * r0, e->d_buf_obs + OBS * r0, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, sc));
+            if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host + 4 * r0, e->d_buf_pd + 4 * r0, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, sc));
+        }
+        RB_CUDA(cudaStreamSynchronize(sc));
+        RB_CUDA(cudaStreamSynchronize(s));
+        return RB_OK;
+    }
     int ends[16];                                                                    // cumulative slab ends
     int nslab = !any_copy ? 1 : (bulk ? nslab_bulk : nslab_small);
     if (nslab > T) nslab = T;

@@ -438,7 +438,8 @@ template <int NOUT, int NT>
 __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
                                                                     int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
                                                                     float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf, uint32_t k0,
-                                                                    uint32_t k1, uint32_t offset, uint32_t stagger_ns) {
+                                                                    uint32_t k1, uint32_t offset, uint32_t stagger_ns, uint32_t* prog_counters,
+                                                                    uint32_t* prog_flags, int prog_slab_len, uint32_t prog_epoch) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
     TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
@@ -463,6 +464,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
         // (physics).  Started together they stay in lock step and fight for the same pipe; a one-time offset of a fraction of the
         // step period lets one tile's epilogue overlap another tile's physics.
         for (uint32_t w = 0; w < (uint32_t)tile * stagger_ns; w += 1000u) __nanosleep(1000u);
+        int next_mark = prog_slab_len > 0 ? min(prog_slab_len, T) : -1;      // step count at which the next time slab is complete (-1: no reporting)
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             float ob[OBS], pd[4];
@@ -477,6 +479,18 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
                 if (pd_buf) pd_buf[r] = make_float4(pd[0], pd[1], pd[2], pd[3]);
                 if (rew_buf) rew_buf[r] = rw;
                 if (done_buf) done_buf[r] = d ? 1 : 0;
+            }
+            if (t + 1 == next_mark) {                                                     // warp-uniform: a time slab of the buffer is complete
+                next_mark = min(next_mark + prog_slab_len, T);
+                __threadfence();                                                          // this lane's buffer rows are visible device-wide ...
+                __syncwarp();                                                             // ... for every lane of the warp, before the count
+                if (lane == 0) {
+                    const int slab = t / prog_slab_len;
+                    if (atomicAdd(prog_counters + slab, 1u) + 1u == (uint32_t)units) {      // counters are zeroed by the host call
+                        __threadfence();
+                        asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(prog_flags + slab), "r"(prog_epoch) : "memory");
+                    }
+                }
             }
         }
         if (valid) store_state(qv, tp, ctr, i, e);
@@ -563,7 +577,8 @@ static int launch_rollout_tc(rb_env* e, const float* params, int T, float* obs_b
     static int stagger = -1;
     if (stagger < 0) { const char* v = getenv("RB_ROLLOUT_STAGGER_NS"); stagger = v ? atoi(v) : ROLLOUT_STAGGER_NS; }
     k_rollout_policy_tc<NOUT, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf, k0, k1,
-                                                                e->offset, (uint32_t)stagger);
+                                                                e->offset, (uint32_t)stagger, e->prog_counters, e->prog_flags_dev,
+                                                                e->prog_counters ? e->prog_slab_len : 0, e->prog_epoch);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }

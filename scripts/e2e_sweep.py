@@ -40,13 +40,14 @@ if __name__ == "__main__":
     if os.environ.get("E2E_CHILD") == "1":
         child()
         sys.exit(0)
-    settings = [dict(),                                                                       # defaults: reward kernel-written, done in 2 slabs
-                dict(RB_HOST_SLABS_SMALL="1"), dict(RB_HOST_SLABS_SMALL="3"),
+    settings = [dict(),                                                                       # defaults: reward kernel-written, done copied per in-kernel progress slab
+                dict(RB_HOST_PROGRESS_SLABS="3"), dict(RB_HOST_PROGRESS_SLABS="10"),
+                dict(RB_HOST_ZEROCOPY="0"), dict(RB_HOST_ZEROCOPY="0", RB_HOST_PROGRESS_SLABS="10"),   # everything by the copy engine, progress slabs
                 dict(RB_HOST_ZEROCOPY="3"),                                                   # reward and done kernel-written
-                dict(RB_HOST_ZEROCOPY="2"),                                                   # done kernel-written, reward by slab copies
-                dict(RB_HOST_ZEROCOPY="0", RB_HOST_SLABS="5", RB_HOST_SLAB_FIRST="100"),      # the first schedule: 5 equal slabs, all copied
-                dict(E2E_FULL="1"),
-                dict(RB_HOST_ZEROCOPY="0", E2E_FULL="1", RB_HOST_SLABS="5", RB_HOST_SLAB_FIRST="100")]
+                dict(RB_HOST_PROGRESS="0"),                                                   # previous default: reward kernel-written, done copied after the kernel
+                dict(RB_HOST_PROGRESS="0", RB_HOST_ZEROCOPY="0", RB_HOST_SLABS="5", RB_HOST_SLAB_FIRST="100"),      # the first schedule: 5 kernel slabs, all copied
+                dict(E2E_FULL="1"), dict(E2E_FULL="1", RB_HOST_PROGRESS_SLABS="10"),
+                dict(RB_HOST_PROGRESS="0", E2E_FULL="1")]
     for s in settings:
         envv = dict(os.environ, E2E_CHILD="1", **s)
         subprocess.run([sys.executable, os.path.abspath(__file__)], env=envv, check=False)
