@@ -332,7 +332,7 @@ def main():
                                                      else "NCCL all-reduce of flat grad") if world > 1 else "single GPU"),
                                e2e=dict(value=float(nd) * Kd * world / de2e, unit="samples/s", h2d_bytes_per_step=0, d2h_bytes_per_step=8,
                                         api="DaggerTrainer.step + wait_loss (rb_dagger_step, rb_dagger_wait_loss: {loss, iteration} posted into mapped host memory)"),
-                               gpu_launches_per_step=(3 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8),
+                               gpu_launches_per_step=(2 if tr.student_mode == MODE_TC and (world == 1 or tr.fused_allreduce) else 8),
                                cuda_graph=bool(tr.use_graph), student_mode=("tc" if tr.student_mode == MODE_TC else "fp32"),
                                last_loss=float(tr.last_loss()),
                                roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",

@@ -2,6 +2,7 @@
 // Replaces the per-env-step body of /root/reference src/distilation/mlp_train.py:143-204 (teacher label :165-167, record
 // :188-193 with dataset.py:118-143 `prev` / `prew` semantics, env.step(s_ac) :196) for N envs at once.
 #include <chrono>
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -28,6 +29,7 @@ struct rb_dagger {
     // and no copy-engine transfer
     volatile uint2* mailbox_host = nullptr;
     uint2* mailbox_dev = nullptr;
+    uint32_t* act_flags = nullptr;       // per-tile forward-done flags of the env step fused into k_student_tc (student_tc.cu: act_*)
 };
 
 namespace rb {
@@ -51,9 +53,9 @@ __global__ void k_dagger_input(int64_t n, const uint2* __restrict__ ctr, const f
 __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint2* ctr, const float4* __restrict__ s_pd,
                                                     const float4* __restrict__ t_pd, float4* prev_t, float* prev_rec_rew, float* last_reward,
                                                     float* __restrict__ rew, uint8_t* __restrict__ done, uint32_t k0, uint32_t k1,
-                                                    uint32_t offset, uint32_t* clock, const float* __restrict__ loss_src, uint2* mailbox) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (clock && i == 0) {                                                        // end of the iteration: advance the device-side step clock
+                                                    uint32_t offset, uint32_t* clock, const float* __restrict__ loss_src, uint2* mailbox, int64_t i0) {
+    const int64_t i = i0 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x;          // envs [i0, n)
+    if (clock && i == i0) {                                                       // end of the iteration: advance the device-side step clock
         const uint32_t it = clock[0] + 1u;
         clock[0] = it; clock[1] += 1u; clock[2] += 1u;
         if (mailbox)                                                              // {loss, iterations done} -> host memory, one 8-byte posted write
@@ -80,8 +82,15 @@ __global__ void k_set_clock(uint32_t* clock, uint32_t iteration, uint32_t adam_t
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
 struct StepClock { const uint32_t* clock; float lr; };
-int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
-                   float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, cudaStream_t st);
+struct ActFuse {
+    float4* qv; float4* tp; uint2* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
+    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox;
+};
+int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
+                      float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
+                      cudaStream_t st);
+int64_t student_tc_act_covered(int64_t B, int grid);
+int student_tc_grid(int* grid);
 
 // implemented in policy_tc.cu
 size_t policy_tc_image_bytes();
@@ -115,7 +124,7 @@ int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_
 
 int rb_dagger_destroy(rb_dagger* d) {
     if (!d) return RB_OK;
-    cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward); cudaFree(d->teacher_img); cudaFree(d->clock);
+    cudaFree(d->prev_t); cudaFree(d->prev_rec_rew); cudaFree(d->last_reward); cudaFree(d->teacher_img); cudaFree(d->clock); cudaFree(d->act_flags);
     if (d->mailbox_host) cudaFreeHost((void*)d->mailbox_host);
     if (d->gexec) cudaGraphExecDestroy(d->gexec);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
@@ -162,7 +171,7 @@ int rb_dagger_act(rb_dagger* d, const float* s_pd, const float* t_pd, float* rew
     rb_env* e = d->env;
     k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd,
                                                                                   d->prev_t, d->prev_rec_rew, d->last_reward, rew, done,
-                                                                                  (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset, nullptr, nullptr, nullptr);
+                                                                                  (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset, nullptr, nullptr, nullptr, 0);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
@@ -170,6 +179,9 @@ int rb_dagger_act(rb_dagger* d, const float* s_pd, const float* t_pd, float* rew
 int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_t, uint32_t epoch, void* stream) {
     RB_REQUIRE(d != nullptr, "NULL argument");
     if (!d->clock) RB_CUDA(cudaMalloc(&d->clock, 4 * sizeof(uint32_t)));
+    const size_t nflags = (size_t)((d->env->n + 127) / 128);
+    if (!d->act_flags) RB_CUDA(cudaMalloc(&d->act_flags, nflags * sizeof(uint32_t)));
+    RB_CUDA(cudaMemsetAsync(d->act_flags, 0, nflags * sizeof(uint32_t), (cudaStream_t)stream));      // flag values are iteration counts: a clock reset voids them
     k_set_clock<<<1, 1, 0, (cudaStream_t)stream>>>(d->clock, iteration, adam_t, epoch);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
@@ -201,17 +213,36 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
         if (rc0) return rc0;
         d->teacher_img_src = teacher_params;
     }
+    static const int fuse_act_knob = [] { const char* v = getenv("RB_DAGGER_FUSE_ACT"); return v ? atoi(v) : 1; }();
+    const bool fuse_act = fuse_act_knob != 0;
     auto issue = [&](cudaStream_t st) -> int {
         int rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, st);
         if (rc) return rc;
         const AdamFuse af{params, m, v, 0.f, b1, b2, eps, gscale};
         const PeerExchange px{world, rank, 0u, slots_even, flags, slots_odd};
         const StepClock clk{d->clock, lr};
-        rc = student_tc_run(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, st);
+        if (fuse_act) {      // env step, clock advance and loss mailbox inside the student launch: two launches per iteration
+            const ActFuse act{e->qv, e->tp, e->ctr, d->prev_t, d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed, (uint32_t)(e->seed >> 32),
+                              e->offset, d->act_flags, d->clock, d->mailbox_dev};
+            rc = student_tc_run_ex(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, &act, st);
+            if (rc) return rc;
+            int grid = 1;
+            rc = student_tc_grid(&grid);
+            if (rc) return rc;
+            const int64_t i0 = student_tc_act_covered(e->n, grid);           // envs the student launch did not step (none at the config-4 shard)
+            if (i0 < e->n) {
+                k_dagger_act<<<(unsigned)((e->n - i0 + 127) / 128), 128, 0, st>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd, d->prev_t,
+                                                                                   d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed,
+                                                                                   (uint32_t)(e->seed >> 32), e->offset, nullptr, nullptr, nullptr, i0);
+                RB_CUDA(cudaGetLastError());
+            }
+            return RB_OK;
+        }
+        rc = student_tc_run_ex(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, nullptr, st);
         if (rc) return rc;
         k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, st>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd, d->prev_t,
                                                                       d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed,
-                                                                      (uint32_t)(e->seed >> 32), e->offset, d->clock, gradloss + loss_index, d->mailbox_dev);
+                                                                      (uint32_t)(e->seed >> 32), e->offset, d->clock, gradloss + loss_index, d->mailbox_dev, 0);
         RB_CUDA(cudaGetLastError());
         return RB_OK;
     };

@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "physics.cuh"
 #include "tc_common.cuh"
 
 namespace rb {
@@ -101,6 +102,18 @@ struct StudentTcArgs {
     const uint32_t* clock;
     float lr;
     uint2* peer_ll2[2][8];
+    // optional fused DAgger env step (rb_dagger_step; sample i == env i): once the forward pass of a tile has written s_out, the envs of
+    // that tile are stepped with the student mean INSIDE this launch by the CTAs that own one tile less than the others and would
+    // otherwise idle at the first grid barrier (per-tile release / acquire flags): two 512-env blocks each, i.e. all envs at the config-4
+    // shard (32 768 envs: 40 such CTAs).  Envs beyond that (student_tc_act_covered()) are left to a k_dagger_act launch behind this
+    // kernel.  One thread of the grid advances the device clock and posts the loss mailbox at the end.
+    int act_on;
+    float4* act_qv; float4* act_tp; uint2* act_ctr;
+    float4* act_prev_t; float* act_prev_rec_rew; float* act_last_reward; float* act_rew; uint8_t* act_done;
+    uint32_t act_k0, act_k1, act_offset;
+    uint32_t* act_flags;          // [ceil(B / 128)] forward-done flag per tile, value = iteration count of the launch that set it
+    uint32_t* act_clock;          // writable alias of `clock`
+    uint2* act_mailbox;           // mapped host memory {loss bits, iterations done}, may be NULL
 };
 
 // Plain (weak) global load.  Data produced earlier in the SAME launch by other CTAs is read only after a grid barrier and is never
@@ -125,6 +138,7 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 struct __align__(16) StudentTcCtl {
     float lr_t;                   // Adam step size of this launch (from the host, or from the device clock)
     uint32_t epoch;
+    uint32_t iter;                // iterations done once this launch has finished (clock[0] + 1): value of the act flags / mailbox
     uint64_t mbar;                // forward layers / dgrad results
     uint64_t mbar2;               // wgrad completion (X_l may be overwritten)
     uint32_t tmem_base;
@@ -476,6 +490,43 @@ __device__ __forceinline__ void st_stamp(int i) {
     }
 }
 
+__device__ __forceinline__ uint32_t ld_acquire_gpu(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_gpu(uint32_t* p, uint32_t v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// env.step(s_ac) for the 512 envs of block `blk` (= 4 tiles; warp w covers 32 envs of tile 4 blk + w / 4) -- the body of k_dagger_act
+// (dagger.cu; mlp_train.py:188-196).  wait: spin until the owner of that tile has published its forward pass.
+__device__ __forceinline__ void act_block(const StudentTcArgs& a, int64_t blk, bool wait, uint32_t iter, int64_t ntiles) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t tile = blk * 4 + (warp >> 2);
+    if (tile >= ntiles) return;                                       // warp-uniform
+    if (wait) {
+        if (lane == 0) while (ld_acquire_gpu(a.act_flags + tile) != iter) __nanosleep(64);
+        __syncwarp();
+    }
+    const int64_t i = blk * ST_THREADS + threadIdx.x;
+    if (i >= a.B) return;
+    EnvState e = load_state(a.act_qv, a.act_tp, a.act_ctr, i);
+    const float4 sp = __ldcg(a.s_out + i);                            // written by another SM in this launch: L2, never L1
+    bool d;
+    const float r = step_env(e, sp.x, sp.y, a.act_k0, a.act_k1, a.act_offset + (uint32_t)i, d);
+    store_state(a.act_qv, a.act_tp, a.act_ctr, i, e);
+    a.act_prev_t[i] = __ldg(reinterpret_cast<const float4*>(a.t) + i);
+    a.act_prev_rec_rew[i] = a.act_last_reward[i];
+    a.act_last_reward[i] = r;
+    if (a.act_rew) a.act_rew[i] = r;
+    if (a.act_done) a.act_done[i] = d ? 1 : 0;
+}
+// end of the iteration: advance the device-side step clock, post {loss, iterations done} into host memory (one thread of the grid)
+__device__ __forceinline__ void act_finish(const StudentTcArgs& a, float loss, uint32_t iter, bool bump_clock, bool post) {
+    if (bump_clock) { a.act_clock[0] = iter; a.act_clock[1] += 1u; a.act_clock[2] += 1u; }
+    if (post && a.act_mailbox)
+        asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(a.act_mailbox), "r"(__float_as_uint(loss)), "r"(iter) : "memory");
+}
+
 // One cooperative launch = fold + weight split (spread over the grid) -> tiles (forward, loss, backward; weight gradients in
 // TMEM) -> partials -> grid-wide fixed-order reduction -> gradient of the un-folded parameters [-> Adam].
 template <class S>
@@ -503,6 +554,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             const double t = (double)(a.clock[1] + 1u);
             ctl.lr_t = (float)((double)a.lr * sqrt(1.0 - pow((double)a.beta2, t)) / (1.0 - pow((double)a.beta1, t)));
             ctl.epoch = a.clock[2] + 1u;
+            ctl.iter = a.clock[0] + 1u;
         }
     }
     for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
@@ -623,6 +675,9 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         fence_before_sync();
         __syncthreads();
         RB_TS(10);
+        // s_out of this tile is published (release: cumulative over the CTA barrier above).  Warp 1 does it: warp 0 issues the backward MMAs
+        // next, and the other warps only wait for them, so the fence latency is hidden.
+        if (a.act_on && tid == 32) st_release_gpu(a.act_flags + tile, ctl.iter);
         if (a.fwd_only) continue;
 
         // ---- backward: wgrad_l (accumulates in TMEM) + dgrad_l, then dZ_{l-1} in place over X_l ------------------------------
@@ -669,9 +724,21 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         if (lane == 0) ctl.red[warp] = v;
         __syncthreads();
         if (tid == 0) part_out[a.ploss] = (ctl.red[0] + ctl.red[1]) + (ctl.red[2] + ctl.red[3]);     // part 0 = warps 0..3
+        // ---- fused env step, part 1: CTAs [r, grid) own one tile less than the others (r = ntiles mod grid) and would idle for one tile
+        // period (~10 us ~ two 512-env blocks) at the barrier below; they step blocks e, e + n_early of the env range instead.
+        const int64_t act_nblocks = (a.B + ST_THREADS - 1) / ST_THREADS;
+        int64_t act_covered = 0;
+        if (a.act_on) {
+            const int r = (int)(ntiles % gridDim.x), n_early = r ? (int)gridDim.x - r : 0;
+            act_covered = min(act_nblocks, (int64_t)2 * n_early);
+            if (r && (int)blockIdx.x >= r)
+                for (int64_t blk = (int)blockIdx.x - r; blk < act_covered; blk += n_early) act_block(a, blk, true, ctl.iter, ntiles);
+        }
         st_stamp(5);
         grid.sync();
         st_stamp(6);
+        // (envs beyond act_covered blocks are stepped by a k_dagger_act launch behind this kernel: 64 warps per SM hide the latency of the
+        // physics chain better than the 16 of this kernel)
         // ---- grid-wide reduction of the partial vectors in CTA order with a fixed tree => bit-reproducible.  A warp owns 32
         // consecutive elements (coalesced 128-byte reads of every partial); 8 warps split the partials, shared memory combines them.
         {
@@ -734,6 +801,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
                     tot += __uint_as_float(w.x);
                 }
                 gl[i] = tot;
+                if (a.act_on && i == a.P) act_finish(a, tot, ctl.iter, false, true);
                 if (a.do_adam && i < a.P) {    // TF1 Adam, same arithmetic as k_adam (student.cu); element i only needs gradient i
                     float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
                     adam_update(pi, mi, vi, tot, ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
@@ -742,8 +810,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
             }
         }
         st_stamp(9);
+        if (a.act_on && a.world > 1 && gtid == 0) act_finish(a, 0.f, ctl.iter, true, false);     // every CTA read the clock before the first barrier
         if (a.do_adam && a.world <= 1) {
             grid.sync();                       // every read of the old parameters (finish) is done, every gradloss entry written
+            if (a.act_on && gtid == 0) act_finish(a, __ldcg(a.gradloss + a.P), ctl.iter, true, true);
             for (int i = gtid; i < a.P; i += gthreads) {
                 float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
                 adam_update(pi, mi, vi, ldw(a.gradloss + i), ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
@@ -792,9 +862,31 @@ template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cuda
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
 struct StepClock { const uint32_t* clock; float lr; };
+struct ActFuse {              // fused env step of rb_dagger_step (see StudentTcArgs::act_*)
+    float4* qv; float4* tp; uint2* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
+    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox;
+};
 
+int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
+                      float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
+                      cudaStream_t st);
+// number of leading envs the fused env step of a B-sample launch covers (same arithmetic as the kernel: two blocks per early CTA)
+int64_t student_tc_act_covered(int64_t B, int grid) {
+    const int64_t ntiles = (B + ST_TILE - 1) / ST_TILE, nblocks = (B + ST_THREADS - 1) / ST_THREADS;
+    const int r = (int)(ntiles % grid), n_early = r ? grid - r : 0;
+    const int64_t covered = nblocks < (int64_t)2 * n_early ? nblocks : (int64_t)2 * n_early;
+    const int64_t envs = covered * ST_THREADS;
+    return envs < B ? envs : B;
+}
+int student_tc_grid(int* grid) { return tc_grid(0, grid); }
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
                    float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, cudaStream_t st) {
+    return student_tc_run_ex(kind, params, x, tpd, B, loss_kind, fwd_only, s_out, gradloss, workspace, adam, px, clk, nullptr, st);
+}
+
+int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
+                      float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
+                      cudaStream_t st) {
     RB_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(params) & 3) == 0, "x must be 16-byte aligned");
     RB_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "workspace must be 16-byte aligned");
     float* ws = (float*)workspace;
@@ -819,6 +911,12 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
         }
     }
     if (clk && clk->clock) { a.clock = clk->clock; a.lr = clk->lr; }
+    if (act) {
+        RB_REQUIRE(!fwd_only && adam && a.clock && s_out && tpd && act->flags && act->clock == a.clock, "fused env step needs the full optimiser step with the device clock");
+        a.act_on = 1; a.act_qv = act->qv; a.act_tp = act->tp; a.act_ctr = act->ctr; a.act_prev_t = act->prev_t; a.act_prev_rec_rew = act->prev_rec_rew;
+        a.act_last_reward = act->last_reward; a.act_rew = act->rew; a.act_done = act->done; a.act_k0 = act->k0; a.act_k1 = act->k1; a.act_offset = act->offset;
+        a.act_flags = act->flags; a.act_clock = act->clock; a.act_mailbox = act->mailbox;
+    }
     if (kind == RB_STUDENT_MLP) {
         a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
         a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
