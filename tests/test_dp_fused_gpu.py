@@ -30,7 +30,9 @@ def _worker(rank, world, port, q):
         losses = []
         for _ in range(25):
             tr.step()
+            posted = tr.wait_loss() if tr.use_graph else None          # graph path: the loss mailbox (host polls mapped memory)
             losses.append(float(tr.last_loss()))
+            assert posted is None or np.float32(posted) == np.float32(losses[-1]), (posted, losses[-1])
         out[name] = (np.array(losses), tr.student.params.cpu().numpy().copy())
         tr.close()
     q.put((rank, out))
