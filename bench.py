@@ -33,14 +33,14 @@ CHUNK_T = 50
 DISTILL_ENVS_PER_GPU = 32768
 STEP_API_ENVS = 1 << 22
 ALG_BYTES_ROLLOUT = 65.0      # fused rollout writes one buffer row per env-step: ob 44 + pdflat 16 + rew 4 + done 1 B (17 scalars)
-ROLLOUT_TRAFFIC_NCU = 159.6e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
+ROLLOUT_TRAFFIC_NCU = 160.0e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
                                 # profiles/r01_ncu_full_k_rollout_policy_tc_final.csv; the rest of the 213 MB is still dirty in L2 at kernel end
 MUFU_PER_ENV_STEP = 169.0       # 128 tanh x 1.25 (ex2 each, one rcp per four) + 8 rcp + 1 sqrt
 XU_LANES_PER_CLK_PER_SM = 16.0  # B200 MUFU rate
 ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
 STEP_TRAFFIC_NCU = 515.4e6    # dram read + write of one k_step launch at 4 194 304 envs (profiles/r01_ncu_full_k_step.csv) = 122.9 B per env-step
-STUDENT_TRAFFIC_NCU = 3.0e6   # dram read + write of one k_student_tc<SpecMLP> launch at 32 768 samples (profiles/r01_ncu_full_k_student_tc_final.csv);
-                              # the 2.6 MB of inputs are read once, everything else stays in L2
+STUDENT_TRAFFIC_NCU = 4.46e6  # dram read + write of one k_student_tc<SpecMLP> launch of the DAgger graph at 32 768 samples
+                              # (profiles/r01_ncu_full_k_student_tc_final.csv): inputs and env state read once, everything else stays in L2
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 FLOP_PER_ENV_STEP = 450.0 + 9856.0          # physics + teacher MLP
 FLOP_PER_SAMPLE = {"mlp": 144.4e3, "policy64": 30.3e3}
