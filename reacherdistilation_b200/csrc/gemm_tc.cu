@@ -358,7 +358,9 @@ int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, 
     int split = 1;
     if (splitk_ws) {
         if (g.force_split > 0) split = g.force_split;
-        else if (tiles < sms && g.K >= 8 * GM_BK) split = min(min(32, (2 * sms + tiles - 1) / tiles), g.K / (4 * GM_BK));
+        // tiles * split <= 2 * sms: one wave of the BN <= 64 kernels (two CTAs per SM), two full waves of the <128> kernel -- rounding the
+        // quotient UP left a nearly empty third wave (LSTM W_l gradient: 14 tiles x 22 slices = 308 CTAs on 148 SMs)
+        else if (tiles < sms && g.K >= 8 * GM_BK) split = min(min(32, max(1, (2 * sms) / tiles)), g.K / (4 * GM_BK));
     }
     split = max(1, split);
     while (split > 1 && (size_t)split * g.batch * g.M * g.N > splitk_ws_floats) --split;

@@ -163,6 +163,23 @@ static int gemm(const float* A, int lda, int a_mn, const float* Bm, int ldb, int
 }
 #define RB_TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
 
+// Side stream for the head weight-gradient GEMMs: dW_l only needs dZ_l and the saved layer input, so the five [wgrad_l + split-K sum] pairs
+// run beside the dgrad chain (and the start of the BPTT kernel) instead of between its links.  Fork / join with events, so the same
+// code is captured as a two-branch CUDA graph by rb_lstm_step and runs as two real streams otherwise.  One set per device.
+struct LstmSide { cudaStream_t s = nullptr; cudaEvent_t ready[5] = {}; cudaEvent_t done = nullptr; };
+static int lstm_side(int device, LstmSide** out) {
+    static LstmSide side[16];
+    RB_REQUIRE(device >= 0 && device < 16, "device ordinal out of range");
+    LstmSide& x = side[device];
+    if (!x.s) {
+        RB_CUDA(cudaStreamCreateWithFlags(&x.s, cudaStreamNonBlocking));
+        for (int i = 0; i < 5; ++i) RB_CUDA(cudaEventCreateWithFlags(&x.ready[i], cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&x.done, cudaEventDisableTiming));
+    }
+    *out = &x;
+    return RB_OK;
+}
+
 static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     int device = 0, sms = 148;
     RB_CUDA(cudaGetDevice(&device));
@@ -224,6 +241,10 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     RB_TRY(sum_serial(loss_part, (int)kl_blocks, c.gradloss + L_P, st));
     float* G = c.gradloss;
     // ---- heads backward, batched over the T steps ----------------------------------------------------------------------------------
+    static int use_side = -1;
+    if (use_side < 0) { const char* v = getenv("RB_LSTM_SIDE_STREAM"); use_side = v ? atoi(v) : 1; }
+    LstmSide* side = nullptr;
+    if (use_side) RB_TRY(lstm_side(device, &side));
     for (int l = 4; l >= 0; --l) {
         const float* W = P + L_HEAD0 + head_w_off(l);
         float* gW = G + L_HEAD0 + head_w_off(l);
@@ -232,10 +253,21 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         const int ld_in = act_ld(l);
         // [dW ; db] = [in | 1]^T dout : HD[l] + 1 output rows, the last one lands on the bias gradient (b follows W in the parameter vector)
         Bat bw; bw.n = LT; bw.sA = B * ld_in; bw.sB = B * HD[l + 1]; bw.sC = L_HEAD_SZ;
-        RB_TRY(gemm(in, ld_in, 1, dout, HD[l + 1], 1, gW, HD[l + 1], HD[l] + 1, HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, st, true, bw));
+        cudaStream_t sw = st;
+        if (side) {                                              // dZ_l is complete on the main stream here: the side stream may start dW_l
+            RB_CUDA(cudaEventRecord(side->ready[l], st));
+            RB_CUDA(cudaStreamWaitEvent(side->s, side->ready[l], 0));
+            sw = side->s;
+        }
+        RB_TRY(gemm(in, ld_in, 1, dout, HD[l + 1], 1, gW, HD[l + 1], HD[l] + 1, HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, sw, true, bw));
         float* din = l == 0 ? w.dh : w.da[l - 1];                                                     // d(in) = dout W^T (* tanh' of the layer input)
         Bat bd; bd.n = LT; bd.sA = B * HD[l + 1]; bd.sB = L_HEAD_SZ; bd.sC = B * HD[l]; bd.sH = B * ld_in;
         RB_TRY(gemm(dout, HD[l + 1], 0, W, HD[l + 1], 0, din, HD[l], Bi, HD[l], HD[l + 1], nullptr, 0, 0, l == 0 ? nullptr : in, ld_in, w, sms, st, false, bd));
+    }
+    if (side && !use_recur) {                                    // the GEMM-per-step fallback below uses the split-K scratch too: join first
+        RB_CUDA(cudaEventRecord(side->done, side->s));
+        RB_CUDA(cudaStreamWaitEvent(st, side->done, 0));
+        side = nullptr;
     }
     // ---- back-propagation through time -------------------------------------------------------------------------------------------
     if (use_recur) {
@@ -250,6 +282,10 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
             RB_CUDA(cudaGetLastError());
             RB_TRY(gemm(dz_t, LG, 0, P + L_WL, LG, 0, dxh_t, LDXH, Bi, LXH, LG, nullptr, 0, 0, nullptr, 0, w, sms, st, true));  // d[x | m_prev] = dz W_l^T
         }
+    }
+    if (side) {                                                  // join: the shared split-K scratch and the gradient vector are next used here
+        RB_CUDA(cudaEventRecord(side->done, side->s));
+        RB_CUDA(cudaStreamWaitEvent(st, side->done, 0));
     }
     // ---- weight gradients of the shared parts, over all T*B rows ---------------------------------------------------------------------
     RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH + 1, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));   // row 243 (ones column) = db_l
