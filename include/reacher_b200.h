@@ -200,8 +200,10 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params_dev, uint32_t it
 int rb_dagger_invalidate_teacher(rb_dagger* d);
 /* One whole DAgger iteration (RB_MODE_TC): rb_dagger_observe + rb_student_step[_dp] + rb_dagger_act, with every per-step quantity
  * (dropout iteration, Adam step, exchange epoch / slot parity) read from a device-side clock set once by rb_dagger_set_clock and
- * advanced by the last kernel -- so the three launches are captured ONCE in a CUDA graph (use_graph != 0) and replayed with a single
- * cudaGraphLaunch per iteration.  world > 1: slots_even / slots_odd / flags as in rb_student_step_dp (the two receive-area sets alternate). */
+ * advanced at the end of the iteration -- so the launches are captured ONCE in a CUDA graph (use_graph != 0) and replayed with a single
+ * cudaGraphLaunch per iteration.  The env step (rb_dagger_act's work) runs inside the student launch (CTAs that would idle at its first
+ * grid barrier step the envs whose forward pass is published), so an iteration is two launches; RB_DAGGER_FUSE_ACT=0 keeps three.
+ * world > 1: slots_even / slots_odd / flags as in rb_student_step_dp (the two receive-area sets alternate). */
 int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_step, uint32_t epoch, void* stream);
 int rb_dagger_step(rb_dagger* d, const float* teacher_params_dev, float* params_dev, float* m_dev, float* v_dev, float* gradloss_dev,
                    void* workspace_dev, float* obs_dev, float* t_pdflat_dev, float* x_dev, float* s_pdflat_dev, float* rew_dev, uint8_t* done_dev,
