@@ -189,7 +189,15 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     LstmWs w;
     lstm_ws_carve(ws, R, B, w);
     const float* P = c.params;
+    static int use_side = -1;
+    if (use_side < 0) { const char* v = getenv("RB_LSTM_SIDE_STREAM"); use_side = v ? atoi(v) : 1; }
+    LstmSide* side = nullptr;
+    if (use_side) RB_TRY(lstm_side(device, &side));
     // ---- inputs: dropout(ob), initial state, embedding of prev_pdflat --------------------------------------------------------
+    if (side) {                                                  // fork: the side branch starts from the same point as the main one
+        RB_CUDA(cudaEventRecord(side->ready[0], st));
+        RB_CUDA(cudaStreamWaitEvent(side->s, side->ready[0], 0));
+    }
     k_lstm_inputs<<<(unsigned)((max(R, B * LU) + 255) / 256), 256, 0, st>>>(R, B, c.ob, c.keep_prob, (uint32_t)c.seed, (uint32_t)(c.seed >> 32),
                                                                            c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c, w.hh, w.a[0], w.a[1], w.a[2], w.a[3]);
     RB_CUDA(cudaGetLastError());
@@ -201,7 +209,13 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     ra.W_l = P + L_WL; ra.b_l = P + L_BL; ra.B = B; ra.xh = w.xh; ra.hh = w.hh; ra.hh_ld = LDHH; ra.c0 = w.c; ra.c_last = w.c + (size_t)LT * B * LU;
     ra.dh = w.dh; ra.dz = w.dz; ra.dxh = w.dxh; ra.scratch = w.recur;
     if (use_recur) {
-        RB_TRY(lstm_recur_build_images(ra, st));
+        if (side) {                                              // W_l images only depend on the parameters: built beside the input kernels
+            RB_TRY(lstm_recur_build_images(ra, side->s));
+            RB_CUDA(cudaEventRecord(side->done, side->s));
+            RB_CUDA(cudaStreamWaitEvent(st, side->done, 0));
+        } else {
+            RB_TRY(lstm_recur_build_images(ra, st));
+        }
         RB_TRY(lstm_recur_forward(ra, st));
     } else {
         for (int t = 0; t < LT; ++t) {
@@ -212,6 +226,10 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
                                                                                w.hh + (size_t)t * B * LDHH, t + 1 < LT ? xh_t + (size_t)B * LDXH : nullptr);
             RB_CUDA(cudaGetLastError());
         }
+    }
+    if (side && !use_recur) {                                    // nothing ran on the side branch: still join it (stream capture needs every fork joined)
+        RB_CUDA(cudaEventRecord(side->done, side->s));
+        RB_CUDA(cudaStreamWaitEvent(st, side->done, 0));
     }
     if (c.final_state) {
         RB_CUDA(cudaMemcpyAsync(c.final_state, w.c + (size_t)LT * B * LU, sizeof(float) * B * LU, cudaMemcpyDeviceToDevice, st));
@@ -238,13 +256,9 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
     float* loss_part = w.splitk + w.splitk_floats;       // 1024 spare floats behind the split-K area (lstm_ws_carve)
     k_lstm_kl<<<kl_blocks, 256, 0, st>>>(R, (const float4*)c.s_out, (const float4*)c.t_pd, c.loss_kind, (float4*)w.da[4], loss_part);
     RB_CUDA(cudaGetLastError());
-    RB_TRY(sum_serial(loss_part, (int)kl_blocks, c.gradloss + L_P, st));
     float* G = c.gradloss;
     // ---- heads backward, batched over the T steps ----------------------------------------------------------------------------------
-    static int use_side = -1;
-    if (use_side < 0) { const char* v = getenv("RB_LSTM_SIDE_STREAM"); use_side = v ? atoi(v) : 1; }
-    LstmSide* side = nullptr;
-    if (use_side) RB_TRY(lstm_side(device, &side));
+    if (!side) RB_TRY(sum_serial(loss_part, (int)kl_blocks, c.gradloss + L_P, st));
     for (int l = 4; l >= 0; --l) {
         const float* W = P + L_HEAD0 + head_w_off(l);
         float* gW = G + L_HEAD0 + head_w_off(l);
@@ -258,6 +272,7 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
             RB_CUDA(cudaEventRecord(side->ready[l], st));
             RB_CUDA(cudaStreamWaitEvent(side->s, side->ready[l], 0));
             sw = side->s;
+            if (l == 4) RB_TRY(sum_serial(loss_part, (int)kl_blocks, c.gradloss + L_P, sw));      // the serial loss sum leaves the critical path too
         }
         RB_TRY(gemm(in, ld_in, 1, dout, HD[l + 1], 1, gW, HD[l + 1], HD[l] + 1, HD[l + 1], Bi, nullptr, 0, 0, nullptr, 0, w, sms, sw, true, bw));
         float* din = l == 0 ? w.dh : w.da[l - 1];                                                     // d(in) = dout W^T (* tanh' of the layer input)
@@ -288,10 +303,25 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         RB_CUDA(cudaStreamWaitEvent(st, side->done, 0));
     }
     // ---- weight gradients of the shared parts, over all T*B rows ---------------------------------------------------------------------
-    RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH + 1, LG, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));   // row 243 (ones column) = db_l
-    RB_TRY(gemm(c.prev_pd, 4, 1, w.dxh + 11, LDXH, 1, G + L_WE, LE, 4, LE, Ri, nullptr, 0, 0, nullptr, 0, w, sms, st, true));
-    RB_TRY(colsum(w.dxh + 11, LDXH, R, LE, 1, 0, G + L_BE, 0, w.colpart, st));
+    // The W_l gradient keeps the first 24 slices' worth of the split-K scratch, the embedding gradient (+ its bias column sum) takes the rest and
+    // runs on the side branch beside it.
+    LstmWs wl = w, we = w;
+    wl.splitk_floats = (size_t)24 * LDXH * LG;
+    we.splitk = w.splitk + wl.splitk_floats; we.splitk_floats = w.splitk_floats - wl.splitk_floats;
+    cudaStream_t se = st;
+    if (side) {
+        RB_CUDA(cudaEventRecord(side->ready[0], st));
+        RB_CUDA(cudaStreamWaitEvent(side->s, side->ready[0], 0));
+        se = side->s;
+    }
+    RB_TRY(gemm(w.xh, LDXH, 1, w.dz, LG, 1, G + L_WL, LG, LXH + 1, LG, Ri, nullptr, 0, 0, nullptr, 0, wl, sms, st, true));   // row 243 (ones column) = db_l
+    RB_TRY(gemm(c.prev_pd, 4, 1, w.dxh + 11, LDXH, 1, G + L_WE, LE, 4, LE, Ri, nullptr, 0, 0, nullptr, 0, we, sms, se, true));
+    RB_TRY(colsum(w.dxh + 11, LDXH, R, LE, 1, 0, G + L_BE, 0, w.colpart, se));
     RB_CUDA(cudaGetLastError());
+    if (side) {
+        RB_CUDA(cudaEventRecord(side->done, side->s));
+        RB_CUDA(cudaStreamWaitEvent(st, side->done, 0));
+    }
     return RB_OK;
 }
 
