@@ -195,6 +195,13 @@ int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_
 int rb_dagger_destroy(rb_dagger* d);
 int rb_dagger_observe(rb_dagger* d, const float* teacher_params_dev, uint32_t iteration, float* obs_dev, float* t_pdflat_dev,
                       float* x_dev, int mode, void* stream);
+/* Checkpoint / resume of the loop (`train(train, restore)`: main.py:24-27, lstm_train.py:86-87,102-107 save / restore the student every episode):
+ * the per-env state the handle carries between iterations -- teacher pdflat of the previous record [N,4], `rew` field of the previous record [N],
+ * reward of the last env.step [N] (dataset.py:118-143 `prev` / `prew`).  Device pointers, device-to-device copies on `stream`; NULL skips a field.
+ * Together with rb_env_get_state / rb_env_set_state, the student parameters + Adam moments and the iteration counter this resumes a run
+ * bit-exactly.                                                                                                                          */
+int rb_dagger_get_state(rb_dagger* d, float* prev_t_pdflat_dev, float* prev_rec_rew_dev, float* last_reward_dev, void* stream);
+int rb_dagger_set_state(rb_dagger* d, const float* prev_t_pdflat_dev, const float* prev_rec_rew_dev, const float* last_reward_dev, void* stream);
 /* RB_MODE_TC observe caches the split-weight image of the (frozen, teacher.py:17-20) teacher keyed by the parameter POINTER;
  * call this after modifying the teacher parameters in place.                                                                */
 int rb_dagger_invalidate_teacher(rb_dagger* d);

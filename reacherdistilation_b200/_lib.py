@@ -61,6 +61,8 @@ _SIGS = {
     "rb_dagger_destroy": (C.c_int, [_vp]),
     "rb_dagger_observe": (C.c_int, [_vp, _fp, C.c_uint32, _fp, _fp, _fp, C.c_int, _vp]),
     "rb_dagger_invalidate_teacher": (C.c_int, [_vp]),
+    "rb_dagger_get_state": (C.c_int, [_vp, _fp, _fp, _fp, _vp]),
+    "rb_dagger_set_state": (C.c_int, [_vp, _fp, _fp, _fp, _vp]),
     "rb_dagger_set_clock": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
     "rb_dagger_step": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _u8p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),

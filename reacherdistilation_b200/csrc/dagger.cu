@@ -132,6 +132,28 @@ int rb_dagger_destroy(rb_dagger* d) {
     return RB_OK;
 }
 
+// Checkpoint / resume (`train(train, restore)`, lstm_train.py:86-87,102-107): the per-env loop state the handle carries from one
+// iteration to the next.  Plain device-to-device copies on the caller's stream; a NULL pointer skips that field.
+int rb_dagger_get_state(rb_dagger* d, float* prev_t, float* prev_rec_rew, float* last_reward, void* stream) {
+    RB_REQUIRE(d != nullptr, "dagger handle is NULL");
+    const size_t n = (size_t)d->env->n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (prev_t) RB_CUDA(cudaMemcpyAsync(prev_t, d->prev_t, sizeof(float4) * n, cudaMemcpyDeviceToDevice, s));
+    if (prev_rec_rew) RB_CUDA(cudaMemcpyAsync(prev_rec_rew, d->prev_rec_rew, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+    if (last_reward) RB_CUDA(cudaMemcpyAsync(last_reward, d->last_reward, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+    return RB_OK;
+}
+
+int rb_dagger_set_state(rb_dagger* d, const float* prev_t, const float* prev_rec_rew, const float* last_reward, void* stream) {
+    RB_REQUIRE(d != nullptr, "dagger handle is NULL");
+    const size_t n = (size_t)d->env->n;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (prev_t) RB_CUDA(cudaMemcpyAsync(d->prev_t, prev_t, sizeof(float4) * n, cudaMemcpyDeviceToDevice, s));
+    if (prev_rec_rew) RB_CUDA(cudaMemcpyAsync(d->prev_rec_rew, prev_rec_rew, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+    if (last_reward) RB_CUDA(cudaMemcpyAsync(d->last_reward, last_reward, sizeof(float) * n, cudaMemcpyDeviceToDevice, s));
+    return RB_OK;
+}
+
 int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iteration, float* obs, float* t_pd, float* x, int mode, void* stream) {
     RB_REQUIRE(d && teacher_params && obs && t_pd && x, "NULL argument");
     rb_env* e = d->env;

@@ -22,7 +22,9 @@ def main(argv=None):
         path = os.path.join(config.base_path, "student_mlp_b200.pt")
         print(" checking saved variables ")
         sd = torch.load(path)
-        print({k: (tuple(v.shape) if hasattr(v, "shape") else v) for k, v in sd.items()})
+        def shapes(d):
+            return {k: (shapes(v) if isinstance(v, dict) else tuple(v.shape) if hasattr(v, "shape") else v) for k, v in d.items()}
+        print(shapes(sd))
     elif args.lstm_train:
         lstm_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob)
     elif args.mlp_train:

@@ -120,6 +120,30 @@ class DaggerTrainer:
             return out.value
         return float(self.last_loss())
 
+    def state_dict(self):
+        """Everything an exact resume needs (the reference checkpoints the student only, lstm_train.py:102-107,199; here also the loop state, so
+        that a restored run continues bit-identically): student parameters + Adam moments, env state (qpos, qvel, target, stale fingertip, step,
+        Philox episode counter), the handle's `prev` / `prew` carry and the iteration counter."""
+        n, dev = self.n, self.device
+        prev_t, prr, lr_ = torch.empty((n, 4), device=dev), torch.empty((n,), device=dev), torch.empty((n,), device=dev)
+        check(lib().rb_dagger_get_state(self._h, ptr(prev_t), ptr(prr), ptr(lr_), stream_ptr()))
+        env = {k: v.cpu() for k, v in self.env.get_state().items()}
+        return dict(student=self.student.state_dict(), env=env, prev_t_pdflat=prev_t.cpu(), prev_rec_rew=prr.cpu(), last_reward=lr_.cpu(),
+                    iteration=self.iteration, num_envs=n, seed=self.env.seed, env_offset=self.env.env_offset)
+
+    def load_state_dict(self, sd):
+        if int(sd["num_envs"]) != self.n or int(sd["seed"]) != int(self.env.seed) or int(sd["env_offset"]) != int(self.env.env_offset):
+            raise ValueError("checkpoint is for num_envs=%d seed=%d env_offset=%d" % (sd["num_envs"], sd["seed"], sd["env_offset"]))
+        self.student.load_state_dict(sd["student"])
+        e = sd["env"]
+        self.env.set_state(qpos=e["qpos"], qvel=e["qvel"], target=e["target"], fingertip=e["fingertip"], step=e["step"], episode=e["episode"])
+        dev = self.device
+        prev_t, prr, lr_ = (sd[k].to(dev, torch.float32).contiguous() for k in ("prev_t_pdflat", "prev_rec_rew", "last_reward"))
+        check(lib().rb_dagger_set_state(self._h, ptr(prev_t), ptr(prr), ptr(lr_), stream_ptr()))
+        torch.cuda.current_stream().synchronize()          # the temporaries must outlive the copies
+        self.iteration = int(sd["iteration"])
+        self._clock_synced = False                         # the device-side step clock is reloaded from the host counters
+
     def close(self):
         if self._h:
             lib().rb_dagger_destroy(self._h)
@@ -140,16 +164,24 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
     tr = DaggerTrainer(num_envs=num_envs, seed=seed, device=device, student_kind=student_kind, keep_prob=keep_prob, mode=mode,
                        env_offset=rank * num_envs)
     ckpt = checkpoint or os.path.join(base_path, "student_mlp_b200.pt")
+    resumed = False
     if restore and os.path.exists(ckpt):
-        tr.student.load_state_dict(torch.load(ckpt))
+        sd = torch.load(ckpt)
+        if "student" in sd and int(sd.get("num_envs", -1)) == int(num_envs) and int(sd.get("env_offset", -1)) == rank * num_envs:
+            tr.load_state_dict(sd)                       # full loop state: continue exactly where the saved run stopped
+            resumed = True
+        else:                                            # student-only checkpoint (or another shard shape): the reference's restore
+            tr.student.load_state_dict(sd["student"] if "student" in sd else sd)
     tr.sync_params()
     if not train:
         return dict(trainer=tr)
     if verbose and rank == 0:
         print("Begin Training! First Accumulate observation with teacher")
-    eps_per_env = max(1, -(-warmup_episodes // (num_envs * world)))
-    warm = tr.env.rollout_policy(tr.teacher.params, 50 * eps_per_env, nout=2, mode=mode)
-    teacher_reward = float(warm["rew"].mean())
+    teacher_reward = None
+    if not resumed:                                      # a resumed run is already past phase A
+        eps_per_env = max(1, -(-warmup_episodes // (num_envs * world)))
+        warm = tr.env.rollout_policy(tr.teacher.params, 50 * eps_per_env, nout=2, mode=mode)
+        teacher_reward = float(warm["rew"].mean())
     if verbose and rank == 0:
         print("Accumulated sufficient data points from teacher. now train")
     if iterations is None:
@@ -165,7 +197,7 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
                 print("recent loss: %f " % losses[-1])
     if rank == 0 and checkpoint is not None:
         os.makedirs(os.path.dirname(ckpt) or ".", exist_ok=True)
-        torch.save(tr.student.state_dict(), ckpt)
+        torch.save(tr.state_dict(), ckpt)
     out = dict(losses=losses, rewards=rewards, teacher_reward=teacher_reward, iterations=iterations, trainer=tr)
     return out
 

@@ -144,3 +144,51 @@ def test_wait_loss_mailbox_matches_device_loss():
     tr.step()
     assert np.isfinite(tr.wait_loss())
     tr.close()
+
+
+@pytest.mark.parametrize("mode_name,use_graph", [("fp32", False), ("tc", True)])
+def test_checkpoint_resume_is_bit_exact(mode_name, use_graph, tmp_path):
+    """DaggerTrainer.state_dict / load_state_dict (rb_env_get/set_state, rb_dagger_get/set_state, student + Adam moments, iteration):
+    a run restored into a FRESH trainer continues bit-identically to the uninterrupted one -- across an episode boundary (auto-reset from the
+    restored Philox episode counter), with dropout (mask keyed by the restored iteration) and the `prev` / `prew` carry."""
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC, STUDENT_MLP
+    from reacherdistilation_b200.mlp_train import DaggerTrainer
+    mode = MODE_TC if mode_name == "tc" else MODE_FP32
+    kw = dict(num_envs=333, seed=6, student_kind=STUDENT_MLP, keep_prob=0.5, mode=mode, lr=1e-3, use_graph=use_graph, env_offset=1000)
+    a = DaggerTrainer(**kw)
+    for _ in range(37):
+        a.step()
+    path = str(tmp_path / "dagger.pt")
+    torch.save(a.state_dict(), path)
+    b = DaggerTrainer(**dict(kw, student_seed=99))              # different init: everything must come from the checkpoint
+    b.load_state_dict(torch.load(path))
+    assert b.iteration == 37 and b.student.t == 37
+    for it in range(30):                                        # steps 37..66 of every env: crosses the reset at step 50
+        a.step(); b.step()
+        assert torch.equal(a.last_loss(), b.last_loss()), it
+        assert torch.equal(a.rew, b.rew) and torch.equal(a.done, b.done) and torch.equal(a.x, b.x), it
+    assert torch.equal(a.student.params, b.student.params) and torch.equal(a.student.m, b.student.m) and torch.equal(a.student.v, b.student.v)
+    sa, sb = a.env.get_state(), b.env.get_state()
+    for k in sa:
+        assert torch.equal(sa[k], sb[k]), k
+    with pytest.raises(ValueError):
+        c = DaggerTrainer(**dict(kw, num_envs=64))
+        try:
+            c.load_state_dict(torch.load(path))
+        finally:
+            c.close()
+    a.close(); b.close()
+
+
+def test_train_entry_point_restore_continues_the_saved_run(tmp_path):
+    """mlp_train.train(train, restore) (main.py:26-27 `-r`): 60 iterations, checkpoint, restore + 40 more == 100 iterations in one go."""
+    from reacherdistilation_b200 import mlp_train
+    ck = str(tmp_path / "student_mlp_b200.pt")
+    full = mlp_train.train(True, False, num_envs=256, iterations=100, log_every=20, verbose=False)
+    first = mlp_train.train(True, False, num_envs=256, iterations=60, log_every=20, verbose=False, checkpoint=ck)
+    first["trainer"].close()
+    rest = mlp_train.train(True, True, num_envs=256, iterations=40, log_every=20, verbose=False, checkpoint=ck)
+    assert rest["teacher_reward"] is None                       # phase A is not replayed
+    assert first["losses"] + rest["losses"] == full["losses"]
+    assert torch.equal(rest["trainer"].student.params, full["trainer"].student.params)
+    rest["trainer"].close(); full["trainer"].close()
