@@ -5,12 +5,15 @@ phase B (:141-201)  per env step: one optimiser step per Dataset.training_batche
                     dropout keep_prob, teacher-forced prev_pdflat, KL loss, Adam lr 1e-3); teacher label for the current observation;
                     student action = last row of the LSTM run over Dataset.test_batch(ob) from the CARRIED state (the reference feeds
                     the previous final state back in, :171-182); record ('s'); step; flush on done.
-All tensor work is on the device (tcgen05 GEMMs); the checkpoint is a torch.save of the flat parameters + Adam moments (:199)."""
+All tensor work is on the device (tcgen05 GEMMs); the checkpoint is a torch.save of the flat parameters + Adam moments (:199).
+`thread_state=True` is the loop of backup/lstm_bbpt.py:120-137: the optimiser steps of one env step run over `training_epochs` successive
+batches and the final LSTM state of each batch is fed to the next as its initial state (forward value only -- the reference feeds it through
+a placeholder, so no gradient crosses the batch boundary); it starts from zeros at every env step."""
 import os
 
 import torch
 
-from .config import KEEP_PROB, LSTM_BATCH_SIZE, SEED, STEPS_UNROLLED, TOTAL_EPISODES, base_path
+from .config import KEEP_PROB, LSTM_BATCH_SIZE, SEED, STEPS_UNROLLED, TOTAL_EPISODES, TRAINING_EPOCHS, base_path
 from .dataset import Dataset
 from .env import VecReacher
 from .student_nn import StudentLSTM
@@ -18,7 +21,7 @@ from .teacher import TeacherAgent
 
 
 def train(train=True, restore=False, num_envs=64, total_episodes=TOTAL_EPISODES, iterations=None, seed=SEED, device=0, keep_prob=KEEP_PROB,
-          batch_size=LSTM_BATCH_SIZE, generations=16, lr=1e-3, checkpoint=None, verbose=True):
+          batch_size=LSTM_BATCH_SIZE, generations=16, lr=1e-3, checkpoint=None, verbose=True, thread_state=False, training_epochs=TRAINING_EPOCHS):
     from ._lib import MODE_TC
     T = STEPS_UNROLLED
     env = VecReacher(num_envs=num_envs, seed=seed, device=device)
@@ -47,10 +50,15 @@ def train(train=True, restore=False, num_envs=64, total_episodes=TOTAL_EPISODES,
     max_it = iterations if iterations is not None else 50 * max(1, -(-total_episodes // num_envs))
     total_loss = 0.0
     while it < max_it:
-        for (ob_b, t_b, prev_b, _prew) in dataset.training_batches(batch_size, T):
-            student.loss_grad(ob_b, prev_b, t_b, None, keep_prob=keep_prob, seed=seed, iteration=it)
+        s_thread = student.zero_state(batch_size) if thread_state else None     # lstm_bbpt.py:122 `s = zero_state_batch`
+        total_loss = 0.0
+        for _ in range(training_epochs):
+            ob_b, t_b, prev_b, _prew = dataset.training_batch(batch_size, T)
+            fin = torch.empty_like(s_thread) if thread_state else None
+            student.loss_grad(ob_b, prev_b, t_b, s_thread, keep_prob=keep_prob, seed=seed, iteration=student.t, final_state_out=fin)
             student.adam_step()
-            total_loss = student.gradloss[student.P]
+            total_loss = total_loss + student.gradloss[student.P]               # `total_loss += l` (lstm_train.py:161, lstm_bbpt.py:137)
+            s_thread = fin
         t_pdflat = teacher.pdflat(ob)
         tb = dataset.test_batch(ob, steps=T)
         ob_w, prev_w = (tb[0], tb[1]) if num_envs > 1 else (tb[0][:, -1:, :].contiguous(), tb[1][:, -1:, :].contiguous())

@@ -189,15 +189,20 @@ class StudentLSTM:
                                 ptr(self._workspace(B)), stream_ptr()))
         return s, fin
 
-    def loss_grad(self, ob, prev_pdflat, t_pdflat, state=None, keep_prob=1.0, seed=0, sample_id0=0, iteration=0, loss_kind=LOSS_KL_ST):
-        """Training window batch (lstm_train.py:145-160): fills self.gradloss = [flat grad | loss]; returns s_pdflat [T,B,4]."""
+    def loss_grad(self, ob, prev_pdflat, t_pdflat, state=None, keep_prob=1.0, seed=0, sample_id0=0, iteration=0, loss_kind=LOSS_KL_ST,
+                  final_state_out=None):
+        """Training window batch (lstm_train.py:145-160): fills self.gradloss = [flat grad | loss]; returns s_pdflat [T,B,4].
+        final_state_out [2,B,200]: receives the (c, m) state after the last unrolled step -- what backup/lstm_bbpt.py:125-137 fetches as
+        `final_state_batch` next to the loss and feeds into the next batch."""
         T, B = ob.shape[0], ob.shape[1]
         assert T == self.T
         ob, prev_pdflat, t_pdflat = ob.contiguous(), prev_pdflat.contiguous(), t_pdflat.contiguous()
+        if final_state_out is not None:
+            assert final_state_out.shape == (2, B, self.U) and final_state_out.is_contiguous() and final_state_out.dtype == torch.float32
         s = torch.empty((T, B, 4), dtype=torch.float32, device=self.device)
         check(lib().rb_lstm_loss_grad(ptr(self.params), ptr(ob), ptr(prev_pdflat), ptr(t_pdflat), ptr(state.contiguous() if state is not None else None), B,
-                                      float(keep_prob), int(seed), int(sample_id0), int(iteration), loss_kind, ptr(s), None, ptr(self.gradloss),
-                                      ptr(self._workspace(B)), stream_ptr()))
+                                      float(keep_prob), int(seed), int(sample_id0), int(iteration), loss_kind, ptr(s), ptr(final_state_out),
+                                      ptr(self.gradloss), ptr(self._workspace(B)), stream_ptr()))
         return s
 
     def adam_step(self, grad_scale=1.0):
