@@ -14,6 +14,7 @@ per GPU.  Weak scaling: every rank owns 65 536 envs (global env ids rank*65536 .
 `distill` BASELINE.json config 4 shard (32 768 envs per GPU): DAgger iterations = env step + teacher label + student
           forward/backward + KL + [NCCL all-reduce of the flat gradient] + Adam; samples/s == env-steps/s of that loop.
 `step_api` the gym-style single-step kernel (HBM-bound) at 4 194 304 envs.
+`config1`  BASELINE.json config 1 (one env, 1000-step teacher rollout): host-thread restatement vs the gym surface at batch 1 vs one fused launch.
 `cpu_baseline` / --impl reference: the float64 C restatement of the reference's CPU path (oracle/, OpenMP over host cores) on a
           bounded sample of the same workload.  The reference itself (TF-1.10 + gym + MuJoCo-1.50) is not installable here.
 """
@@ -147,6 +148,48 @@ def cpu_distill_leg(kind="mlp", seconds=6.0):
     dt = time.perf_counter() - t0
     return dict(value=B * n_it / dt, unit="samples/s", cores=os.cpu_count(), kind="port",
                 sample="%d optimiser steps of batch %d, numpy float64 restatement (oracle/nn_np.py), %.1f s" % (n_it, B, dt))
+
+
+def config1_leg(steps=1000):
+    """BASELINE config 1, the reference's own CPU-runnable case (SURVEY 8(d).1 / CPU plan (i)): ONE env, a 1000-step teacher rollout in the
+    per-step loop shape of mlp_train.py:120-139 -- (cpu) the restatement on one host thread, (gpu_gym_loop) the drop-in gym surface at batch 1
+    (one rb_policy_fwd + one rb_env_step_host per step: launch-latency bound, reported for honesty), (gpu_fused) the same 1000 steps as ONE
+    rb_env_rollout_policy launch with the result read back.  A context figure; batch 1 is not what the GPU path is built for."""
+    import numpy as np
+    import torch
+    from oracle import nn_np as NN
+    from oracle import reacher_c as RC
+    from reacherdistilation_b200 import MODE_FP32
+    from reacherdistilation_b200.env import VecReacher, make_mujoco_env
+    from reacherdistilation_b200.teacher import TeacherAgent, init_policy_params
+    p = init_policy_params(seed=0)
+    c = RC.ReacherOracleC(1, seed=0, nthreads=1)
+    ob = c.reset()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        flat = NN.policy_fwd(ob.astype(np.float32), p)
+        ob, r, d = c.step(flat[:, :2])
+    cpu = steps / (time.perf_counter() - t0)
+    env = make_mujoco_env("Reacher-v2", 0)
+    teacher = TeacherAgent(env, params=p, mode=MODE_FP32)
+    ob = env.reset()
+    for rep in range(2):                                   # first pass = warm-up
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        for _ in range(steps):
+            mean, _flat = teacher.mean_and_flat(ob)
+            ob, r, new, _ = env.step(mean.cpu().numpy())
+        gym_loop = steps / (time.perf_counter() - t0)
+    env.close()
+    v = VecReacher(num_envs=1, seed=0); v.reset()
+    pd = torch.from_numpy(p).cuda()
+    for rep in range(2):
+        torch.cuda.synchronize(); t0 = time.perf_counter()
+        out = v.rollout_policy(pd, steps, mode=MODE_FP32)
+        ret = float(out["rew"].sum())                      # device -> host read of the result
+        fused = steps / (time.perf_counter() - t0)
+    v.close()
+    return dict(workload="config1: 1 env, %d-step teacher rollout (20 episodes)" % steps, unit="env-steps/s", cpu_restatement_1_thread=cpu,
+                gpu_gym_loop_batch1=gym_loop, gpu_fused_one_launch=fused, teacher_return_per_episode=ret / (steps / 50.0))
 
 
 def run_reference(args):
@@ -421,6 +464,7 @@ def main():
             cb, _, _ = cpu_reference_leg()
             line["cpu_baseline"] = cb
             line["distill"]["cpu_baseline"] = cpu_distill_leg(args.student)
+            line["config1"] = config1_leg()
     if sampler:
         sampler.stop()
     if rank == 0:
