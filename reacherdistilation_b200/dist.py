@@ -45,3 +45,17 @@ def max_over_ranks(value, device=None):
     t = torch.tensor([float(value)], dtype=torch.float64, device=device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu"))
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t.item())
+
+
+def rank_checkpoint_path(path, rank, world):
+    """Loop checkpoints hold per-shard state (env state, Philox episode counters, `prev` carry): one file per rank when world > 1."""
+    return path if world <= 1 else "%s.rank%d" % (path, rank)
+
+
+def all_ranks_agree(flag, device=None):
+    """True only if `flag` is true on every rank (e.g. every rank found its shard's checkpoint: either all resume or none does)."""
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() == 1:
+        return bool(flag)
+    t = torch.tensor([1 if flag else 0], dtype=torch.int32, device=device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu"))
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())

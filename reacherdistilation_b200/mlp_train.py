@@ -18,6 +18,7 @@ import torch
 from . import _lib
 from ._lib import LOSS_KL_ST, MODE_FP32, STUDENT_MLP, check, lib, ptr, stream_ptr
 from .config import KEEP_PROB, MLP_BATCH_SIZE, NUM_ENVS, SEED, base_path
+from .dist import all_ranks_agree, rank_checkpoint_path
 from .env import VecReacher
 from .student_nn import StudentNet
 from .teacher import TeacherAgent
@@ -164,13 +165,16 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
     tr = DaggerTrainer(num_envs=num_envs, seed=seed, device=device, student_kind=student_kind, keep_prob=keep_prob, mode=mode,
                        env_offset=rank * num_envs)
     ckpt = checkpoint or os.path.join(base_path, "student_mlp_b200.pt")
+    my_ckpt = rank_checkpoint_path(ckpt, rank, world)    # per-shard loop state: one file per rank when world > 1
     resumed = False
-    if restore and os.path.exists(ckpt):
-        sd = torch.load(ckpt)
-        if "student" in sd and int(sd.get("num_envs", -1)) == int(num_envs) and int(sd.get("env_offset", -1)) == rank * num_envs:
+    if restore:
+        sd = torch.load(my_ckpt) if os.path.exists(my_ckpt) else (torch.load(ckpt) if os.path.exists(ckpt) else None)
+        full = (sd is not None and "student" in sd and int(sd.get("num_envs", -1)) == int(num_envs)
+                and int(sd.get("env_offset", -1)) == rank * num_envs)
+        if all_ranks_agree(full, tr.device if world > 1 and torch.distributed.get_backend() == "nccl" else None):
             tr.load_state_dict(sd)                       # full loop state: continue exactly where the saved run stopped
             resumed = True
-        else:                                            # student-only checkpoint (or another shard shape): the reference's restore
+        elif sd is not None:                             # student-only checkpoint (or another shard shape): the reference's restore
             tr.student.load_state_dict(sd["student"] if "student" in sd else sd)
     tr.sync_params()
     if not train:
@@ -195,9 +199,9 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
             if verbose and rank == 0:
                 print("************** Episode %d ****************" % ((it + 1) // 50 * num_envs * world))
                 print("recent loss: %f " % losses[-1])
-    if rank == 0 and checkpoint is not None:
-        os.makedirs(os.path.dirname(ckpt) or ".", exist_ok=True)
-        torch.save(tr.state_dict(), ckpt)
+    if checkpoint is not None:
+        os.makedirs(os.path.dirname(my_ckpt) or ".", exist_ok=True)
+        torch.save(tr.state_dict(), my_ckpt)
     out = dict(losses=losses, rewards=rewards, teacher_reward=teacher_reward, iterations=iterations, trainer=tr)
     return out
 

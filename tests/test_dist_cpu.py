@@ -43,6 +43,9 @@ def _worker(rank, world, port, total, q):
     gl = torch.from_numpy(np.concatenate([NN.mlp_bwd(hs, P, ds), [l]]))
     allreduce_gradloss(gl)
     tmax = max_over_ranks(float(rank + 1))
+    from reacherdistilation_b200.dist import all_ranks_agree, rank_checkpoint_path
+    assert all_ranks_agree(True) is True and all_ranks_agree(rank == 0) is False and all_ranks_agree(False) is False
+    assert rank_checkpoint_path("a/b.pt", rank, world) == "a/b.pt.rank%d" % rank and rank_checkpoint_path("a/b.pt", 0, 1) == "a/b.pt"
     if rank == 0:
         q.put((gl.numpy(), obs, tmax))
     else:
