@@ -30,6 +30,38 @@ def init_policy_params(seed=0, nout=2, logstd=TEACHER_LOGSTD, ob_mean=None, ob_s
     return p
 
 
+def policy_params_from_named(variables, nout=2, scope="pi"):
+    """Flat C-ABI parameter vector from the variables of a baselines MlpPolicy checkpoint -- what `teacher.py:17-20` restores from
+    `teacher.ckpt` (dump them once with `tf.train.load_checkpoint(...).get_tensor(name)` into a dict / npz and pass it here).
+    Names as in the reference's graph (tfevents `pi/*`): `<scope>/obfilter/{runningsum, runningsumsq, count}`,
+    `<scope>/pol/{fc1, fc2, final}/{w, b}` (`kernel` / `bias` accepted too), `<scope>/pol/logstd`; a trailing `:0` is ignored.
+    obfilter: mean = runningsum / count, std = sqrt(max(runningsumsq / count - mean^2, 0.01))."""
+    v = {k[:-2] if k.endswith(":0") else k: np.asarray(a, dtype=np.float64) for k, a in dict(variables).items()}
+
+    def get(*names):
+        for nm in names:
+            if scope + "/" + nm in v:
+                return v[scope + "/" + nm]
+        raise KeyError("checkpoint has none of " + ", ".join(scope + "/" + nm for nm in names))
+
+    count = float(np.ravel(get("obfilter/count"))[0])
+    mean = np.ravel(get("obfilter/runningsum")) / count
+    std = np.sqrt(np.maximum(np.ravel(get("obfilter/runningsumsq")) / count - mean * mean, 1e-2))
+    parts = [mean, std]
+    for layer, shape in (("fc1", (11, 64)), ("fc2", (64, 64)), ("final", (64, nout))):
+        w, b = get("pol/%s/w" % layer, "pol/%s/kernel" % layer), get("pol/%s/b" % layer, "pol/%s/bias" % layer)
+        if w.shape != shape or b.size != shape[1]:
+            raise ValueError("%s/pol/%s: expected w %s, b [%d], got %s, %s" % (scope, layer, shape, shape[1], w.shape, b.shape))
+        parts += [w.ravel(), np.ravel(b)]
+    logstd = np.ravel(get("pol/logstd"))
+    if logstd.size != 2 or mean.size != 11:
+        raise ValueError("expected logstd [1,2] and an 11-d obfilter")
+    parts.append(logstd)
+    p = np.concatenate(parts).astype(np.float32)
+    assert p.size == lib().rb_policy_param_count(nout)
+    return p
+
+
 class _Pd:
     def __init__(self, agent):
         self._a = agent
