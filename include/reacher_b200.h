@@ -79,13 +79,15 @@ int rb_env_step(rb_env* env, const float* act_dev, float* obs_dev, float* rew_de
 int rb_env_reset_host(rb_env* env, float* obs_host);
 int rb_env_step_host(rb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host);
 
-/* explicit state access (parity tests start device and oracle from identical states):
+/* explicit state access (parity tests start device and oracle from identical states; checkpoint / resume):
  * qpos_dev[N,2], qvel_dev[N,2], target_dev[N,2], fingertip_dev[N,2] (MuJoCo's stale xpos), step_dev[N] int32,
- * episode_dev[N] uint32.  Any pointer may be NULL.  set: fingertip NULL => recomputed by forward kinematics.      */
+ * episode_dev[N] uint32, qpos_lo_dev[N,2].  Any pointer may be NULL.  The joint angles are carried as two floats (qpos + qpos_lo,
+ * |qpos_lo| <= ulp(qpos) / 2: compensated accumulation over the RK4 sub-steps); qpos alone is the angle rounded to fp32.
+ * set: fingertip NULL => recomputed by forward kinematics; qpos given without qpos_lo => low parts zero.                       */
 int rb_env_get_state(rb_env* env, float* qpos_dev, float* qvel_dev, float* target_dev, float* fingertip_dev,
-                     int32_t* step_dev, uint32_t* episode_dev, void* stream);
+                     int32_t* step_dev, uint32_t* episode_dev, float* qpos_lo_dev, void* stream);
 int rb_env_set_state(rb_env* env, const float* qpos_dev, const float* qvel_dev, const float* target_dev,
-                     const float* fingertip_dev, const int32_t* step_dev, const uint32_t* episode_dev, void* stream);
+                     const float* fingertip_dev, const int32_t* step_dev, const uint32_t* episode_dev, const float* qpos_lo_dev, void* stream);
 /* current observation of every env (no stepping) */
 int rb_env_observe(rb_env* env, float* obs_dev, void* stream);
 

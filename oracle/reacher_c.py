@@ -23,6 +23,7 @@ def lib():
         L.ro_max_threads.restype = C.c_int
         L.ro_reset_all.argtypes = [C.c_int, C.c_uint64, C.c_uint32, dp, ip, up, dp, C.c_int]
         L.ro_step.argtypes = [C.c_int, C.c_uint64, C.c_uint32, dp, ip, up, dp, dp, dp, bp, C.c_int, C.c_int]
+        L.ro_step_graze.argtypes = [C.c_int, C.c_uint64, C.c_uint32, dp, ip, up, dp, dp, dp, bp, C.c_int, C.c_int, dp]
         L.ro_rollout_random.argtypes = [C.c_int, C.c_uint64, C.c_uint32, dp, ip, up, C.c_int, C.c_uint32, dp, C.c_int]
         L.ro_rollout_random.restype = C.c_double
         L.ro_policy_fwd.argtypes = [C.c_int, dp, fp, C.c_int, dp, C.c_int]
@@ -67,13 +68,16 @@ class ReacherOracleC:
                            _p(self.episode, C.c_uint32), _p(obs, C.c_double), self.nthreads)
         return obs
 
-    def step(self, a, auto_reset=True):
+    def step(self, a, auto_reset=True, graze=False):
+        """graze=True also returns, per env, the smallest | |q1| - 3 | over the 8 RK4 stage evaluations of this step: the distance of the
+        trajectory from the joint-limit activation threshold, where the model itself is discontinuous."""
         a = np.ascontiguousarray(a, dtype=np.float64).reshape(self.n, 2)
         obs, rew, done = np.zeros((self.n, 11)), np.zeros(self.n), np.zeros(self.n, np.uint8)
-        lib().ro_step(self.n, self.seed, self.env_offset, _p(self.st, C.c_double), _p(self.step_count, C.c_int32),
-                      _p(self.episode, C.c_uint32), _p(a, C.c_double), _p(obs, C.c_double), _p(rew, C.c_double),
-                      _p(done, C.c_uint8), int(auto_reset), self.nthreads)
-        return obs, rew, done.astype(bool)
+        gz = np.zeros(self.n) if graze else None
+        lib().ro_step_graze(self.n, self.seed, self.env_offset, _p(self.st, C.c_double), _p(self.step_count, C.c_int32),
+                            _p(self.episode, C.c_uint32), _p(a, C.c_double), _p(obs, C.c_double), _p(rew, C.c_double),
+                            _p(done, C.c_uint8), int(auto_reset), self.nthreads, _p(gz, C.c_double))
+        return (obs, rew, done.astype(bool), gz) if graze else (obs, rew, done.astype(bool))
 
     def rollout_random(self, T, step0=0, record=True):
         traj = np.zeros((T, self.n, 12)) if record else None

@@ -66,8 +66,13 @@ static void init_consts(void) {
 }
 void ro_constants(double* out) { init_consts(); out[0] = A_; out[1] = B_; out[2] = C_; out[3] = INVW0; out[4] = K_LIM; out[5] = B_LIM; }
 
+/* smallest | |q1| - 3 | any RK4 stage of the current env step has seen: the soft joint limit switches on discontinuously at dist = 0
+ * (MuJoCo activates the constraint with its damping term in full), so a stage that lands within rounding distance of the threshold is
+ * where an fp32 trajectory may legitimately take the other branch.  Parity tests use it to set such episodes aside (ro_step_graze). */
+static _Thread_local double tl_graze = 1e300;
 static inline void accel(double q1, double v0, double v1, double u0, double u1, double* a0o, double* a1o) {
     double c1 = cos(q1), s1 = sin(q1);
+    { double gz = fabs(fabs(q1) - 3.0); if (gz < tl_graze) tl_graze = gz; }
     double m00 = 1.0 + A_ + 2 * B_ * c1, m01 = C_ + B_ * c1, m11 = 1.0 + C_;
     double cor0 = -B_ * s1 * (2 * v0 * v1 + v1 * v1), cor1 = B_ * s1 * v0 * v0;
     double t0 = 200.0 * u0 - v0 - cor0, t1 = 200.0 * u1 - v1 - cor1;
@@ -178,17 +183,24 @@ void ro_reset_all(int n, uint64_t seed, uint32_t env_offset, double* st, int32_t
         if (obs) write_obs(&e, obs + (size_t)i * 11);
     }
 }
-void ro_step(int n, uint64_t seed, uint32_t env_offset, double* st, int32_t* step, uint32_t* episode, const double* act,
-             double* obs, double* rew, uint8_t* done, int auto_reset, int nthreads) {
+/* graze (may be NULL): per env, min over the 8 RK4 stage evaluations of this step of | |q1| - 3 | (see tl_graze) */
+void ro_step_graze(int n, uint64_t seed, uint32_t env_offset, double* st, int32_t* step, uint32_t* episode, const double* act,
+                   double* obs, double* rew, uint8_t* done, int auto_reset, int nthreads, double* graze) {
     init_consts(); set_threads(nthreads);
 #pragma omp parallel for schedule(static)
     for (int i = 0; i < n; ++i) {
         Env e; load_env(st, n, i, &e);
+        tl_graze = 1e300;
         rew[i] = step_env(&e, act[2 * (size_t)i], act[2 * (size_t)i + 1], &step[i], &episode[i], seed, env_offset + (uint32_t)i,
                           auto_reset, &done[i]);
+        if (graze) graze[i] = tl_graze;
         store_env(st, n, i, &e);
         write_obs(&e, obs + (size_t)i * 11);
     }
+}
+void ro_step(int n, uint64_t seed, uint32_t env_offset, double* st, int32_t* step, uint32_t* episode, const double* act,
+             double* obs, double* rew, uint8_t* done, int auto_reset, int nthreads) {
+    ro_step_graze(n, seed, env_offset, st, step, episode, act, obs, rew, done, auto_reset, nthreads, 0);
 }
 /* T steps with Philox random actions a~U(-1,1)^2 keyed (env, step0+t).
  * If traj != NULL it receives [T][n][12] = obs(11) + reward per step.  Returns sum of rewards (keeps work live). */

@@ -33,8 +33,8 @@ _SIGS = {
     "rb_env_step": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
     "rb_env_reset_host": (C.c_int, [_vp, _fp]),
     "rb_env_step_host": (C.c_int, [_vp, _fp, _fp, _fp, _u8p]),
-    "rb_env_get_state": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i32p, _u32p, _vp]),
-    "rb_env_set_state": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i32p, _u32p, _vp]),
+    "rb_env_get_state": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i32p, _u32p, _fp, _vp]),
+    "rb_env_set_state": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i32p, _u32p, _fp, _vp]),
     "rb_env_observe": (C.c_int, [_vp, _fp, _vp]),
     "rb_env_rollout_random": (C.c_int, [_vp, C.c_int, C.c_uint32, _fp, _fp, _fp, _u8p, _vp]),
     "rb_policy_param_count": (C.c_int64, [C.c_int]),

@@ -13,7 +13,7 @@ struct rb_env {
     uint32_t offset = 0;
     float4* qv = nullptr;
     float4* tp = nullptr;
-    uint2* ctr = nullptr;
+    uint4* ctr = nullptr;
     // staging for the *_host entry points
     float* d_act = nullptr; float* d_obs = nullptr; float* d_rew = nullptr; uint8_t* d_done = nullptr;
     float* d_params = nullptr;
@@ -66,10 +66,17 @@ __device__ __forceinline__ void warp_store_rows(float* __restrict__ g, int64_t r
     for (int k = 0; k < W; ++k) strip[lane * W + k] = vals[k];
     __syncwarp();
     float* dst = g + row0 * W;
-    const int total = nvalid * W;
-    const int n4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (total >> 2) : 0;
     const float4* s4 = reinterpret_cast<const float4*>(strip);
     float4* d4 = reinterpret_cast<float4*>(dst);
+    if (nvalid == 32 && (reinterpret_cast<uintptr_t>(dst) & 15) == 0) {      // full aligned warp (the hot case): fixed trip count, immediate offsets
+        constexpr int N4 = 32 * W / 4;
+#pragma unroll
+        for (int u = 0; u < (N4 + 31) / 32; ++u)
+            if (u * 32 + 31 < N4 || lane + u * 32 < N4) d4[lane + u * 32] = s4[lane + u * 32];
+        return;
+    }
+    const int total = nvalid * W;
+    const int n4 = ((reinterpret_cast<uintptr_t>(dst) & 15) == 0) ? (total >> 2) : 0;
     for (int i = lane; i < n4; i += 32) d4[i] = s4[i];
     for (int i = (n4 << 2) + lane; i < total; i += 32) dst[i] = strip[i];
 }

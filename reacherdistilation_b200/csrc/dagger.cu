@@ -34,7 +34,7 @@ struct rb_dagger {
 
 namespace rb {
 
-__global__ void k_dagger_input(int64_t n, const uint2* __restrict__ ctr, const float* __restrict__ obs, const float4* __restrict__ prev_t,
+__global__ void k_dagger_input(int64_t n, const uint4* __restrict__ ctr, const float* __restrict__ obs, const float4* __restrict__ prev_t,
                                const float* __restrict__ prev_rec_rew, float keep_prob, uint32_t k0, uint32_t k1, uint32_t offset,
                                uint32_t iteration, float4* __restrict__ x) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -50,7 +50,7 @@ __global__ void k_dagger_input(int64_t n, const uint2* __restrict__ ctr, const f
     x[i * 4 + 0] = o[0]; x[i * 4 + 1] = o[1]; x[i * 4 + 2] = o[2]; x[i * 4 + 3] = o[3];
 }
 
-__global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint2* ctr, const float4* __restrict__ s_pd,
+__global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint4* ctr, const float4* __restrict__ s_pd,
                                                     const float4* __restrict__ t_pd, float4* prev_t, float* prev_rec_rew, float* last_reward,
                                                     float* __restrict__ rew, uint8_t* __restrict__ done, uint32_t k0, uint32_t k1,
                                                     uint32_t offset, uint32_t* clock, const float* __restrict__ loss_src, uint2* mailbox, int64_t i0) {
@@ -83,7 +83,7 @@ struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, g
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
 struct StepClock { const uint32_t* clock; float lr; };
 struct ActFuse {
-    float4* qv; float4* tp; uint2* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
+    float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
     uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox;
 };
 int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,

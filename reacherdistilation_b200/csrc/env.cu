@@ -3,7 +3,7 @@
 // lstm_train.py:21,111,133,136,192,196) -- see include/reacher_b200.h for the per-entry-point mapping.
 //
 // HBM layout (one env per thread, 128-bit coalesced state I/O):
-//   qv  float4[N] = (q0, q1, v0, v1)       tp  float4[N] = (tx, ty, px, py)      ctr uint2[N] = (step, episode)
+//   qv  float4[N] = (q0, q1, v0, v1)   tp  float4[N] = (tx, ty, px, py)   ctr uint4[N] = (step, episode, low parts of q0 / q1: physics.cuh)
 // Observation rows ([N,11] fp32, 44 B) are staged through a warp-private shared-memory strip so that the global
 // stores are 128-bit and contiguous.
 #include <chrono>
@@ -18,7 +18,7 @@ namespace rb {
 
 constexpr int ENV_BLOCK = 128;
 
-__global__ void __launch_bounds__(ENV_BLOCK) k_reset(int64_t n, float4* qv, float4* tp, uint2* ctr, float* obs, uint32_t k0,
+__global__ void __launch_bounds__(ENV_BLOCK) k_reset(int64_t n, float4* qv, float4* tp, uint4* ctr, float* obs, uint32_t k0,
                                                      uint32_t k1, uint32_t offset) {
     __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -37,7 +37,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_reset(int64_t n, float4* qv, floa
     if (obs) warp_store_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
 }
 
-__global__ void __launch_bounds__(ENV_BLOCK) k_observe(int64_t n, const float4* qv, const float4* tp, const uint2* ctr, float* obs) {
+__global__ void __launch_bounds__(ENV_BLOCK) k_observe(int64_t n, const float4* qv, const float4* tp, const uint4* ctr, float* obs) {
     __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int64_t i = (int64_t)blockIdx.x * ENV_BLOCK + threadIdx.x;
@@ -50,7 +50,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_observe(int64_t n, const float4* 
 }
 
 // env.step: the single-step API kernel (HBM-bound: 113 algorithmic bytes per env-step)
-__global__ void __launch_bounds__(ENV_BLOCK) k_step(int64_t n, float4* __restrict__ qv, float4* __restrict__ tp, uint2* __restrict__ ctr,
+__global__ void __launch_bounds__(ENV_BLOCK) k_step(int64_t n, float4* __restrict__ qv, float4* __restrict__ tp, uint4* __restrict__ ctr,
                                                     const float2* __restrict__ act, float* __restrict__ obs, float* __restrict__ rew,
                                                     uint8_t* __restrict__ done, uint32_t k0, uint32_t k1, uint32_t offset) {
     __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
@@ -73,26 +73,28 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_step(int64_t n, float4* __restric
     if (obs) warp_store_rows<OBS>(obs, row0, nvalid, ob, strips[warp], lane);
 }
 
-__global__ void k_get_state(int64_t n, const float4* qv, const float4* tp, const uint2* ctr, float2* qpos, float2* qvel,
-                            float2* target, float2* tip, int32_t* step, uint32_t* episode) {
+__global__ void k_get_state(int64_t n, const float4* qv, const float4* tp, const uint4* ctr, float2* qpos, float2* qvel,
+                            float2* target, float2* tip, int32_t* step, uint32_t* episode, float2* qpos_lo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const float4 a = qv[i], b = tp[i];
-    const uint2 c = ctr[i];
+    const uint4 c = ctr[i];
     if (qpos) qpos[i] = make_float2(a.x, a.y);
+    if (qpos_lo) qpos_lo[i] = make_float2(__uint_as_float(c.z), __uint_as_float(c.w));
     if (qvel) qvel[i] = make_float2(a.z, a.w);
     if (target) target[i] = make_float2(b.x, b.y);
     if (tip) tip[i] = make_float2(b.z, b.w);
     if (step) step[i] = (int32_t)c.x;
     if (episode) episode[i] = c.y;
 }
-__global__ void k_set_state(int64_t n, float4* qv, float4* tp, uint2* ctr, const float2* qpos, const float2* qvel,
-                            const float2* target, const float2* tip, const int32_t* step, const uint32_t* episode) {
+__global__ void k_set_state(int64_t n, float4* qv, float4* tp, uint4* ctr, const float2* qpos, const float2* qvel,
+                            const float2* target, const float2* tip, const int32_t* step, const uint32_t* episode, const float2* qpos_lo) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float4 a = qv[i], b = tp[i];
-    uint2 c = ctr[i];
-    if (qpos) { const float2 v = qpos[i]; a.x = v.x; a.y = v.y; }
+    uint4 c = ctr[i];
+    if (qpos) { const float2 v = qpos[i]; a.x = v.x; a.y = v.y; c.z = c.w = 0u; }       // new angles: low parts start at zero ...
+    if (qpos_lo) { const float2 v = qpos_lo[i]; c.z = __float_as_uint(v.x); c.w = __float_as_uint(v.y); }   // ... unless given (exact resume)
     if (qvel) { const float2 v = qvel[i]; a.z = v.x; a.w = v.y; }
     if (target) { const float2 v = target[i]; b.x = v.x; b.y = v.y; }
     if (tip) { const float2 v = tip[i]; b.z = v.x; b.w = v.y; }
@@ -103,7 +105,7 @@ __global__ void k_set_state(int64_t n, float4* qv, float4* tp, uint2* ctr, const
 }
 
 // Fused T-step rollout with Philox random actions: state lives in registers for all T steps (FP32-pipe bound).
-__global__ void __launch_bounds__(ENV_BLOCK) k_rollout_random(int64_t n, float4* qv, float4* tp, uint2* ctr, int T, uint32_t step0,
+__global__ void __launch_bounds__(ENV_BLOCK) k_rollout_random(int64_t n, float4* qv, float4* tp, uint4* ctr, int T, uint32_t step0,
                                                               float* __restrict__ obs_buf, float2* __restrict__ act_buf,
                                                               float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf,
                                                               uint32_t k0, uint32_t k1, uint32_t offset) {
@@ -161,7 +163,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_policy_fwd_fp32(const float* __re
 
 // Fused policy-in-the-loop rollout (teacher warm-up loop, mlp_train.py:120-139), fp32 CUDA-core policy.
 template <int NOUT>
-__global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
+__global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, float4* qv, float4* tp, uint4* ctr, const float* __restrict__ params,
                                                                    int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
                                                                    float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf,
                                                                    uint32_t k0, uint32_t k1, uint32_t offset) {
@@ -218,10 +220,10 @@ int rb_env_create(rb_env** out, int64_t num_envs, uint64_t seed, int device, uin
     e->n = num_envs; e->seed = seed; e->device = device; e->offset = global_env_offset;
     cudaError_t err = cudaMalloc(&e->qv, sizeof(float4) * num_envs);
     if (err == cudaSuccess) err = cudaMalloc(&e->tp, sizeof(float4) * num_envs);
-    if (err == cudaSuccess) err = cudaMalloc(&e->ctr, sizeof(uint2) * num_envs);
+    if (err == cudaSuccess) err = cudaMalloc(&e->ctr, sizeof(uint4) * num_envs);
     if (err == cudaSuccess) err = cudaMemset(e->qv, 0, sizeof(float4) * num_envs);
     if (err == cudaSuccess) err = cudaMemset(e->tp, 0, sizeof(float4) * num_envs);
-    if (err == cudaSuccess) err = cudaMemset(e->ctr, 0, sizeof(uint2) * num_envs);
+    if (err == cudaSuccess) err = cudaMemset(e->ctr, 0, sizeof(uint4) * num_envs);
     cudaDeviceProp prop;
     if (err == cudaSuccess) err = cudaGetDeviceProperties(&prop, device);
     if (err != cudaSuccess) { rb_env_destroy(e); return cuda_fail(err, "rb_env_create"); }
@@ -317,20 +319,21 @@ int rb_env_step_host(rb_env* e, const float* act_host, float* obs_host, float* r
     return RB_OK;
 }
 
-int rb_env_get_state(rb_env* e, float* qpos, float* qvel, float* target, float* tip, int32_t* step, uint32_t* episode, void* stream) {
+int rb_env_get_state(rb_env* e, float* qpos, float* qvel, float* target, float* tip, int32_t* step, uint32_t* episode, float* qpos_lo,
+                     void* stream) {
     RB_REQUIRE(e != nullptr, "env is NULL");
     k_get_state<<<(unsigned)((e->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (float2*)qpos, (float2*)qvel,
-                                                                                 (float2*)target, (float2*)tip, step, episode);
+                                                                                 (float2*)target, (float2*)tip, step, episode, (float2*)qpos_lo);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
 
 int rb_env_set_state(rb_env* e, const float* qpos, const float* qvel, const float* target, const float* tip, const int32_t* step,
-                     const uint32_t* episode, void* stream) {
+                     const uint32_t* episode, const float* qpos_lo, void* stream) {
     RB_REQUIRE(e != nullptr, "env is NULL");
     k_set_state<<<(unsigned)((e->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float2*)qpos,
                                                                                  (const float2*)qvel, (const float2*)target,
-                                                                                 (const float2*)tip, step, episode);
+                                                                                 (const float2*)tip, step, episode, (const float2*)qpos_lo);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }

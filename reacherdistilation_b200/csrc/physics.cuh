@@ -3,15 +3,62 @@
 // trajectories (oracle/reacher_np.py is the float64 statement of the same model).
 // Replaces env.step / env.reset at /root/reference src/distilation/mlp_train.py:112,135,138,196,200.
 //
-// fp32, state in registers.  Every rounding is spelled out with __fmaf_rn / __fmul_rn / __fadd_rn so that each kernel
-// that inlines these functions (single step, fused rollouts, DAgger act) produces bit-identical trajectories whatever
-// the surrounding code lets the compiler contract.  Per env-step: 10 sincos (Cody-Waite + minimax polynomials, FMA pipe
-// only, no slow path / local memory), 8 MUFU.RCP, 1 MUFU.SQRT; the sin/cos of the current joint angles ride along in
-// the state ("trig cache") so the observation costs nothing and the first RK4 stage reuses them.
+// fp32, state in registers.  Every rounding is spelled out (RB_FMA / RB_MUL / RB_ADD / RB_SUB) so that each kernel that inlines these
+// functions (single step, fused rollouts, DAgger act) produces bit-identical trajectories whatever the surrounding code lets the
+// compiler contract -- and so that the SAME source compiled for the host (tests/twin/, fmaf + IEEE float ops, -ffp-contract=off) is a
+// bit-exact CPU twin of the device arithmetic: the dynamics use no approximate instruction (the only MUFU is the sqrt of the reward).
+//
+// Arithmetic per env-step (round 2; instruction counts in profiles/README.md):
+//  * TWO range-reduced sincos (Cody-Waite + minimax polynomials) -- of the final joint angles, which the observation needs.  The six
+//    RK4 stage angles, the start of the second sub-step and the stale last-stage q0 are ROTATIONS of an already known (sin, cos) pair by
+//    the small increment (h/2 v, h v, ...: |d| < 0.5 rad): Taylor polynomials, no range reduction, ~half the instructions.  The dynamics
+//    see sin/cos of q1 only through b = 2.2e-4, so the 1e-8 truncation error of the polynomials is invisible.
+//  * 1 / det(M) as a quadratic in cos(q1) (det = d0 + d1 c + d2 c^2 with d1 / d0 = 4.4e-4: the truncated series is exact to 1e-10): no MUFU.RCP, and
+//    more accurate than rcp.approx.
+//  * joint angles carried as two floats (hi + lo, Fast2Sum): the per-sub-step rounding of q drops from ulp(q)/2 (1.2e-7 at the joint
+//    limit, 2e-6 at q0 = 40 rad) to ulp(dq)/2; the joint-limit penetration of every RK4 stage is formed from the EXACT |q1| - 3 of the
+//    sub-step start plus the small increment instead of from a stage angle rounded at magnitude 3.
 #pragma once
+#include <cmath>
+#include <cstring>
+
 #include "philox.cuh"
 
 namespace rb {
+
+#ifdef __CUDA_ARCH__
+#define RB_FMA(a, b, c) __fmaf_rn((a), (b), (c))
+#define RB_MUL(a, b) __fmul_rn((a), (b))
+#define RB_ADD(a, b) __fadd_rn((a), (b))
+#define RB_SUB(a, b) __fsub_rn((a), (b))
+#define RB_DIV(a, b) __fdiv_rn((a), (b))
+#else   // host twin: IEEE single operations (compile with -ffp-contract=off)
+#define RB_FMA(a, b, c) fmaf((a), (b), (c))
+#define RB_MUL(a, b) ((float)((float)(a) * (float)(b)))
+#define RB_ADD(a, b) ((float)((float)(a) + (float)(b)))
+#define RB_SUB(a, b) ((float)((float)(a) - (float)(b)))
+#define RB_DIV(a, b) ((float)((float)(a) / (float)(b)))
+#endif
+#define RB_HD __host__ __device__ __forceinline__
+
+RB_HD float u2f(uint32_t u) {
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f;
+    memcpy(&f, &u, 4);
+    return f;
+#endif
+}
+RB_HD uint32_t f2u(float f) {
+#ifdef __CUDA_ARCH__
+    return __float_as_uint(f);
+#else
+    uint32_t u;
+    memcpy(&u, &f, 4);
+    return u;
+#endif
+}
 
 struct Model {
     // c, b, a of the 2-link inertia matrix (armature 1 added on the diagonal); see oracle/reacher_np.py for the derivation
@@ -19,6 +66,11 @@ struct Model {
     static constexpr float M11 = (float)(1.0 + C_d);
     static constexpr float M00c = (float)(1.0 + A_d);
     static constexpr float B = (float)B_d, B2 = (float)(2.0 * B_d), C = (float)C_d;
+    // det(M) = d0 + d1 c1 + d2 c1^2;  1 / det = (1 / d0) (1 - e + e^2 - ...), e = (d1 c1 + d2 c1^2) / d0 <= 4.4e-4, collected in powers of c1
+    // and cut after c1^2: the first neglected term is e^3 = 8e-11 (fp32 epsilon is 6e-8)
+    static constexpr double D0 = (1.0 + A_d) * (1.0 + C_d) - C_d * C_d, D1 = 2.0 * B_d * (1.0 + C_d) - 2.0 * C_d * B_d, D2 = -B_d * B_d;
+    static constexpr double E1 = D1 / D0, E2 = D2 / D0;
+    static constexpr float ID0 = (float)(1.0 / D0), ID1 = (float)(-E1 / D0), ID2 = (float)((E1 * E1 - E2) / D0);
     static constexpr float GEAR = 200.0f;
     static constexpr float LIMIT = 3.0f;
     static constexpr float K_LIM = (float)2770.0831024930749, B_LIM = (float)105.26315789473685, INVW0 = (float)0.9998272280584255;
@@ -26,28 +78,22 @@ struct Model {
     static constexpr float L0 = 0.1f, LT = 0.11f;
 };
 
-#define RB_FMA(a, b, c) __fmaf_rn((a), (b), (c))
-#define RB_MUL(a, b) __fmul_rn((a), (b))
-#define RB_ADD(a, b) __fadd_rn((a), (b))
-#define RB_SUB(a, b) __fsub_rn((a), (b))
-
-__device__ __forceinline__ float rcp_approx(float x) {
-    float r;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
-    return r;
-}
-__device__ __forceinline__ float sqrt_approx(float x) {
+RB_HD float sqrt_approx(float x) {
+#ifdef __CUDA_ARCH__
     float r;
     asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
     return r;
+#else
+    return sqrtf(x);
+#endif
 }
 
 // sin and cos for |x| < 2^21: x = q*pi/2 + r (three-constant Cody-Waite with FMAs, q from the 1.5*2^23 trick), minimax
 // polynomials on [-pi/4, pi/4]; max abs error 9e-8 (measured against float64 over +-50 rad).  Joint angles stay below
 // ~40 rad inside an episode (|qvel| <= 38 rad/s for 1 s), far inside the valid range.
-__device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
+RB_HD void sincos_cw(float x, float& s, float& c) {
     const float t = RB_FMA(x, 0.6366197466850281f, 12582912.0f);
-    const int j = __float_as_int(t);
+    const uint32_t j = f2u(t);
     const float q = RB_SUB(t, 12582912.0f);
     float r = RB_FMA(q, -1.5707963705062866f, x);
     r = RB_FMA(q, 4.371138828673793e-08f, r);
@@ -61,45 +107,82 @@ __device__ __forceinline__ void sincos_cw(float x, float& s, float& c) {
     const float cs = RB_FMA(RB_MUL(g, z), z, RB_FMA(z, -0.5f, 1.0f));
     const bool swap = (j & 1) != 0;
     const float ss = swap ? cs : sn, cc = swap ? sn : cs;
-    s = __int_as_float(__float_as_int(ss) ^ ((j & 2) << 30));
-    c = __int_as_float(__float_as_int(cc) ^ (((j + 1) & 2) << 30));
+    s = u2f(f2u(ss) ^ ((j & 2u) << 30));
+    c = u2f(f2u(cc) ^ (((j + 1u) & 2u) << 30));
+}
+
+// (sin, cos)(a + d) from (s, c) = (sin, cos)(a) for a small increment d, by angle addition with Taylor polynomials of sin d and
+// cos d - 1 (no range reduction).  ORDER 7: sin to d^7, cos to d^6.  ORDER 5: sin to d^5, cos to d^4 -- truncation d^7 / 5040 and
+// d^6 / 720:  (a) the RK4 stage angles (|d| = h |v|, 0.4 rad at the 38 rad/s random actions reach, 1.3 rad at the terminal velocity
+// of a saturated torque): these pairs enter the dynamics only through b = 2.2e-4, i.e. 1e-9 (1e-6) of the acceleration;  (b) the stale
+// last-stage angles of the fingertip, rotated from the CANONICAL final pair by the h^2-sized difference (|d| < 0.2): < 1e-8.
+template <int ORDER> RB_HD void rotate_sc(float s, float c, float d, float& s2, float& c2) {
+    const float z = RB_MUL(d, d);
+    float p, g;
+    if (ORDER >= 7) {
+        p = RB_FMA(-1.9841270e-04f, z, 8.3333333e-03f);
+        p = RB_FMA(p, z, -1.6666667e-01f);
+        g = RB_FMA(-1.3888889e-03f, z, 4.1666667e-02f);
+    } else {
+        p = RB_FMA(8.3333333e-03f, z, -1.6666667e-01f);
+        g = 4.1666667e-02f;
+    }
+    g = RB_FMA(g, z, -0.5f);
+    const float sd = RB_FMA(RB_MUL(p, z), d, d);     // sin d
+    const float cm = RB_MUL(g, z);                   // cos d - 1
+    s2 = RB_FMA(c, sd, RB_FMA(s, cm, s));
+    c2 = RB_FMA(-s, sd, RB_FMA(c, cm, c));
 }
 
 struct EnvState {
-    float q0, q1, v0, v1;   // joint angles / velocities
+    float q0, q1, v0, v1;   // joint angles (high parts) / velocities
+    float q0l, q1l;         // low parts of the joint angles: angle = q + ql exactly as accumulated (|ql| <= ulp(q) / 2)
     float tx, ty;           // target
     float px, py;           // fingertip position as MuJoCo's xpos holds it (last RK4 stage of the previous step)
-    float s0, c0, s1, c1;   // trig cache: sin / cos of q0, q1 (always consistent with q0, q1)
+    float s0, c0, s1, c1;   // trig cache: sin / cos of (q0 + q0l), (q1 + q1l) (always consistent with the angles)
     int step;               // steps taken in the current episode, [0,50)
     uint32_t episode;       // index into this env's Philox reset stream
 };
 
-__device__ __forceinline__ void refresh_trig(EnvState& e) {
-    sincos_cw(e.q0, e.s0, e.c0);
-    sincos_cw(e.q1, e.s1, e.c1);
+// canonical trig pair of a two-float angle: range-reduced sincos of the high part, first-order correction by the low part
+RB_HD void sincos2(float q, float ql, float& s, float& c) {
+    float sh, ch;
+    sincos_cw(q, sh, ch);
+    s = RB_FMA(ql, ch, sh);
+    c = RB_FMA(-ql, sh, ch);
+}
+RB_HD void refresh_trig(EnvState& e) {
+    sincos2(e.q0, e.q0l, e.s0, e.c0);
+    sincos2(e.q1, e.q1l, e.s1, e.c1);
+}
+// (q, ql) += dq, Fast2Sum: exact whenever |q| >= |dq + ql| (otherwise q is small and so is its ulp)
+RB_HD void acc2(float& q, float& ql, float dq) {
+    const float d = RB_ADD(dq, ql);
+    const float s = RB_ADD(q, d);
+    ql = RB_SUB(d, RB_SUB(s, q));
+    q = s;
 }
 
-// joint accelerations from sin/cos of q1; g = gear * clipped ctrl
-__device__ __forceinline__ void accel(float q1, float s1, float c1, float v0, float v1, float g0, float g1, float& a0, float& a1) {
+// joint accelerations from sin/cos of q1; g = gear * clipped ctrl; over = |q1| - 3 (> 0: limit violated, dist = -over);
+// sgn = constraint Jacobian sign, J = [0, sgn] = [0, -sign(q1)]
+RB_HD void accel(float s1, float c1, float v0, float v1, float g0, float g1, float over, float sgn, float& a0, float& a1) {
     using M = Model;
     const float m00 = RB_FMA(M::B2, c1, M::M00c), m01 = RB_FMA(M::B, c1, M::C);
     const float bs = RB_MUL(M::B, s1);
     const float t0 = RB_FMA(RB_MUL(bs, v1), RB_FMA(2.0f, v0, v1), RB_SUB(g0, v0));     // g0 - v0 + b s1 (2 v0 v1 + v1^2)
     const float t1 = RB_FMA(-RB_MUL(bs, v0), v0, RB_SUB(g1, v1));                      // g1 - v1 - b s1 v0^2
-    const float idet = rcp_approx(RB_FMA(m00, M::M11, -RB_MUL(m01, m01)));
+    const float idet = RB_FMA(RB_FMA(M::ID2, c1, M::ID1), c1, M::ID0);
     a0 = RB_MUL(RB_FMA(M::M11, t0, -RB_MUL(m01, t1)), idet);
     a1 = RB_MUL(RB_FMA(m00, t1, -RB_MUL(m01, t0)), idet);
-    const float over = RB_SUB(fabsf(q1), M::LIMIT);   // > 0  <=>  limit violated, dist = -over
     if (over > 0.0f) {
-        const float sgn = q1 > 0.0f ? -1.0f : 1.0f;   // constraint Jacobian J = [0, sgn]
         const float x = fminf(RB_MUL(over, 1000.0f), 1.0f);
         const float omx = RB_SUB(1.0f, x);
         const float y = x <= 0.5f ? RB_MUL(2.0f, RB_MUL(x, x)) : RB_FMA(-2.0f, RB_MUL(omx, omx), 1.0f);
         const float imp = RB_FMA(0.05f, y, 0.9f);
         const float aref = RB_FMA(M::K_LIM, RB_MUL(imp, over), -RB_MUL(M::B_LIM, RB_MUL(sgn, v1)));   // -beta J.v - k imp dist
         const float mi01 = -RB_MUL(m01, idet), mi11 = RB_MUL(m00, idet);
-        const float R = RB_MUL(__fdiv_rn(RB_SUB(1.0f, imp), imp), M::INVW0);
-        float f = __fdiv_rn(RB_SUB(aref, RB_MUL(sgn, a1)), RB_ADD(mi11, R));
+        const float R = RB_MUL(RB_DIV(RB_SUB(1.0f, imp), imp), M::INVW0);
+        float f = RB_DIV(RB_SUB(aref, RB_MUL(sgn, a1)), RB_ADD(mi11, R));
         f = fmaxf(f, 0.0f);
         const float sf = RB_MUL(sgn, f);
         a0 = RB_FMA(mi01, sf, a0);
@@ -107,47 +190,54 @@ __device__ __forceinline__ void accel(float q1, float s1, float c1, float v0, fl
     }
 }
 
-// one mj_step (RK4).  In: (s1, c1) = sin/cos of e.q1.  Out: q/v advanced; (sq0, sq1) = qpos of the LAST stage (what xpos is
-// computed from) and (s1, c1) = sin/cos of sq1.
-__device__ __forceinline__ void substep(EnvState& e, float g0, float g1, float& s1, float& c1, float& sq0, float& sq1) {
+// one mj_step (RK4).  In: (s1, c1) = sin/cos of the current q1.  Out: q/v advanced; d0 / d1 = (LAST stage's q0 / q1, what xpos is
+// computed from) - (new q0 / q1); dq1 = the increment q1 received.
+RB_HD void substep(EnvState& e, float g0, float g1, float s1, float c1, float& d0, float& d1, float& dq1) {
     using M = Model;
-    const float q0 = e.q0, q1 = e.q1, v0 = e.v0, v1 = e.v1;
-    float f00, f01, f10, f11, f20, f21, f30, f31;
-    accel(q1, s1, c1, v0, v1, g0, g1, f00, f01);
-    const float qa1 = RB_FMA(M::H2, v1, q1), va0 = RB_FMA(M::H2, f00, v0), va1 = RB_FMA(M::H2, f01, v1);
-    sincos_cw(qa1, s1, c1);
-    accel(qa1, s1, c1, va0, va1, g0, g1, f10, f11);
-    const float qb1 = RB_FMA(M::H2, va1, q1), vb0 = RB_FMA(M::H2, f10, v0), vb1 = RB_FMA(M::H2, f11, v1);
-    sincos_cw(qb1, s1, c1);
-    accel(qb1, s1, c1, vb0, vb1, g0, g1, f20, f21);
-    const float qc0 = RB_FMA(M::H, vb0, q0), qc1 = RB_FMA(M::H, vb1, q1), vc0 = RB_FMA(M::H, f20, v0), vc1 = RB_FMA(M::H, f21, v1);
-    sincos_cw(qc1, s1, c1);
-    accel(qc1, s1, c1, vc0, vc1, g0, g1, f30, f31);
-    e.q0 = RB_FMA(M::H6, RB_ADD(RB_ADD(v0, vc0), RB_MUL(2.0f, RB_ADD(va0, vb0))), q0);
-    e.q1 = RB_FMA(M::H6, RB_ADD(RB_ADD(v1, vc1), RB_MUL(2.0f, RB_ADD(va1, vb1))), q1);
-    e.v0 = RB_FMA(M::H6, RB_ADD(RB_ADD(f00, f30), RB_MUL(2.0f, RB_ADD(f10, f20))), v0);
-    e.v1 = RB_FMA(M::H6, RB_ADD(RB_ADD(f01, f31), RB_MUL(2.0f, RB_ADD(f11, f21))), v1);
-    sq0 = qc0; sq1 = qc1;
+    const float v0 = e.v0, v1 = e.v1;
+    const float sq = copysignf(1.0f, e.q1), sgn = -sq;
+    const float p0 = RB_FMA(sq, e.q1l, RB_SUB(fabsf(e.q1), M::LIMIT));       // |q1| - 3: the subtraction is exact near the limit
+    const float hs2 = RB_MUL(sq, M::H2), hs = RB_MUL(sq, M::H);
+    float f00, f01, f10, f11, f20, f21, f30, f31, sa, ca;
+    accel(s1, c1, v0, v1, g0, g1, p0, sgn, f00, f01);
+    const float va0 = RB_FMA(M::H2, f00, v0), va1 = RB_FMA(M::H2, f01, v1);
+    rotate_sc<5>(s1, c1, RB_MUL(M::H2, v1), sa, ca);
+    accel(sa, ca, va0, va1, g0, g1, RB_FMA(hs2, v1, p0), sgn, f10, f11);
+    const float vb0 = RB_FMA(M::H2, f10, v0), vb1 = RB_FMA(M::H2, f11, v1);
+    rotate_sc<5>(s1, c1, RB_MUL(M::H2, va1), sa, ca);
+    accel(sa, ca, vb0, vb1, g0, g1, RB_FMA(hs2, va1, p0), sgn, f20, f21);
+    const float vc0 = RB_FMA(M::H, f20, v0), vc1 = RB_FMA(M::H, f21, v1);
+    rotate_sc<5>(s1, c1, RB_MUL(M::H, vb1), sa, ca);
+    accel(sa, ca, vc0, vc1, g0, g1, RB_FMA(hs, vb1, p0), sgn, f30, f31);
+    const float dq0 = RB_MUL(M::H6, RB_FMA(2.0f, RB_ADD(va0, vb0), RB_ADD(v0, vc0)));
+    dq1 = RB_MUL(M::H6, RB_FMA(2.0f, RB_ADD(va1, vb1), RB_ADD(v1, vc1)));
+    d0 = RB_FMA(M::H, vb0, -dq0);
+    d1 = RB_FMA(M::H, vb1, -dq1);
+    acc2(e.q0, e.q0l, dq0);
+    acc2(e.q1, e.q1l, dq1);
+    e.v0 = RB_FMA(M::H6, RB_FMA(2.0f, RB_ADD(f10, f20), RB_ADD(f00, f30)), v0);
+    e.v1 = RB_FMA(M::H6, RB_FMA(2.0f, RB_ADD(f11, f21), RB_ADD(f01, f31)), v1);
 }
 
 // fingertip from sin/cos of q0 and of q1 (angle addition for q0 + q1)
-__device__ __forceinline__ void fk_sc(float s0, float c0, float s1, float c1, float& px, float& py) {
+RB_HD void fk_sc(float s0, float c0, float s1, float c1, float& px, float& py) {
     const float c01 = RB_FMA(c0, c1, -RB_MUL(s0, s1)), s01 = RB_FMA(s0, c1, RB_MUL(c0, s1));
     px = RB_FMA(Model::LT, c01, RB_MUL(Model::L0, c0));
     py = RB_FMA(Model::LT, s01, RB_MUL(Model::L0, s0));
 }
-__device__ __forceinline__ void fk(float q0, float q1, float& px, float& py) {
+RB_HD void fk(float q0, float q1, float& px, float& py) {
     float s0, c0, s1, c1;
     sincos_cw(q0, s0, c0);
     sincos_cw(q1, s1, c1);
     fk_sc(s0, c0, s1, c1, px, py);
 }
 
-__device__ __forceinline__ void reset_env(EnvState& e, uint32_t k0, uint32_t k1, uint32_t gid) {
+RB_HD void reset_env(EnvState& e, uint32_t k0, uint32_t k1, uint32_t gid) {
     const uint4 r0 = philox4x32_10(gid, e.episode, 0u, STREAM_RESET, k0, k1);
     const uint4 r1 = philox4x32_10(gid, e.episode, 1u, STREAM_RESET, k0, k1);
     e.q0 = uniform_f32(r0.x, -0.1f, 0.1f);
     e.q1 = uniform_f32(r0.y, -0.1f, 0.1f);
+    e.q0l = e.q1l = 0.f;
     e.tx = uniform_f32(r0.z, -0.2f, 0.2f);
     e.ty = uniform_f32(r0.w, -0.2f, 0.2f);
     e.v0 = uniform_f32(r1.x, -0.005f, 0.005f);
@@ -159,22 +249,23 @@ __device__ __forceinline__ void reset_env(EnvState& e, uint32_t k0, uint32_t k1,
 
 // gym ReacherEnv.step + TimeLimit(50) + auto-reset.  Returns reward; done set when this step ended the episode.
 // Requires a valid trig cache on entry and leaves one on exit.
-__device__ __forceinline__ float step_env(EnvState& e, float a0, float a1, uint32_t k0, uint32_t k1, uint32_t gid, bool& done) {
+RB_HD float step_env(EnvState& e, float a0, float a1, uint32_t k0, uint32_t k1, uint32_t gid, bool& done) {
     const float dx = RB_SUB(e.px, e.tx), dy = RB_SUB(e.py, e.ty);
     // stale fingertip, unclipped action
     const float rew = -RB_ADD(sqrt_approx(RB_FMA(dx, dx, RB_MUL(dy, dy))), RB_FMA(a0, a0, RB_MUL(a1, a1)));
     const float g0 = RB_MUL(Model::GEAR, fminf(1.0f, fmaxf(-1.0f, a0)));
     const float g1 = RB_MUL(Model::GEAR, fminf(1.0f, fmaxf(-1.0f, a1)));
-    float s1 = e.s1, c1 = e.c1, sq0, sq1;
+    float s1 = e.s1, c1 = e.c1, d0, d1, dq1 = 0.f;
 #pragma unroll 1
     for (int sub = 0; sub < 2; ++sub) {              // frame_skip = 2; one copy of the RK4 body keeps the kernels inside the i-cache
-        if (sub) sincos_cw(e.q1, s1, c1);
-        substep(e, g0, g1, s1, c1, sq0, sq1);
+        if (sub) rotate_sc<5>(s1, c1, dq1, s1, c1);  // q1 at the start of the second sub-step = first start + dq1
+        substep(e, g0, g1, s1, c1, d0, d1, dq1);
     }
-    float ss0, sc0;
-    sincos_cw(sq0, ss0, sc0);
-    fk_sc(ss0, sc0, s1, c1, e.px, e.py);      // xpos is left at the last RK4 stage of the last sub-step
     refresh_trig(e);
+    float ss0, sc0, ss1, sc1;                  // xpos is left at the last RK4 stage of the last sub-step: angles there = new angles + d0 / d1
+    rotate_sc<5>(e.s0, e.c0, d0, ss0, sc0);
+    rotate_sc<5>(e.s1, e.c1, d1, ss1, sc1);
+    fk_sc(ss0, sc0, ss1, sc1, e.px, e.py);
     e.step += 1;
     done = e.step >= 50;
     if (done) { e.episode += 1u; reset_env(e, k0, k1, gid); }
@@ -182,33 +273,34 @@ __device__ __forceinline__ float step_env(EnvState& e, float a0, float a1, uint3
 }
 
 // 11-d observation: [cos q0, cos q1, sin q0, sin q1, tx, ty, v0, v1, px-tx, py-ty, 0]  (free: trig cache)
-__device__ __forceinline__ void observe(const EnvState& e, float* ob) {
+RB_HD void observe(const EnvState& e, float* ob) {
     ob[0] = e.c0; ob[1] = e.c1; ob[2] = e.s0; ob[3] = e.s1;
     ob[4] = e.tx; ob[5] = e.ty; ob[6] = e.v0; ob[7] = e.v1;
     ob[8] = RB_SUB(e.px, e.tx); ob[9] = RB_SUB(e.py, e.ty); ob[10] = 0.f;
 }
 
-// HBM state layout: qv float4[N] = (q0, q1, v0, v1), tp float4[N] = (tx, ty, px, py), ctr uint2[N] = (step, episode)
-__device__ __forceinline__ EnvState load_state(const float4* qv, const float4* tp, const uint2* ctr, int64_t i) {
+// HBM state layout: qv float4[N] = (q0, q1, v0, v1), tp float4[N] = (tx, ty, px, py), ctr uint4[N] = (step, episode, q0l bits, q1l bits)
+typedef uint4 EnvCtr;
+RB_HD EnvState load_state(const float4* qv, const float4* tp, const EnvCtr* ctr, int64_t i) {
     const float4 a = qv[i], b = tp[i];
-    const uint2 c = ctr[i];
+    const uint4 c = ctr[i];
     EnvState e;
     e.q0 = a.x; e.q1 = a.y; e.v0 = a.z; e.v1 = a.w; e.tx = b.x; e.ty = b.y; e.px = b.z; e.py = b.w;
-    e.step = (int)c.x; e.episode = c.y;
+    e.step = (int)c.x; e.episode = c.y; e.q0l = u2f(c.z); e.q1l = u2f(c.w);
     refresh_trig(e);
     return e;
 }
-__device__ __forceinline__ EnvState zero_state() {
+RB_HD void store_state(float4* qv, float4* tp, EnvCtr* ctr, int64_t i, const EnvState& e) {
+    qv[i] = make_float4(e.q0, e.q1, e.v0, e.v1);
+    tp[i] = make_float4(e.tx, e.ty, e.px, e.py);
+    ctr[i] = make_uint4((uint32_t)e.step, e.episode, f2u(e.q0l), f2u(e.q1l));
+}
+RB_HD EnvState zero_state() {
     EnvState e;
-    e.q0 = e.q1 = e.v0 = e.v1 = e.tx = e.ty = e.px = e.py = 0.f;
+    e.q0 = e.q1 = e.v0 = e.v1 = e.q0l = e.q1l = e.tx = e.ty = e.px = e.py = 0.f;
     e.s0 = e.s1 = 0.f; e.c0 = e.c1 = 1.f;
     e.step = 0; e.episode = 0;
     return e;
-}
-__device__ __forceinline__ void store_state(float4* qv, float4* tp, uint2* ctr, int64_t i, const EnvState& e) {
-    qv[i] = make_float4(e.q0, e.q1, e.v0, e.v1);
-    tp[i] = make_float4(e.tx, e.ty, e.px, e.py);
-    ctr[i] = make_uint2((uint32_t)e.step, e.episode);
 }
 
 }  // namespace rb

@@ -381,7 +381,7 @@ __global__ void k_policy_tc_build_image(const float* __restrict__ params, int no
 // mlp_train.py:50-52, dataset.py:118-143; 2x64 student: x = ob).  One pass over the env state, teacher on tcgen05.
 template <int KIND, int NT>
 __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, const float4* __restrict__ qv, const float4* __restrict__ tp,
-                                                                    const uint2* __restrict__ ctr, const void* __restrict__ teacher_img,
+                                                                    const uint4* __restrict__ ctr, const void* __restrict__ teacher_img,
                                                                     const float4* __restrict__ prev_t, const float* __restrict__ prev_rec_rew,
                                                                     float keep_prob, uint32_t k0, uint32_t k1, uint32_t offset, uint32_t iteration,
                                                                     const uint32_t* __restrict__ clock, float* __restrict__ obs_out,
@@ -435,7 +435,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, co
 
 // Fused policy-in-the-loop rollout (teacher warm-up loop, mlp_train.py:120-139).  Envs are dealt to CTAs in warp units.
 template <int NOUT, int NT>
-__global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, float4* qv, float4* tp, uint2* ctr, const float* __restrict__ params,
+__global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, float4* qv, float4* tp, uint4* ctr, const float* __restrict__ params,
                                                                     int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
                                                                     float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf, uint32_t k0,
                                                                     uint32_t k1, uint32_t offset, uint32_t stagger_ns, uint32_t* prog_counters,

@@ -108,7 +108,7 @@ struct StudentTcArgs {
     // shard (32 768 envs: 40 such CTAs).  Envs beyond that (student_tc_act_covered()) are left to a k_dagger_act launch behind this
     // kernel.  One thread of the grid advances the device clock and posts the loss mailbox at the end.
     int act_on;
-    float4* act_qv; float4* act_tp; uint2* act_ctr;
+    float4* act_qv; float4* act_tp; uint4* act_ctr;
     float4* act_prev_t; float* act_prev_rec_rew; float* act_last_reward; float* act_rew; uint8_t* act_done;
     uint32_t act_k0, act_k1, act_offset;
     uint32_t* act_flags;          // [ceil(B / 128)] forward-done flag per tile, value = iteration count of the launch that set it
@@ -863,7 +863,7 @@ struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, g
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
 struct StepClock { const uint32_t* clock; float lr; };
 struct ActFuse {              // fused env step of rb_dagger_step (see StudentTcArgs::act_*)
-    float4* qv; float4* tp; uint2* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
+    float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
     uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox;
 };
 

@@ -95,16 +95,17 @@ class VecReacher:
         n, dev = self.num_envs, self.device
         out = dict(qpos=torch.empty((n, 2), device=dev), qvel=torch.empty((n, 2), device=dev), target=torch.empty((n, 2), device=dev),
                    fingertip=torch.empty((n, 2), device=dev), step=torch.empty((n,), dtype=torch.int32, device=dev),
-                   episode=torch.empty((n,), dtype=torch.int32, device=dev))
+                   episode=torch.empty((n,), dtype=torch.int32, device=dev), qpos_lo=torch.empty((n, 2), device=dev))
         check(lib().rb_env_get_state(self._h, ptr(out["qpos"]), ptr(out["qvel"]), ptr(out["target"]), ptr(out["fingertip"]),
-                                     ptr(out["step"]), ptr(out["episode"]), stream_ptr()))
+                                     ptr(out["step"]), ptr(out["episode"]), ptr(out["qpos_lo"]), stream_ptr()))
         return out
 
-    def set_state(self, qpos=None, qvel=None, target=None, fingertip=None, step=None, episode=None):
+    def set_state(self, qpos=None, qvel=None, target=None, fingertip=None, step=None, episode=None, qpos_lo=None):
+        """qpos_lo: low parts of the two-float joint angles (get_state()["qpos_lo"]); omitted -> zero (qpos is then the whole angle)."""
         def prep(t, dt):
             return None if t is None else torch.as_tensor(t, dtype=dt).to(self.device).contiguous()
         ts = [prep(qpos, torch.float32), prep(qvel, torch.float32), prep(target, torch.float32), prep(fingertip, torch.float32),
-              prep(step, torch.int32), prep(episode, torch.int32)]
+              prep(step, torch.int32), prep(episode, torch.int32), prep(qpos_lo, torch.float32)]
         check(lib().rb_env_set_state(self._h, *[ptr(t) for t in ts], stream_ptr()))
         torch.cuda.current_stream().synchronize()   # keep the temporaries alive until the kernel has read them
 

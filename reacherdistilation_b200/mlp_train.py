@@ -137,7 +137,8 @@ class DaggerTrainer:
             raise ValueError("checkpoint is for num_envs=%d seed=%d env_offset=%d" % (sd["num_envs"], sd["seed"], sd["env_offset"]))
         self.student.load_state_dict(sd["student"])
         e = sd["env"]
-        self.env.set_state(qpos=e["qpos"], qvel=e["qvel"], target=e["target"], fingertip=e["fingertip"], step=e["step"], episode=e["episode"])
+        self.env.set_state(qpos=e["qpos"], qvel=e["qvel"], target=e["target"], fingertip=e["fingertip"], step=e["step"], episode=e["episode"],
+                           qpos_lo=e.get("qpos_lo"))
         dev = self.device
         prev_t, prr, lr_ = (sd[k].to(dev, torch.float32).contiguous() for k in ("prev_t_pdflat", "prev_rec_rew", "last_reward"))
         check(lib().rb_dagger_set_state(self._h, ptr(prev_t), ptr(prr), ptr(lr_), stream_ptr()))
