@@ -48,7 +48,10 @@ typedef enum {
 /* loss kinds */
 #define RB_LOSS_KL_ST 0 /* loss.py:3-13  KL(student || teacher), summed                       */
 #define RB_LOSS_KL_TS 1 /* backup/student_rollout.py:639-640  KL(teacher || student), summed  */
-#define RB_LOSS_MSE 2   /* backup/student_rollout_mlp_vf.py:276, student_rollout.py:328  sum of squared errors (dense stacks only) */
+#define RB_LOSS_MSE 2   /* backup/student_rollout_mlp_vf.py:276, student_rollout.py:328  sum of squared errors over every output
+                           (students: over the 4 pdflat entries)                                                          */
+#define RB_LOSS_MSE_ACTION 3 /* students only: sum of squared errors on the MEAN half of pdflat, i.e. on the actions the two
+                                policies would take (mlp_train.py:63-66 acts with the mean); the logstd outputs get no gradient */
 
 const char* rb_last_error(void);
 int rb_version(void);
@@ -190,13 +193,15 @@ int rb_debug_student_timers(unsigned long long* host_out16);
  * One lock-step DAgger iteration pieces (src/distilation/mlp_train.py:143-204 batched):
  * rb_dagger_observe: for every env write ob[N,11], teacher label t_pdflat[N,4] and the student input x[N,in]
  *   (POLICY64: x = ob; MLP: x = [dropout(ob), prev teacher pdflat, prev recorded reward], dataset.py:118-143 semantics,
- *   zeros at the first step of an episode).
+ *   zeros at the first step of an episode) and, when x_act_dev is not NULL (MLP student), x_act[N,16] = the same rows WITHOUT the
+ *   observation dropout: the reference applies dropout to the TRAINING batch only (keep_prob = KEEP_PROB, mlp_train.py:151) and
+ *   acts on the clean observation (keep_prob 1, mlp_train.py:171-186, lstm_train.py:176).
  * rb_dagger_act: step every env with the mean half of s_pdflat[N,4]; records rew[N], done[N]; keeps prev-pdflat / prev-rew. */
 typedef struct rb_dagger rb_dagger;
 int rb_dagger_create(rb_dagger** out, rb_env* env, int student_kind, float keep_prob);
 int rb_dagger_destroy(rb_dagger* d);
 int rb_dagger_observe(rb_dagger* d, const float* teacher_params_dev, uint32_t iteration, float* obs_dev, float* t_pdflat_dev,
-                      float* x_dev, int mode, void* stream);
+                      float* x_dev, float* x_act_dev, int mode, void* stream);
 /* Checkpoint / resume of the loop (`train(train, restore)`: main.py:24-27, lstm_train.py:86-87,102-107 save / restore the student every episode):
  * the per-env state the handle carries between iterations -- teacher pdflat of the previous record [N,4], `rew` field of the previous record [N],
  * reward of the last env.step [N] (dataset.py:118-143 `prev` / `prew`).  Device pointers, device-to-device copies on `stream`; NULL skips a field.
@@ -211,11 +216,14 @@ int rb_dagger_invalidate_teacher(rb_dagger* d);
  * (dropout iteration, Adam step, exchange epoch / slot parity) read from a device-side clock set once by rb_dagger_set_clock and
  * advanced at the end of the iteration -- so the launches are captured ONCE in a CUDA graph (use_graph != 0) and replayed with a single
  * cudaGraphLaunch per iteration.  The env step (rb_dagger_act's work) runs inside the student launch (CTAs that would idle at its first
- * grid barrier step the envs whose forward pass is published), so an iteration is two launches; RB_DAGGER_FUSE_ACT=0 keeps three.
+ * grid barrier step the envs whose forward pass is published), so an iteration is two launches.  x_act_dev (MLP student, may be NULL):
+ * un-dropped input rows; when given, every tile of the student launch runs the forward pass twice -- on x_act for s_pdflat_dev, the
+ * pdflat the envs are stepped with, then on x for the loss and the gradient (NULL: one pass, the student acts on its training input).
  * world > 1: slots_even / slots_odd / flags as in rb_student_step_dp (the two receive-area sets alternate). */
 int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_step, uint32_t epoch, void* stream);
 int rb_dagger_step(rb_dagger* d, const float* teacher_params_dev, float* params_dev, float* m_dev, float* v_dev, float* gradloss_dev,
-                   void* workspace_dev, float* obs_dev, float* t_pdflat_dev, float* x_dev, float* s_pdflat_dev, float* rew_dev, uint8_t* done_dev,
+                   void* workspace_dev, float* obs_dev, float* t_pdflat_dev, float* x_dev, float* x_act_dev, float* s_pdflat_dev, float* rew_dev,
+                   uint8_t* done_dev,
                    int loss_kind, float lr, float beta1, float beta2, float eps, float grad_scale, int rank, int world,
                    const uint64_t* slots_even, const uint64_t* slots_odd, const uint64_t* flags, int use_graph, void* stream);
 int rb_dagger_act(rb_dagger* d, const float* s_pdflat_dev, const float* t_pdflat_dev, float* rew_dev, uint8_t* done_dev,
@@ -302,6 +310,14 @@ int rb_dataset_episode_len(const rb_dataset* d);        /* len(curr_episode)    
  * with[50,N] -- what Dataset.dump (dataset.py:80-85 -> DatasetStore.store :31-40) serialises into gzip-JSON pages.  Synchronises.  */
 int64_t rb_dataset_generations(const rb_dataset* d);
 int rb_dataset_export_host(rb_dataset* d, int64_t generation, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host);
+/* Whole-ring snapshot / restore (exact resume of the loops that train from the Dataset; the reference restores its student every episode,
+ * lstm_train.py:86-87,102-107 -- here the replay buffer comes back too): rb_dataset_ring_rows() rows of every field (ob [rows,11], rew [rows],
+ * t / s [rows,4], with [rows]) + the cursor (records in the open episodes, generations flushed).  HOST buffers; synchronises.       */
+int64_t rb_dataset_ring_rows(const rb_dataset* d);
+int rb_dataset_save_host(rb_dataset* d, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host, int* step_out,
+                         int64_t* generations_out);
+int rb_dataset_load_host(rb_dataset* d, const float* ob_host, const float* rew_host, const float* t_host, const float* s_host,
+                         const uint8_t* with_host, int step, int64_t generations);
 /* Dataset.training_batches  dataset.py:179-210: B episodes drawn with replacement and ONE shared start in [0, 50-T], Philox keyed
  * (seed; draw, b).  Time-major outputs ob[T,B,11], t[T,B,4], prev[T,B,4], prew[T,B,1]; episodes_out[B] / start_out[1] (optional)
  * report what was drawn.                                                                                                      */

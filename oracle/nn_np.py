@@ -155,6 +155,21 @@ def kl_loss_rev(s, t, dtype=np.float64):
     return per.sum(), grad
 
 
+def mse_loss(s, t, actions_only=False, dtype=np.float64):
+    """Squared-error distillation (north_star (2) "MSE/KL on actions"; backup/student_rollout.py:328 uses the same sum-of-squares form for
+    its reward head): SUM of (s - t)^2 over the pdflat row, or over its mean half only (the actions).  Returns (loss, dL/ds)."""
+    s, t = np.asarray(s, dtype=dtype), np.asarray(t, dtype=dtype)
+    e = s - t
+    if actions_only:
+        e = np.concatenate([e[..., :2], np.zeros_like(e[..., 2:])], -1)
+    return (e * e).sum(), 2.0 * e
+
+
+def pd_loss(s, t, kind, dtype=np.float64):
+    """Loss by the C-ABI constant: 0 KL(s||t), 1 KL(t||s), 2 squared error on pdflat, 3 squared error on the actions."""
+    return (kl_loss, kl_loss_rev, mse_loss, lambda a, b, dtype=np.float64: mse_loss(a, b, True, dtype))[kind](s, t, dtype=dtype)
+
+
 # ------------------------------------------------------------------ optimiser ---------------------------------
 class AdamTF:
     """tf.train.AdamOptimizer / baselines MpiAdam update rule (epsilon added to the UNcorrected sqrt(v))."""

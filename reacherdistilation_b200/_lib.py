@@ -59,12 +59,12 @@ _SIGS = {
     "rb_adam_step": (C.c_int, [_fp, _fp, _fp, _fp, C.c_int64, C.c_int64, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, _vp]),
     "rb_dagger_create": (C.c_int, [C.POINTER(C.c_void_p), _vp, C.c_int, C.c_float]),
     "rb_dagger_destroy": (C.c_int, [_vp]),
-    "rb_dagger_observe": (C.c_int, [_vp, _fp, C.c_uint32, _fp, _fp, _fp, C.c_int, _vp]),
+    "rb_dagger_observe": (C.c_int, [_vp, _fp, C.c_uint32, _fp, _fp, _fp, _fp, C.c_int, _vp]),
     "rb_dagger_invalidate_teacher": (C.c_int, [_vp]),
     "rb_dagger_get_state": (C.c_int, [_vp, _fp, _fp, _fp, _vp]),
     "rb_dagger_set_state": (C.c_int, [_vp, _fp, _fp, _fp, _vp]),
     "rb_dagger_set_clock": (C.c_int, [_vp, C.c_uint32, C.c_uint32, C.c_uint32, _vp]),
-    "rb_dagger_step": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _u8p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
+    "rb_dagger_step": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _vp, _fp, _fp, _fp, _fp, _fp, _fp, _u8p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float,
                                  C.c_float, C.c_int, C.c_int, _vp, _vp, _vp, C.c_int, _vp]),
     "rb_dagger_act": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
     "rb_dagger_wait_loss": (C.c_int, [_vp, C.c_uint32, C.POINTER(C.c_float)]),
@@ -95,13 +95,16 @@ _SIGS = {
     "rb_dataset_episode_len": (C.c_int, [_vp]),
     "rb_dataset_generations": (C.c_int64, [_vp]),
     "rb_dataset_export_host": (C.c_int, [_vp, C.c_int64, _fp, _fp, _fp, _fp, _u8p]),
+    "rb_dataset_ring_rows": (C.c_int64, [_vp]),
+    "rb_dataset_save_host": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _u8p, C.POINTER(C.c_int), C.POINTER(C.c_int64)]),
+    "rb_dataset_load_host": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _u8p, C.c_int, C.c_int64]),
     "rb_dataset_training_batch": (C.c_int, [_vp, C.c_uint64, C.c_uint32, C.c_int, C.c_int, _fp, _fp, _fp, _fp, _i32p, _i32p, _vp]),
     "rb_dataset_test_batch": (C.c_int, [_vp, _fp, C.c_int, _fp, _fp, _fp, _vp]),
 }
 
 MODE_FP32, MODE_TC = 0, 1
 STUDENT_POLICY64, STUDENT_MLP = 0, 1
-LOSS_KL_ST, LOSS_KL_TS, LOSS_MSE = 0, 1, 2
+LOSS_KL_ST, LOSS_KL_TS, LOSS_MSE, LOSS_MSE_ACTION = 0, 1, 2, 3
 
 
 def header_symbols():

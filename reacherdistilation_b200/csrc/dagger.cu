@@ -36,7 +36,7 @@ namespace rb {
 
 __global__ void k_dagger_input(int64_t n, const uint4* __restrict__ ctr, const float* __restrict__ obs, const float4* __restrict__ prev_t,
                                const float* __restrict__ prev_rec_rew, float keep_prob, uint32_t k0, uint32_t k1, uint32_t offset,
-                               uint32_t iteration, float4* __restrict__ x) {
+                               uint32_t iteration, float4* __restrict__ x, float4* __restrict__ x_act) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     float ob[11];
@@ -48,6 +48,10 @@ __global__ void k_dagger_input(int64_t n, const uint4* __restrict__ ctr, const f
     float4 o[4];
     mlp_input_row(ob, keep_prob, k0, k1, offset + (uint32_t)i, iteration, pp, pr, o);
     x[i * 4 + 0] = o[0]; x[i * 4 + 1] = o[1]; x[i * 4 + 2] = o[2]; x[i * 4 + 3] = o[3];
+    if (x_act) {                         // the same row without observation dropout: what the student ACTS on (mlp_train.py:171-186, keep_prob 1)
+        x_act[i * 4 + 0] = make_float4(ob[0], ob[1], ob[2], ob[3]); x_act[i * 4 + 1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
+        x_act[i * 4 + 2] = make_float4(ob[8], ob[9], ob[10], pp.x); x_act[i * 4 + 3] = make_float4(pp.y, pp.z, pp.w, pr);
+    }
 }
 
 __global__ void __launch_bounds__(128) k_dagger_act(int64_t n, float4* qv, float4* tp, uint4* ctr, const float4* __restrict__ s_pd,
@@ -84,7 +88,7 @@ struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; 
 struct StepClock { const uint32_t* clock; float lr; };
 struct ActFuse {
     float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
-    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox;
+    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act;
 };
 int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
                       float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
@@ -96,7 +100,7 @@ int student_tc_grid(int* grid);
 size_t policy_tc_image_bytes();
 int policy_tc_build_image(const float* params, int nout, void* img, cudaStream_t s);
 int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, float keep_prob, const float4* prev_t, const float* prev_rec_rew,
-                      uint32_t iteration, const uint32_t* clock, float* obs, float* t_pd, float* x, cudaStream_t s);
+                      uint32_t iteration, const uint32_t* clock, float* obs, float* t_pd, float* x, float* x_act, cudaStream_t s);
 
 }  // namespace rb
 
@@ -154,7 +158,8 @@ int rb_dagger_set_state(rb_dagger* d, const float* prev_t, const float* prev_rec
     return RB_OK;
 }
 
-int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iteration, float* obs, float* t_pd, float* x, int mode, void* stream) {
+int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iteration, float* obs, float* t_pd, float* x, float* x_act, int mode,
+                      void* stream) {
     RB_REQUIRE(d && teacher_params && obs && t_pd && x, "NULL argument");
     rb_env* e = d->env;
     if (mode == RB_MODE_TC) {            // one fused kernel: observe + teacher (tcgen05) + student input
@@ -165,7 +170,7 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iterat
             d->teacher_img_src = teacher_params;
         }
         return dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, iteration, nullptr, obs, t_pd, x,
-                                 (cudaStream_t)stream);
+                                 d->kind == RB_STUDENT_MLP ? x_act : nullptr, (cudaStream_t)stream);
     }
     int rc = rb_env_observe(e, obs, stream);
     if (rc) return rc;
@@ -176,7 +181,7 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iterat
     } else {
         k_dagger_input<<<(unsigned)((e->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->n, e->ctr, obs, d->prev_t, d->prev_rec_rew, d->keep_prob,
                                                                                         (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset,
-                                                                                        iteration, (float4*)x);
+                                                                                        iteration, (float4*)x, (float4*)x_act);
         RB_CUDA(cudaGetLastError());
     }
     return RB_OK;
@@ -213,7 +218,7 @@ int rb_dagger_set_clock(rb_dagger* d, uint32_t iteration, uint32_t adam_t, uint3
 // three launches that take every per-step quantity from the device-side clock, so the sequence is captured once in a CUDA graph and
 // replayed with a single cudaGraphLaunch.
 int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, float* m, float* v, float* gradloss, void* ws, float* obs, float* t_pd,
-                   float* x, float* s_pd, float* rew, uint8_t* done, int loss_kind, float lr, float b1, float b2, float eps, float gscale, int rank,
+                   float* x, float* x_act, float* s_pd, float* rew, uint8_t* done, int loss_kind, float lr, float b1, float b2, float eps, float gscale, int rank,
                    int world, const uint64_t* slots_even, const uint64_t* slots_odd, const uint64_t* flags, int use_graph, void* stream) {
     RB_REQUIRE(d && teacher_params && params && m && v && gradloss && ws && obs && t_pd && x && s_pd, "NULL argument");
     RB_REQUIRE(d->clock != nullptr, "call rb_dagger_set_clock first");
@@ -238,14 +243,15 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
     static const int fuse_act_knob = [] { const char* v = getenv("RB_DAGGER_FUSE_ACT"); return v ? atoi(v) : 1; }();
     const bool fuse_act = fuse_act_knob != 0;
     auto issue = [&](cudaStream_t st) -> int {
-        int rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, st);
+        const float* xa = d->kind == RB_STUDENT_MLP ? x_act : nullptr;       // the 2x64 student sees the raw observation: nothing to un-drop
+        int rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, (float*)xa, st);
         if (rc) return rc;
         const AdamFuse af{params, m, v, 0.f, b1, b2, eps, gscale};
         const PeerExchange px{world, rank, 0u, slots_even, flags, slots_odd};
         const StepClock clk{d->clock, lr};
         if (fuse_act) {      // env step, clock advance and loss mailbox inside the student launch: two launches per iteration
             const ActFuse act{e->qv, e->tp, e->ctr, d->prev_t, d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed, (uint32_t)(e->seed >> 32),
-                              e->offset, d->act_flags, d->clock, d->mailbox_dev};
+                              e->offset, d->act_flags, d->clock, d->mailbox_dev, xa};
             rc = student_tc_run_ex(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, &act, st);
             if (rc) return rc;
             int grid = 1;
@@ -260,6 +266,7 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
             }
             return RB_OK;
         }
+        RB_REQUIRE(xa == nullptr, "x_act needs the env step fused into the student launch");
         rc = student_tc_run_ex(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, nullptr, st);
         if (rc) return rc;
         k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, st>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd, d->prev_t,
@@ -272,7 +279,7 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
     // graph key: everything the captured launches bake in
     uint64_t key = 1469598103934665603ull;
     auto mix = [&](uint64_t vv) { key = (key ^ vv) * 1099511628211ull; };
-    const void* ptrs[] = {teacher_params, params, m, v, gradloss, ws, obs, t_pd, x, s_pd, rew, done, stream, slots_even, slots_odd, flags};
+    const void* ptrs[] = {teacher_params, params, m, v, gradloss, ws, obs, t_pd, x, x_act, s_pd, rew, done, stream, slots_even, slots_odd, flags};
     for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
     const float fl[] = {lr, b1, b2, eps, gscale};
     for (float f : fl) { uint32_t u; memcpy(&u, &f, 4); mix(u); }

@@ -169,6 +169,39 @@ int rb_dataset_export_host(rb_dataset* d, int64_t generation, float* ob_host, fl
     return RB_OK;
 }
 
+// Whole-ring snapshot for an exact resume of the loops that train from the Dataset (lstm_train.py:86-87,102-107 restore every episode; here the
+// replay buffer comes back too, so the restored run draws the same windows): all rows of the ring + the cursor.  Synchronises.
+int64_t rb_dataset_ring_rows(const rb_dataset* d) { return d ? d->G * EP * d->n : 0; }
+int rb_dataset_save_host(rb_dataset* d, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host, int* step_out,
+                         int64_t* generations_out) {
+    RB_REQUIRE(d && ob_host && rew_host && t_host && s_host && with_host && step_out && generations_out, "NULL argument");
+    RB_CUDA(cudaSetDevice(d->device));
+    const size_t rows = (size_t)rb_dataset_ring_rows(d);
+    RB_CUDA(cudaDeviceSynchronize());
+    RB_CUDA(cudaMemcpy(ob_host, d->ob, rows * 11 * sizeof(float), cudaMemcpyDeviceToHost));
+    RB_CUDA(cudaMemcpy(rew_host, d->rew, rows * sizeof(float), cudaMemcpyDeviceToHost));
+    RB_CUDA(cudaMemcpy(t_host, d->t, rows * sizeof(float4), cudaMemcpyDeviceToHost));
+    RB_CUDA(cudaMemcpy(s_host, d->s, rows * sizeof(float4), cudaMemcpyDeviceToHost));
+    RB_CUDA(cudaMemcpy(with_host, d->with, rows, cudaMemcpyDeviceToHost));
+    *step_out = d->k; *generations_out = d->gen;
+    return RB_OK;
+}
+int rb_dataset_load_host(rb_dataset* d, const float* ob_host, const float* rew_host, const float* t_host, const float* s_host,
+                         const uint8_t* with_host, int step, int64_t generations) {
+    RB_REQUIRE(d && ob_host && rew_host && t_host && s_host && with_host, "NULL argument");
+    RB_REQUIRE(step >= 0 && step <= EP && generations >= 0, "bad cursor");
+    RB_CUDA(cudaSetDevice(d->device));
+    const size_t rows = (size_t)rb_dataset_ring_rows(d);
+    RB_CUDA(cudaDeviceSynchronize());
+    RB_CUDA(cudaMemcpy(d->ob, ob_host, rows * 11 * sizeof(float), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(d->rew, rew_host, rows * sizeof(float), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(d->t, t_host, rows * sizeof(float4), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(d->s, s_host, rows * sizeof(float4), cudaMemcpyHostToDevice));
+    RB_CUDA(cudaMemcpy(d->with, with_host, rows, cudaMemcpyHostToDevice));
+    d->k = step; d->gen = generations;
+    return RB_OK;
+}
+
 int rb_dataset_training_batch(rb_dataset* d, uint64_t seed, uint32_t draw, int B, int T, float* ob_out, float* t_out, float* prev_out, float* prew_out,
                               int32_t* episodes_out, int32_t* start_out, void* stream) {
     RB_REQUIRE(d && ob_out && t_out && prev_out && prew_out, "NULL argument");

@@ -17,4 +17,17 @@ __device__ __forceinline__ float kl_row(const float4 sv, const float4 tv, int lo
     return (sv.z - tv.z + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (sv.w - tv.w + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
 }
 
+// any loss kind a pdflat student can be trained with: the two KL directions, the squared error on the whole pdflat row (RB_LOSS_MSE)
+// or on its mean half only -- the ACTIONS, north_star (2) "MSE/KL on actions" (RB_LOSS_MSE_ACTION: the logstd outputs get no gradient)
+__device__ __forceinline__ float pd_loss_row(const float4 sv, const float4 tv, int loss_kind, float4& d) {
+    if (loss_kind == RB_LOSS_MSE || loss_kind == RB_LOSS_MSE_ACTION) {
+        const float e0 = sv.x - tv.x, e1 = sv.y - tv.y;
+        const float e2 = loss_kind == RB_LOSS_MSE ? sv.z - tv.z : 0.f, e3 = loss_kind == RB_LOSS_MSE ? sv.w - tv.w : 0.f;
+        d = make_float4(2.f * e0, 2.f * e1, 2.f * e2, 2.f * e3);
+        return (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+    }
+    return kl_row(sv, tv, loss_kind, d);
+}
+__host__ __device__ inline bool pd_loss_kind_ok(int k) { return k == RB_LOSS_KL_ST || k == RB_LOSS_KL_TS || k == RB_LOSS_MSE || k == RB_LOSS_MSE_ACTION; }
+
 }  // namespace rb

@@ -131,7 +131,7 @@ __global__ void k_lstm_kl(int64_t R, const float4* __restrict__ s, const float4*
     float l = 0.f;
     if (i < R) {
         float4 d;
-        l = kl_row(s[i], t[i], loss_kind, d);
+        l = pd_loss_row(s[i], t[i], loss_kind, d);
         ds[i] = d;
     }
 #pragma unroll
@@ -379,7 +379,7 @@ int rb_lstm_loss_grad(const float* params, const float* ob, const float* prev_pd
     RB_REQUIRE(params && ob && prev_pd && t_pd && s_out && gradloss && workspace, "NULL argument");
     RB_REQUIRE(B > 0 && B * LT < ((int64_t)1 << 30), "bad batch");
     RB_REQUIRE(keep_prob > 0.f, "keep_prob must be > 0");
-    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    RB_REQUIRE(pd_loss_kind_ok(loss_kind), "unknown loss kind");
     LstmCall c{};
     c.params = params; c.ob = ob; c.prev_pd = prev_pd; c.t_pd = t_pd; c.init_state = init_state; c.keep_prob = keep_prob; c.seed = seed;
     c.sample_id0 = sample_id0; c.iteration = iteration; c.B = B; c.loss_kind = loss_kind; c.s_out = s_out; c.final_state = final_state;
@@ -422,7 +422,7 @@ int rb_lstm_step(rb_lstm_ctx* ctx, float* params, float* m, float* v, const floa
                  float lr, float b1, float b2, float eps, float gscale, int use_graph, void* stream) {
     RB_REQUIRE(ctx && params && m && v && ob && prev_pd && t_pd && s_out && gradloss && workspace, "NULL argument");
     RB_REQUIRE(B > 0 && B * LT < ((int64_t)1 << 30) && keep_prob > 0.f, "bad batch / keep_prob");
-    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    RB_REQUIRE(pd_loss_kind_ok(loss_kind), "unknown loss kind");
     cudaStream_t st = (cudaStream_t)stream;
     auto issue = [&](cudaStream_t s) -> int {
         k_lstm_clock_prep<<<1, 1, 0, s>>>(ctx->clock, lr, b1, b2, ctx->lr_t);

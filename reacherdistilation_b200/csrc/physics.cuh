@@ -181,8 +181,9 @@ RB_HD void accel(float s1, float c1, float v0, float v1, float g0, float g1, flo
         const float imp = RB_FMA(0.05f, y, 0.9f);
         const float aref = RB_FMA(M::K_LIM, RB_MUL(imp, over), -RB_MUL(M::B_LIM, RB_MUL(sgn, v1)));   // -beta J.v - k imp dist
         const float mi01 = -RB_MUL(m01, idet), mi11 = RB_MUL(m00, idet);
-        const float R = RB_MUL(RB_DIV(RB_SUB(1.0f, imp), imp), M::INVW0);
-        float f = RB_DIV(RB_SUB(aref, RB_MUL(sgn, a1)), RB_ADD(mi11, R));
+        // f = max(0, (aref - J.a) / (A + R)), R = (1 - imp) / imp * invweight0, with ONE division: numerator and denominator times imp
+        const float den = RB_FMA(mi11, imp, RB_MUL(RB_SUB(1.0f, imp), M::INVW0));
+        float f = RB_DIV(RB_MUL(RB_SUB(aref, RB_MUL(sgn, a1)), imp), den);
         f = fmaxf(f, 0.0f);
         const float sf = RB_MUL(sgn, f);
         a0 = RB_FMA(mi01, sf, a0);

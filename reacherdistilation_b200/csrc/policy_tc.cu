@@ -385,7 +385,7 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, co
                                                                     const float4* __restrict__ prev_t, const float* __restrict__ prev_rec_rew,
                                                                     float keep_prob, uint32_t k0, uint32_t k1, uint32_t offset, uint32_t iteration,
                                                                     const uint32_t* __restrict__ clock, float* __restrict__ obs_out,
-                                                                    float4* __restrict__ t_out, float* __restrict__ x_out) {
+                                                                    float4* __restrict__ t_out, float* __restrict__ x_out, float* __restrict__ x_act_out) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     if (clock) iteration = clock[0];          // device-side step clock (CUDA-graph replay)
     TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
@@ -427,6 +427,11 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_dagger_observe_tc(int64_t n, co
                 mlp_input_row(ob, keep_prob, k0, k1, offset + (uint32_t)i, iteration, pp, pr, o);
                 float4* xr = reinterpret_cast<float4*>(x_out) + i * 4;
                 xr[0] = o[0]; xr[1] = o[1]; xr[2] = o[2]; xr[3] = o[3];
+                if (x_act_out) {         // the same row without observation dropout: what the student ACTS on (mlp_train.py:171-186, keep_prob 1)
+                    float4* xa = reinterpret_cast<float4*>(x_act_out) + i * 4;
+                    xa[0] = make_float4(ob[0], ob[1], ob[2], ob[3]); xa[1] = make_float4(ob[4], ob[5], ob[6], ob[7]);
+                    xa[2] = make_float4(ob[8], ob[9], ob[10], pp.x); xa[3] = make_float4(pp.y, pp.z, pp.w, pr);
+                }
             }
         }
     }
@@ -543,7 +548,7 @@ int policy_tc_build_image(const float* params, int nout, void* img, cudaStream_t
 }
 
 int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, float keep_prob, const float4* prev_t, const float* prev_rec_rew,
-                      uint32_t iteration, const uint32_t* clock, float* obs, float* t_pd, float* x, cudaStream_t s) {
+                      uint32_t iteration, const uint32_t* clock, float* obs, float* t_pd, float* x, float* x_act, cudaStream_t s) {
     constexpr int NT = FWD_NT;
     const int64_t ngroups = (e->n + NT * TILE - 1) / (NT * TILE);
     const unsigned grid = (unsigned)min((int64_t)e->sm_count * 2, ngroups);
@@ -553,12 +558,12 @@ int dagger_observe_tc(rb_env* e, const void* teacher_img, int student_kind, floa
         int rc = set_smem_attr(k_dagger_observe_tc<RB_STUDENT_MLP, NT>, smem);
         if (rc) return rc;
         k_dagger_observe_tc<RB_STUDENT_MLP, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, teacher_img, prev_t, prev_rec_rew, keep_prob, k0,
-                                                                            k1, e->offset, iteration, clock, obs, (float4*)t_pd, x);
+                                                                            k1, e->offset, iteration, clock, obs, (float4*)t_pd, x, x_act);
     } else {
         int rc = set_smem_attr(k_dagger_observe_tc<RB_STUDENT_POLICY64, NT>, smem);
         if (rc) return rc;
         k_dagger_observe_tc<RB_STUDENT_POLICY64, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, teacher_img, prev_t, prev_rec_rew,
-                                                                                 keep_prob, k0, k1, e->offset, iteration, clock, obs, (float4*)t_pd, x);
+                                                                                 keep_prob, k0, k1, e->offset, iteration, clock, obs, (float4*)t_pd, x, x_act);
     }
     RB_CUDA(cudaGetLastError());
     return RB_OK;

@@ -12,6 +12,7 @@
 // memory (one owner thread per parameter -> no atomics) and writes it to partials[block]; a second kernel sums the
 // partials in block order, so the result is bit-reproducible run to run.
 #include "common.cuh"
+#include "loss.cuh"
 #include "philox.cuh"
 
 namespace rb {
@@ -138,16 +139,10 @@ __global__ void __launch_bounds__(TILE* TPS) k_student(const NetSpec S, const fl
             if (!fwd_only) {
                 float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
                 if (s < nvalid) {
-                    const float tm0 = trow[0 * LD + s], tm1 = trow[1 * LD + s], tl0 = trow[2 * LD + s], tl1 = trow[3 * LD + s];
-                    const float vs0 = expf(2.f * l0), vs1 = expf(2.f * l1), vt0 = expf(2.f * tl0), vt1 = expf(2.f * tl1);
-                    const float e0 = m0 - tm0, e1 = m1 - tm1;
-                    if (loss_kind == RB_LOSS_KL_ST) {
-                        lsum = (tl0 - l0 + (vs0 + e0 * e0) / (2.f * vt0) - 0.5f) + (tl1 - l1 + (vs1 + e1 * e1) / (2.f * vt1) - 0.5f);
-                        d0 = e0 / vt0; d1 = e1 / vt1; d2 = vs0 / vt0 - 1.f; d3 = vs1 / vt1 - 1.f;
-                    } else {
-                        lsum = (l0 - tl0 + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (l1 - tl1 + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
-                        d0 = e0 / vs0; d1 = e1 / vs1; d2 = 1.f - (vt0 + e0 * e0) / vs0; d3 = 1.f - (vt1 + e1 * e1) / vs1;
-                    }
+                    float4 dd;
+                    lsum = pd_loss_row(make_float4(m0, m1, l0, l1), make_float4(trow[0 * LD + s], trow[1 * LD + s], trow[2 * LD + s], trow[3 * LD + s]),
+                                       loss_kind, dd);
+                    d0 = dd.x; d1 = dd.y; d2 = dd.z; d3 = dd.w;
                 }
                 O[0 * LD + s] = d0; O[1 * LD + s] = d1; O[2 * LD + s] = d2; O[3 * LD + s] = d3;
             }
@@ -383,7 +378,7 @@ int rb_student_loss_grad(int kind, const float* params, const float* x, const fl
                          float* gradloss, void* ws, int mode, void* stream) {
     RB_REQUIRE(params && x && tpd && gradloss && ws, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
-    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    RB_REQUIRE(pd_loss_kind_ok(loss_kind), "unknown loss kind");
     RB_REQUIRE(B > 0, "empty batch");
     if (mode == RB_MODE_TC) return student_tc_run(kind, params, x, tpd, B, loss_kind, 0, s_pd, gradloss, ws, nullptr, nullptr, nullptr, (cudaStream_t)stream);
     RB_REQUIRE(mode == RB_MODE_FP32, "unknown mode");
@@ -398,7 +393,7 @@ int rb_student_step(int kind, float* params, float* m, float* v, const float* x,
                     float* gradloss, void* ws, int64_t t, float lr, float b1, float b2, float eps, float gscale, int mode, void* stream) {
     RB_REQUIRE(params && m && v && x && tpd && gradloss && ws, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
-    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    RB_REQUIRE(pd_loss_kind_ok(loss_kind), "unknown loss kind");
     RB_REQUIRE(B > 0 && t >= 1, "empty batch / bad step");
     if (mode == RB_MODE_TC) {
         const AdamFuse af{params, m, v, adam_lr_t(lr, b1, b2, t), b1, b2, eps, gscale};
@@ -414,7 +409,7 @@ int rb_student_step_dp(int kind, float* params, float* m, float* v, const float*
                        const uint64_t* peer_grad_slots, const uint64_t* peer_flags, uint32_t epoch, void* stream) {
     RB_REQUIRE(params && m && v && x && tpd && gradloss && ws && peer_grad_slots && peer_flags, "NULL argument");
     RB_REQUIRE(kind == RB_STUDENT_POLICY64 || kind == RB_STUDENT_MLP, "unknown student kind");
-    RB_REQUIRE(loss_kind == RB_LOSS_KL_ST || loss_kind == RB_LOSS_KL_TS, "unknown loss kind");
+    RB_REQUIRE(pd_loss_kind_ok(loss_kind), "unknown loss kind");
     RB_REQUIRE(B > 0 && t >= 1 && epoch >= 1, "empty batch / bad step / epoch must start at 1");
     RB_REQUIRE(world >= 2 && world <= 8 && rank >= 0 && rank < world, "2..8 ranks");
     const AdamFuse af{params, m, v, adam_lr_t(lr, b1, b2, t), b1, b2, eps, gscale};

@@ -24,6 +24,7 @@
 #include <cooperative_groups.h>
 
 #include "common.cuh"
+#include "loss.cuh"
 #include "physics.cuh"
 #include "tc_common.cuh"
 
@@ -76,6 +77,9 @@ struct StudentTcArgs {
     int ploss, pstride;           // offset of the loss, floats per partial vector
     const float* obf;             // SpecPOL: ob_mean[11] ob_std[11]
     const float* x;               // [B, IN0]
+    const float* x_act;           // SpecMLP, optional: [B, 16] the same rows WITHOUT observation dropout.  When given, every tile runs the forward
+                                  // pass twice: first on x_act -> s_out (the pdflat the student ACTS with: the reference acts with keep_prob 1,
+                                  // mlp_train.py:171-186), then on x for the loss and the gradient (keep_prob = KEEP_PROB, mlp_train.py:151)
     const float* t;               // [B, 4] teacher pdflat (NULL: forward only)
     float4* s_out;                // [B] student pdflat (may be NULL)
     float* partials;              // [grid][pstride]
@@ -581,11 +585,15 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
 
     st_stamp(3);
     const int64_t ntiles = (a.B + ST_TILE - 1) / ST_TILE;
-    // software prefetch of the next tile's inputs (SpecMLP: one float4 of x per thread) while the current tile computes
-    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f);
+    // software prefetch of the next tile's inputs (SpecMLP: one float4 of x -- and of x_act -- per thread) while the current tile computes
+    const bool two_pass = S::IN0 == 16 && a.x_act != nullptr && !a.fwd_only;
+    float4 xv = make_float4(0.f, 0.f, 0.f, 0.f), xav = xv;
     if constexpr (S::IN0 == 16) {
         const int64_t r0 = (int64_t)blockIdx.x * ST_TILE + (tid >> 2);
-        if (blockIdx.x < ntiles && r0 < a.B) xv = __ldg(reinterpret_cast<const float4*>(a.x + r0 * 16) + (tid & 3));
+        if (blockIdx.x < ntiles && r0 < a.B) {
+            xv = __ldg(reinterpret_cast<const float4*>(a.x + r0 * 16) + (tid & 3));
+            if (two_pass) xav = __ldg(reinterpret_cast<const float4*>(a.x_act + r0 * 16) + (tid & 3));
+        }
     }
     for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const int64_t base = tile * ST_TILE;
@@ -593,18 +601,31 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         const bool prof = tile == blockIdx.x;
 #define RB_TS(i) do { if (prof) st_stamp(16 + (i)); } while (0)
         RB_TS(0);
+        float4 tpd = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (!a.fwd_only && part == 0 && row < nvalid) tpd = __ldg(reinterpret_cast<const float4*>(a.t) + base + row);
+        // pass 0 (only with x_act): acting forward on the un-dropped rows -> s_out.  pass 1: the training pass (forward, loss, backward).
+#pragma unroll 1
+        for (int pass = two_pass ? 0 : 1; pass < 2; ++pass) {
+        const bool act_pass = pass == 0;
+        const bool emit_s = two_pass ? act_pass : true;              // which forward pass produces the pdflat the caller (and the env step) sees
         // ---- X0: global fp32 -> (obfilter) -> bf16 hi/lo rows ---------------------------------------------------------------
         if constexpr (S::IN0 == 16) {
             const int r = tid >> 2, q = tid & 3;                       // 4 threads per sample row, 4 features each
+            const float4 xin = act_pass ? xav : xv;
             uint32_t h0, l0, h1, l1;
-            split_pair(xv.x, xv.y, h0, l0);
-            split_pair(xv.z, xv.w, h1, l1);
+            split_pair(xin.x, xin.y, h0, l0);
+            split_pair(xin.z, xin.w, h1, l1);
             const uint32_t off = (S::slot(0) + (q >> 1)) * 2048 + r * 16 + (q & 1) * 8;
             *reinterpret_cast<uint2*>(act_hi + off) = make_uint2(h0, h1);
             *reinterpret_cast<uint2*>(act_lo + off) = make_uint2(l0, l1);
-            const int64_t rn = (tile + gridDim.x) * ST_TILE + r;
-            xv = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (rn < a.B) xv = __ldg(reinterpret_cast<const float4*>(a.x + rn * 16) + q);
+            if (!act_pass) {
+                const int64_t rn = (tile + gridDim.x) * ST_TILE + r;
+                xv = make_float4(0.f, 0.f, 0.f, 0.f); xav = xv;
+                if (rn < a.B) {
+                    xv = __ldg(reinterpret_cast<const float4*>(a.x + rn * 16) + q);
+                    if (two_pass) xav = __ldg(reinterpret_cast<const float4*>(a.x_act + rn * 16) + q);
+                }
+            }
         } else {
             for (int e = tid; e < ST_TILE * S::IN0; e += ST_THREADS) {
                 const int r = e / S::IN0, f = e - r * S::IN0;
@@ -620,8 +641,6 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
                 *reinterpret_cast<uint16_t*>(act_lo + off) = lo;
             }
         }
-        float4 tpd = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (!a.fwd_only && part == 0 && row < nvalid) tpd = __ldg(reinterpret_cast<const float4*>(a.t) + base + row);
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
@@ -648,25 +667,18 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         }
         RB_ST_FWD(0) RB_ST_FWD(1) RB_ST_FWD(2) RB_ST_FWD(3)
 #undef RB_ST_FWD
-        // ---- output epilogue: s = ACC[:, 0:4]; KL loss and dL/ds (loss.py:8-13; reverse: backup/student_rollout.py:639-640) ---
+        // ---- output epilogue: s = ACC[:, 0:4]; loss and dL/ds (loss.py:8-13; reverse: backup/student_rollout.py:639-640; squared errors) ---
         if (part == 0) {
             float s[4];
             tmem_ld_x4(tacc, s);
             tmem_ld_wait();
-            if (row < nvalid && a.s_out) a.s_out[base + row] = make_float4(s[0], s[1], s[2], s[3]);
-            if (!a.fwd_only) {
+            if (emit_s && row < nvalid && a.s_out) a.s_out[base + row] = make_float4(s[0], s[1], s[2], s[3]);
+            if (!a.fwd_only && !act_pass) {
                 float d[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                 if (row < nvalid) {
-                    const float m0 = s[0], m1 = s[1], l0 = s[2], l1 = s[3];
-                    const float vs0 = expf(2.f * l0), vs1 = expf(2.f * l1), vt0 = expf(2.f * tpd.z), vt1 = expf(2.f * tpd.w);
-                    const float e0 = m0 - tpd.x, e1 = m1 - tpd.y;
-                    if (a.loss_kind == RB_LOSS_KL_ST) {
-                        loss_acc += (tpd.z - l0 + (vs0 + e0 * e0) / (2.f * vt0) - 0.5f) + (tpd.w - l1 + (vs1 + e1 * e1) / (2.f * vt1) - 0.5f);
-                        d[0] = e0 / vt0; d[1] = e1 / vt1; d[2] = vs0 / vt0 - 1.f; d[3] = vs1 / vt1 - 1.f;
-                    } else {
-                        loss_acc += (l0 - tpd.z + (vt0 + e0 * e0) / (2.f * vs0) - 0.5f) + (l1 - tpd.w + (vt1 + e1 * e1) / (2.f * vs1) - 0.5f);
-                        d[0] = e0 / vs0; d[1] = e1 / vs1; d[2] = 1.f - (vt0 + e0 * e0) / vs0; d[3] = 1.f - (vt1 + e1 * e1) / vs1;
-                    }
+                    float4 dd;
+                    loss_acc += pd_loss_row(make_float4(s[0], s[1], s[2], s[3]), tpd, a.loss_kind, dd);
+                    d[0] = dd.x; d[1] = dd.y; d[2] = dd.z; d[3] = dd.w;
                 }
                 store_split8(act_hi, act_lo, 0, row, d);
             }
@@ -675,9 +687,10 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         fence_before_sync();
         __syncthreads();
         RB_TS(10);
-        // s_out of this tile is published (release: cumulative over the CTA barrier above).  Warp 1 does it: warp 0 issues the backward MMAs
-        // next, and the other warps only wait for them, so the fence latency is hidden.
-        if (a.act_on && tid == 32) st_release_gpu(a.act_flags + tile, ctl.iter);
+        // s_out of this tile is published (release: cumulative over the CTA barrier above).  Warp 1 does it: warp 0 issues the next MMAs,
+        // and the other warps only wait for them, so the fence latency is hidden.
+        if (a.act_on && emit_s && tid == 32) st_release_gpu(a.act_flags + tile, ctl.iter);
+        }   // pass
         if (a.fwd_only) continue;
 
         // ---- backward: wgrad_l (accumulates in TMEM) + dgrad_l, then dZ_{l-1} in place over X_l ------------------------------
@@ -862,9 +875,9 @@ template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cuda
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
 struct StepClock { const uint32_t* clock; float lr; };
-struct ActFuse {              // fused env step of rb_dagger_step (see StudentTcArgs::act_*)
+struct ActFuse {              // fused env step of rb_dagger_step (see StudentTcArgs::act_*); x_act: un-dropped input rows or NULL
     float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
-    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox;
+    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act;
 };
 
 int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
@@ -916,6 +929,7 @@ int student_tc_run_ex(int kind, const float* params, const float* x, const float
         a.act_on = 1; a.act_qv = act->qv; a.act_tp = act->tp; a.act_ctr = act->ctr; a.act_prev_t = act->prev_t; a.act_prev_rec_rew = act->prev_rec_rew;
         a.act_last_reward = act->last_reward; a.act_rew = act->rew; a.act_done = act->done; a.act_k0 = act->k0; a.act_k1 = act->k1; a.act_offset = act->offset;
         a.act_flags = act->flags; a.act_clock = act->clock; a.act_mailbox = act->mailbox;
+        if (kind == RB_STUDENT_MLP) a.x_act = act->x_act;
     }
     if (kind == RB_STUDENT_MLP) {
         a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;

@@ -79,9 +79,10 @@ class Dataset:
 
     def write(self, ob, reward=None, t_pdflat=None, s_pdflat=None, stepped_with="t"):
         """dataset.py:118-143.  ob [N,11], reward [N], pdflats [N,4] (device tensors or array-likes)."""
+        args = (ob, reward, t_pdflat, s_pdflat)               # as given: host arrays become temporaries on the device below
         ob, rw, t, s = self._dev(ob, 11), self._dev(reward, 0), self._dev(t_pdflat, 4), self._dev(s_pdflat, 4)
         check(lib().rb_dataset_write(self._h, ptr(ob), ptr(rw), ptr(t), ptr(s), 0 if stepped_with == "t" else 1, stream_ptr()))
-        if any(x is not None and not torch.is_tensor(a) for x, a in ((ob, ob), (rw, reward), (t, t_pdflat), (s, s_pdflat))):
+        if any(a is not None and not torch.is_tensor(a) for a in args):
             torch.cuda.current_stream().synchronize()        # temporaries made from host data must outlive the copy
 
     def flush(self):
@@ -94,13 +95,17 @@ class Dataset:
         return int(lib().rb_dataset_episode_len(self._h)) - 1
 
     # ---- batches -------------------------------------------------------------------------------------------
-    def training_batch(self, batch_size=LSTM_BATCH_SIZE, steps=STEPS_UNROLLED, draw=None, with_indices=False):
-        """One batch of dataset.py:184-194: (ob[T,B,11], t[T,B,4], prev[T,B,4], prew[T,B,1]) as device tensors."""
+    def training_batch(self, batch_size=LSTM_BATCH_SIZE, steps=STEPS_UNROLLED, draw=None, with_indices=False, out=None):
+        """One batch of dataset.py:184-194: (ob[T,B,11], t[T,B,4], prev[T,B,4], prew[T,B,1]) as device tensors.
+        out: the four tensors to fill (static buffers keep a captured CUDA graph of the optimiser step valid from batch to batch)."""
         if draw is None:
             draw, self._draw = self._draw, self._draw + 1
         dev = self.device
-        ob, t = torch.empty((steps, batch_size, 11), device=dev), torch.empty((steps, batch_size, 4), device=dev)
-        prev, prew = torch.empty((steps, batch_size, 4), device=dev), torch.empty((steps, batch_size, 1), device=dev)
+        if out is not None:
+            ob, t, prev, prew = out
+        else:
+            ob, t = torch.empty((steps, batch_size, 11), device=dev), torch.empty((steps, batch_size, 4), device=dev)
+            prev, prew = torch.empty((steps, batch_size, 4), device=dev), torch.empty((steps, batch_size, 1), device=dev)
         eps = torch.empty(batch_size, dtype=torch.int32, device=dev) if with_indices else None
         start = torch.empty(1, dtype=torch.int32, device=dev) if with_indices else None
         check(lib().rb_dataset_training_batch(self._h, self.seed, int(draw), batch_size, steps, ptr(ob), ptr(t), ptr(prev), ptr(prew), ptr(eps),
@@ -176,6 +181,25 @@ class Dataset:
             self.flush()
             loaded += n
         return loaded
+
+    # ---- exact resume ------------------------------------------------------------------------------------------
+    def state_dict(self):
+        """The whole ring + cursor + sampling counter (host tensors): a restored loop draws the same windows."""
+        rows = int(lib().rb_dataset_ring_rows(self._h))
+        ob, rew = np.empty((rows, 11), np.float32), np.empty(rows, np.float32)
+        t, s, w = np.empty((rows, 4), np.float32), np.empty((rows, 4), np.float32), np.empty(rows, np.uint8)
+        k, gen = C.c_int(), C.c_int64()
+        check(lib().rb_dataset_save_host(self._h, ob.ctypes.data, rew.ctypes.data, t.ctypes.data, s.ctypes.data, w.ctypes.data, C.byref(k), C.byref(gen)))
+        return dict(ob=torch.from_numpy(ob), rew=torch.from_numpy(rew), t=torch.from_numpy(t), s=torch.from_numpy(s), stepped_with=torch.from_numpy(w),
+                    step=k.value, generations=gen.value, draw=self._draw, dumped=self._dumped, num_envs=self.num_envs, rows=rows)
+
+    def load_state_dict(self, sd):
+        rows = int(lib().rb_dataset_ring_rows(self._h))
+        if int(sd["rows"]) != rows or int(sd["num_envs"]) != self.num_envs:
+            raise ValueError("Dataset checkpoint is for %d envs / %d ring rows" % (sd["num_envs"], sd["rows"]))
+        a = [np.ascontiguousarray(sd[k].numpy()) for k in ("ob", "rew", "t", "s", "stepped_with")]
+        check(lib().rb_dataset_load_host(self._h, *[x.ctypes.data for x in a], int(sd["step"]), int(sd["generations"])))
+        self._draw, self._dumped = int(sd["draw"]), int(sd["dumped"])
 
     def close(self):
         if getattr(self, "_h", None):

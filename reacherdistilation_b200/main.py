@@ -14,21 +14,30 @@ def main(argv=None):
     parser.add_argument("-r", "--restore", help="restore", action="store_true")
     parser.add_argument("--num_envs", type=int, default=config.NUM_ENVS)
     parser.add_argument("--iterations", type=int, default=None)
+    parser.add_argument("--teacher", default=None, help=".npz with the teacher weights teacher.py:17-20 restores from teacher.ckpt (flat `params` or the "
+                        "baselines variables pi/obfilter/*, pi/pol/*); default: <base_path>/teacher.npz, else a seeded UNTRAINED teacher (announced)")
+    parser.add_argument("--checkpoint", default=None, help="loop checkpoint written at the end of -ct / every episode of -lt, read by -r and -ch "
+                        "(default: <base_path>/student_mlp_b200.pt, student_lstm_b200.pt)")
     args = parser.parse_args(argv)
     keep_prob = float(args.keep_prob[0]) if args.keep_prob else config.KEEP_PROB
     if args.check:
         import os
         import torch
-        path = os.path.join(config.base_path, "student_mlp_b200.pt")
+        default = "student_lstm_b200.pt" if args.lstm_train else "student_mlp_b200.pt"
+        path = args.checkpoint or os.path.join(config.base_path, default)
         print(" checking saved variables ")
         sd = torch.load(path)
         def shapes(d):
             return {k: (shapes(v) if isinstance(v, dict) else tuple(v.shape) if hasattr(v, "shape") else v) for k, v in d.items()}
-        print(shapes(sd))
+        out = shapes(sd)
+        print(out)
+        return out
     elif args.lstm_train:
-        lstm_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob)
+        return lstm_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob, teacher_ckpt=args.teacher,
+                                checkpoint=args.checkpoint)
     elif args.mlp_train:
-        mlp_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob)
+        return mlp_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob, teacher_ckpt=args.teacher,
+                               checkpoint=args.checkpoint)
 
 
 if __name__ == "__main__":

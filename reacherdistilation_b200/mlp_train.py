@@ -21,7 +21,7 @@ from .config import KEEP_PROB, MLP_BATCH_SIZE, NUM_ENVS, SEED, base_path
 from .dist import all_ranks_agree, rank_checkpoint_path
 from .env import VecReacher
 from .student_nn import StudentNet
-from .teacher import TeacherAgent
+from .teacher import TeacherAgent, load_teacher_params
 
 
 class DaggerTrainer:
@@ -46,6 +46,11 @@ class DaggerTrainer:
             self.t_pd = torch.empty((n, 4), device=dev)
             self.s_pd = torch.empty((n, 4), device=dev)
             self.x = torch.empty((n, self.student.in_dim), device=dev)
+            # The reference drops observations only in the TRAINING batch (keep_prob = KEEP_PROB, mlp_train.py:151) and acts on the clean
+            # observation (keep_prob 1, mlp_train.py:171-186): with dropout on, the observe kernel also writes the un-dropped input rows and the
+            # student acts on those (s_pd); the loss and the gradient use the dropped rows (x).  The 2x64 student has no input dropout.
+            self.x_act = torch.empty((n, self.student.in_dim), device=dev) if (student_kind == STUDENT_MLP and keep_prob < 1.0) else None
+            self.s_train = torch.empty((n, 4), device=dev) if self.x_act is not None else None
             self.rew = torch.empty((n,), device=dev)
             self.done = torch.empty((n,), dtype=torch.uint8, device=dev)
         self.pg = process_group
@@ -75,15 +80,20 @@ class DaggerTrainer:
         if self.use_graph:
             return self._step_graph(L, st)
         self._clock_synced = False
-        check(L.rb_dagger_observe(self._h, ptr(self.teacher.params), self.iteration, ptr(self.obs), ptr(self.t_pd), ptr(self.x), self.mode, st))
+        check(L.rb_dagger_observe(self._h, ptr(self.teacher.params), self.iteration, ptr(self.obs), ptr(self.t_pd), ptr(self.x), ptr(self.x_act),
+                                  self.mode, st))
+        s_train = self.s_pd
+        if self.x_act is not None:         # acting forward on the un-dropped rows, with the parameters this iteration's gradient is taken at
+            self.student.forward(self.x_act, out=self.s_pd)
+            s_train = self.s_train
         if self.fused_allreduce:
-            self.student.step_dp(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd, grad_scale=self.grad_scale)
+            self.student.step_dp(self.x, self.t_pd, self.loss_kind, s_out=s_train, grad_scale=self.grad_scale)
         elif self.world > 1:
-            self.student.loss_grad(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd)
+            self.student.loss_grad(self.x, self.t_pd, self.loss_kind, s_out=s_train)
             torch.distributed.all_reduce(self.student.gradloss, group=self.pg)
             self.student.adam_step(self.grad_scale)
         else:
-            self.student.step(self.x, self.t_pd, self.loss_kind, s_out=self.s_pd, grad_scale=self.grad_scale)
+            self.student.step(self.x, self.t_pd, self.loss_kind, s_out=s_train, grad_scale=self.grad_scale)
         check(L.rb_dagger_act(self._h, ptr(self.s_pd), ptr(self.t_pd), ptr(self.rew), ptr(self.done), st))
         self.iteration += 1
 
@@ -100,7 +110,7 @@ class DaggerTrainer:
             se = so = fl = None
             rank, world = 0, 1
         check(L.rb_dagger_step(self._h, ptr(self.teacher.params), ptr(stu.params), ptr(stu.m), ptr(stu.v), ptr(stu.gradloss), ptr(stu.workspace),
-                               ptr(self.obs), ptr(self.t_pd), ptr(self.x), ptr(self.s_pd), ptr(self.rew), ptr(self.done), self.loss_kind,
+                               ptr(self.obs), ptr(self.t_pd), ptr(self.x), ptr(self.x_act), ptr(self.s_pd), ptr(self.rew), ptr(self.done), self.loss_kind,
                                stu.lr, stu.beta1, stu.beta2, stu.eps, self.grad_scale, rank, world, se, so, fl, 1, st))
         self.iteration += 1
         stu.t += 1
@@ -153,9 +163,26 @@ class DaggerTrainer:
         self.env.close()
 
 
+def _teacher_for_run(teacher_params, teacher_ckpt, verbose, rank=0):
+    """Teacher weights of a training run: supplied vector / checkpoint file / `base_path/teacher.npz`; without any of them the run distils a
+    SEEDED UNTRAINED teacher and says so (the reference's teacher.ckpt is not in its repository) -- the returned description goes into the
+    result dict so that no run mistakes the synthetic teacher for a trained one."""
+    if teacher_params is None and teacher_ckpt is None and os.path.exists(os.path.join(base_path, "teacher.npz")):
+        teacher_ckpt = os.path.join(base_path, "teacher.npz")
+    p, desc = load_teacher_params(teacher_params, teacher_ckpt)
+    if p is None:
+        desc = "SYNTHETIC: seeded baselines-initialised (untrained) teacher -- no teacher_params / teacher_ckpt given"
+        if verbose and rank == 0:
+            print("teacher: " + desc)
+    return p, desc
+
+
 def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_episodes=5000, seed=SEED, device=0, student_kind=STUDENT_MLP,
-          keep_prob=KEEP_PROB, mode=MODE_FP32, warmup_episodes=2 * MLP_BATCH_SIZE + 1, log_every=50, checkpoint=None, verbose=True):
+          keep_prob=KEEP_PROB, mode=MODE_FP32, warmup_episodes=2 * MLP_BATCH_SIZE + 1, log_every=50, checkpoint=None, verbose=True,
+          teacher_params=None, teacher_ckpt=None):
     """Same entry point as the reference (`mlp_train.train(train, restore)`, main.py:26-27).
+    teacher_params / teacher_ckpt: the weights `teacher.py:17-20` restores (flat vector, or an .npz of the baselines variables).
+    The loop state is saved to `checkpoint` (default base_path/student_mlp_b200.pt, the file `restore` and `main.py -ch` read) at the end.
 
     Phase A (mlp_train.py:120-139): every env plays `warmup_episodes / num_envs` (>= 1) teacher episodes into the device buffer.
     Phase B (mlp_train.py:143-204): DAgger iterations until `total_episodes` episodes (5000 in the reference) or `iterations`.
@@ -163,8 +190,9 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
     rank, world = 0, 1
     if torch.distributed.is_available() and torch.distributed.is_initialized():
         rank, world = torch.distributed.get_rank(), torch.distributed.get_world_size()
+    tparams, tdesc = _teacher_for_run(teacher_params, teacher_ckpt, verbose, rank)
     tr = DaggerTrainer(num_envs=num_envs, seed=seed, device=device, student_kind=student_kind, keep_prob=keep_prob, mode=mode,
-                       env_offset=rank * num_envs)
+                       env_offset=rank * num_envs, teacher_params=tparams)
     ckpt = checkpoint or os.path.join(base_path, "student_mlp_b200.pt")
     my_ckpt = rank_checkpoint_path(ckpt, rank, world)    # per-shard loop state: one file per rank when world > 1
     resumed = False
@@ -200,15 +228,16 @@ def train(train=True, restore=False, num_envs=NUM_ENVS, iterations=None, total_e
             if verbose and rank == 0:
                 print("************** Episode %d ****************" % ((it + 1) // 50 * num_envs * world))
                 print("recent loss: %f " % losses[-1])
-    if checkpoint is not None:
-        os.makedirs(os.path.dirname(my_ckpt) or ".", exist_ok=True)
-        torch.save(tr.state_dict(), my_ckpt)
-    out = dict(losses=losses, rewards=rewards, teacher_reward=teacher_reward, iterations=iterations, trainer=tr)
+    os.makedirs(os.path.dirname(my_ckpt) or ".", exist_ok=True)       # always: `-r` and `-ch` read this file (the reference saves every episode)
+    torch.save(tr.state_dict(), my_ckpt)
+    out = dict(losses=losses, rewards=rewards, teacher_reward=teacher_reward, iterations=iterations, trainer=tr, checkpoint=my_ckpt, teacher=tdesc,
+               resumed=resumed)
     return out
 
 
 def train_replay(train=True, restore=False, num_envs=64, total_episodes=5000, iterations=None, seed=SEED, device=0, keep_prob=KEEP_PROB,
-                 mode=MODE_FP32, batch_size=MLP_BATCH_SIZE, steps_unrolled=None, generations=64, lr=None, verbose=True):
+                 mode=MODE_FP32, batch_size=MLP_BATCH_SIZE, steps_unrolled=None, generations=64, lr=None, verbose=True, teacher_params=None,
+                 teacher_ckpt=None):
     """The reference loop in its own shape (mlp_train.py:110-204), N envs wide, with the device Dataset as replay buffer:
 
     phase A (:120-139)  teacher acts; every record {ob, reward, t_pdflat, s=0, 't'} is written; flush on done, until more than
@@ -224,7 +253,7 @@ def train_replay(train=True, restore=False, num_envs=64, total_episodes=5000, it
     from .student_nn import student_mlp_input
     T = steps_unrolled or STEPS_UNROLLED
     env = VecReacher(num_envs=num_envs, seed=seed, device=device)
-    teacher = TeacherAgent(env, restore=restore, mode=mode)
+    teacher = TeacherAgent(env, params=_teacher_for_run(teacher_params, teacher_ckpt, verbose)[0], mode=mode)
     student = StudentNet(kind=STUDENT_MLP, seed=1, device=env.device, mode=mode, lr=lr)
     dataset = Dataset(num_envs=num_envs, generations=generations, device=device, seed=seed)
     ob = env.reset()

@@ -26,8 +26,14 @@ def init_policy_params(seed=0, nout=2, logstd=TEACHER_LOGSTD, ob_mean=None, ob_s
     parts = [mu, sd, normc(rng, (11, 64), 1.0).ravel(), np.zeros(64, np.float32), normc(rng, (64, 64), 1.0).ravel(), np.zeros(64, np.float32),
              normc(rng, (64, nout), final_std).ravel(), np.zeros(nout, np.float32), np.asarray(logstd, np.float32)]
     p = np.concatenate(parts).astype(np.float32)
-    assert p.size == lib().rb_policy_param_count(nout)
+    assert p.size == policy_param_count(nout)
     return p
+
+
+def policy_param_count(nout):
+    """rb_policy_param_count of the C ABI, restated on the host (ob_mean 11, ob_std 11, W1 b1 W2 b2 W3 b3, logstd 2) so that building a
+    parameter vector needs no CUDA library (tests/test_abi.py checks the two agree)."""
+    return 22 + 11 * 64 + 64 + 64 * 64 + 64 + 64 * nout + nout + 2
 
 
 def policy_params_from_named(variables, nout=2, scope="pi"):
@@ -58,13 +64,25 @@ def policy_params_from_named(variables, nout=2, scope="pi"):
         raise ValueError("expected logstd [1,2] and an 11-d obfilter")
     parts.append(logstd)
     p = np.concatenate(parts).astype(np.float32)
-    assert p.size == lib().rb_policy_param_count(nout)
+    assert p.size == policy_param_count(nout)
     return p
 
 
-class _Pd:
-    def __init__(self, agent):
-        self._a = agent
+def load_teacher_params(teacher_params=None, teacher_ckpt=None, nout=2):
+    """The teacher weights a run distils (`teacher.py:17-20` restores teacher.ckpt; that file is not part of the reference repository).
+    teacher_params: flat fp32 vector in the C-ABI layout.  teacher_ckpt: path of an .npz holding either `params` (flat) or the named
+    variables of the baselines checkpoint (policy_params_from_named).  Returns (params, description); (None, None) when neither is given."""
+    if teacher_params is not None:
+        p = np.ascontiguousarray(np.asarray(teacher_params, dtype=np.float32).ravel())
+        if p.size != policy_param_count(nout):
+            raise ValueError("teacher_params has %d entries, the %d-output policy has %d" % (p.size, nout, policy_param_count(nout)))
+        return p, "supplied parameter vector"
+    if teacher_ckpt is not None:
+        with np.load(teacher_ckpt) as z:
+            if "params" in z.files:
+                return load_teacher_params(z["params"], None, nout)[0], "flat parameters of %s" % teacher_ckpt
+            return policy_params_from_named({k: z[k] for k in z.files}, nout=nout), "named variables of %s" % teacher_ckpt
+    return None, None
 
 
 class _Pi:
@@ -85,9 +103,10 @@ class TeacherAgent:
         self.device = torch.device(dev)
         self.nout, self.mode = nout, mode
         if params is None:
-            if restore:
-                print("teacher.ckpt is not part of the reference repository; using seeded baselines-initialised weights")
-            params = init_policy_params(seed=seed, nout=nout)
+            if restore:          # the reference ALWAYS restores teacher.ckpt (teacher.py:17-20): never substitute random weights for it silently
+                raise _lib.ReacherB200Error("TeacherAgent(restore=True) needs weights: teacher.ckpt is not part of the reference repository -- pass "
+                                            "params= (teacher.load_teacher_params / policy_params_from_named)")
+            params = init_policy_params(seed=seed, nout=nout)     # untrained baselines-initialised teacher, seeded (synthetic workloads, tests)
         self.params_host = np.ascontiguousarray(params, dtype=np.float32)
         self.params = torch.from_numpy(self.params_host).to(self.device)
         self.pi = _Pi(self)

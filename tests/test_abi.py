@@ -48,3 +48,22 @@ def test_bad_arguments_are_rejected():
     assert L.rb_env_create(None, 4, 0, 0, 0) == -1
     assert L.rb_env_create(C.byref(h), 16, 0, 0, 2 ** 32 - 4) == -1      # global env id would overflow
     assert b"num_envs" in L.rb_last_error() or b"overflow" in L.rb_last_error()
+
+
+def test_host_side_param_count_matches_the_library_and_teacher_loader(tmp_path):
+    """teacher.policy_param_count restates rb_policy_param_count so that building / loading a teacher vector maps no CUDA library (the
+    reference arm of bench.py relies on that); load_teacher_params reads a flat vector or the baselines variable names."""
+    import numpy as np
+    from reacherdistilation_b200 import teacher as T
+    L = _lib.lib()
+    for nout in (2, 4):
+        assert T.policy_param_count(nout) == L.rb_policy_param_count(nout)
+    p = T.init_policy_params(seed=5)
+    np.savez(tmp_path / "flat.npz", params=p)
+    q, desc = T.load_teacher_params(teacher_ckpt=str(tmp_path / "flat.npz"))
+    assert np.array_equal(p, q) and "flat" in desc
+    assert T.load_teacher_params() == (None, None)
+    with pytest.raises(ValueError):
+        T.load_teacher_params(teacher_params=p[:-1])
+    with pytest.raises(_lib.ReacherB200Error):
+        T.TeacherAgent(restore=True)                       # the reference always restores teacher.ckpt: never silently randomised

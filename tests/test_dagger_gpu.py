@@ -30,6 +30,8 @@ def _oracle_loop(kind, n, iters, seed, teacher_p, student_p, keep_prob, lr, eps,
             s, hs = NN.mlp_fwd(x, th32)
             l, ds = NN.kl_loss(s, t)
             g = NN.mlp_bwd(hs, th32, ds)
+            if keep_prob < 1.0:            # dropout is for the training batch (mlp_train.py:151); the student ACTS on the clean observation (:171-186)
+                s, _ = NN.mlp_fwd(NN.student_input(ob32, pp, pr, 1.0, seed, env.env_ids, it), th32)
         else:
             s = NN.policy_fwd(ob32, th32, nout=4)
             l, ds = NN.kl_loss(s, t)

@@ -19,7 +19,7 @@ def _modes():
 
 def _ref(kind, P, x, t, loss_kind):
     from reacherdistilation_b200 import STUDENT_MLP
-    loss = NN.kl_loss if loss_kind == 0 else NN.kl_loss_rev
+    loss = lambda a, b: NN.pd_loss(a, b, loss_kind)     # 0 / 1: the two KL directions, 2: squared error on pdflat, 3: on the actions
     if kind == STUDENT_MLP:
         s, hs = NN.mlp_fwd(x, P)
         l, ds = loss(s, t)
@@ -31,7 +31,7 @@ def _ref(kind, P, x, t, loss_kind):
 
 @pytest.mark.parametrize("kind_name", ["mlp", "policy64"])
 @pytest.mark.parametrize("B", [1, 63, 64, 65, 200, 1000, 4097])
-@pytest.mark.parametrize("loss_kind", [0, 1])
+@pytest.mark.parametrize("loss_kind", [0, 1, 2, 3])
 def test_loss_grad_matches_oracle(kind_name, B, loss_kind):
     from reacherdistilation_b200 import STUDENT_MLP, STUDENT_POLICY64
     from reacherdistilation_b200.student_nn import StudentNet
