@@ -31,20 +31,44 @@ sys.path.insert(0, ROOT)
 
 ENVS_PER_GPU = 65536
 CHUNK_T = 50
+CHUNKS_PER_STEP = 20          # one bench step = 20 launches of the 50-step chunk (1000 steps of every env): `--steps 20` times >= 100 ms
 DISTILL_ENVS_PER_GPU = 32768
 STEP_API_ENVS = 1 << 22
 ALG_BYTES_ROLLOUT = 65.0      # fused rollout writes one buffer row per env-step: ob 44 + pdflat 16 + rew 4 + done 1 B (17 scalars)
-ROLLOUT_TRAFFIC_NCU = 160.0e6   # dram__bytes_read.sum + dram__bytes_write.sum of one k_rollout_policy_tc launch (65 536 envs x 50 steps),
-                                # profiles/r01_ncu_full_k_rollout_policy_tc_final.csv; the rest of the 213 MB is still dirty in L2 at kernel end
-MUFU_PER_ENV_STEP = 169.0       # 128 tanh x 1.25 (ex2 each, one rcp per four) + 8 rcp + 1 sqrt
+MUFU_PER_ENV_STEP = 161.0       # 128 tanh x 1.25 (ex2 each, one rcp per four) + 1 sqrt; the physics no longer uses a reciprocal (csrc/physics.cuh)
 XU_LANES_PER_CLK_PER_SM = 16.0  # B200 MUFU rate
 ALG_BYTES_STEP = 113.0        # single-step API, I/O 57 B + state round trip 56 B
-STEP_TRAFFIC_NCU = 515.4e6    # dram read + write of one k_step launch at 4 194 304 envs (profiles/r01_ncu_full_k_step.csv) = 122.9 B per env-step
-STUDENT_TRAFFIC_NCU = 4.46e6  # dram read + write of one k_student_tc<SpecMLP> launch of the DAgger graph at 32 768 samples
-                              # (profiles/r01_ncu_full_k_student_tc_final.csv): inputs and env state read once, everything else stays in L2
+# ncu counters of the dominant kernels come from the committed captures under profiles/ (never typed in here): see ncu_counters()
+NCU_FILES = dict(rollout="profiles/r02_ncu_counts_k_rollout_policy_tc.csv", step="profiles/r02_ncu_counts_k_step.csv",
+                 student="profiles/r02_ncu_counts_k_student_tc.csv")
 FP32_PEAK_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 FLOP_PER_ENV_STEP = 450.0 + 9856.0          # physics + teacher MLP
 FLOP_PER_SAMPLE = {"mlp": 144.4e3, "policy64": 30.3e3}
+
+
+def ncu_counters(which):
+    """Per-launch counters of a kernel from the committed ncu capture (`--csv` long format: one row per launch and metric; averaged over the
+    captured launches).  Returns {} when the file is missing: the bench then prints null for those fields instead of inventing them."""
+    import csv
+    path = os.path.join(ROOT, NCU_FILES[which])
+    if not os.path.exists(path):
+        return {}
+    acc = {}
+    with open(path) as fh:
+        rows = [r for r in csv.reader(l for l in fh if l.startswith('"'))]
+    if not rows or "Metric Name" not in rows[0]:
+        return {}
+    iname, ival, iunit = rows[0].index("Metric Name"), rows[0].index("Metric Value"), rows[0].index("Metric Unit")
+    for r in rows[1:]:
+        try:
+            v = float(r[ival].replace(",", ""))
+        except ValueError:
+            continue
+        v *= {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "us": 1e3, "ms": 1e6}.get(r[iunit], 1.0)       # bytes / ns
+        acc.setdefault(r[iname], []).append(v)
+    out = {k: sum(v) / len(v) for k, v in acc.items()}
+    out["file"] = NCU_FILES[which]
+    return out
 
 
 def peaks():
@@ -99,27 +123,46 @@ class ClockSampler:
             self.proc.kill()
 
 
-def cpu_reference_leg(seconds=12.0, nthreads=0):
-    """Time the C restatement of the reference's CPU rollout (teacher in the loop) on the host cores, bounded sample."""
-    import numpy as np
+def host_cores():
+    """Host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which must not decide the CPU baseline's width)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def teacher_params():
+    from reacherdistilation_b200.teacher import init_policy_params      # numpy only: maps no CUDA library
+    return init_policy_params(seed=0)
+
+
+def cpu_rollout(n, chunks, nthreads, p, first_chunk_reward_envs=0):
+    """`chunks` teacher-in-the-loop 50-step chunks of n envs (global env ids 0..n-1, seed 0, from reset) on the float64 C restatement.
+    Returns (seconds, mean reward of the first chunk over the first `first_chunk_reward_envs` envs)."""
     from oracle import reacher_c as RC
-    from reacherdistilation_b200.teacher import init_policy_params
-    p = init_policy_params(seed=0)
-    cores = RC.max_threads() if nthreads <= 0 else nthreads
-    cal = RC.ReacherOracleC(2048, seed=0, nthreads=nthreads); cal.reset()
-    t0 = time.perf_counter(); cal.rollout_policy(CHUNK_T, p, record=False); dt = time.perf_counter() - t0
-    rate = 2048 * CHUNK_T / dt
-    n = int(min(ENVS_PER_GPU, max(2048, rate * seconds / CHUNK_T)))
     env = RC.ReacherOracleC(n, seed=0, nthreads=nthreads); env.reset()
-    obs, pd, rw, dn = (np.zeros((CHUNK_T, n, 11)), np.zeros((CHUNK_T, n, 4)), np.zeros((CHUNK_T, n)), np.zeros((CHUNK_T, n), np.uint8))
-    reps, t0 = 0, time.perf_counter()
-    while reps == 0 or time.perf_counter() - t0 < seconds:          # bounded sample: ~`seconds` of CPU work on all host cores
-        env.rollout_policy(CHUNK_T, p, record=True)
-        reps += 1
-    dt = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    first = None
+    for c in range(chunks):
+        _ob, _pd, rw, _dn, _ = env.rollout_policy(CHUNK_T, p, record=True)
+        if c == 0 and first_chunk_reward_envs:
+            first = float(rw[:, :first_chunk_reward_envs].mean())
+    return time.perf_counter() - t0, first
+
+
+def cpu_reference_leg(seconds=12.0):
+    """Time the C restatement of the reference's CPU rollout (teacher in the loop) on ALL host cores, bounded sample."""
+    from oracle import reacher_c as RC
+    p, cores = teacher_params(), host_cores()
+    cpu_rollout(2048, 1, cores, p)                                       # warm-up (library load, thread pool)
+    dt, _ = cpu_rollout(8192, 2, cores, p)
+    rate = 8192 * 2 * CHUNK_T / dt
+    n = int(min(ENVS_PER_GPU, max(2048, rate * seconds / CHUNK_T)))
+    reps = max(1, int(round(seconds * rate / (n * CHUNK_T))))
+    dt, _ = cpu_rollout(n, reps, cores, p)
     return dict(value=n * CHUNK_T * reps / dt, unit="env-steps/s", cores=cores, kind="port",
-                sample="%d x (%d envs x %d steps) teacher-in-the-loop rollout chunks, float64 C restatement (oracle/reacher_oracle.c, OpenMP), %.1f s"
-                       % (reps, n, CHUNK_T, dt)), n, dt
+                sample="%d x (%d envs x %d steps) teacher-in-the-loop rollout chunks, float64 C restatement (oracle/reacher_oracle.c, OpenMP %d threads), %.1f s"
+                       % (reps, n, CHUNK_T, cores, dt))
 
 
 def cpu_distill_leg(kind="mlp", seconds=6.0):
@@ -146,7 +189,7 @@ def cpu_distill_leg(kind="mlp", seconds=6.0):
         theta = opt.update(theta, g)
         n_it += 1
     dt = time.perf_counter() - t0
-    return dict(value=B * n_it / dt, unit="samples/s", cores=os.cpu_count(), kind="port",
+    return dict(value=B * n_it / dt, unit="samples/s", cores=host_cores(), kind="port",
                 sample="%d optimiser steps of batch %d, numpy float64 restatement (oracle/nn_np.py), %.1f s" % (n_it, B, dt))
 
 
@@ -192,38 +235,162 @@ def config1_leg(steps=1000):
                 gpu_gym_loop_batch1=gym_loop, gpu_fused_one_launch=fused, teacher_return_per_episode=ret / (steps / 50.0))
 
 
+REWARD_CHECK_ENVS = 1024      # both arms print the mean reward of the first 50-step chunk after reset over envs 0..1023 (cross-check)
+
+
+def workload_config(n):
+    return dict(workload="config3: %d envs/GPU, fused teacher MLP (11-64-64-2 tanh) in the loop, rollout buffer device-resident; one step = %d "
+                         "chunks of %d env steps" % (n, CHUNKS_PER_STEP, CHUNK_T), envs_per_gpu=n, chunk_steps=CHUNK_T, chunks_per_step=CHUNKS_PER_STEP)
+
+
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path (restated; see module docstring)."""
+    """--impl reference: the reference's CPU implementation of the path (restated in float64 C, oracle/; the reference itself is Python over
+    TF-1.10 / gym / MuJoCo-1.50 and cannot be installed here) on ALL host cores.  Each step = the bench step (CHUNKS_PER_STEP chunks) on a
+    bounded sample of the envs, sized so that the whole run takes a couple of minutes.  Maps no library of the repo but oracle/."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     steps, warm = max(1, args.steps), max(0, args.warmup)
-    import numpy as np
+    p, cores = teacher_params(), host_cores()
+    _, rew0 = cpu_rollout(2048, 1, cores, p, REWARD_CHECK_ENVS)          # also warms the library and the thread pool up
+    dt, _ = cpu_rollout(8192, 2, cores, p)
+    rate = 8192 * 2 * CHUNK_T / dt
+    per_step_s = min(6.0, 150.0 / (steps + warm))                        # whole run within a few minutes
+    n = int(min(ENVS_PER_GPU, max(1024, rate * per_step_s / (CHUNK_T * CHUNKS_PER_STEP))))
     from oracle import reacher_c as RC
-    from reacherdistilation_b200.teacher import init_policy_params
-    p = init_policy_params(seed=0)
-    cores = RC.max_threads()
-    cal = RC.ReacherOracleC(2048, seed=0); cal.reset()
-    t0 = time.perf_counter(); cal.rollout_policy(CHUNK_T, p, record=False); rate = 2048 * CHUNK_T / (time.perf_counter() - t0)
-    budget = 120.0 / (steps + warm)                                  # whole run within a few minutes
-    n = int(min(ENVS_PER_GPU, max(1024, rate * min(budget, 10.0) / CHUNK_T)))
-    env = RC.ReacherOracleC(n, seed=0); env.reset()
+    env = RC.ReacherOracleC(n, seed=0, nthreads=cores); env.reset()
+    def step():
+        for _ in range(CHUNKS_PER_STEP):
+            env.rollout_policy(CHUNK_T, p, record=True)
     for _ in range(warm):
-        env.rollout_policy(CHUNK_T, p, record=True)
+        step()
     t0 = time.perf_counter()
     for _ in range(steps):
-        env.rollout_policy(CHUNK_T, p, record=True)
+        step()
     dt = time.perf_counter() - t0
-    val = n * CHUNK_T * steps / dt
-    sample = "%d of %d envs per step x %d steps/chunk, float64 C restatement of the MuJoCo+TF CPU path, OpenMP %d threads" % (n, ENVS_PER_GPU, CHUNK_T, cores)
+    val = n * CHUNK_T * CHUNKS_PER_STEP * steps / dt
+    sample = ("each step = %d of the %d envs x %d chunks x %d steps, float64 C restatement of the MuJoCo + TF CPU path (oracle/reacher_oracle.c), "
+              "OpenMP %d threads" % (n, ENVS_PER_GPU, CHUNKS_PER_STEP, CHUNK_T, cores))
+    cfg = workload_config(ENVS_PER_GPU)
+    cfg["reference_sample"] = sample
+    cfg["mean_reward_first_chunk_envs_0_%d" % REWARD_CHECK_ENVS] = rew0
     line = dict(impl="reference", metric="reacher_env_steps_per_sec", value=val, unit="env-steps/s", n_gpus=args.gpus, steps=steps, warmup=warm,
-                ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic",
-                config=dict(workload="config3: %d envs/GPU, fused teacher MLP (11-64-64-2 tanh) in the loop, 50-step chunk per step, "
-                                     "rollout buffer device-resident" % ENVS_PER_GPU, envs_per_gpu=ENVS_PER_GPU, chunk_steps=CHUNK_T,
-                            reference_sample="each step = %d of the %d envs x %d steps on the host cores (bounded sample)" % (n, ENVS_PER_GPU, CHUNK_T)),
+                ms_per_step=1e3 * dt / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f64", data="synthetic", config=cfg,
                 cpu_baseline=dict(value=val, unit="env-steps/s", cores=cores, kind="port", sample=sample),
                 e2e=dict(value=val, unit="env-steps/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     print(json.dumps(line))
+
+
+def distill_parity(DaggerTrainer, kind, mode, nd, rank, world, local, dev, iters=3):
+    """Data-parallel parity of the student step at this world size, from a fixed seed (MpiAdam.update = Allreduce + Adam,
+    backup/student_rollout.py:658-659,709):  (a) `iters` DAgger iterations with the exchange fused into k_student_tc vs the same with NCCL
+    all-reduce + rb_adam_step;  (b) vs ONE GPU running the concatenated batch (world x nd envs, same global env ids => same samples and
+    dropout masks; KL is a sum, so the summed shard gradients are the gradient of the concatenated batch up to fp32 summation order)."""
+    import torch
+    out = dict(iterations=iters, world=world, envs_per_rank=nd)
+
+    def run(**kw):
+        tr = DaggerTrainer(num_envs=kw.pop("n", nd), seed=0, device=local, student_kind=kind, mode=mode, lr=1e-3, **kw)
+        tr.sync_params()
+        losses = []
+        for _ in range(iters):
+            tr.step()
+            losses.append(float(tr.last_loss()))
+        p = tr.student.params.double().cpu()
+        tr.close()
+        return losses, p
+    lf, pf = run(env_offset=rank * nd)                                    # fused exchange (default at world > 1 in tc mode)
+    ln, pn = run(env_offset=rank * nd, fused_allreduce=False)             # NCCL
+    rel = lambda a, b: max(abs(x - y) / max(1.0, abs(y)) for x, y in zip(a, b))
+    out["fused_vs_nccl"] = dict(loss_rel=rel(lf, ln), param_abs=float((pf - pn).abs().max()), tol=dict(loss_rel=1e-5, param_abs=1e-5))
+    torch.distributed.barrier()
+    if rank == 0:                                                         # a single-rank trainer inside the multi-rank job; the others wait below
+        tr = DaggerTrainer(num_envs=world * nd, seed=0, device=local, student_kind=kind, mode=mode, lr=1e-3, env_offset=0, solo=True)
+        l1 = []
+        for _ in range(iters):
+            tr.step()
+            l1.append(float(tr.last_loss()))
+        p1 = tr.student.params.double().cpu()
+        tr.close()
+        scale = float(max(1.0, p1.abs().max()))
+        out["fused_vs_single_gpu_concatenated_batch"] = dict(loss_rel=rel(lf, l1), param_abs=float((pf - p1).abs().max()), param_scale=scale,
+                                                              tol=dict(loss_rel=2e-6, param_abs=2e-5 * scale), envs=world * nd)
+    torch.distributed.barrier()
+    ok = out["fused_vs_nccl"]["loss_rel"] <= 1e-5 and out["fused_vs_nccl"]["param_abs"] <= 1e-5
+    if rank == 0:
+        c = out["fused_vs_single_gpu_concatenated_batch"]
+        ok = ok and c["loss_rel"] <= c["tol"]["loss_rel"] and c["param_abs"] <= c["tol"]["param_abs"]
+    flag = torch.tensor([1 if ok else 0], device=dev)
+    torch.distributed.all_reduce(flag, op=torch.distributed.ReduceOp.MIN)
+    out["ok"] = bool(flag.item())
+    return out
+
+
+def run_sweep(args):
+    """--sweep: BASELINE.json config 5 -- total envs 2^10 .. 2^22 over the launched GPUs (contiguous global-id shards, weak per-size work split):
+    fused teacher rollout and single-step API, CUDA-event time, max over ranks; on rank 0 the host-core restatement at EVERY size (bounded)."""
+    import torch
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC, _lib
+    from reacherdistilation_b200.dist import init_from_env, max_over_ranks, shard_range
+    from reacherdistilation_b200.env import VecReacher
+    rank, world, local = init_from_env()
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L = _lib.lib()
+    mode = MODE_TC if L.rb_mode_available(MODE_TC) else MODE_FP32
+    p_host = teacher_params()
+    teacher = torch.from_numpy(p_host).to(dev)
+    cores = host_cores()
+    rows = []
+
+    def timed(fn, iters):
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return max_over_ranks(e0.elapsed_time(e1) / 1e3, dev)
+    for lg in range(10, 23):
+        total = 1 << lg
+        lo, hi = shard_range(total, rank, world)
+        n = hi - lo
+        env = VecReacher(num_envs=max(n, 1), seed=0, device=local, env_offset=lo)
+        env.reset()
+        buf = dict(obs=torch.empty((CHUNK_T, max(n, 1), 11), device=dev), pdflat=torch.empty((CHUNK_T, max(n, 1), 4), device=dev),
+                   rew=torch.empty((CHUNK_T, max(n, 1)), device=dev), done=torch.empty((CHUNK_T, max(n, 1)), dtype=torch.uint8, device=dev))
+        roll = lambda: env.rollout_policy(teacher, CHUNK_T, nout=2, mode=mode, out=buf)
+        for _ in range(3):
+            roll()
+        it = 20 if lg <= 18 else 6
+        rsec = timed(roll, it)
+        act = torch.rand((max(n, 1), 2), device=dev) * 2 - 1
+        stp = lambda: env.step(act)
+        for _ in range(3):
+            stp()
+        ssec = timed(stp, 50)
+        env.close()
+        del buf
+        row = dict(total_envs=total, envs_per_gpu=n, rollout_env_steps_per_s=float(total) * CHUNK_T * it / rsec, rollout_ms_per_chunk=1e3 * rsec / it,
+                   step_api_env_steps_per_s=float(total) * 50 / ssec)
+        if rank == 0:                                                    # host-core baseline at every size: ~1.5 s each
+            nc = min(total, 65536)
+            dt, _ = cpu_rollout(nc, 1, cores, p_host)
+            reps = max(1, int(1.5 / max(dt, 1e-3)))
+            dt, _ = cpu_rollout(nc, reps, cores, p_host)
+            row["cpu_env_steps_per_s"] = nc * CHUNK_T * reps / dt
+            row["cpu_sample"] = "%d x (%d envs x %d steps)" % (reps, nc, CHUNK_T)
+        rows.append(row)
+    if rank == 0:
+        print(json.dumps(dict(metric="reacher_env_steps_per_sec", sweep="config5: total envs 2^10..2^22 over %d GPU(s)" % world, n_gpus=world, unit="env-steps/s",
+                              scaling="strong (fixed total per row, sharded by contiguous global env id)", cpu_cores=cores,
+                              cpu_kind="port (float64 C restatement, OpenMP)", rows=rows)))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
 
 
 def main():
@@ -235,9 +402,12 @@ def main():
     ap.add_argument("--mode", default="auto", choices=["auto", "fp32", "tc"])
     ap.add_argument("--student", default="mlp", choices=["mlp", "policy64"])
     ap.add_argument("--quick", action="store_true", help="skip the secondary measurements (distill, step API, CPU legs)")
+    ap.add_argument("--sweep", action="store_true", help="BASELINE config 5: 1 k .. 4 M envs on the launched GPUs + host-core baseline at every size")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.sweep:
+        return run_sweep(args)
 
     import numpy as np
     import torch
@@ -276,19 +446,25 @@ def main():
         return max_over_ranks(e0.elapsed_time(e1) / 1e3, dev), (h0, h1)
 
     sampler = ClockSampler(local) if rank == 0 else None
-    n = ENVS_PER_GPU
+    n, R = ENVS_PER_GPU, CHUNKS_PER_STEP
     teacher = torch.from_numpy(init_policy_params(seed=0)).to(dev)
     env = VecReacher(num_envs=n, seed=0, device=local, env_offset=rank * n)
     env.reset()
     buf = dict(obs=torch.empty((CHUNK_T, n, 11), device=dev), pdflat=torch.empty((CHUNK_T, n, 4), device=dev),
                rew=torch.empty((CHUNK_T, n), device=dev), done=torch.empty((CHUNK_T, n), dtype=torch.uint8, device=dev))
-    step_fn = lambda: env.rollout_policy(teacher, CHUNK_T, nout=2, mode=mode, out=buf)
+    chunk_fn = lambda: env.rollout_policy(teacher, CHUNK_T, nout=2, mode=mode, out=buf)
+
+    def step_fn():                                                     # one bench step = R chunk launches (1000 env steps of every env)
+        for _ in range(R):
+            chunk_fn()
+    chunk_fn()                                                         # first chunk after reset: the reward both arms print (cross-check)
+    rew_check = float(buf["rew"][:, :REWARD_CHECK_ENVS].mean()) if rank == 0 else None
     for _ in range(W):
         step_fn()
     sec, win = timed(step_fn, K)
-    env_steps = float(n) * CHUNK_T * K * world
+    env_steps = float(n) * CHUNK_T * R * K * world
     value = env_steps / sec
-    kernel_s = sec / K                                                 # one kernel launch per step
+    kernel_s = sec / (K * R)                                           # one kernel launch per chunk
     clocks = sampler.window(*win) if sampler else None
     mean_rew = float(buf["rew"].mean())
 
@@ -302,47 +478,56 @@ def main():
     hres = dict(obs=None, pdflat=None, rew=hbuf["rew"], done=hbuf["done"])
     tparams_host = torch.from_numpy(init_policy_params(seed=0)).pin_memory()
 
-    def e2e_time(out):
+    def e2e_time(out, chunks):
         fn = lambda: env.rollout_policy_host(tparams_host, CHUNK_T, nout=2, mode=mode, out=out)
         for _ in range(2):
             fn()
         barrier()
         t0 = time.perf_counter()
-        for _ in range(Ke):
+        for _ in range(Ke * chunks):
             fn()                                                       # synchronous call (copies + sync inside)
         barrier()
         return max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_sec, e2e_full_sec = e2e_time(hres), e2e_time(hbuf)
-    e2e = dict(value=float(n) * CHUNK_T * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
-               d2h_bytes_per_step=int(n * CHUNK_T * (4 + 1)), steps=Ke, api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host)",
-               result="reward[T,N] f32 + done[T,N] u8 to pinned host memory (reward written by the kernel into the mapped buffer, done "
-                      "copied after it); obs / pdflat are written to the device-resident rollout buffer (rb_env_rollout_buffer) and stay there",
+    e2e_sec, e2e_full_sec = e2e_time(hres, R), e2e_time(hbuf, 1)
+    e2e = dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4) * R,
+               d2h_bytes_per_step=int(n * CHUNK_T * (4 + 1)) * R, steps=Ke, api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host), %d calls per step" % R,
+               result="reward[T,N] f32 + done[T,N] u8 of every chunk to pinned host memory (reward written by the kernel into the mapped buffer, done "
+                      "copied per in-kernel progress slab); obs / pdflat are written to the device-resident rollout buffer (rb_env_rollout_buffer) and stay there",
                mean_reward_host=float(hbuf["rew"].mean()))
     e2e_full = dict(value=float(n) * CHUNK_T * Ke * world / e2e_full_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
-                    d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke, note="whole rollout buffer to the host: PCIe-bound")
+                    d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke, note="ONE chunk per step, whole rollout buffer to the host: PCIe-bound")
     env.close()
     del buf, hbuf
 
+    cfg = workload_config(n)
+    cfg.update(policy_mode=mode_name, seed=0, mean_teacher_reward=mean_rew,
+               l2="no flush: each chunk writes a fresh %.0f MB rollout buffer (> 126 MB L2); state 3.1 MB stays in registers" % (n * CHUNK_T * 68 / 1e6))
+    cfg["mean_reward_first_chunk_envs_0_%d" % REWARD_CHECK_ENVS] = rew_check
     line = dict(metric="reacher_env_steps_per_sec", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W, ms_per_step=1e3 * sec / K,
-                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload="config3: %d envs/GPU, fused teacher MLP (11-64-64-2 tanh) in the loop, 50-step chunk per step, "
-                                     "rollout buffer device-resident" % n, envs_per_gpu=n, chunk_steps=CHUNK_T, policy_mode=mode_name,
-                            l2="no flush: each step writes a fresh %.0f MB rollout buffer (> 126 MB L2); state 2.6 MB stays in registers"
-                               % (n * CHUNK_T * 68 / 1e6), seed=0, mean_teacher_reward=mean_rew),
-                e2e=e2e, e2e_full_buffer=e2e_full, gpu_launches=K, clocks=clocks)
-    line["roofline"] = dict(bound="hbm", achieved=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9, peak=pk["hbm"], unit="GB/s",
-                            frac=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9 / pk["hbm"],
-                            traffic=(ROLLOUT_TRAFFIC_NCU if (mode == MODE_TC and n == 65536) else None), peak_source=pk["src"],
-                            kernel="k_rollout_policy_%s" % ("tc" if mode == MODE_TC else "fp32"),
-                            note="HBM is NOT the limiter of the fused rollout (it only writes the 65 B buffer row per env-step, state stays in "
-                                 "registers, SURVEY 8(d)); the binding resources are instruction issue and the XU (MUFU) pipe: see `pipes`")
+                higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
+                e2e=e2e, e2e_full_buffer=e2e_full, gpu_launches=K * R, clocks=clocks)
+    nc = ncu_counters("rollout") if (mode == MODE_TC and n == 65536) else {}
+    warps = n / 32.0 * CHUNK_T
     sms = L.rb_sm_count(local)
     xu_ceiling = sms * XU_LANES_PER_CLK_PER_SM * 1.965e9 / MUFU_PER_ENV_STEP
+    line["roofline"] = dict(bound="hbm", achieved=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9, peak=pk["hbm"], unit="GB/s",
+                            frac=ALG_BYTES_ROLLOUT * n * CHUNK_T / kernel_s / 1e9 / pk["hbm"],
+                            traffic=(nc["dram__bytes_read.sum"] + nc["dram__bytes_write.sum"]) if "dram__bytes_read.sum" in nc else None,
+                            peak_source=pk["src"], kernel="k_rollout_policy_%s" % ("tc" if mode == MODE_TC else "fp32"), kernel_ms=1e3 * kernel_s,
+                            bound_binding="xu+issue",
+                            binding=dict(frac_of_xu_ceiling=value / world / xu_ceiling, xu_ceiling_env_steps_per_s=xu_ceiling,
+                                         issue_active_pct=nc.get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                         tensor_pipe_active_pct=nc.get("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                                         warp_instructions_per_warp_step=(nc["smsp__inst_executed.sum"] / warps) if "smsp__inst_executed.sum" in nc else None,
+                                         xu_warp_instructions_per_warp_step=(nc["sm__inst_executed_pipe_xu.sum"] / warps) if "sm__inst_executed_pipe_xu.sum" in nc else None,
+                                         ncu_file=nc.get("file")),
+                            note="`frac` is the contract's HBM figure (65 algorithmic bytes per env-step over the measured copy peak); HBM is NOT what binds "
+                                 "the fused rollout -- it only writes the buffer row, the state stays in registers (SURVEY 8(d)).  The binding resources are "
+                                 "the XU (MUFU) pipe and instruction issue on 13.8 warps per SM: `binding` (ncu counters read from the committed capture)")
     line["pipes"] = dict(xu_mufu_per_env_step=MUFU_PER_ENV_STEP, xu_ceiling_env_steps_per_s=xu_ceiling, frac_of_xu_ceiling=value / world / xu_ceiling,
                          tensor_tflops_bf16x3=3 * 9856.0 * n * CHUNK_T / kernel_s / 1e12, tensor_peak_tflops=pk["bf16_burst"],
                          physics_flop_per_env_step=450.0, teacher_flop_per_env_step=9856.0,
-                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 169 MUFU per env-step; ncu (profiles/README.md): XU pipe 40 % of active "
-                              "cycles, issue slots 57 %, tensor pipe 18 %; only 13.8 warps/SM exist at 65 536 envs (latency-bound, see DESIGN.md 4.1)")
+                         note="XU ceiling = SMs x 16 MUFU lanes/clk x 1.965 GHz / 161 MUFU per env-step (128 tanh x 1.25 + 1 sqrt)")
 
     if not args.quick:
         # ---- distill: DAgger iterations on the config-4 shard ---------------------------------------------------
@@ -380,7 +565,8 @@ def main():
                                last_loss=float(tr.last_loss()),
                                roofline=dict(bound="tensor", achieved=fl * nd / (ksec / 20) / 1e12, peak=pk["bf16_burst"], unit="TFLOP/s",
                                              frac=fl * nd / (ksec / 20) / 1e12 / pk["bf16_burst"],
-                                             traffic=(STUDENT_TRAFFIC_NCU if (tr.student_mode == MODE_TC and nd == 32768 and args.student == "mlp") else None),
+                                             traffic=((lambda c: (c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"]) if "dram__bytes_read.sum" in c else None)(
+                                                 ncu_counters("student")) if (tr.student_mode == MODE_TC and nd == 32768 and args.student == "mlp") else None),
                                              peak_source=pk["src"],
                                              kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
                                                      else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
@@ -412,6 +598,7 @@ def main():
             nsec, _ = timed(trn.step, Kd)
             line["distill"]["nccl_baseline"] = dict(value=float(nd) * Kd * world / nsec, unit="samples/s", ms_per_step=1e3 * nsec / Kd)
             trn.close()
+            line["distill"]["parity"] = distill_parity(DaggerTrainer, kind, mode, nd, rank, world, local, dev)
         if world == 1:
             # the whole config-4 batch (262 144 envs) on ONE GPU: fixed phases of the cooperative kernel amortise over 14 tiles per SM
             nl = 8 * DISTILL_ENVS_PER_GPU
@@ -455,14 +642,15 @@ def main():
         ssec, _ = timed(sfn, 50)
         line["step_api"] = dict(metric="reacher_env_steps_per_sec", value=float(ns) * 50 * world / ssec, unit="env-steps/s", envs_per_gpu=ns,
                                 roofline=dict(bound="hbm", achieved=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9, peak=pk["hbm"], unit="GB/s",
-                                              frac=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9 / pk["hbm"], traffic=(STEP_TRAFFIC_NCU if ns == (1 << 22) else None),
-                                              peak_source=pk["src"], kernel="k_step",
-                                              note="working set %.0f MB > L2; ncu: 122.9 B of DRAM traffic per env-step (algorithmic 113), issue slots 82 %% "
-                                                   "active: the RK4 physics (~750 warp-instructions per step) bounds this kernel before HBM does" % (ns * 97 / 1e6)))
+                                              frac=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9 / pk["hbm"],
+                                              traffic=(lambda c: (c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"]) if ("dram__bytes_read.sum" in c and ns == (1 << 22)) else None)(ncu_counters("step")),
+                                              peak_source=pk["src"], kernel="k_step", kernel_ms=1e3 * ssec / 50,
+                                              issue_active_pct=ncu_counters("step").get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+                                              note="working set %.0f MB > L2, constant random action per env (most envs sit on the joint limit: the contact "
+                                                   "branch runs in nearly every RK4 stage); instruction issue bounds this kernel before HBM does" % (ns * 105 / 1e6)))
         env2.close()
         if rank == 0 and world == 1:
-            cb, _, _ = cpu_reference_leg()
-            line["cpu_baseline"] = cb
+            line["cpu_baseline"] = cpu_reference_leg()
             line["distill"]["cpu_baseline"] = cpu_distill_leg(args.student)
             line["config1"] = config1_leg()
     if sampler:

@@ -51,6 +51,26 @@ int cuda_fail(cudaError_t e, const char* what);
         }                                            \
     } while (0)
 
+// Launch state CUDA keeps PER DEVICE (function attributes, occupancy, SM count) is cached per (call site, device): the Python layer takes
+// device = N everywhere, so one process may drive several GPUs.  True the first time it is called on the current device for `seen`
+// (a repeated set after a race between two host threads is harmless: the cached calls are idempotent).
+constexpr int RB_MAX_DEVICES = 64;
+inline bool first_use_on_device(bool (&seen)[RB_MAX_DEVICES], int* device_out = nullptr) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) { cudaGetLastError(); return true; }
+    if (device_out) *device_out = dev;
+    if (dev < 0 || dev >= RB_MAX_DEVICES) return true;
+    if (seen[dev]) return false;
+    seen[dev] = true;
+    return true;
+}
+// RAII: entry points that must select a handle's device put the caller's device back on return
+struct DeviceGuard {
+    int prev = -1;
+    explicit DeviceGuard(int device) { if (cudaGetDevice(&prev) != cudaSuccess) { cudaGetLastError(); prev = -1; } if (prev != device) cudaSetDevice(device); else prev = -1; }
+    ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 constexpr int OBS = RB_OBS_DIM;
 constexpr int HID = 64;
 

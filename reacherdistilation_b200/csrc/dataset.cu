@@ -107,7 +107,7 @@ extern "C" {
 
 int rb_dataset_destroy(rb_dataset* d) {
     if (!d) return RB_OK;
-    cudaSetDevice(d->device);
+    DeviceGuard guard(d->device);
     cudaFree(d->ob); cudaFree(d->rew); cudaFree(d->t); cudaFree(d->s); cudaFree(d->with);
     delete d;
     return RB_OK;
@@ -116,7 +116,7 @@ int rb_dataset_destroy(rb_dataset* d) {
 int rb_dataset_create(rb_dataset** out, int64_t num_envs, int64_t generations, int device) {
     RB_REQUIRE(out != nullptr, "out is NULL");
     RB_REQUIRE(num_envs > 0 && generations > 0, "num_envs and generations must be positive");
-    RB_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     rb_dataset* d = new rb_dataset();
     d->n = num_envs; d->G = generations; d->device = device;
     const size_t rows = (size_t)generations * EP * num_envs;
@@ -158,7 +158,7 @@ int64_t rb_dataset_generations(const rb_dataset* d) { return d ? d->gen : 0; }
 int rb_dataset_export_host(rb_dataset* d, int64_t generation, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host) {
     RB_REQUIRE(d != nullptr, "NULL argument");
     RB_REQUIRE(generation >= 0 && generation < d->gen && generation >= d->gen - d->G + (d->k > 0 ? 1 : 0), "generation is not in the ring any more");
-    RB_CUDA(cudaSetDevice(d->device));
+    DeviceGuard guard(d->device);
     const size_t rows = (size_t)EP * d->n, r0 = (size_t)(generation % d->G) * rows;
     RB_CUDA(cudaDeviceSynchronize());
     if (ob_host) RB_CUDA(cudaMemcpy(ob_host, d->ob + r0 * 11, rows * 11 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -175,7 +175,7 @@ int64_t rb_dataset_ring_rows(const rb_dataset* d) { return d ? d->G * EP * d->n 
 int rb_dataset_save_host(rb_dataset* d, float* ob_host, float* rew_host, float* t_host, float* s_host, uint8_t* with_host, int* step_out,
                          int64_t* generations_out) {
     RB_REQUIRE(d && ob_host && rew_host && t_host && s_host && with_host && step_out && generations_out, "NULL argument");
-    RB_CUDA(cudaSetDevice(d->device));
+    DeviceGuard guard(d->device);
     const size_t rows = (size_t)rb_dataset_ring_rows(d);
     RB_CUDA(cudaDeviceSynchronize());
     RB_CUDA(cudaMemcpy(ob_host, d->ob, rows * 11 * sizeof(float), cudaMemcpyDeviceToHost));
@@ -190,7 +190,7 @@ int rb_dataset_load_host(rb_dataset* d, const float* ob_host, const float* rew_h
                          const uint8_t* with_host, int step, int64_t generations) {
     RB_REQUIRE(d && ob_host && rew_host && t_host && s_host && with_host, "NULL argument");
     RB_REQUIRE(step >= 0 && step <= EP && generations >= 0, "bad cursor");
-    RB_CUDA(cudaSetDevice(d->device));
+    DeviceGuard guard(d->device);
     const size_t rows = (size_t)rb_dataset_ring_rows(d);
     RB_CUDA(cudaDeviceSynchronize());
     RB_CUDA(cudaMemcpy(d->ob, ob_host, rows * 11 * sizeof(float), cudaMemcpyHostToDevice));

@@ -215,7 +215,8 @@ int rb_env_create(rb_env** out, int64_t num_envs, uint64_t seed, int device, uin
     RB_REQUIRE(out != nullptr, "out is NULL");
     RB_REQUIRE(num_envs > 0 && num_envs <= (int64_t)1 << 31, "num_envs out of range");
     RB_REQUIRE((uint64_t)global_env_offset + (uint64_t)num_envs <= (uint64_t)1 << 32, "global env id overflows 32 bits");
-    RB_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);             // the caller's current device is put back on return
+    RB_CUDA(cudaGetLastError());
     rb_env* e = new rb_env();
     e->n = num_envs; e->seed = seed; e->device = device; e->offset = global_env_offset;
     cudaError_t err = cudaMalloc(&e->qv, sizeof(float4) * num_envs);
@@ -234,7 +235,7 @@ int rb_env_create(rb_env** out, int64_t num_envs, uint64_t seed, int device, uin
 
 int rb_env_destroy(rb_env* e) {
     if (!e) return RB_OK;
-    cudaSetDevice(e->device);
+    DeviceGuard guard(e->device);
     cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
@@ -274,7 +275,7 @@ int rb_env_step(rb_env* e, const float* act_dev, float* obs_dev, float* rew_dev,
 
 static int ensure_host_staging(rb_env* e) {
     if (e->d_act) return RB_OK;
-    RB_CUDA(cudaSetDevice(e->device));
+    DeviceGuard guard(e->device);
     RB_CUDA(cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking));
     RB_CUDA(cudaStreamCreateWithFlags(&e->copy_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 16; ++i) RB_CUDA(cudaEventCreateWithFlags(&e->slab_done[i], cudaEventDisableTiming));
@@ -367,7 +368,7 @@ int rb_policy_fwd(const float* params, int nout, const float* obs, int64_t n, fl
 int rb_policy_fwd_host(const float* params_host, int nout, const float* obs_host, int64_t n, float* pd_host, int mode, int device) {
     RB_REQUIRE(params_host && obs_host && pd_host, "NULL argument");
     RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
-    RB_CUDA(cudaSetDevice(device));
+    DeviceGuard guard(device);
     float *dp = nullptr, *dob = nullptr, *dpd = nullptr;
     const int64_t P = rb_policy_param_count(nout);
     RB_CUDA(cudaMalloc(&dp, sizeof(float) * P));
@@ -408,11 +409,13 @@ static void* mapped_alias(const void* host) {
     if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return (a.type == cudaMemoryTypeHost) ? a.devicePointer : nullptr;
 }
-static int env_knob(const char* name, int dflt, int lo, int hi) {
-    const char* v = getenv(name);
-    const int x = v ? atoi(v) : dflt;
-    return x < lo ? lo : (x > hi ? hi : x);
-}
+// Transport constants of rb_env_rollout_policy_host (each measured against its alternatives on B200, see the comment inside the call and
+// profiles/r01_e2e_transport_sweep.jsonl; they were environment knobs while being tuned):
+constexpr int HOST_ZEROCOPY = 1;        // bit 0: reward stored by the kernel into the mapped host buffer, bit 1: done too
+constexpr int HOST_SLABS = 6;           // fp32-mode slab launches when bulk fields (obs / pdflat / pageable reward) go to the host
+constexpr int HOST_SLAB_FIRST = 2;      // ... with a short first slab so that the copy engine starts early
+constexpr int HOST_SLABS_SMALL = 1;     // ... and when only small fields are copied
+constexpr int HOST_PROGRESS_SLABS = 5;  // tensor-core mode: time slabs reported by the ONE launch through in-kernel progress flags
 
 int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
                                uint8_t* done_host, int mode) {
@@ -449,17 +452,16 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
     //  result alone 0.30 at the 55 GB/s this box copies at): 0.362 progress path with the defaults (reward kernel-written, done copied per
     //  progress slab); 0.435 progress path with everything on the copy engine; 0.403 reward kernel-written + done copied after the kernel;
     //  0.419 the same with 2 kernel slabs; 0.428 both fields kernel-written; 0.448 everything copied in 5 equal kernel slabs.
-    static const int zc = env_knob("RB_HOST_ZEROCOPY", 1, 0, 3), nslab_bulk = env_knob("RB_HOST_SLABS", 6, 1, 16),
-                     first_steps = env_knob("RB_HOST_SLAB_FIRST", 2, 1, 1 << 20), nslab_small = env_knob("RB_HOST_SLABS_SMALL", 1, 1, 16);
+    constexpr int zc = HOST_ZEROCOPY, nslab_bulk = HOST_SLABS, first_steps = HOST_SLAB_FIRST, nslab_small = HOST_SLABS_SMALL;
     float* rew_zc = (zc & 1) ? (float*)mapped_alias(rew_host) : nullptr;
     uint8_t* done_zc = (zc & 2) ? (uint8_t*)mapped_alias(done_host) : nullptr;
     const bool copy_rew = rew_host && !rew_zc, copy_done = done_host && !done_zc;
     const bool bulk = obs_host || pd_host || copy_rew, any_copy = bulk || copy_done;
-    if (mode == RB_MODE_TC && any_copy && env_knob("RB_HOST_PROGRESS", 1, 0, 1)) {
+    if (mode == RB_MODE_TC && any_copy) {
         // Tensor-core rollout: ONE launch for all T steps; the kernel posts per-slab completion flags into mapped host memory (common.cuh:
         // rb_env::prog_*) and this thread, polling them, queues the copy of slab i on the copy stream while the launch computes slab i+1.
         // No slab boundaries in the kernel (each costs ~10 us), only the last slab's copy is left after it.
-        static const int nprog = env_knob("RB_HOST_PROGRESS_SLABS", 5, 1, 16);
+        constexpr int nprog = HOST_PROGRESS_SLABS;
         const int slab_len = (T + nprog - 1) / nprog, nsl = (T + slab_len - 1) / slab_len;
         e->prog_epoch += 1u;
         RB_CUDA(cudaMemsetAsync(e->prog_counters, 0, 16 * sizeof(uint32_t), s));
@@ -468,9 +470,6 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
         e->prog_slab_len = 0;
         if (rc) return rc;
         const auto t_start = std::chrono::steady_clock::now();
-        static const int trace = env_knob("RB_HOST_TRACE", 0, 0, 1);      // host-side timeline of the call on stderr (every 16th call)
-        double tr_flag[16] = {}, tr_enq[16] = {};
-        auto us_since = [&](void) { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now() - t_start).count(); };
         for (int i = 0; i < nsl; ++i) {
             uint64_t spins = 0;
             while (e->prog_flags_host[i] != e->prog_epoch) {
@@ -481,23 +480,15 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
                     if (std::chrono::steady_clock::now() - t_start > std::chrono::seconds(60)) { set_error("rb_env_rollout_policy_host: timed out"); return RB_ERR_CUDA; }
                 }
             }
-            if (trace) tr_flag[i] = us_since();
             const int t0 = i * slab_len, tn = (t0 + slab_len <= T ? slab_len : T - t0);
             const int64_t r0 = (int64_t)t0 * e->n, rows = (int64_t)tn * e->n;
             if (copy_done) RB_CUDA(cudaMemcpyAsync(done_host + r0, e->d_buf_done + r0, rows, cudaMemcpyDeviceToHost, sc));
             if (copy_rew) RB_CUDA(cudaMemcpyAsync(rew_host + r0, e->d_buf_rew + r0, sizeof(float) * rows, cudaMemcpyDeviceToHost, sc));
             if (obs_host) RB_CUDA(cudaMemcpyAsync(obs_host + OBS * r0, e->d_buf_obs + OBS * r0, sizeof(float) * OBS * rows, cudaMemcpyDeviceToHost, sc));
             if (pd_host) RB_CUDA(cudaMemcpyAsync(pd_host + 4 * r0, e->d_buf_pd + 4 * r0, sizeof(float) * 4 * rows, cudaMemcpyDeviceToHost, sc));
-            if (trace) tr_enq[i] = us_since();
         }
         RB_CUDA(cudaStreamSynchronize(sc));
-        const double t_sc = trace ? us_since() : 0.0;
         RB_CUDA(cudaStreamSynchronize(s));
-        if (trace && (e->prog_epoch % 16u) == 0u) {                 // us after the launch returned: slab flag seen / copies queued, then the two syncs
-            fprintf(stderr, "[rb host rollout] flags:");
-            for (int i = 0; i < nsl; ++i) fprintf(stderr, " %.0f/%.0f", tr_flag[i], tr_enq[i]);
-            fprintf(stderr, "  copy-sync %.0f  kernel-sync %.0f\n", t_sc, us_since());
-        }
         // Measured (config 3, B200): flags at 75 / 138 / 195 / 257 / 316 us, the last copy done at ~340, call returns at ~350 (+ ~12 us before the
         // launch).  Tried on top and dropped (no gain, PCIe is shared by the kernel's reward stores and the copy engine): `done` of the last slab
         // kernel-written too (last slab 20 us slower, 0.367 ms per call), kernel sync before copy sync, self-resetting counters (0.3626).

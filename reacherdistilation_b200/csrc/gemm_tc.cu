@@ -343,8 +343,8 @@ __global__ void k_gemm_splitk_reduce(const GemmArgs g, int nsplit, int batch) {
 
 template <int BN> static int launch_gemm(const GemmArgs& g, dim3 grid, cudaStream_t st) {
     constexpr size_t smem = GemmCfg<BN>::SMEM;
-    static bool attr = false;
-    if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
+    static bool seen[RB_MAX_DEVICES] = {};             // function attributes are per device
+    if (first_use_on_device(seen)) RB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     k_gemm_bf16x3<BN><<<grid, GM_THREADS, smem, st>>>(g);
     RB_CUDA(cudaGetLastError());
     return RB_OK;

@@ -485,12 +485,9 @@ Carve carve(float* s, int64_t B) {
 }
 // groups of 8 CTAs that are co-resident (one CTA per SM: the weight slice fills the shared memory)
 int group_count(int64_t nrb, int* out) {
-    static int sms = 0;
-    if (!sms) {
-        int device = 0;
-        RB_CUDA(cudaGetDevice(&device));
-        RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
-    }
+    int device = 0, sms = 0;
+    RB_CUDA(cudaGetDevice(&device));
+    RB_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
     const int64_t g = sms / RC_SPLIT;
     RB_REQUIRE(g >= 1, "the LSTM recurrence kernels need at least 8 SMs");
     *out = (int)(nrb < g ? nrb : (g < RC_MAX_GROUPS ? g : RC_MAX_GROUPS));

@@ -22,7 +22,6 @@
 // element: the XU pipe sits inside the serial chain of every env step) and packed FADD2 / FMUL2 / FFMA2 arithmetic, then the
 // bf16 hi/lo split written straight into the next layer's A tile (no-swizzle K-major layout, see tc_common.cuh).
 #include <cstddef>
-#include <cstdlib>
 
 #include "common.cuh"
 #include "dagger_input.cuh"
@@ -487,12 +486,12 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
             }
             if (t + 1 == next_mark) {                                                     // warp-uniform: a time slab of the buffer is complete
                 next_mark = min(next_mark + prog_slab_len, T);
-                __threadfence();                                                          // this lane's buffer rows are visible device-wide ...
+                __threadfence_system();                                                   // this lane's buffer rows are visible to the copy engine / host ...
                 __syncwarp();                                                             // ... for every lane of the warp, before the count
                 if (lane == 0) {
                     const int slab = t / prog_slab_len;
                     if (atomicAdd(prog_counters + slab, 1u) + 1u == (uint32_t)units) {      // counters are zeroed by the host call
-                        __threadfence();
+                        __threadfence_system();                                           // kernel -> host -> copy engine: system-scope ordering
                         asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(prog_flags + slab), "r"(prog_epoch) : "memory");
                     }
                 }
@@ -579,8 +578,7 @@ static int launch_rollout_tc(rb_env* e, const float* params, int T, float* obs_b
     const size_t smem = tc_smem_bytes<NT>();
     int rc = set_smem_attr(k_rollout_policy_tc<NOUT, NT>, smem);
     if (rc) return rc;
-    static int stagger = -1;
-    if (stagger < 0) { const char* v = getenv("RB_ROLLOUT_STAGGER_NS"); stagger = v ? atoi(v) : ROLLOUT_STAGGER_NS; }
+    const int stagger = ROLLOUT_STAGGER_NS;
     k_rollout_policy_tc<NOUT, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf, k0, k1,
                                                                 e->offset, (uint32_t)stagger, e->prog_counters, e->prog_flags_dev,
                                                                 e->prog_counters ? e->prog_slab_len : 0, e->prog_epoch);
@@ -590,20 +588,8 @@ static int launch_rollout_tc(rb_env* e, const float* params, int T, float* obs_b
 
 int rollout_policy_tc(rb_env* e, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf, uint8_t* done_buf,
                       cudaStream_t s) {
-    static int nt = 0;
-    if (nt == 0) {                                   // tiles per CTA: RB_ROLLOUT_NT = 4 | 5 | 6 (tuning knob, default ROLLOUT_NT)
-        const char* v = getenv("RB_ROLLOUT_NT");
-        nt = v ? atoi(v) : ROLLOUT_NT;
-        if (nt < 4 || nt > 6) nt = ROLLOUT_NT;
-    }
-    if (nout == 2) {
-        if (nt == 5) return launch_rollout_tc<2, 5>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
-        if (nt == 6) return launch_rollout_tc<2, 6>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
-        return launch_rollout_tc<2, 4>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
-    }
-    if (nt == 5) return launch_rollout_tc<4, 5>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
-    if (nt == 6) return launch_rollout_tc<4, 6>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
-    return launch_rollout_tc<4, 4>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+    if (nout == 2) return launch_rollout_tc<2, ROLLOUT_NT>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
+    return launch_rollout_tc<4, ROLLOUT_NT>(e, params, T, obs_buf, pd_buf, rew_buf, done_buf, s);
 }
 
 }  // namespace rb

@@ -292,11 +292,8 @@ static int launch_student(const NetSpec& S, const float* params, const float* x,
     const int per_sm = smem * 2 + 4096 <= 227 * 1024 ? 2 : 1;
     const int grid = (int)min((int64_t)min(per_sm * sm_count_of(device), MAX_STUDENT_BLOCKS), ntiles);
     auto kern = k_student<TILE, TPS, WS>;
-    static bool attr_set = false;
-    if (!attr_set) {
-        RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
-        attr_set = true;
-    }
+    static bool seen[RB_MAX_DEVICES] = {};             // function attributes are per device
+    if (first_use_on_device(seen)) RB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
     RB_REQUIRE(smem <= 224 * 1024, "shared memory budget exceeded");
     RB_REQUIRE((reinterpret_cast<uintptr_t>(params) & 15) == 0 && (reinterpret_cast<uintptr_t>(x) & 15) == 0, "params / x must be 16-byte aligned");
     kern<<<grid, TILE * TPS, smem, st>>>(S, params, x, tpd, B, loss_kind, fwd_only, (float4*)s_out, partials);

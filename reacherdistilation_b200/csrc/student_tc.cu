@@ -862,11 +862,13 @@ size_t student_tc_workspace_floats() { return WS_PART + (size_t)ST_MAX_GRID * WS
 template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cudaStream_t st) {
     static_assert(2 * Geo<S>::wtile_bytes() <= 12288 * 4, "weight image does not fit its workspace slot");
     const size_t smem = student_tc_smem<S>();
-    static bool attr = false;
-    if (!attr) { RB_CUDA(cudaFuncSetAttribute(k_student_tc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); attr = true; }
-    static int occ = -1;                           // a cooperative grid must be co-resident: check once that one CTA per SM fits
-    if (occ < 0) RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_student_tc<S>, ST_THREADS, smem));
-    RB_REQUIRE(occ >= 1, "k_student_tc does not fit on this device (shared memory / registers)");
+    static bool seen[RB_MAX_DEVICES] = {};             // function attributes and occupancy are per device
+    if (first_use_on_device(seen)) {
+        RB_CUDA(cudaFuncSetAttribute(k_student_tc<S>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int occ = 0;                                   // a cooperative grid must be co-resident: one CTA per SM has to fit
+        RB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k_student_tc<S>, ST_THREADS, smem));
+        RB_REQUIRE(occ >= 1, "k_student_tc does not fit on this device (shared memory / registers)");
+    }
     void* args[] = {(void*)&a};
     RB_CUDA(cudaLaunchCooperativeKernel((const void*)k_student_tc<S>, dim3(grid), dim3(ST_THREADS), args, smem, st));
     return RB_OK;

@@ -27,7 +27,7 @@ from .teacher import TeacherAgent, load_teacher_params
 class DaggerTrainer:
     def __init__(self, num_envs=NUM_ENVS, seed=SEED, device=0, student_kind=STUDENT_MLP, keep_prob=KEEP_PROB, mode=MODE_FP32,
                  teacher_params=None, teacher_seed=0, student_seed=1, env_offset=0, loss_kind=LOSS_KL_ST, lr=None, eps=None,
-                 process_group=None, average_grads=False, student_params=None, student_mode=None, fused_allreduce=None, use_graph=None):
+                 process_group=None, average_grads=False, student_params=None, student_mode=None, fused_allreduce=None, use_graph=None, solo=False):
         import ctypes as C
         self.env = VecReacher(num_envs=num_envs, seed=seed, device=device, env_offset=env_offset)
         self.device = self.env.device
@@ -55,8 +55,8 @@ class DaggerTrainer:
             self.done = torch.empty((n,), dtype=torch.uint8, device=dev)
         self.pg = process_group
         self.world = 1
-        if process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized()):
-            self.world = torch.distributed.get_world_size(process_group)
+        if not solo and (process_group is not None or (torch.distributed.is_available() and torch.distributed.is_initialized())):
+            self.world = torch.distributed.get_world_size(process_group)      # solo: a single-rank trainer inside a multi-rank job (no exchange)
         self.grad_scale = (1.0 / self.world) if average_grads else 1.0   # MpiAdam averages (backup :709); KL sum = concatenated batch
         # world > 1: exchange the gradient inside the student kernel over NVLink peer memory (tensor-core path) unless told to use NCCL
         self.fused_allreduce = (self.world > 1 and self.student_mode == _lib.MODE_TC) if fused_allreduce is None else bool(fused_allreduce)
