@@ -540,7 +540,7 @@ def main():
             tr.step()
         dsec, _ = timed(tr.step, Kd)
         # student kernel alone (device time of the dominant kernel of this loop)
-        lg = lambda: tr.student.loss_grad(tr.x, tr.t_pd, s_out=tr.s_pd)      # ONE cooperative launch in tc mode (fold, tiles, reduce, un-fold)
+        lg = lambda: tr.student.loss_grad(tr.x, tr.t_pd, s_out=tr.s_pd)      # tc mode: weight-image kernel + ONE cooperative launch (tiles, reduce, un-fold)
         for _ in range(3):
             lg()
         ksec, _ = timed(lg, 20)
@@ -568,7 +568,7 @@ def main():
                                              traffic=((lambda c: (c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"]) if "dram__bytes_read.sum" in c else None)(
                                                  ncu_counters("student")) if (tr.student_mode == MODE_TC and nd == 32768 and args.student == "mlp") else None),
                                              peak_source=pk["src"],
-                                             kernel=("k_student_tc (cooperative: fold + tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
+                                             kernel=("k_student_image + k_student_tc (cooperative: tiles + grid reduce + un-fold)" if tr.student_mode == MODE_TC
                                                      else "k_student(loss_grad) + k_reduce_partials"), kernel_ms=1e3 * ksec / 20,
                                              note="tile GEMMs run bf16x3 (3 MMAs per product): tensor-pipe work is 3x the algorithmic FLOP"))
         if tr.student_mode == MODE_TC:                                  # phase stamps (CTA 0, globaltimer) of the last cooperative launch on rank 0
@@ -576,10 +576,12 @@ def main():
             tb = (ctypes.c_ulonglong * 48)()
             L.rb_debug_student_timers(tb)
             us = lambda i, j: round((tb[j] - tb[i]) / 1e3, 2)
-            ph = dict(fold_image=us(0, 1), sync=us(1, 2), image_load=us(2, 3), tiles=us(3, 4), dump=us(4, 5), sync2=us(5, 6), reduce=us(6, 7), sync3=us(7, 8),
-                      unfold=us(8, 32), sync_adam_teardown=us(9, 11), total=us(0, 11))
+            ph = dict(setup=us(0, 1), image_wait=us(1, 3), tiles=us(3, 4), dump_and_env_step=us(4, 5), sync1=us(5, 6), reduce=us(6, 7), sync2=us(7, 8),
+                      teardown=us(9, 11), total=us(0, 11), grid_barriers=2)
             if world > 1:
-                ph.update(exch_sync=us(32, 33), exch_push=us(33, 34), exch_recv_sum_adam=us(34, 9))
+                ph.update(unfold_push=us(8, 34), recv_sum_adam=us(34, 9))
+            else:
+                ph.update(unfold_adam=us(8, 9))
             line["distill"]["student_kernel_phases_us"] = ph
         if world > 1:                                                   # every rank must hold bit-identical student parameters
             chk = torch.stack([tr.student.params.double().sum(), tr.student.params.double().abs().sum()]).to(dev)

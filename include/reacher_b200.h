@@ -185,8 +185,10 @@ int rb_student_step_dp(int kind, float* params_dev, float* m_dev, float* v_dev, 
                        float beta2, float eps, float grad_scale, int rank, int world, const uint64_t* peer_grad_slots,
                        const uint64_t* peer_flags, uint32_t epoch, void* stream);
 
-/* Debug aid: globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last RB_MODE_TC student launch (48 values: [0,12) launch phases, [16,31) phases of
- * CTA 0's first tile, [32,35) un-fold done / local gradient visible / pushed to the peers; see student_tc.cu).  Synchronises the device.                                                                            */
+/* Debug aid: globaltimer stamps (ns) of CTA 0 at the phase boundaries of the last RB_MODE_TC student launch (48 values: [0,12) launch phases --
+ * 0 start, 1 set up, 2 weight image in shared memory, 3 first tile, 4 tiles done, 5 partials written (+ fused env step), 6 after the first grid
+ * barrier, 7 reduced, 8 after the second grid barrier, 9 un-fold [exchange] Adam done, 11 end; [16,31) phases of CTA 0's first tile; 34 gradient pushed
+ * to the peers; see student_tc.cu).  Synchronises the device.                                                                          */
 int rb_debug_student_timers(unsigned long long* host_out16);
 
 /* ------------------------------------------------------------------------------------------------ DAgger --

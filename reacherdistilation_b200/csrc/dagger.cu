@@ -23,6 +23,8 @@ struct rb_dagger {
     cudaGraphExec_t gexec = nullptr;
     uint64_t gkey = 0;
     cudaStream_t cap_stream = nullptr;   // capture happens here (the legacy default stream cannot be captured); replay on the caller's stream
+    cudaStream_t side_stream = nullptr;  // forked branch: the student's weight image is built beside the observe kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     // result mailbox in page-locked mapped HOST memory: {loss bits, iteration count} stored by the last kernel of rb_dagger_step as one 8-byte
     // word; rb_dagger_wait_loss polls it, so the per-iteration loss read-back (mlp_train.py:148-161 prints it) needs no stream synchronise
     // and no copy-engine transfer
@@ -87,12 +89,13 @@ struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; 
 struct StepClock { const uint32_t* clock; float lr; };
 struct ActFuse {
     float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
-    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act;
+    uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act; int image_prebuilt;
 };
 int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
                       float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
                       cudaStream_t st);
 int64_t student_tc_act_covered(int64_t B, int grid);
+int student_tc_build_image(int kind, const float* params, void* workspace, cudaStream_t st);
 int student_tc_grid(int* grid);
 
 // implemented in policy_tc.cu
@@ -131,6 +134,9 @@ int rb_dagger_destroy(rb_dagger* d) {
     if (d->mailbox_host) cudaFreeHost((void*)d->mailbox_host);
     if (d->gexec) cudaGraphExecDestroy(d->gexec);
     if (d->cap_stream) cudaStreamDestroy(d->cap_stream);
+    if (d->side_stream) cudaStreamDestroy(d->side_stream);
+    if (d->ev_fork) cudaEventDestroy(d->ev_fork);
+    if (d->ev_join) cudaEventDestroy(d->ev_join);
     delete d;
     return RB_OK;
 }
@@ -240,16 +246,29 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
         d->teacher_img_src = teacher_params;
     }
     constexpr bool fuse_act = true;      // the env step runs inside the student launch (the three-launch form below is kept for reference timing)
+    if (!d->side_stream) {
+        RB_CUDA(cudaStreamCreateWithFlags(&d->side_stream, cudaStreamNonBlocking));
+        RB_CUDA(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+        RB_CUDA(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+    }
     auto issue = [&](cudaStream_t st) -> int {
         const float* xa = d->kind == RB_STUDENT_MLP ? x_act : nullptr;       // the 2x64 student sees the raw observation: nothing to un-drop
-        int rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, (float*)xa, st);
+        // fork: the student's weight image (bf16 hi / lo tiles, folded layers, un-fold snapshot) only needs the parameters, so it is built on a
+        // second branch beside the observe kernel (two parallel nodes of the captured graph) and joined in front of the student launch
+        RB_CUDA(cudaEventRecord(d->ev_fork, st));
+        RB_CUDA(cudaStreamWaitEvent(d->side_stream, d->ev_fork, 0));
+        int rc = student_tc_build_image(d->kind, params, ws, d->side_stream);
         if (rc) return rc;
+        RB_CUDA(cudaEventRecord(d->ev_join, d->side_stream));
+        rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, (float*)xa, st);
+        if (rc) return rc;
+        RB_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));                      // join
         const AdamFuse af{params, m, v, 0.f, b1, b2, eps, gscale};
         const PeerExchange px{world, rank, 0u, slots_even, flags, slots_odd};
         const StepClock clk{d->clock, lr};
         if (fuse_act) {      // env step, clock advance and loss mailbox inside the student launch: two launches per iteration
             const ActFuse act{e->qv, e->tp, e->ctr, d->prev_t, d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed, (uint32_t)(e->seed >> 32),
-                              e->offset, d->act_flags, d->clock, d->mailbox_dev, xa};
+                              e->offset, d->act_flags, d->clock, d->mailbox_dev, xa, 1};
             rc = student_tc_run_ex(d->kind, params, x, t_pd, e->n, loss_kind, 0, s_pd, gradloss, ws, &af, world > 1 ? &px : nullptr, &clk, &act, st);
             if (rc) return rc;
             int grid = 1;

@@ -87,8 +87,8 @@ struct StudentTcArgs {
     int loss_kind, fwd_only;
     // cooperative phases (all global scratch lives in the caller's workspace)
     const float* params;          // flat parameter vector (fold / finish / Adam)
-    float* fold;                  // SpecMLP: W34 (128x32) | b34 (32)
-    uint8_t* wimg;                // split weight image: hi tiles then lo tiles, exactly the shared-memory layout
+    float* snap;                  // SpecMLP: snapshot of W3 | b3 | W4 (params[M_W3 .. M_B4)) taken by k_student_image: what the un-fold reads
+    uint8_t* wimg;                // split weight image: hi tiles then lo tiles, exactly the shared-memory layout (built by k_student_image)
     float* red;                   // reduced partial vector [pstride]
     float* gradloss;              // final flat gradient [P] + loss
     int P;                        // parameter count
@@ -145,6 +145,7 @@ struct __align__(16) StudentTcCtl {
     uint32_t iter;                // iterations done once this launch has finished (clock[0] + 1): value of the act flags / mailbox
     uint64_t mbar;                // forward layers / dgrad results
     uint64_t mbar2;               // wgrad completion (X_l may be overwritten)
+    uint64_t mbar_load;           // TMA bulk copy of the weight image
     uint32_t tmem_base;
     float red[ST_THREADS / 32];
 };
@@ -425,8 +426,11 @@ __device__ __forceinline__ void fold_into_image(const float* p, uint8_t* img, in
 }
 
 // reduced folded gradient -> flat MLP gradient.  dW3 = G34 W4^T and dW4 = W3^T G34 + b3 (x) g34 are dealt one row per CTA
-// (row-contiguous loads); the pass-through entries and db3 go to the last threads of the grid.
-__device__ __forceinline__ void finish_mlp(const float* p, const float* red, float* gradloss, int gtid, int gthreads) {
+// (row-contiguous loads); the pass-through entries and db3 go to the last threads of the grid.  `p` is a pointer with which p[M_W3 ..
+// M_B4) addresses the SNAPSHOT of W3 | b3 | W4 taken when the weight image was built (k_student_image): the live parameters are being
+// updated by other threads while this runs.  Every produced entry goes to sink(flat index, value) exactly once; owned_mlp() below
+// enumerates the same (thread -> flat index) ownership without the arithmetic.
+template <class F> __device__ __forceinline__ void finish_mlp(const float* p, const float* red, int gtid, int gthreads, F&& sink) {
     const int tid = threadIdx.x;
     for (int r = blockIdx.x; r < 128; r += gridDim.x) {
         // all loads of both products are issued before the first use: one L2 round trip instead of two
@@ -443,26 +447,24 @@ __device__ __forceinline__ void finish_mlp(const float* p, const float* red, flo
 #pragma unroll
         for (int m = 0; m < 8; ++m) { const int aa = sub + 16 * m; w3[m] = ldw(p + M_W3 + aa * 128 + r); g4[m] = ldw(red + R_G34 + aa * 32 + j); }
         const float b3r = ldw(p + M_B3 + r), g34j = ldw(red + R_g34 + j);
+        float acc3 = 0.f;
         if (tid < 128) {                                             // dW3[r][k] = sum_j G34[r][j] W4[k][j],  k = tid
-            float acc = 0.f;
 #pragma unroll
             for (int j4 = 0; j4 < 8; ++j4) {
-                acc = fmaf(g[j4].x, w[j4].x, acc); acc = fmaf(g[j4].y, w[j4].y, acc); acc = fmaf(g[j4].z, w[j4].z, acc); acc = fmaf(g[j4].w, w[j4].w, acc);
+                acc3 = fmaf(g[j4].x, w[j4].x, acc3); acc3 = fmaf(g[j4].y, w[j4].y, acc3); acc3 = fmaf(g[j4].z, w[j4].z, acc3); acc3 = fmaf(g[j4].w, w[j4].w, acc3);
             }
-            gradloss[M_W3 + r * 128 + tid] = acc;
         }
-        {                                                            // dW4[r][j] = sum_a W3[a][r] G34[a][j] + b3[r] g34[j],  16 lanes per j
-            float acc = 0.f;
+        float acc4 = 0.f;                                            // dW4[r][j] = sum_a W3[a][r] G34[a][j] + b3[r] g34[j],  16 lanes per j
 #pragma unroll
-            for (int m = 0; m < 8; ++m) acc = fmaf(w3[m], g4[m], acc);
+        for (int m = 0; m < 8; ++m) acc4 = fmaf(w3[m], g4[m], acc4);
 #pragma unroll
-            for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (sub == 0) gradloss[M_W4 + r * 32 + j] = fmaf(b3r, g34j, acc);
-        }
+        for (int o = 8; o > 0; o >>= 1) acc4 += __shfl_xor_sync(0xffffffffu, acc4, o);
+        if (tid < 128) sink(M_W3 + r * 128 + tid, acc3);
+        if (sub == 0) sink(M_W4 + r * 32 + j, fmaf(b3r, g34j, acc4));
     }
     constexpr int n_a = M_W3, n_b = M_W4 - M_B3, n_c = M_P + 1 - M_B4;       // [0, W3) | db3 | [db4 .. loss]
     for (int q = gthreads - 1 - gtid; q < n_a + n_b + n_c; q += gthreads) {
-        if (q < n_a) gradloss[q] = ldw(red + q);                  // dW1 db1 dW2 db2 share offsets
+        if (q < n_a) sink(q, ldw(red + q));                       // dW1 db1 dW2 db2 share offsets
         else if (q < n_a + n_b) {                                    // db3[k] = sum_j W4[k][j] g34[j]
             const int k = q - n_a;
             float4 wv[8], gv[8];                                      // row k of W4 and g34 as 16 vector loads, all in flight together
@@ -476,12 +478,22 @@ __device__ __forceinline__ void finish_mlp(const float* p, const float* red, flo
             for (int j4 = 0; j4 < 8; ++j4) {
                 acc = fmaf(wv[j4].x, gv[j4].x, acc); acc = fmaf(wv[j4].y, gv[j4].y, acc); acc = fmaf(wv[j4].z, gv[j4].z, acc); acc = fmaf(wv[j4].w, gv[j4].w, acc);
             }
-            gradloss[M_B3 + k] = acc;
+            sink(M_B3 + k, acc);
         } else {
             const int i = M_B4 + (q - n_a - n_b);
-            gradloss[i] = i == M_P ? ldw(red + R_LOSS) : (i < M_W5 ? ldw(red + R_g34 + (i - M_B4)) : ldw(red + R_W5 + (i - M_W5)));
+            sink(i, i == M_P ? ldw(red + R_LOSS) : (i < M_W5 ? ldw(red + R_g34 + (i - M_B4)) : ldw(red + R_W5 + (i - M_W5))));
         }
     }
+}
+// the flat indices finish_mlp() hands to its sink in THIS thread, in the same order
+template <class F> __device__ __forceinline__ void owned_mlp(int gtid, int gthreads, F&& f) {
+    const int tid = threadIdx.x;
+    for (int r = blockIdx.x; r < 128; r += gridDim.x) {
+        if (tid < 128) f(M_W3 + r * 128 + tid);
+        if ((tid & 15) == 0) f(M_W4 + r * 32 + (tid >> 4));
+    }
+    constexpr int n_a = M_W3, n_b = M_W4 - M_B3, n_c = M_P + 1 - M_B4;
+    for (int q = gthreads - 1 - gtid; q < n_a + n_b + n_c; q += gthreads) f(q < n_a ? q : (q < n_a + n_b ? M_B3 + (q - n_a) : M_B4 + (q - n_a - n_b)));
 }
 
 // phase timestamps of CTA 0 (globaltimer, ns) of the last launch -- read back with rb_debug_student_timers()
@@ -531,8 +543,21 @@ __device__ __forceinline__ void act_finish(const StudentTcArgs& a, float loss, u
         asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(a.act_mailbox), "r"(__float_as_uint(loss)), "r"(iter) : "memory");
 }
 
-// One cooperative launch = fold + weight split (spread over the grid) -> tiles (forward, loss, backward; weight gradients in
-// TMEM) -> partials -> grid-wide fixed-order reduction -> gradient of the un-folded parameters [-> Adam].
+// The weights as the tiles want them: bf16 hi / lo split K-major tiles with the bias rows, layers 3-4 of the MLP folded (fp32), plus the
+// fp32 snapshot of W3 | b3 | W4 the un-fold at the end of the step reads.  An ordinary launch in front of k_student_tc; inside
+// rb_dagger_step it sits on a forked branch of the CUDA graph and runs beside the observe kernel (it only needs the parameters).
+constexpr int M_SNAP = 16384 + 128 + 4096;                 // W3 | b3 | W4 are contiguous in the flat layout
+template <class S> __global__ void __launch_bounds__(256) k_student_image(const StudentTcArgs a) {
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x, gthreads = gridDim.x * blockDim.x;
+    if constexpr (S::L == 4) {
+        fold_into_image(a.params, a.wimg, gtid, gthreads);
+        for (int i = gthreads - 1 - gtid; i < M_SNAP; i += gthreads) a.snap[i] = ldw(a.params + M_W3 + i);
+    }
+    LayerLoop<S>::build_image(a, gtid, gthreads);
+}
+
+// One cooperative launch = tiles (forward, loss, backward; weight gradients in TMEM) -> partials -> grid-wide fixed-order reduction ->
+// gradient of the un-folded parameters [-> peer all-reduce] [-> Adam]: two grid barriers.
 template <class S>
 __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArgs a) {
     using G = Geo<S>;
@@ -548,11 +573,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, sub = warp & 3, part = warp >> 2, row = sub * 32 + lane;
     const int gtid = blockIdx.x * ST_THREADS + tid, gthreads = gridDim.x * ST_THREADS;
 
-    // ---- phase 0: TMEM, barrier, zeroed activations + ONES groups; fold and split the weights once for the whole grid -----
+    // ---- phase 0: TMEM, barriers, the weight image (built by k_student_image BEFORE this launch: one TMA bulk copy), zeroed activations,
+    // ONES groups.  No grid-wide work and no grid barrier in front of the tiles.
     st_stamp(0);
     if (warp == 0) tmem_alloc<512>(&ctl.tmem_base);
     if (tid == 0) {
-        mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); fence_mbar_init();
+        mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); mbar_init(&ctl.mbar_load, 1); fence_mbar_init();
+        mbar_expect_tx(&ctl.mbar_load, 2 * G::wtile_bytes());
+        bulk_g2s(w_hi, a.wimg, 2 * G::wtile_bytes(), &ctl.mbar_load);
         ctl.lr_t = a.lr_t; ctl.epoch = a.epoch;
         if (a.clock) {                             // same formula as the host (student.cu: adam_lr_t), in double
             const double t = (double)(a.clock[1] + 1u);
@@ -562,16 +590,14 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         }
     }
     for (int i = tid; i < 2 * ST_ACT_BYTES / 16; i += ST_THREADS) reinterpret_cast<uint4*>(smem)[i] = make_uint4(0u, 0u, 0u, 0u);
-    if constexpr (S::L == 4) fold_into_image(a.params, a.wimg, gtid, gthreads);       // SpecMLP: W34, b34
-    LayerLoop<S>::build_image(a, gtid, gthreads);
+    __syncthreads();                               // barrier inits visible before anyone waits; zero fill complete before the ONES stores
     st_stamp(1);
-    grid.sync();
-    st_stamp(2);
     if (tid < ST_TILE) {
 #pragma unroll
         for (int l = 0; l < L; ++l) *reinterpret_cast<uint16_t*>(act_hi + (S::slot(l) + G::ig(l)) * 2048 + tid * 16) = (uint16_t)0x3F80u;
     }
-    for (int i = tid; i < 2 * G::wtile_bytes() / 16; i += ST_THREADS) reinterpret_cast<uint4*>(w_hi)[i] = ldw(reinterpret_cast<const uint4*>(a.wimg) + i);
+    mbar_wait(&ctl.mbar_load, 0);
+    st_stamp(2);
     fence_async_smem();
     fence_before_sync();
     __syncthreads();
@@ -783,55 +809,56 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         st_stamp(7);
         grid.sync();
         st_stamp(8);
-        // ---- gradient of the un-folded parameters ---------------------------------------------------------------------------------
+        // ---- last phase, NO further grid barrier: gradient of the un-folded parameters -> [data parallel: one-shot all-reduce over NVLink peer
+        // memory] -> TF-form Adam, element by element.  Whoever produces gradient entry i also exchanges it and updates parameter i, and the
+        // un-fold reads the W3 | b3 | W4 snapshot (a.snap) instead of the live parameters, so no thread waits for another one of this GPU.
         const uint32_t epoch = ctl.epoch;
         float* gl = a.gradloss;
-        if constexpr (S::L == 4) finish_mlp(a.params, a.red, gl, gtid, gthreads);
-        else
-            for (int i = gtid; i <= a.P; i += gthreads) gl[i] = ldw(a.red + i);
-        st_stamp(32);
-        if (a.world > 1) {
-            // ---- one-shot all-reduce over NVLink peer memory (MpiAdam.update's Allreduce, backup/student_rollout.py:709), low-latency form:
-            // every rank PUSHES {value, epoch} pairs (one 8-byte store each, delivered atomically) into every rank's receive area, then sums
-            // its own area in rank order as the pairs of this epoch arrive -- no flag round trip, no remote loads, no extra grid barrier; the
-            // one-way NVLink latency overlaps the pushes still in flight.  Areas are double buffered by epoch parity (a fast rank may push
-            // step k + 1 while a slow one still reads step k).
-            grid.sync();                       // the local gradient is complete, and every read of the old parameters (finish) is done
-            st_stamp(33);
+        const float lr_t = ctl.lr_t;
+        auto apply = [&](int i, float g) {                   // final value of entry i: gradient vector, loss mailbox, Adam (same arithmetic as k_adam)
+            gl[i] = g;
+            if (i == a.P) { if (a.act_on) act_finish(a, g, ctl.iter, a.world <= 1, true); }
+            else if (a.do_adam) {
+                float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
+                adam_update(pi, mi, vi, g, lr_t, a.beta1, a.beta2, a.eps, a.gscale);
+                a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
+            }
+        };
+        if (a.world <= 1) {
+            if constexpr (S::L == 4) finish_mlp(a.snap - M_W3, a.red, gtid, gthreads, apply);
+            else
+                for (int i = gtid; i <= a.P; i += gthreads) apply(i, ldw(a.red + i));
+            st_stamp(9);
+        } else {
+            // One-shot all-reduce (MpiAdam.update's Allreduce, backup/student_rollout.py:709), low-latency form: every rank PUSHES {value, epoch}
+            // pairs (one 8-byte store each, delivered atomically) into every rank's receive area, then sums its own area in rank order as the
+            // pairs of this epoch arrive -- no flag round trip, no remote loads; the one-way NVLink latency overlaps the pushes still in flight.
+            // Areas are double buffered by epoch parity (a fast rank may push step k + 1 while a slow one still reads step k).
             const int SL = (a.P + 1 + 63) / 64 * 64;                               // slot stride (elements) inside a receive area
             uint2* const* ll = a.clock ? a.peer_ll2[epoch & 1u] : a.peer_ll;
-            for (int i = gtid; i <= a.P; i += gthreads) {
-                const uint32_t v = __float_as_uint(ldw(gl + i));
+            auto push = [&](int i, float g) {
+                const uint32_t v = __float_as_uint(g);
                 for (int q = 0; q < a.world; ++q) st_ll(ll[q] + (size_t)a.rank * SL + i, v, epoch);
-            }
+            };
+            if constexpr (S::L == 4) finish_mlp(a.snap - M_W3, a.red, gtid, gthreads, push);
+            else
+                for (int i = gtid; i <= a.P; i += gthreads) push(i, ldw(a.red + i));
             st_stamp(34);
             const uint2* mine = ll[a.rank];
-            for (int i = gtid; i <= a.P; i += gthreads) {                           // rank order: bit-identical sums on every rank
+            auto recv = [&](int i) {                                                // rank order: bit-identical sums on every rank
                 float tot = 0.f;
                 for (int r = 0; r < a.world; ++r) {
                     uint2 w;
                     do { w = ld_ll(mine + (size_t)r * SL + i); } while (w.y != epoch);
                     tot += __uint_as_float(w.x);
                 }
-                gl[i] = tot;
-                if (a.act_on && i == a.P) act_finish(a, tot, ctl.iter, false, true);
-                if (a.do_adam && i < a.P) {    // TF1 Adam, same arithmetic as k_adam (student.cu); element i only needs gradient i
-                    float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
-                    adam_update(pi, mi, vi, tot, ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
-                    a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
-                }
-            }
-        }
-        st_stamp(9);
-        if (a.act_on && a.world > 1 && gtid == 0) act_finish(a, 0.f, ctl.iter, true, false);     // every CTA read the clock before the first barrier
-        if (a.do_adam && a.world <= 1) {
-            grid.sync();                       // every read of the old parameters (finish) is done, every gradloss entry written
-            if (a.act_on && gtid == 0) act_finish(a, __ldcg(a.gradloss + a.P), ctl.iter, true, true);
-            for (int i = gtid; i < a.P; i += gthreads) {
-                float pi = a.adam_p[i], mi = a.adam_m[i], vi = a.adam_v[i];
-                adam_update(pi, mi, vi, ldw(a.gradloss + i), ctl.lr_t, a.beta1, a.beta2, a.eps, a.gscale);
-                a.adam_p[i] = pi; a.adam_m[i] = mi; a.adam_v[i] = vi;
-            }
+                apply(i, tot);
+            };
+            if constexpr (S::L == 4) owned_mlp(gtid, gthreads, recv);
+            else
+                for (int i = gtid; i <= a.P; i += gthreads) recv(i);
+            st_stamp(9);
+            if (a.act_on && gtid == 0) act_finish(a, 0.f, ctl.iter, true, false);     // every CTA read the clock before the first barrier
         }
     }
     st_stamp(10);
@@ -854,13 +881,21 @@ static int tc_grid(int64_t B, int* grid) {
     return RB_OK;
 }
 
-// workspace (floats): [fold 4160][reduced 8192][weight image 12288 (48 KB)][partials ST_MAX_GRID * 8192]
-constexpr size_t WS_FOLD = 0, WS_RED = 4160, WS_IMG = WS_RED + 8192, WS_PART = WS_IMG + 12288, WS_PSTRIDE_MAX = 8192;
+// workspace (floats): [snapshot W3 | b3 | W4 20608][reduced 8192][weight image 12288 (48 KB)][partials ST_MAX_GRID * 8192]
+constexpr size_t WS_SNAP = 0, WS_RED = 20608, WS_IMG = WS_RED + 8192, WS_PART = WS_IMG + 12288, WS_PSTRIDE_MAX = 8192;
+static_assert(M_SNAP <= (int)WS_RED && M_W3 + 16384 == M_B3 && M_B3 + 128 == M_W4 && M_W4 + 4096 == M_B4, "W3 | b3 | W4 snapshot layout");
 
 size_t student_tc_workspace_floats() { return WS_PART + (size_t)ST_MAX_GRID * WS_PSTRIDE_MAX; }
 
-template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cudaStream_t st) {
+template <class S> static int launch_student_image(const StudentTcArgs& a, cudaStream_t st) {
+    k_student_image<S><<<132, 256, 0, st>>>(a);
+    RB_CUDA(cudaGetLastError());
+    return RB_OK;
+}
+template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cudaStream_t st, bool image_prebuilt) {
     static_assert(2 * Geo<S>::wtile_bytes() <= 12288 * 4, "weight image does not fit its workspace slot");
+    static_assert((2 * Geo<S>::wtile_bytes()) % 16 == 0, "TMA bulk copies move multiples of 16 bytes");
+    if (!image_prebuilt) { const int rc = launch_student_image<S>(a, st); if (rc) return rc; }
     const size_t smem = student_tc_smem<S>();
     static bool seen[RB_MAX_DEVICES] = {};             // function attributes and occupancy are per device
     if (first_use_on_device(seen)) {
@@ -880,6 +915,7 @@ struct StepClock { const uint32_t* clock; float lr; };
 struct ActFuse {              // fused env step of rb_dagger_step (see StudentTcArgs::act_*); x_act: un-dropped input rows or NULL
     float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
     uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act;
+    int image_prebuilt;       // the caller already ran student_tc_build_image() on these parameters (rb_dagger_step: on a forked graph branch)
 };
 
 int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
@@ -899,6 +935,22 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
     return student_tc_run_ex(kind, params, x, tpd, B, loss_kind, fwd_only, s_out, gradloss, workspace, adam, px, clk, nullptr, st);
 }
 
+// weight image (+ un-fold snapshot) of `params` into the workspace: what every k_student_tc launch on these parameters starts from
+int student_tc_build_image(int kind, const float* params, void* workspace, cudaStream_t st) {
+    RB_REQUIRE(params != nullptr && workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "bad arguments");
+    float* ws = (float*)workspace;
+    StudentTcArgs a{};
+    a.params = params; a.snap = ws + WS_SNAP; a.wimg = (uint8_t*)(ws + WS_IMG);
+    if (kind == RB_STUDENT_MLP) {
+        a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
+        a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
+        return launch_student_image<SpecMLP>(a, st);
+    }
+    const PolicyOffsets o = policy_offsets(4);
+    a.w[0] = params + o.W1; a.b[0] = params + o.b1; a.w[1] = params + o.W2; a.b[1] = params + o.b2; a.w[2] = params + o.W3; a.b[2] = params + o.b3;
+    return launch_student_image<SpecPOL>(a, st);
+}
+
 int student_tc_run_ex(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
                       float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
                       cudaStream_t st) {
@@ -910,7 +962,7 @@ int student_tc_run_ex(int kind, const float* params, const float* x, const float
     if (rc) return rc;
     StudentTcArgs a{};
     a.x = x; a.t = tpd; a.s_out = (float4*)s_out; a.B = B; a.loss_kind = loss_kind; a.fwd_only = fwd_only; a.partials = ws + WS_PART;
-    a.params = params; a.fold = ws + WS_FOLD; a.wimg = (uint8_t*)(ws + WS_IMG); a.red = ws + WS_RED; a.gradloss = gradloss;
+    a.params = params; a.snap = ws + WS_SNAP; a.wimg = (uint8_t*)(ws + WS_IMG); a.red = ws + WS_RED; a.gradloss = gradloss;
     if (adam && !fwd_only) {
         a.do_adam = 1; a.adam_p = adam->p; a.adam_m = adam->m; a.adam_v = adam->v;
         a.lr_t = adam->lr_t; a.beta1 = adam->beta1; a.beta2 = adam->beta2; a.eps = adam->eps; a.gscale = adam->gscale;
@@ -938,7 +990,7 @@ int student_tc_run_ex(int kind, const float* params, const float* x, const float
         a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
         a.pw[0] = R_W1; a.pb[0] = R_B1; a.pw[1] = R_W2; a.pb[1] = R_B2; a.pw[2] = R_G34; a.pb[2] = R_g34; a.pw[3] = R_W5; a.pb[3] = R_B5;
         a.ploss = R_LOSS; a.pstride = R_N; a.P = M_P;            // R_N: multiple of 4 floats, keeps every CTA's partial 16-byte aligned
-        return launch_student_tc<SpecMLP>(a, grid, st);
+        return launch_student_tc<SpecMLP>(a, grid, st, act && act->image_prebuilt);
     }
     const PolicyOffsets o = policy_offsets(4);
     a.obf = params;
@@ -947,7 +999,7 @@ int student_tc_run_ex(int kind, const float* params, const float* x, const float
     a.ploss = o.total; a.pstride = o.total + 1; a.P = o.total;
     // obfilter / logstd entries of the partial vectors are never written by the kernel: keep them zero
     if (!fwd_only) RB_CUDA(cudaMemsetAsync(ws + WS_PART, 0, sizeof(float) * (size_t)grid * a.pstride, st));
-    return launch_student_tc<SpecPOL>(a, grid, st);
+    return launch_student_tc<SpecPOL>(a, grid, st, act && act->image_prebuilt);
 }
 
 }  // namespace rb

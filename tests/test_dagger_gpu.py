@@ -64,9 +64,9 @@ def test_loss_curve_matches_cpu_restatement(kind_name, keep_prob, mode_name):
     print("%s %s kp=%.1f loss curve: first %.4g last %.4g, max rel err %.3g; reward err %.3g" %
           (kind_name, mode_name, keep_prob, ref_losses[0], ref_losses[-1], rel.max(), np.abs(np.array(dev_rews) - ref_rews).max()))
     assert ref_losses[-1] < ref_losses[0]                 # it learns
-    # stated loss-curve tolerance, closed loop over 70 iterations vs the float64 restatement: 2e-3 (fp32 kernels); 1e-2 for the
-    # tensor-core kernels, whose bf16x3 products are good to ~1e-5 per evaluation (teacher label AND student) before feedback
-    tol = 2e-3 if mode_name == "fp32" else 1e-2
+    # stated loss-curve tolerance, closed loop over 70 iterations vs the float64 restatement, at ~4x the measured values: fp32 kernels 1.8e-5
+    # -> 1e-4; tensor-core kernels (bf16x3 products, ~1e-5 per evaluation of teacher label AND student, then fed back) 2.8e-4 -> 1e-3
+    tol = 1e-4 if mode_name == "fp32" else 1e-3
     assert rel.max() <= tol
     assert np.abs(np.array(dev_rews) - ref_rews).max() <= tol
     assert np.abs(tr.student.params.cpu().numpy() - theta).max() <= tol

@@ -8,7 +8,7 @@ from oracle import lstm_np as L
 from oracle import nn_np as NN
 
 pytestmark = pytest.mark.gpu
-TOL = 2e-3      # stated tolerance of the tensor-core (bf16x3) student kernels, relative to max(1, |ref|)
+TOL = 3e-5      # tensor-core (bf16x3) LSTM kernels vs float64, relative to max(1, |ref|): measured 7.7e-6 over the cases below, gate at ~4x
 
 
 def _data(B, seed):
@@ -51,8 +51,12 @@ def test_loss_and_bptt_gradient_match_oracle(B, keep_prob, loss_kind):
     assert e_s <= TOL and e_l <= TOL and e_g <= TOL
     blocks = dict(We=(0, 128), be=(128, 160), Wl=(160, L.L_BL), bl=(L.L_BL, L.L_HEAD0), head0=(L.L_HEAD0, L.L_HEAD0 + L.L_HEAD_SZ),
                   head9=(L.L_HEAD0 + 9 * L.L_HEAD_SZ, L.P))
+    worst_block = 0.0
     for name, (a, b) in blocks.items():
-        assert np.abs(gl[a:b] - rg[a:b]).max() <= TOL * max(1.0, np.abs(rg[a:b]).max()), name
+        e_b = np.abs(gl[a:b] - rg[a:b]).max() / max(1.0, np.abs(rg[a:b]).max())
+        worst_block = max(worst_block, e_b)
+        assert e_b <= 10 * TOL, name                       # every parameter block relative to ITS OWN largest gradient entry
+    print("  worst per-block gradient error (relative to the block's own max) %.3g" % worst_block)
     net.loss_grad(torch.from_numpy(ob).cuda(), torch.from_numpy(pp).cuda(), torch.from_numpy(tp).cuda(), torch.from_numpy(st).cuda(),
                   keep_prob=keep_prob, seed=seed, sample_id0=sid0, iteration=it, loss_kind=loss_kind)
     assert np.array_equal(gl, net.gradloss.cpu().numpy().astype(np.float64))            # deterministic
@@ -147,7 +151,7 @@ def test_state_threaded_bptt_matches_oracle():
         e_fin, e_l = np.abs(fin.cpu().numpy() - rfin).max(), abs(dev_loss - rl) / max(1.0, abs(rl))
         print("threaded batch %d: final state err %.3g (same parameters) / %.3g (independent chain, |state| max %.3g), loss %.5g rel err %.3g"
               % (it, e_k, e_fin, np.abs(rfin).max(), rl, e_l))
-        assert e_k <= 1e-4 and e_fin <= TOL and e_l <= 1e-4
+        assert e_k <= 2e-5 and e_fin <= 2.5e-3 and e_l <= 1e-4       # measured 4e-6 / 7.4e-4 (independent chain: see above) / 1e-5
         assert it == 0 or np.abs(rfin).max() > 1e-2                          # a non-trivial state is being threaded
         s_dev, s_ref = fin, np.asarray(rfin, np.float32)
 

@@ -12,9 +12,9 @@ pytestmark = pytest.mark.gpu
 def _modes():
     from reacherdistilation_b200 import MODE_FP32, MODE_TC
     from reacherdistilation_b200._lib import lib
-    out = [("fp32", MODE_FP32, 2e-6)]
+    out = [("fp32", MODE_FP32, 1e-6)]              # measured 2.4e-7 (fp32 FMA order vs float64) / 6.6e-6 (tcgen05, bf16x3 operands): gates at ~3x
     if lib().rb_mode_available(MODE_TC):
-        out.append(("tc", MODE_TC, 5e-5))
+        out.append(("tc", MODE_TC, 2e-5))
     return out
 
 
@@ -48,11 +48,47 @@ def test_policy_forward_host_entry_point():
 
 
 @pytest.mark.parametrize("mode_name", ["fp32", "tc"])
-def test_fused_teacher_rollout_vs_oracle(mode_name):
-    """Closed loop for 60 steps incl. an auto-reset: buffers (obs, pdflat, rew, done) vs the C oracle running the same policy.
-    The policy is in the loop, so a difference d in the action feeds back and is amplified ~1e3 over an episode (measured:
-    fp32 d~2e-7 -> 3e-4; tc d~1e-5 -> 3e-3 typical, far more on the worst env).  Closed-loop gate: see below; the teacher-forced check
-    pins the policy itself to kernel precision (2e-6 fp32, 5e-5 tc)."""
+def test_fused_teacher_rollout_teacher_forced_policy_and_action_forced_physics(mode_name):
+    """THE parity gate of the fused rollout (60 steps incl. an auto-reset), free of closed-loop amplification:
+      * teacher-forced: the recorded pdflat is the oracle policy of the recorded observation, to kernel precision (1e-6 fp32, 2e-5 tcgen05);
+      * action-forced: the recorded observations / done flags are, BIT FOR BIT, what the host build of csrc/physics.cuh (tests/twin/) produces
+        when it is stepped with the recorded actions -- the physics inside the fused kernel is exactly the arithmetic whose tolerance against
+        the float64 oracle tests/test_physics_twin_cpu.py states (rewards: to the last ulp of the MUFU square root)."""
+    from twin.physics_twin import PhysicsTwin
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.teacher import init_policy_params
+    sel = [m for m in _modes() if m[0] == mode_name]
+    if not sel:
+        pytest.skip("RB_MODE_TC not compiled into this build")
+    name, mode, ptol = sel[0]
+    n, T, seed = 1000, 60, 2
+    p = init_policy_params(seed=0, final_std=0.3)
+    env = VecReacher(num_envs=n, seed=seed)
+    ob0 = env.reset().cpu().numpy()
+    out = env.rollout_policy(torch.from_numpy(p).cuda(), T, nout=2, mode=mode)
+    d_obs, d_pd, d_rew, d_done = (out[k].cpu().numpy() for k in ("obs", "pdflat", "rew", "done"))
+    ref_pd = NN.policy_fwd(d_obs.reshape(-1, 11), p).reshape(T, n, 4)
+    e_pd = np.abs(d_pd - ref_pd).max()
+    tw = PhysicsTwin(n, seed=seed)
+    assert np.array_equal(tw.reset(), ob0) and np.array_equal(d_obs[0], ob0)
+    e_rew = 0.0
+    for t in range(T):
+        ob, rw, dn = tw.step(d_pd[t, :, :2])
+        if t + 1 < T:
+            assert np.array_equal(ob, d_obs[t + 1]), "fused-kernel physics differs from the host build at step %d" % t
+        assert np.array_equal(dn, d_done[t].astype(bool))
+        e_rew = max(e_rew, float(np.abs(rw - d_rew[t]).max()))
+    print("fused rollout %s: teacher-forced pdflat err %.3g (gate %.1g); action-forced obs bit-identical to the host twin, reward err %.3g" % (name, e_pd, ptol, e_rew))
+    assert e_pd <= ptol and e_rew <= 5e-7
+    env.close()
+
+
+@pytest.mark.parametrize("mode_name", ["fp32", "tc"])
+def test_fused_teacher_rollout_closed_loop_distribution_vs_oracle(mode_name):
+    """Closed loop (policy in the loop) vs the C oracle running the same policy: informative, not the parity gate.  A difference d in the
+    action feeds back through gear 200 and the stiff joint limit (an oracle-vs-oracle perturbation study gives 1e-5 -> 1e-1 on the worst of
+    ~1000 envs within an episode), so the gate is on the distribution over envs of the per-env worst error, at ~4x the measured values:
+    median / 99 % / max  fp32 1.6e-6 / 4.1e-5 / 3.9e-4 -> 1e-5 / 2e-4 / 2e-3,  tcgen05 2.5e-5 / 5.7e-4 / 2.4e-2 -> 1e-4 / 2.5e-3 / 1e-1."""
     from reacherdistilation_b200.env import VecReacher
     from reacherdistilation_b200.teacher import init_policy_params
     sel = [m for m in _modes() if m[0] == mode_name]
@@ -68,17 +104,10 @@ def test_fused_teacher_rollout_vs_oracle(mode_name):
     obs, pd, rew, done, _ = c.rollout_policy(T, p)
     assert np.array_equal(out["done"].cpu().numpy(), done)
     d_obs, d_pd, d_rew = out["obs"].cpu().numpy(), out["pdflat"].cpu().numpy(), out["rew"].cpu().numpy()
-    e_obs, e_pd, e_rew = np.abs(d_obs - obs).max(), np.abs(d_pd - pd).max(), np.abs(d_rew - rew).max()
-    print("fused rollout %s: obs %.3g pdflat %.3g rew %.3g" % (name, e_obs, e_pd, e_rew))
-    # The feedback through gear 200 and the stiff joint limit amplifies a 1e-5 action perturbation to ~1e-1 on the worst of ~1000 envs within
-    # one episode (oracle perturbation study, __graft_entry__.smoke), so the closed-loop gate is on the distribution over envs of the per-env
-    # worst error (median / 99th percentile / max): fp32 1e-4 / 1e-3 / 5e-2, tc 1e-3 / 1e-2 / 2.5e-1.
     e_env = np.maximum(np.maximum(np.abs(d_obs - obs).max(axis=(0, 2)), np.abs(d_pd - pd).max(axis=(0, 2))), np.abs(d_rew - rew).max(axis=0))
-    lim = (1e-4, 1e-3, 5e-2) if name == "fp32" else (1e-3, 1e-2, 2.5e-1)
+    print("fused rollout %s closed loop, per-env worst error: median %.3g, 99%% %.3g, max %.3g" % (name, np.median(e_env), np.quantile(e_env, 0.99), e_env.max()))
+    lim = (1e-5, 2e-4, 2e-3) if name == "fp32" else (1e-4, 2.5e-3, 1e-1)
     assert np.median(e_env) <= lim[0] and np.quantile(e_env, 0.99) <= lim[1] and e_env.max() <= lim[2], (np.median(e_env), np.quantile(e_env, 0.99), e_env.max())
-    # teacher-forced check: the recorded pdflat is the policy of the recorded obs, to kernel precision
-    ref_pd = NN.policy_fwd(out["obs"].cpu().numpy().reshape(-1, 11), p).reshape(T, n, 4)
-    assert np.abs(out["pdflat"].cpu().numpy() - ref_pd).max() <= ptol
     env.close()
 
 

@@ -11,9 +11,9 @@ pytestmark = pytest.mark.gpu
 def _modes():
     from reacherdistilation_b200 import MODE_FP32, MODE_TC
     from reacherdistilation_b200._lib import lib
-    out = [("fp32", MODE_FP32, 3e-5)]
+    out = [("fp32", MODE_FP32, 3e-6)]               # measured over all cases below: 8.7e-7 (fp32 kernels) / 2.4e-5 (tcgen05, bf16x3 operands): gates at ~4x
     if lib().rb_student_mode_available(MODE_TC):
-        out.append(("tc", MODE_TC, 2e-3))
+        out.append(("tc", MODE_TC, 1e-4))
     return out
 
 
