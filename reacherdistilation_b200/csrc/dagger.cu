@@ -86,7 +86,7 @@ __global__ void k_set_clock(uint32_t* clock, uint32_t iteration, uint32_t adam_t
 // implemented in student_tc.cu
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
-struct StepClock { const uint32_t* clock; float lr; };
+struct StepClock { const uint32_t* clock; float lr, beta1, beta2; };
 struct ActFuse {
     float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
     uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act; int image_prebuilt;
@@ -95,7 +95,7 @@ int student_tc_run_ex(int kind, const float* params, const float* x, const float
                       float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, const ActFuse* act,
                       cudaStream_t st);
 int64_t student_tc_act_covered(int64_t B, int grid);
-int student_tc_build_image(int kind, const float* params, void* workspace, cudaStream_t st);
+int student_tc_build_image(int kind, const float* params, void* workspace, const StepClock* clk, cudaStream_t st);
 int student_tc_grid(int* grid);
 
 // implemented in policy_tc.cu
@@ -257,7 +257,8 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
         // second branch beside the observe kernel (two parallel nodes of the captured graph) and joined in front of the student launch
         RB_CUDA(cudaEventRecord(d->ev_fork, st));
         RB_CUDA(cudaStreamWaitEvent(d->side_stream, d->ev_fork, 0));
-        int rc = student_tc_build_image(d->kind, params, ws, d->side_stream);
+        const StepClock clk{d->clock, lr, b1, b2};
+        int rc = student_tc_build_image(d->kind, params, ws, &clk, d->side_stream);
         if (rc) return rc;
         RB_CUDA(cudaEventRecord(d->ev_join, d->side_stream));
         rc = dagger_observe_tc(e, d->teacher_img, d->kind, d->keep_prob, (const float4*)d->prev_t, d->prev_rec_rew, 0u, d->clock, obs, t_pd, x, (float*)xa, st);
@@ -265,7 +266,6 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
         RB_CUDA(cudaStreamWaitEvent(st, d->ev_join, 0));                      // join
         const AdamFuse af{params, m, v, 0.f, b1, b2, eps, gscale};
         const PeerExchange px{world, rank, 0u, slots_even, flags, slots_odd};
-        const StepClock clk{d->clock, lr};
         if (fuse_act) {      // env step, clock advance and loss mailbox inside the student launch: two launches per iteration
             const ActFuse act{e->qv, e->tp, e->ctr, d->prev_t, d->prev_rec_rew, d->last_reward, rew, done, (uint32_t)e->seed, (uint32_t)(e->seed >> 32),
                               e->offset, d->act_flags, d->clock, d->mailbox_dev, xa, 1};

@@ -309,7 +309,7 @@ static int launch_student(const NetSpec& S, const float* params, const float* x,
 // implemented in student_tc.cu (tcgen05 path)
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
-struct StepClock { const uint32_t* clock; float lr; };
+struct StepClock { const uint32_t* clock; float lr, beta1, beta2; };
 int student_tc_run(int kind, const float* params, const float* x, const float* tpd, int64_t B, int loss_kind, int fwd_only, float* s_out,
                    float* gradloss, void* workspace, const AdamFuse* adam, const PeerExchange* px, const StepClock* clk, cudaStream_t st);
 size_t student_tc_workspace_floats();

@@ -87,6 +87,7 @@ struct StudentTcArgs {
     int loss_kind, fwd_only;
     // cooperative phases (all global scratch lives in the caller's workspace)
     const float* params;          // flat parameter vector (fold / finish / Adam)
+    float* ctlws;                 // [64] scalars handed from k_student_image to k_student_tc: [0] = Adam step size lr_t of this step (device-clock mode)
     float* snap;                  // SpecMLP: snapshot of W3 | b3 | W4 (params[M_W3 .. M_B4)) taken by k_student_image: what the un-fold reads
     uint8_t* wimg;                // split weight image: hi tiles then lo tiles, exactly the shared-memory layout (built by k_student_image)
     float* red;                   // reduced partial vector [pstride]
@@ -140,7 +141,6 @@ __device__ __forceinline__ float ld_relaxed_sys(const float* p) {
 }
 
 struct __align__(16) StudentTcCtl {
-    float lr_t;                   // Adam step size of this launch (from the host, or from the device clock)
     uint32_t epoch;
     uint32_t iter;                // iterations done once this launch has finished (clock[0] + 1): value of the act flags / mailbox
     uint64_t mbar;                // forward layers / dgrad results
@@ -554,6 +554,10 @@ template <class S> __global__ void __launch_bounds__(256) k_student_image(const 
         for (int i = gthreads - 1 - gtid; i < M_SNAP; i += gthreads) a.snap[i] = ldw(a.params + M_W3 + i);
     }
     LayerLoop<S>::build_image(a, gtid, gthreads);
+    if (gtid == gthreads - 1 && a.clock) {         // same formula as the host (student.cu: adam_lr_t), in double: ~2 us of FP64, kept off k_student_tc's path
+        const double t = (double)(a.clock[1] + 1u);
+        a.ctlws[0] = (float)((double)a.lr * sqrt(1.0 - pow((double)a.beta2, t)) / (1.0 - pow((double)a.beta1, t)));
+    }
 }
 
 // One cooperative launch = tiles (forward, loss, backward; weight gradients in TMEM) -> partials -> grid-wide fixed-order reduction ->
@@ -581,10 +585,8 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         mbar_init(&ctl.mbar, 1); mbar_init(&ctl.mbar2, 1); mbar_init(&ctl.mbar_load, 1); fence_mbar_init();
         mbar_expect_tx(&ctl.mbar_load, 2 * G::wtile_bytes());
         bulk_g2s(w_hi, a.wimg, 2 * G::wtile_bytes(), &ctl.mbar_load);
-        ctl.lr_t = a.lr_t; ctl.epoch = a.epoch;
-        if (a.clock) {                             // same formula as the host (student.cu: adam_lr_t), in double
-            const double t = (double)(a.clock[1] + 1u);
-            ctl.lr_t = (float)((double)a.lr * sqrt(1.0 - pow((double)a.beta2, t)) / (1.0 - pow((double)a.beta1, t)));
+        ctl.epoch = a.epoch;
+        if (a.clock) {                             // device-side step clock (CUDA-graph replay); lr_t of this step comes from k_student_image (a.ctlws)
             ctl.epoch = a.clock[2] + 1u;
             ctl.iter = a.clock[0] + 1u;
         }
@@ -814,7 +816,7 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
         // un-fold reads the W3 | b3 | W4 snapshot (a.snap) instead of the live parameters, so no thread waits for another one of this GPU.
         const uint32_t epoch = ctl.epoch;
         float* gl = a.gradloss;
-        const float lr_t = ctl.lr_t;
+        const float lr_t = a.clock ? ldw(a.ctlws) : a.lr_t;
         auto apply = [&](int i, float g) {                   // final value of entry i: gradient vector, loss mailbox, Adam (same arithmetic as k_adam)
             gl[i] = g;
             if (i == a.P) { if (a.act_on) act_finish(a, g, ctl.iter, a.world <= 1, true); }
@@ -881,9 +883,9 @@ static int tc_grid(int64_t B, int* grid) {
     return RB_OK;
 }
 
-// workspace (floats): [snapshot W3 | b3 | W4 20608][reduced 8192][weight image 12288 (48 KB)][partials ST_MAX_GRID * 8192]
-constexpr size_t WS_SNAP = 0, WS_RED = 20608, WS_IMG = WS_RED + 8192, WS_PART = WS_IMG + 12288, WS_PSTRIDE_MAX = 8192;
-static_assert(M_SNAP <= (int)WS_RED && M_W3 + 16384 == M_B3 && M_B3 + 128 == M_W4 && M_W4 + 4096 == M_B4, "W3 | b3 | W4 snapshot layout");
+// workspace (floats): [snapshot W3 | b3 | W4 20608][hand-over scalars 64][reduced 8192][weight image 12288 (48 KB)][partials ST_MAX_GRID * 8192]
+constexpr size_t WS_SNAP = 0, WS_CTL = 20608, WS_RED = WS_CTL + 64, WS_IMG = WS_RED + 8192, WS_PART = WS_IMG + 12288, WS_PSTRIDE_MAX = 8192;
+static_assert(M_SNAP <= (int)WS_CTL && (WS_IMG * 4) % 16 == 0 && M_W3 + 16384 == M_B3 && M_B3 + 128 == M_W4 && M_W4 + 4096 == M_B4, "W3 | b3 | W4 snapshot layout");
 
 size_t student_tc_workspace_floats() { return WS_PART + (size_t)ST_MAX_GRID * WS_PSTRIDE_MAX; }
 
@@ -911,7 +913,7 @@ template <class S> static int launch_student_tc(StudentTcArgs& a, int grid, cuda
 
 struct AdamFuse { float* p; float* m; float* v; float lr_t, beta1, beta2, eps, gscale; };
 struct PeerExchange { int world, rank; uint32_t epoch; const uint64_t* gl_ptrs; const uint64_t* flag_ptrs; const uint64_t* gl_ptrs_alt; };
-struct StepClock { const uint32_t* clock; float lr; };
+struct StepClock { const uint32_t* clock; float lr, beta1, beta2; };
 struct ActFuse {              // fused env step of rb_dagger_step (see StudentTcArgs::act_*); x_act: un-dropped input rows or NULL
     float4* qv; float4* tp; uint4* ctr; float4* prev_t; float* prev_rec_rew; float* last_reward; float* rew; uint8_t* done;
     uint32_t k0, k1, offset; uint32_t* flags; uint32_t* clock; uint2* mailbox; const float* x_act;
@@ -936,11 +938,12 @@ int student_tc_run(int kind, const float* params, const float* x, const float* t
 }
 
 // weight image (+ un-fold snapshot) of `params` into the workspace: what every k_student_tc launch on these parameters starts from
-int student_tc_build_image(int kind, const float* params, void* workspace, cudaStream_t st) {
+int student_tc_build_image(int kind, const float* params, void* workspace, const StepClock* clk, cudaStream_t st) {
     RB_REQUIRE(params != nullptr && workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & 15) == 0, "bad arguments");
     float* ws = (float*)workspace;
     StudentTcArgs a{};
-    a.params = params; a.snap = ws + WS_SNAP; a.wimg = (uint8_t*)(ws + WS_IMG);
+    a.params = params; a.snap = ws + WS_SNAP; a.ctlws = ws + WS_CTL; a.wimg = (uint8_t*)(ws + WS_IMG);
+    if (clk && clk->clock) { a.clock = clk->clock; a.lr = clk->lr; a.beta1 = clk->beta1; a.beta2 = clk->beta2; }
     if (kind == RB_STUDENT_MLP) {
         a.w[0] = params + M_W1; a.b[0] = params + M_B1; a.w[1] = params + M_W2; a.b[1] = params + M_B2;
         a.w[2] = nullptr; a.b[2] = nullptr; a.w[3] = params + M_W5; a.b[3] = params + M_B5;
@@ -962,7 +965,7 @@ int student_tc_run_ex(int kind, const float* params, const float* x, const float
     if (rc) return rc;
     StudentTcArgs a{};
     a.x = x; a.t = tpd; a.s_out = (float4*)s_out; a.B = B; a.loss_kind = loss_kind; a.fwd_only = fwd_only; a.partials = ws + WS_PART;
-    a.params = params; a.snap = ws + WS_SNAP; a.wimg = (uint8_t*)(ws + WS_IMG); a.red = ws + WS_RED; a.gradloss = gradloss;
+    a.params = params; a.snap = ws + WS_SNAP; a.ctlws = ws + WS_CTL; a.wimg = (uint8_t*)(ws + WS_IMG); a.red = ws + WS_RED; a.gradloss = gradloss;
     if (adam && !fwd_only) {
         a.do_adam = 1; a.adam_p = adam->p; a.adam_m = adam->m; a.adam_v = adam->v;
         a.lr_t = adam->lr_t; a.beta1 = adam->beta1; a.beta2 = adam->beta2; a.eps = adam->eps; a.gscale = adam->gscale;
