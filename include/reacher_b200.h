@@ -264,6 +264,30 @@ int rb_lstm_step(rb_lstm_ctx* ctx, float* params_dev, float* m_dev, float* v_dev
                  const float* t_pdflat_dev, const float* init_state_dev, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0,
                  int loss_kind, float* s_pdflat_dev, float* gradloss_dev, void* workspace_dev, float lr, float beta1, float beta2, float eps,
                  float grad_scale, int use_graph, void* stream);
+/* ------------------------------------------------------------------------------------------------ two-headed LSTM student -
+ * lstm_graph + total loss of the backup experiment  src/distilation/backup/student_rollout.py:130-200 (graph), :303-328 (loss = KL(student ||
+ * teacher) + sum (reward - reward_target)^2), :331-338 (Adam 1e-3): a shared LSTMCell(units) over `steps` unrolled steps of
+ * [dropout(ob) (11) | stepped action (2)], and per unrolled step an un-shared head: trunk = tanh(dense_trunk(m)); reward = dense_1 over
+ * n_reward_hidden tanh layers on the trunk; pdflat = dense_4(tanh(dense_action_hidden(trunk))).
+ * spec = RB_LSTM2_SPEC_LEN ints {units, steps, carry_state, trunk, action_hidden, n_reward_hidden, reward_hidden[0..3]}:
+ *   the checked-in source is {NUM_UNITS, STEPS_UNROLLED, 0, 128, 64, 1, 64} -- its loop never reassigns `state` (:156), so every unrolled step
+ *   starts from the fed initial state and final_state is that state; the graph in the reference's tfevents files (src/~/reacher/data/viz/1) is
+ *   {1, 2, 1, 128, 64, 3, 64, 32, 64} with the state carried through the unroll.
+ * Windows are time-major: ob [T,B,11], action [T,B,2], t_pdflat / s_pdflat [T,B,4], reward / reward_target [T,B]; state [2,B,units] (c, m),
+ * NULL = zeros.  Flat parameters: W_l[13+units][4 units] b_l, then per step: Wd bd | Wr_k br_k ... | Wro bro | Wa ba | Wp bp (row-major
+ * [in][out] kernels, as tf.layers.dense).  gradloss = P + 3 floats: flat gradient | total loss | KL part | reward part.
+ * Adam: rb_adam_step on the flat vectors.  All products run on tcgen05 (rb_gemm_bf16x3); results are bit-reproducible.               */
+#define RB_LSTM2_SPEC_LEN 10
+int64_t rb_lstm2_param_count(const int* spec);
+int64_t rb_lstm2_workspace_bytes(const int* spec, int64_t batch);
+/* sess.run((s_ac, final_state_combined))  backup/student_rollout.py:527-535: forward only, keep_prob = 1 */
+int rb_lstm2_fwd(const int* spec, const float* params_dev, const float* ob_dev, const float* action_dev, const float* init_state_dev, int64_t B,
+                 float* s_pdflat_dev, float* reward_dev, float* final_state_dev /* may be NULL */, void* workspace_dev, void* stream);
+/* sess.run([loss, minimize_adam]) minus Adam  backup/student_rollout.py:508-522 */
+int rb_lstm2_loss_grad(const int* spec, const float* params_dev, const float* ob_dev, const float* action_dev, const float* t_pdflat_dev,
+                       const float* reward_target_dev, const float* init_state_dev, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0,
+                       uint32_t iteration, int loss_kind, float* s_pdflat_dev, float* reward_dev, float* final_state_dev /* may be NULL */,
+                       float* gradloss_dev, void* workspace_dev, void* stream);
 /* The tensor-core GEMM the LSTM is built from: C[M,N] (+)= epilogue(A[M,K] B[K,N]), fp32 in/out, bf16x3 inside.
  * x_mn = 0: element (row, k) of the operand at X[row * ld + k]; 1: at X[k * ld + row].  epilogue: + bias[n], tanh (act = 1),
  * * (1 - H[m,n]^2).  workspace (optional, floats) enables deterministic split-K.                                              */

@@ -79,6 +79,11 @@ _SIGS = {
     "rb_lstm_ctx_set_clock": (C.c_int, [_vp, C.c_uint32, C.c_uint32, _vp]),
     "rb_lstm_step": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_int, _fp, _fp, _vp, C.c_float,
                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp]),
+    "rb_lstm2_param_count": (C.c_int64, [C.POINTER(C.c_int)]),
+    "rb_lstm2_workspace_bytes": (C.c_int64, [C.POINTER(C.c_int), C.c_int64]),
+    "rb_lstm2_fwd": (C.c_int, [C.POINTER(C.c_int), _fp, _fp, _fp, _fp, C.c_int64, _fp, _fp, _fp, _vp, _vp]),
+    "rb_lstm2_loss_grad": (C.c_int, [C.POINTER(C.c_int), _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
+                                     _fp, _fp, _fp, _fp, _vp, _vp]),
     "rb_gemm_bf16x3": (C.c_int, [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
                                  C.c_int, _fp, C.c_int64, _vp]),
     "rb_dense_param_count": (C.c_int64, [C.c_int, C.POINTER(C.c_int)]),

@@ -2,7 +2,7 @@
 """CLI with the reference's flags (/root/reference src/distilation/main.py:9-27): -lt / -ct / -k / -ch / -r."""
 import argparse
 
-from . import config, lstm_train, mlp_train
+from . import config, lstm2_train, lstm_train, mlp_train
 
 
 def main(argv=None):
@@ -13,6 +13,8 @@ def main(argv=None):
     parser.add_argument("-ch", "--check", help="check point", action="store_true")
     parser.add_argument("-r", "--restore", help="restore", action="store_true")
     parser.add_argument("--num_envs", type=int, default=config.NUM_ENVS)
+    parser.add_argument("--two_headed", action="store_true", help="with -lt: the two-headed LSTM graph (action + reward heads, loss = KL + squared reward "
+                        "error) of backup/student_rollout.py:130-200,328 instead of student_nn.student_lstm_graph")
     parser.add_argument("--iterations", type=int, default=None)
     parser.add_argument("--teacher", default=None, help=".npz with the teacher weights teacher.py:17-20 restores from teacher.ckpt (flat `params` or the "
                         "baselines variables pi/obfilter/*, pi/pol/*); default: <base_path>/teacher.npz, else a seeded UNTRAINED teacher (announced)")
@@ -32,6 +34,9 @@ def main(argv=None):
         out = shapes(sd)
         print(out)
         return out
+    elif args.lstm_train and args.two_headed:
+        return lstm2_train.lstm_train(True, keep_prob, args.checkpoint, args.restore, num_envs=args.num_envs, iterations=args.iterations,
+                                      teacher_ckpt=args.teacher)
     elif args.lstm_train:
         return lstm_train.train(True, args.restore, num_envs=args.num_envs, iterations=args.iterations, keep_prob=keep_prob, teacher_ckpt=args.teacher,
                                 checkpoint=args.checkpoint)

@@ -266,3 +266,116 @@ def student_lstm_graph(ob_batch, keep_prob, prev_pdflat_batch, initial_state_bat
     if keep_prob >= 1.0:
         return net.forward(ob_batch, prev_pdflat_batch, initial_state_batch)
     raise NotImplementedError("dropout forward is part of loss_grad (training); acting uses keep_prob = 1 (lstm_train.py:176)")
+
+
+# ---------------------------------------------------------------------------------------------- two-headed LSTM student (backup experiment)
+def lstm2_spec(units=1, steps=2, carry_state=False, trunk=128, action_hidden=64, reward_hidden=(64,)):
+    """spec of rb_lstm2_* (include/reacher_b200.h).  Defaults = the checked-in source, backup/student_rollout.py:38-50,130-172 (NUM_UNITS 1,
+    STEPS_UNROLLED 2; its loop never reassigns `state`, so no state is carried); `LSTM2_TFEVENTS_SPEC` is the graph of the recorded tfevents."""
+    a = np.zeros(10, np.int32)
+    a[:6] = (units, steps, 1 if carry_state else 0, trunk, action_hidden, len(reward_hidden))
+    a[6:6 + len(reward_hidden)] = reward_hidden
+    return a
+
+
+LSTM2_TFEVENTS_SPEC = dict(units=1, steps=2, carry_state=True, reward_hidden=(64, 32, 64))
+
+
+def init_lstm2_params(spec, seed=0):
+    """glorot-uniform kernels, zero biases; layout: include/reacher_b200.h (cell, then per step trunk | reward layers | reward_out | action | pd)."""
+    U, T, _, D, A, nR = (int(v) for v in spec[:6])
+    rh = [int(v) for v in spec[6:6 + nR]]
+    rng = np.random.default_rng(seed)
+    parts = []
+    def glorot(fi, fo):
+        lim = np.sqrt(6.0 / (fi + fo))
+        parts.append(rng.uniform(-lim, lim, fi * fo).astype(np.float32)); parts.append(np.zeros(fo, np.float32))
+    glorot(13 + U, 4 * U)
+    for _ in range(T):
+        glorot(U, D)
+        prev = D
+        for r in rh:
+            glorot(prev, r)
+            prev = r
+        glorot(prev, 1)
+        glorot(D, A)
+        glorot(A, 4)
+    return np.concatenate(parts)
+
+
+class StudentLSTM2:
+    """lstm_graph + lstm_loss + the reward term (backup/student_rollout.py:130-200,328): flat parameters, Adam moments (lr 1e-3, :331-336) and
+    workspace of the two-headed LSTM student.  Windows are time-major [T,B,.]; state [2,B,units] (c, m)."""
+
+    def __init__(self, spec=None, seed=0, device=0, lr=1e-3, beta1=0.9, beta2=0.999, eps=1e-8, params=None):
+        import ctypes as C
+        self.device = torch.device("cuda", device) if isinstance(device, int) else torch.device(device)
+        self.spec = np.ascontiguousarray(lstm2_spec() if spec is None else spec, np.int32)
+        assert self.spec.size == 10
+        self._spec_p = self.spec.ctypes.data_as(C.POINTER(C.c_int))
+        self.P = int(lib().rb_lstm2_param_count(self._spec_p))
+        if self.P < 0:
+            raise _lib.ReacherB200Error(lib().rb_last_error().decode())
+        self.U, self.T, self.carry_state = int(self.spec[0]), int(self.spec[1]), bool(self.spec[2])
+        if params is None:
+            params = init_lstm2_params(self.spec, seed)
+        assert params.size == self.P
+        self.lr, self.beta1, self.beta2, self.eps = lr, beta1, beta2, eps
+        with torch.cuda.device(self.device):
+            self.params = torch.from_numpy(np.ascontiguousarray(params, np.float32)).to(self.device)
+            self.m, self.v = torch.zeros_like(self.params), torch.zeros_like(self.params)
+            self.gradloss = torch.zeros(self.P + 3, dtype=torch.float32, device=self.device)       # grad | total | KL part | reward part
+        self.t, self._ws, self._ws_batch = 0, None, 0
+
+    def _workspace(self, B):
+        if B > self._ws_batch:
+            nbytes = int(lib().rb_lstm2_workspace_bytes(self._spec_p, B))
+            with torch.cuda.device(self.device):
+                self._ws = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+            self._ws_batch = B
+        return self._ws
+
+    def zero_state(self, B):
+        return torch.zeros((2, B, self.U), dtype=torch.float32, device=self.device)
+
+    def forward(self, ob, action, state=None):
+        """Acting (:527-535): -> (s_pdflat [T,B,4], reward [T,B], final_state [2,B,units])."""
+        T, B = ob.shape[0], ob.shape[1]
+        assert T == self.T and action.shape == (T, B, 2)
+        ob, action = ob.contiguous(), action.contiguous()
+        s = torch.empty((T, B, 4), dtype=torch.float32, device=self.device)
+        rew = torch.empty((T, B), dtype=torch.float32, device=self.device)
+        fin = torch.empty((2, B, self.U), dtype=torch.float32, device=self.device)
+        check(lib().rb_lstm2_fwd(self._spec_p, ptr(self.params), ptr(ob), ptr(action), ptr(state.contiguous() if state is not None else None), B, ptr(s),
+                                 ptr(rew), ptr(fin), ptr(self._workspace(B)), stream_ptr()))
+        return s, rew, fin
+
+    def loss_grad(self, ob, action, t_pdflat, reward_target, state=None, keep_prob=1.0, seed=0, sample_id0=0, iteration=0, loss_kind=LOSS_KL_ST):
+        """Training windows (:508-522): fills self.gradloss = [flat grad | total loss | KL | reward sse]; returns (s_pdflat, reward)."""
+        T, B = ob.shape[0], ob.shape[1]
+        assert T == self.T and action.shape == (T, B, 2) and t_pdflat.shape == (T, B, 4) and reward_target.shape == (T, B)
+        ob, action, t_pdflat, reward_target = ob.contiguous(), action.contiguous(), t_pdflat.contiguous(), reward_target.contiguous()
+        s = torch.empty((T, B, 4), dtype=torch.float32, device=self.device)
+        rew = torch.empty((T, B), dtype=torch.float32, device=self.device)
+        check(lib().rb_lstm2_loss_grad(self._spec_p, ptr(self.params), ptr(ob), ptr(action), ptr(t_pdflat), ptr(reward_target),
+                                       ptr(state.contiguous() if state is not None else None), B, float(keep_prob), int(seed), int(sample_id0),
+                                       int(iteration), loss_kind, ptr(s), ptr(rew), None, ptr(self.gradloss), ptr(self._workspace(B)), stream_ptr()))
+        return s, rew
+
+    def adam_step(self, grad_scale=1.0):
+        self.t += 1
+        check(lib().rb_adam_step(ptr(self.params), ptr(self.m), ptr(self.v), ptr(self.gradloss), self.P, self.t, self.lr, self.beta1, self.beta2,
+                                 self.eps, grad_scale, stream_ptr()))
+
+    def state_dict(self):
+        return dict(kind="lstm2", spec=self.spec.tolist(), params=self.params.cpu(), m=self.m.cpu(), v=self.v.cpu(), t=self.t)
+
+    def load_state_dict(self, sd):
+        assert sd["kind"] == "lstm2" and list(sd["spec"]) == self.spec.tolist()
+        self.params.copy_(sd["params"]); self.m.copy_(sd["m"]); self.v.copy_(sd["v"]); self.t = int(sd["t"])
+
+
+def lstm_graph(input_ob, input_action, hidden_combined, net):
+    """Reference name (backup/student_rollout.py:130): forward of the two-headed graph -> (s_pdflat, final_state, reward)."""
+    s, rew, fin = net.forward(input_ob, input_action, hidden_combined)
+    return s, fin, rew
