@@ -196,7 +196,7 @@ def cpu_distill_leg(kind="mlp", seconds=6.0):
 def config1_leg(steps=1000):
     """BASELINE config 1, the reference's own CPU-runnable case (SURVEY 8(d).1 / CPU plan (i)): ONE env, a 1000-step teacher rollout in the
     per-step loop shape of mlp_train.py:120-139 -- (cpu) the restatement on one host thread, (gpu_gym_loop) the drop-in gym surface at batch 1
-    (one rb_policy_fwd + one rb_env_step_host per step: launch-latency bound, reported for honesty), (gpu_fused) the same 1000 steps as ONE
+    (make_mujoco_env(...).step() + TeacherAgent.mean_and_flat(): one round trip per step to the resident env server, csrc/serve.cu), (gpu_fused) the same 1000 steps as ONE
     rb_env_rollout_policy launch with the result read back.  A context figure; batch 1 is not what the GPU path is built for."""
     import numpy as np
     import torch
@@ -218,9 +218,9 @@ def config1_leg(steps=1000):
     ob = env.reset()
     for rep in range(2):                                   # first pass = warm-up
         torch.cuda.synchronize(); t0 = time.perf_counter()
-        for _ in range(steps):
+        for _ in range(steps):                              # `ac, _ = pi.act(False, ob); ob, reward, new, _ = env.step(ac)` (mlp_train.py:123-135)
             mean, _flat = teacher.mean_and_flat(ob)
-            ob, r, new, _ = env.step(mean.cpu().numpy())
+            ob, r, new, _ = env.step(mean)
         gym_loop = steps / (time.perf_counter() - t0)
     env.close()
     v = VecReacher(num_envs=1, seed=0); v.reset()

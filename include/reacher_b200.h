@@ -78,9 +78,20 @@ int rb_env_reset(rb_env* env, float* obs_dev, void* stream);
  * act_dev[N,2] -> obs_dev[N,11], rew_dev[N], done_dev[N] (1 at the 50th step).  Finished envs are auto-reset and
  * return their reset observation (the reference caller does `if new: ob = env.reset()`, mlp_train.py:137-139).   */
 int rb_env_step(rb_env* env, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream);
-/* same calls with HOST buffers (copies + synchronise inside) -- the gym-style surface for a host-resident caller */
+/* same calls with HOST buffers -- the gym-style surface for a host-resident caller.  N > 32: copies + launch + synchronise inside the call.
+ * N <= 32 (the reference's own shape, ONE env: BASELINE config 1): a resident server warp keeps the env state in registers and is driven
+ * through a 64-byte command line in mapped host memory -- no launch, no copy-engine transfer, ~5 us per call (csrc/serve.cu); it retires by
+ * itself after 1 ms without a call, and any device-side entry point on the same env retires it first.  Same arithmetic: bit-identical. */
 int rb_env_reset_host(rb_env* env, float* obs_host);
 int rb_env_step_host(rb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host);
+/* The per-step loop of the teacher warm-up at batch 1  src/distilation/mlp_train.py:120-139  (`ac = pi.act(ob)`; `ob, r, new, _ = env.step(ac)`)
+ * on the resident server (N <= 32): rb_env_serve_policy registers the policy (teacher.py:12-20; flat layout of rb_policy_param_count);
+ * rb_env_act_step_host = env.step(act) AND the policy's pdflat for the observation it returns (pd_next_host[N,4], may be NULL), one round
+ * trip; rb_env_serve_policy_fwd = sess.run(pi.pd.flat) for arbitrary observation rows obs_host[N,11].  Results are bit-identical to
+ * rb_env_step / rb_policy_fwd(RB_MODE_FP32).                                                                                        */
+int rb_env_serve_policy(rb_env* env, const float* params_host, int nout);
+int rb_env_serve_policy_fwd(rb_env* env, const float* obs_host, float* pdflat_host);
+int rb_env_act_step_host(rb_env* env, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* pd_next_host);
 
 /* explicit state access (parity tests start device and oracle from identical states; checkpoint / resume):
  * qpos_dev[N,2], qvel_dev[N,2], target_dev[N,2], fingertip_dev[N,2] (MuJoCo's stale xpos), step_dev[N] int32,

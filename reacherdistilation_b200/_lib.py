@@ -33,6 +33,9 @@ _SIGS = {
     "rb_env_step": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _vp]),
     "rb_env_reset_host": (C.c_int, [_vp, _fp]),
     "rb_env_step_host": (C.c_int, [_vp, _fp, _fp, _fp, _u8p]),
+    "rb_env_serve_policy": (C.c_int, [_vp, _fp, C.c_int]),
+    "rb_env_serve_policy_fwd": (C.c_int, [_vp, _fp, _fp]),
+    "rb_env_act_step_host": (C.c_int, [_vp, _fp, _fp, _fp, _u8p, _fp]),
     "rb_env_get_state": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i32p, _u32p, _fp, _vp]),
     "rb_env_set_state": (C.c_int, [_vp, _fp, _fp, _fp, _fp, _i32p, _u32p, _fp, _vp]),
     "rb_env_observe": (C.c_int, [_vp, _fp, _vp]),

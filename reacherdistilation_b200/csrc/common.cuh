@@ -31,12 +31,21 @@ struct rb_env {
     uint32_t* prog_flags_dev = nullptr;           // device alias of prog_flags_host
     uint32_t prog_epoch = 0;
     int prog_slab_len = 0;                        // > 0 only while the host call launches its kernel
+    void* serve = nullptr;                        // resident env server of the small host-surface envs (serve.cu), NULL until first used
 };
 
 namespace rb {
 
 void set_error(const char* fmt, ...);
 int cuda_fail(cudaError_t e, const char* what);
+
+// serve.cu: the resident env server of small host-surface envs (n <= 32).  env_quiesce retires it (state back in HBM) and is called by every
+// entry point that reads or writes the env state with ordinary launches; a no-op when no server is resident.
+int env_quiesce(rb_env* e);
+void env_serve_destroy(rb_env* e);
+bool env_serve_eligible(const rb_env* e);
+int env_serve_reset(rb_env* e, float* obs_host, float* pd_host);
+int env_serve_step(rb_env* e, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host, float* pd_host);
 
 #define RB_CUDA(call)                                             \
     do {                                                          \

@@ -167,6 +167,7 @@ int rb_dagger_observe(rb_dagger* d, const float* teacher_params, uint32_t iterat
                       void* stream) {
     RB_REQUIRE(d && teacher_params && obs && t_pd && x, "NULL argument");
     rb_env* e = d->env;
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     if (mode == RB_MODE_TC) {            // one fused kernel: observe + teacher (tcgen05) + student input
         if (!d->teacher_img) RB_CUDA(cudaMalloc(&d->teacher_img, policy_tc_image_bytes()));
         if (d->teacher_img_src != teacher_params) {
@@ -201,6 +202,7 @@ int rb_dagger_invalidate_teacher(rb_dagger* d) {
 int rb_dagger_act(rb_dagger* d, const float* s_pd, const float* t_pd, float* rew, uint8_t* done, void* stream) {
     RB_REQUIRE(d && s_pd, "NULL argument");
     rb_env* e = d->env;
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     k_dagger_act<<<(unsigned)((e->n + 127) / 128), 128, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float4*)s_pd, (const float4*)t_pd,
                                                                                   d->prev_t, d->prev_rec_rew, d->last_reward, rew, done,
                                                                                   (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset, nullptr, nullptr, nullptr, 0);
@@ -229,6 +231,7 @@ int rb_dagger_step(rb_dagger* d, const float* teacher_params, float* params, flo
     RB_REQUIRE(d->clock != nullptr, "call rb_dagger_set_clock first");
     RB_REQUIRE(world == 1 || (world >= 2 && world <= 8 && slots_even && slots_odd && flags), "data parallel: 2..8 ranks with peer slots and flags");
     rb_env* e = d->env;
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t loss_index = rb_student_param_count(d->kind);          // gradloss = [grad P | loss]
     if (!d->mailbox_host) {

@@ -235,6 +235,7 @@ int rb_env_create(rb_env** out, int64_t num_envs, uint64_t seed, int device, uin
 
 int rb_env_destroy(rb_env* e) {
     if (!e) return RB_OK;
+    env_serve_destroy(e);
     DeviceGuard guard(e->device);
     cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
@@ -252,6 +253,7 @@ int64_t rb_env_num_envs(const rb_env* e) { return e ? e->n : 0; }
 
 int rb_env_reset(rb_env* e, float* obs_dev, void* stream) {
     RB_REQUIRE(e != nullptr, "env is NULL");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     k_reset<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, obs_dev, (uint32_t)e->seed,
                                                                     (uint32_t)(e->seed >> 32), e->offset);
     RB_CUDA(cudaGetLastError());
@@ -260,6 +262,7 @@ int rb_env_reset(rb_env* e, float* obs_dev, void* stream) {
 
 int rb_env_observe(rb_env* e, float* obs_dev, void* stream) {
     RB_REQUIRE(e != nullptr && obs_dev != nullptr, "NULL argument");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     k_observe<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, obs_dev);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
@@ -267,6 +270,7 @@ int rb_env_observe(rb_env* e, float* obs_dev, void* stream) {
 
 int rb_env_step(rb_env* e, const float* act_dev, float* obs_dev, float* rew_dev, uint8_t* done_dev, void* stream) {
     RB_REQUIRE(e != nullptr && act_dev != nullptr, "NULL argument");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     k_step<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float2*)act_dev, obs_dev, rew_dev,
                                                                    done_dev, (uint32_t)e->seed, (uint32_t)(e->seed >> 32), e->offset);
     RB_CUDA(cudaGetLastError());
@@ -296,6 +300,7 @@ static int ensure_host_staging(rb_env* e) {
 
 int rb_env_reset_host(rb_env* e, float* obs_host) {
     RB_REQUIRE(e != nullptr && obs_host != nullptr, "NULL argument");
+    if (env_serve_eligible(e)) return env_serve_reset(e, obs_host, nullptr);      // small host-surface envs: resident server, no launch (serve.cu)
     int rc = ensure_host_staging(e);
     if (rc) return rc;
     rc = rb_env_reset(e, e->d_obs, e->host_stream);
@@ -307,6 +312,7 @@ int rb_env_reset_host(rb_env* e, float* obs_host) {
 
 int rb_env_step_host(rb_env* e, const float* act_host, float* obs_host, float* rew_host, uint8_t* done_host) {
     RB_REQUIRE(e != nullptr && act_host != nullptr && obs_host != nullptr, "NULL argument");
+    if (env_serve_eligible(e)) return env_serve_step(e, act_host, obs_host, rew_host, done_host, nullptr);
     int rc = ensure_host_staging(e);
     if (rc) return rc;
     cudaStream_t s = e->host_stream;
@@ -323,6 +329,7 @@ int rb_env_step_host(rb_env* e, const float* act_host, float* obs_host, float* r
 int rb_env_get_state(rb_env* e, float* qpos, float* qvel, float* target, float* tip, int32_t* step, uint32_t* episode, float* qpos_lo,
                      void* stream) {
     RB_REQUIRE(e != nullptr, "env is NULL");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     k_get_state<<<(unsigned)((e->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (float2*)qpos, (float2*)qvel,
                                                                                  (float2*)target, (float2*)tip, step, episode, (float2*)qpos_lo);
     RB_CUDA(cudaGetLastError());
@@ -332,6 +339,7 @@ int rb_env_get_state(rb_env* e, float* qpos, float* qvel, float* target, float* 
 int rb_env_set_state(rb_env* e, const float* qpos, const float* qvel, const float* target, const float* tip, const int32_t* step,
                      const uint32_t* episode, const float* qpos_lo, void* stream) {
     RB_REQUIRE(e != nullptr, "env is NULL");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     k_set_state<<<(unsigned)((e->n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, (const float2*)qpos,
                                                                                  (const float2*)qvel, (const float2*)target,
                                                                                  (const float2*)tip, step, episode, (const float2*)qpos_lo);
@@ -341,6 +349,7 @@ int rb_env_set_state(rb_env* e, const float* qpos, const float* qvel, const floa
 
 int rb_env_rollout_random(rb_env* e, int T, uint32_t step0, float* obs_buf, float* act_buf, float* rew_buf, uint8_t* done_buf, void* stream) {
     RB_REQUIRE(e != nullptr && T >= 0, "bad argument");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     if (T == 0) return RB_OK;
     k_rollout_random<<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, T, step0, obs_buf, (float2*)act_buf,
                                                                              rew_buf, done_buf, (uint32_t)e->seed,
@@ -387,6 +396,7 @@ int rb_policy_fwd_host(const float* params_host, int nout, const float* obs_host
 int rb_env_rollout_policy(rb_env* e, const float* params, int nout, int T, float* obs_buf, float* pd_buf, float* rew_buf,
                           uint8_t* done_buf, int mode, void* stream) {
     RB_REQUIRE(e != nullptr && params != nullptr && T >= 0, "bad argument");
+    { const int qrc = env_quiesce(e); if (qrc) return qrc; }
     RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
     if (T == 0) return RB_OK;
     if (mode == RB_MODE_TC) return rollout_policy_tc(e, params, nout, T, obs_buf, pd_buf, rew_buf, done_buf, (cudaStream_t)stream);

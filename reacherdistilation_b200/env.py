@@ -41,30 +41,63 @@ class VecReacher:
             self._rew = torch.empty((n,), dtype=torch.float32).pin_memory()
             self._done = torch.empty((n,), dtype=torch.uint8).pin_memory()
             self._act = torch.empty((n, 2), dtype=torch.float32).pin_memory()
+            self._pd = torch.empty((n, 4), dtype=torch.float32).pin_memory()
+            # numpy views + raw addresses, taken once: the per-step path below is a few hundred nanoseconds of Python around one C call
+            self._obs_np, self._rew_np, self._done_np, self._act_np, self._pd_np = (t.numpy() for t in (self._obs, self._rew, self._done, self._act, self._pd))
+            self._p_obs, self._p_rew, self._p_done, self._p_act, self._p_pd = (t.data_ptr() for t in (self._obs, self._rew, self._done, self._act, self._pd))
+            self._policy = None            # TeacherAgent registered with the resident env server (N <= 32): step() also returns its pdflat
+            self._last_ob = self._last_pd = None
         else:
             with torch.cuda.device(self.device):
                 self._obs = torch.empty((n, 11), dtype=torch.float32, device=self.device)
                 self._rew = torch.empty((n,), dtype=torch.float32, device=self.device)
                 self._done = torch.empty((n,), dtype=torch.uint8, device=self.device)
 
+    SERVE_MAX_ENVS = 32                    # csrc/serve.cu
+
+    def serve_policy(self, agent, params_host, nout):
+        """Register a policy with the resident env server (host surface, N <= 32): every step() then also evaluates it on the observation it
+        returns (one round trip for `ac = pi.act(ob); ob = env.step(ac)`, mlp_train.py:123-135).  Returns False when not applicable."""
+        if not self.host or self.num_envs > self.SERVE_MAX_ENVS:
+            return False
+        self._params_keep = np.ascontiguousarray(params_host, np.float32)
+        check(lib().rb_env_serve_policy(self._h, self._params_keep.ctypes.data, int(nout)))
+        self._policy, self._last_ob, self._last_pd = agent, None, None
+        return True
+
+    def _host_ob(self, with_pd):
+        ob = self._obs_np.copy()                                       # a fresh array per call, like gym (callers keep observations in lists)
+        ob = ob[0] if self.squeeze else ob
+        if with_pd:
+            self._last_ob, self._last_pd = ob, self._pd_np.copy()
+        return ob
+
     # ---- gym protocol --------------------------------------------------------------------------------------
     def reset(self):
         if self.host:
-            check(lib().rb_env_reset_host(self._h, ptr(self._obs)))
-            ob = self._obs.numpy()
-            return ob[0] if self.squeeze else ob
+            check(lib().rb_env_reset_host(self._h, self._p_obs))
+            self._last_ob = self._last_pd = None
+            return self._host_ob(False)
         check(lib().rb_env_reset(self._h, ptr(self._obs), stream_ptr()))
         return self._obs
 
     def step(self, action):
         n = self.num_envs
         if self.host:
-            self._act.copy_(torch.as_tensor(np.asarray(action, dtype=np.float32).reshape(n, 2)))
-            check(lib().rb_env_step_host(self._h, ptr(self._act), ptr(self._obs), ptr(self._rew), ptr(self._done)))
-            ob, rew, done = self._obs.numpy(), self._rew.numpy(), self._done.numpy().astype(bool)
+            if torch.is_tensor(action):
+                action = action.detach().cpu().numpy()
+            self._act_np[...] = np.asarray(action, dtype=np.float32).reshape(n, 2)
+            served = self._policy is not None
+            if served:
+                rc = lib().rb_env_act_step_host(self._h, self._p_act, self._p_obs, self._p_rew, self._p_done, self._p_pd)
+            else:
+                rc = lib().rb_env_step_host(self._h, self._p_act, self._p_obs, self._p_rew, self._p_done)
+            if rc:
+                check(rc)
+            ob = self._host_ob(served)
             if self.squeeze:
-                return ob[0], float(rew[0]), bool(done[0]), {}
-            return ob, rew, done, {}
+                return ob, float(self._rew_np[0]), bool(self._done_np[0]), {}
+            return ob, self._rew_np.copy(), self._done_np.astype(bool), {}
         a = action
         assert a.is_cuda and a.dtype == torch.float32 and a.numel() == 2 * n, "action must be a float32 CUDA tensor [N,2]"
         a = a.contiguous()

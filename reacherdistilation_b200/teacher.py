@@ -110,9 +110,22 @@ class TeacherAgent:
         self.params_host = np.ascontiguousarray(params, dtype=np.float32)
         self.params = torch.from_numpy(self.params_host).to(self.device)
         self.pi = _Pi(self)
+        # host-surface env at small batch (the reference's own shape: one env): the policy is evaluated by the env's resident server warp --
+        # no launch, no copies per call, bit-identical to rb_policy_fwd(RB_MODE_FP32) (csrc/serve.cu)
+        self._served_env = env if (env is not None and hasattr(env, "serve_policy") and env.serve_policy(self, self.params_host, nout)) else None
+        self._pd_host = np.empty((env.num_envs, 4), np.float32) if self._served_env is not None else None
 
     def pdflat(self, ob, out=None):
-        """sess.run(pi.pd.flat): ob [B,11] CUDA fp32 -> [B,4] (mean, logstd)."""
+        """sess.run(pi.pd.flat): ob [B,11] CUDA fp32 -> [B,4] (mean, logstd).  Host observations of a served env (numpy in -> numpy out): the
+        pdflat the env server computed with the step that produced `ob`, else one server round trip."""
+        env = self._served_env
+        if env is not None and not torch.is_tensor(ob) and env._policy is self:
+            if ob is env._last_ob:
+                return env._last_pd
+            o = np.ascontiguousarray(np.asarray(ob, dtype=np.float32).reshape(-1, 11))
+            if o.shape[0] == env.num_envs:
+                check(lib().rb_env_serve_policy_fwd(env._h, o.ctypes.data, self._pd_host.ctypes.data))
+                return self._pd_host.copy()
         if not torch.is_tensor(ob):
             ob = torch.as_tensor(np.asarray(ob, dtype=np.float32).reshape(-1, 11)).to(self.device)
         ob = ob.reshape(-1, 11).contiguous()

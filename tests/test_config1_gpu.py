@@ -73,3 +73,66 @@ def test_config1_single_env_1000_step_teacher_rollout_then_one_student_epoch():
     # the sign of its first update: 2 * lr)
     assert rel.max() <= 3e-5
     assert perr <= 2.5 * lr
+
+
+def test_gym_loop_on_the_resident_server_is_bit_identical_to_the_batch_kernels():
+    """The reference's per-step loop at batch 1 (`ac, _ = pi.act(False, ob); ob, r, new, _ = env.step(ac)`, mlp_train.py:120-139) through
+    make_mujoco_env(...).step() / TeacherAgent: served by the resident warp (csrc/serve.cu), no launch per call -- and bit-identical to the
+    fused fp32 rollout kernel of the same env (same step_env / policy arithmetic)."""
+    import time
+    from reacherdistilation_b200 import MODE_FP32
+    from reacherdistilation_b200.env import VecReacher, make_mujoco_env
+    from reacherdistilation_b200.teacher import TeacherAgent, init_policy_params
+    p = init_policy_params(seed=0, final_std=0.3)
+    T = 230
+    ref_env = VecReacher(num_envs=1, seed=7)
+    ob0 = ref_env.reset().cpu().numpy().copy()
+    ref = {k: v.cpu().numpy() for k, v in ref_env.rollout_policy(torch.from_numpy(p).cuda(), T, nout=2, mode=MODE_FP32).items()}
+    ref_env.close()
+    env = make_mujoco_env("Reacher-v2", 7)
+    teacher = TeacherAgent(env, params=p, mode=MODE_FP32)
+    assert teacher._served_env is env
+    ob = env.reset()
+    assert np.array_equal(ob, ob0[0])
+    for t in range(T):
+        if t == 100:
+            time.sleep(0.05)                                        # the server warp retires after 1 ms idle; the next call restarts it from HBM state
+        if t == 150:
+            torch.cuda.synchronize()                                # a device-wide synchronize must not hang on the resident warp
+        assert np.array_equal(ob, ref["obs"][t, 0]), t
+        ac, _ = teacher.pi.act(False, ob)
+        flat = teacher.pdflat(ob)
+        assert np.array_equal(flat[0], ref["pdflat"][t, 0]) and np.array_equal(np.ravel(ac), ref["pdflat"][t, 0, :2]), t
+        if t % 37 == 0:                                              # an observation the env did not just hand out: explicit policy round trip
+            assert np.array_equal(teacher.pdflat(ob.copy())[0], ref["pdflat"][t, 0])
+        ob, r, new, _ = env.step(ac)
+        assert isinstance(r, float) and isinstance(new, bool)
+        assert np.float32(r) == ref["rew"][t, 0] and new == bool(ref["done"][t, 0]), t
+    env.close()
+
+
+@pytest.mark.parametrize("n", [1, 3, 20, 32])
+def test_host_surface_small_batches_match_device_step(n):
+    """rb_env_step_host on the resident server (N <= 32) vs rb_env_step launches on an identical env: bit-identical over two episodes, and the
+    device-side entry points retire the server before touching the state."""
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.teacher import TeacherAgent, init_policy_params
+    host, dev = VecReacher(num_envs=n, seed=11, host=True), VecReacher(num_envs=n, seed=11)
+    teacher = TeacherAgent(host, params=init_policy_params(seed=2, final_std=0.3)) if n in (3, 32) else None
+    oh, od = host.reset(), dev.reset()
+    assert np.array_equal(oh, od.cpu().numpy())
+    rng = np.random.default_rng(n)
+    for t in range(105):
+        a = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        oh, rh, dh, _ = host.step(a)
+        od, rd, dd, _ = dev.step(torch.from_numpy(a).cuda())
+        assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy()) and np.array_equal(dh, dd.cpu().numpy().astype(bool)), t
+        if teacher is not None:
+            from reacherdistilation_b200 import MODE_FP32
+            want = TeacherAgent(None, params=teacher.params_host, mode=MODE_FP32).pdflat(od).cpu().numpy()
+            assert np.array_equal(teacher.pdflat(oh), want), t
+        if t == 60:                                                  # a device-side call on the served env: state handed back through HBM, exactly
+            st = host.get_state()
+            sd = dev.get_state()
+            assert all(torch.equal(st[k], sd[k]) for k in st)
+    host.close(); dev.close()
