@@ -633,6 +633,26 @@ def main():
                                 note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads: 34 launches (two persistent tcgen05 recurrence kernels, batched k_gemm_bf16x3 over the un-shared heads) captured once in a CUDA graph (rb_lstm_step, device-side step clock)"
                                      "un-shared heads, element-wise kernels) captured once in a CUDA graph (rb_lstm_step, device-side step clock)")
             del lnet
+            # ---- two-headed LSTM student of the backup experiment (backup/student_rollout.py:130-200,328) at the sizes the source comments
+            # beside its debug values (NUM_UNITS 100, STEPS_UNROLLED 20, LSTM_BATCH_SIZE 100) and at 2048 windows: loss_grad + Adam ------------
+            from reacherdistilation_b200.student_nn import StudentLSTM2, lstm2_spec
+            l2 = {}
+            for Bw2 in (100, 2048):
+                n2 = StudentLSTM2(spec=lstm2_spec(units=100, steps=20), seed=1, device=local)
+                o2, a2 = torch.randn((20, Bw2, 11), device=dev), torch.randn((20, Bw2, 2), device=dev) * 0.3
+                t2 = torch.cat([torch.randn((20, Bw2, 2), device=dev) * 0.3, -1 + 0.2 * torch.randn((20, Bw2, 2), device=dev)], -1)
+                r2 = torch.randn((20, Bw2), device=dev) * 0.2
+                def l2step():
+                    n2.loss_grad(o2, a2, t2, r2, None, keep_prob=0.5, seed=0, iteration=n2.t)
+                    n2.adam_step()
+                for _ in range(3):
+                    l2step()
+                s2, _ = timed(l2step, 10)
+                l2["windows_%d" % Bw2] = dict(ms_per_step=1e3 * s2 / 10, value=20.0 * Bw2 * 10 / s2, unit="sample-steps/s")
+                l2["params"] = int(n2.P)
+                del n2
+            line["lstm2"] = dict(metric="lstm2_window_rows_per_sec", graph="source variant: units 100, 20 unrolled steps, state not carried, trunk 128 -> "
+                                 "reward 64-1 || action 64-4, loss = KL + squared reward error", **l2)
         # ---- step API: HBM-bound single-step kernel at 4M envs ---------------------------------------------------
         ns = STEP_API_ENVS
         env2 = VecReacher(num_envs=ns, seed=0, device=local, env_offset=0)

@@ -136,6 +136,10 @@ int rb_env_rollout_policy(rb_env* env, const float* params_dev, int nout, int T,
  * done buffers are written by the kernel directly; everything else is copied in time slabs that overlap the next slab's kernel. */
 int rb_env_rollout_policy_host(rb_env* env, const float* params_host, int nout, int T, float* obs_buf_host, float* pd_buf_host,
                                float* rew_buf_host, uint8_t* done_buf_host, int mode);
+/* How rb_env_rollout_policy_host brings reward / done into PAGE-LOCKED host buffers: bit 0 set = the kernel stores reward straight into the
+ * mapped buffer (posted PCIe writes under the rollout), bit 1 = done too; a clear bit = device buffer + copy engine, slab by slab behind the
+ * in-kernel progress flags.  Default 1 (fastest with one GPU per host; measured variants: csrc/env.cu, profiles/README.md).             */
+int rb_env_set_host_transport(rb_env* env, int kernel_stores);
 /* device pointers of the resident rollout buffer the last rb_env_rollout_policy_host call filled ([T,N,11], [T,N,4], [T,N], [T,N]);
  * any out pointer may be NULL.  Owned by the env, valid until the next host rollout or rb_env_destroy.  (reward / done are only
  * present on the device when the host buffers of that call were pageable or NULL.) */

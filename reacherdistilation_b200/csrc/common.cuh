@@ -31,6 +31,7 @@ struct rb_env {
     uint32_t* prog_flags_dev = nullptr;           // device alias of prog_flags_host
     uint32_t prog_epoch = 0;
     int prog_slab_len = 0;                        // > 0 only while the host call launches its kernel
+    int host_zerocopy = 1;                        // rb_env_set_host_transport: bit 0 reward, bit 1 done stored by the kernel into mapped host memory
     void* serve = nullptr;                        // resident env server of the small host-surface envs (serve.cu), NULL until first used
 };
 

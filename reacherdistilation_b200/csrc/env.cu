@@ -421,7 +421,6 @@ static void* mapped_alias(const void* host) {
 }
 // Transport constants of rb_env_rollout_policy_host (each measured against its alternatives on B200, see the comment inside the call and
 // profiles/r01_e2e_transport_sweep.jsonl; they were environment knobs while being tuned):
-constexpr int HOST_ZEROCOPY = 1;        // bit 0: reward stored by the kernel into the mapped host buffer, bit 1: done too
 constexpr int HOST_SLABS = 6;           // fp32-mode slab launches when bulk fields (obs / pdflat / pageable reward) go to the host
 constexpr int HOST_SLAB_FIRST = 2;      // ... with a short first slab so that the copy engine starts early
 constexpr int HOST_SLABS_SMALL = 1;     // ... and when only small fields are copied
@@ -462,7 +461,8 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
     //  result alone 0.30 at the 55 GB/s this box copies at): 0.362 progress path with the defaults (reward kernel-written, done copied per
     //  progress slab); 0.435 progress path with everything on the copy engine; 0.403 reward kernel-written + done copied after the kernel;
     //  0.419 the same with 2 kernel slabs; 0.428 both fields kernel-written; 0.448 everything copied in 5 equal kernel slabs.
-    constexpr int zc = HOST_ZEROCOPY, nslab_bulk = HOST_SLABS, first_steps = HOST_SLAB_FIRST, nslab_small = HOST_SLABS_SMALL;
+    const int zc = e->host_zerocopy;
+    constexpr int nslab_bulk = HOST_SLABS, first_steps = HOST_SLAB_FIRST, nslab_small = HOST_SLABS_SMALL;
     float* rew_zc = (zc & 1) ? (float*)mapped_alias(rew_host) : nullptr;
     uint8_t* done_zc = (zc & 2) ? (uint8_t*)mapped_alias(done_host) : nullptr;
     const bool copy_rew = rew_host && !rew_zc, copy_done = done_host && !done_zc;
@@ -534,6 +534,12 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
     }
     if (any_copy) RB_CUDA(cudaStreamSynchronize(sc));
     RB_CUDA(cudaStreamSynchronize(s));
+    return RB_OK;
+}
+
+int rb_env_set_host_transport(rb_env* e, int kernel_stores) {
+    RB_REQUIRE(e != nullptr && kernel_stores >= 0 && kernel_stores <= 3, "bad argument");
+    e->host_zerocopy = kernel_stores;
     return RB_OK;
 }
 

@@ -847,13 +847,23 @@ __global__ void __launch_bounds__(ST_THREADS, 1) k_student_tc(const StudentTcArg
                 for (int i = gtid; i <= a.P; i += gthreads) push(i, ldw(a.red + i));
             st_stamp(34);
             const uint2* mine = ll[a.rank];
-            auto recv = [&](int i) {                                                // rank order: bit-identical sums on every rank
-                float tot = 0.f;
-                for (int r = 0; r < a.world; ++r) {
-                    uint2 w;
-                    do { w = ld_ll(mine + (size_t)r * SL + i); } while (w.y != epoch);
-                    tot += __uint_as_float(w.x);
+            // All `world` pairs of an element are requested TOGETHER (one L2 round trip instead of `world` serial ones: polling rank by rank cost
+            // 8 x 0.7 us at 8 ranks), re-read only while a pair still carries an older epoch, then added in rank order: bit-identical sums on every rank.
+            auto recv = [&](int i) {
+                uint2 w[8];
+#pragma unroll
+                for (int r = 0; r < 8; ++r) w[r] = r < a.world ? ld_ll(mine + (size_t)r * SL + i) : make_uint2(0u, epoch);
+                for (;;) {
+                    bool ready = true;
+#pragma unroll
+                    for (int r = 0; r < 8; ++r) {
+                        if (w[r].y != epoch) { w[r] = ld_ll(mine + (size_t)r * SL + i); ready = ready && w[r].y == epoch; }
+                    }
+                    if (ready) break;
                 }
+                float tot = 0.f;
+#pragma unroll
+                for (int r = 0; r < 8; ++r) if (r < a.world) tot += __uint_as_float(w[r].x);
                 apply(i, tot);
             };
             if constexpr (S::L == 4) owned_mlp(gtid, gthreads, recv);
