@@ -5,12 +5,14 @@
   N > 1: launched by torchrun (one rank per GPU, NCCL); rank 0 prints ONE JSON line.
 
 Headline workload = BASELINE.json config 3 per GPU: 65 536 lock-step Reacher-v2 envs, fused teacher MLP (2x64 tanh) in the
-loop, device-resident rollout buffer; one bench "step" = one 50-step chunk (one episode of every env) = 3 276 800 env-steps
-per GPU.  Weak scaling: every rank owns 65 536 envs (global env ids rank*65536 ..), no data-path collective.
+loop, device-resident rollout buffer; one bench "step" = 20 launches of the 50-step chunk (one episode of every env each) =
+65 536 000 env-steps per GPU.  Weak scaling: every rank owns 65 536 envs (global env ids rank*65536 ..), no data-path collective.
 `value`   env-steps/s, inputs resident in HBM, CUDA-event timed, max over ranks.
-`e2e`     same metric through the host-buffer C-ABI call (rb_env_rollout_policy_host): H2D of the teacher parameters and D2H of
-          the step's result (reward + done of every env-step) inside the timed region; the rollout buffer (obs, pdflat) is written
-          and stays on the device.  `e2e_full_buffer`: the same call bringing the whole buffer to the host (PCIe-bound).
+`e2e`     same metric through the host-buffer C-ABI call (rb_env_rollout_policy_host_ex): H2D of the teacher parameters and D2H of
+          the step's result -- the reward of EVERY env-step [T,N] f32 + the per-env done mask [N] u64 (bit t = episode ended at step t) --
+          inside the timed region; the rollout buffer (obs, pdflat) is written and stays on the device.  `e2e.done_as_u8`: the same with
+          done as [T,N] bytes (round-1 format).  `e2e_episode_returns`: a SECOND figure with the result reduced on the device to per-episode
+          returns + done mask.  `e2e_full_buffer`: the same call bringing the whole buffer to the host (PCIe-bound).
 `distill` BASELINE.json config 4 shard (32 768 envs per GPU): DAgger iterations = env step + teacher label + student
           forward/backward + KL + [NCCL all-reduce of the flat gradient] + Adam; samples/s == env-steps/s of that loop.
 `step_api` the gym-style single-step kernel (HBM-bound) at 4 194 304 envs.
@@ -475,7 +477,9 @@ def main():
     Ke = max(3, min(K, 20))
     hbuf = dict(obs=torch.empty((CHUNK_T, n, 11)).pin_memory(), pdflat=torch.empty((CHUNK_T, n, 4)).pin_memory(),
                 rew=torch.empty((CHUNK_T, n)).pin_memory(), done=torch.empty((CHUNK_T, n), dtype=torch.uint8).pin_memory())
-    hres = dict(obs=None, pdflat=None, rew=hbuf["rew"], done=hbuf["done"])
+    hmask = torch.empty((n,), dtype=torch.int64).pin_memory()
+    hres = dict(obs=None, pdflat=None, rew=hbuf["rew"], done=None, done_mask=hmask)         # the step's RESULT: reward of every env-step + the done mask
+    hres_u8 = dict(obs=None, pdflat=None, rew=hbuf["rew"], done=hbuf["done"])               # same with `done` as T bytes per env (copy engine, slab by slab)
     tparams_host = torch.from_numpy(init_policy_params(seed=0)).pin_memory()
 
     def e2e_time(out, chunks):
@@ -488,12 +492,23 @@ def main():
             fn()                                                       # synchronous call (copies + sync inside)
         barrier()
         return max_over_ranks(time.perf_counter() - t0, dev)
-    e2e_sec, e2e_full_sec = e2e_time(hres, R), e2e_time(hbuf, 1)
+    hret = torch.empty((n,), dtype=torch.float32).pin_memory()
+    hres_ret = dict(obs=None, pdflat=None, rew=None, done=None, done_mask=hmask, return_sum=hret)   # per-episode returns reduced on the device
+    e2e_sec, e2e_u8_sec, e2e_ret_sec, e2e_full_sec = e2e_time(hres, R), e2e_time(hres_u8, R), e2e_time(hres_ret, R), e2e_time(hbuf, 1)
     e2e = dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4) * R,
-               d2h_bytes_per_step=int(n * CHUNK_T * (4 + 1)) * R, steps=Ke, api="rb_env_rollout_policy_host (VecReacher.rollout_policy_host), %d calls per step" % R,
-               result="reward[T,N] f32 + done[T,N] u8 of every chunk to pinned host memory (reward written by the kernel into the mapped buffer, done "
-                      "copied per in-kernel progress slab); obs / pdflat are written to the device-resident rollout buffer (rb_env_rollout_buffer) and stay there",
-               mean_reward_host=float(hbuf["rew"].mean()))
+               d2h_bytes_per_step=int(n * CHUNK_T * 4 + n * 8) * R, steps=Ke,
+               api="rb_env_rollout_policy_host_ex (VecReacher.rollout_policy_host), %d calls per step" % R,
+               result="reward[T,N] f32 of every env-step + done_mask[N] u64 (bit t = the env finished an episode at step t of the chunk) of every chunk, "
+                      "both written by the kernel into the caller's page-locked buffers (no copy-engine transfer); obs / pdflat are written to the "
+                      "device-resident rollout buffer (rb_env_rollout_buffer) and stay there",
+               mean_reward_host=float(hbuf["rew"].mean()), episodes_finished_last_chunk=int(sum(bin(int(v) & ((1 << 64) - 1)).count("1") for v in hmask[:4096].tolist())),
+               done_as_u8=dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_u8_sec, d2h_bytes_per_step=int(n * CHUNK_T * (4 + 1)) * R,
+                               note="round-1 result format: done[T,N] u8 copied per in-kernel progress slab while the launch runs"))
+    e2e_ret = dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_ret_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4) * R,
+                   d2h_bytes_per_step=int(n * (4 + 8)) * R, steps=Ke, mean_episode_return_host=float(hret.mean()),
+                   note="a SECOND end-to-end figure, not the headline: the step's result reduced on the device to what the reference logs per episode "
+                        "(mlp_train.py:129-139) -- return_sum[N] f32 (each 50-step chunk starts at an episode boundary, so it is the episode return) + "
+                        "done_mask[N] u64; 12 bytes per env and chunk instead of 208")
     e2e_full = dict(value=float(n) * CHUNK_T * Ke * world / e2e_full_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4),
                     d2h_bytes_per_step=int(n * CHUNK_T * (44 + 16 + 4 + 1)), steps=Ke, note="ONE chunk per step, whole rollout buffer to the host: PCIe-bound")
     env.close()
@@ -505,7 +520,7 @@ def main():
     cfg["mean_reward_first_chunk_envs_0_%d" % REWARD_CHECK_ENVS] = rew_check
     line = dict(metric="reacher_env_steps_per_sec", value=value, unit="env-steps/s", n_gpus=world, steps=K, warmup=W, ms_per_step=1e3 * sec / K,
                 higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic", config=cfg,
-                e2e=e2e, e2e_full_buffer=e2e_full, gpu_launches=K * R, clocks=clocks)
+                e2e=e2e, e2e_episode_returns=e2e_ret, e2e_full_buffer=e2e_full, gpu_launches=K * R, clocks=clocks)
     nc = ncu_counters("rollout") if (mode == MODE_TC and n == 65536) else {}
     warps = n / 32.0 * CHUNK_T
     sms = L.rb_sm_count(local)

@@ -136,6 +136,12 @@ int rb_env_rollout_policy(rb_env* env, const float* params_dev, int nout, int T,
  * done buffers are written by the kernel directly; everything else is copied in time slabs that overlap the next slab's kernel. */
 int rb_env_rollout_policy_host(rb_env* env, const float* params_host, int nout, int T, float* obs_buf_host, float* pd_buf_host,
                                float* rew_buf_host, uint8_t* done_buf_host, int mode);
+/* Same call with two more optional per-env outputs (8 + 4 bytes per env instead of 5 T): done_mask_host[N] uint64, bit t = the env finished
+ * an episode (TimeLimit 50) at step t of this call (T <= 64); return_sum_host[N] float = the sum of the env's rewards over the T steps of the
+ * call, added in step order (a 50-step call issued at an episode boundary gives the episode return the reference logs, mlp_train.py:129-139).
+ * Page-locked buffers are written by the kernel directly: {reward, done_mask} or {return_sum, done_mask} need no copy-engine transfer. */
+int rb_env_rollout_policy_host_ex(rb_env* env, const float* params_host, int nout, int T, float* obs_buf_host, float* pd_buf_host,
+                                  float* rew_buf_host, uint8_t* done_buf_host, uint64_t* done_mask_host, float* return_sum_host, int mode);
 /* How rb_env_rollout_policy_host brings reward / done into PAGE-LOCKED host buffers: bit 0 set = the kernel stores reward straight into the
  * mapped buffer (posted PCIe writes under the rollout), bit 1 = done too; a clear bit = device buffer + copy engine, slab by slab behind the
  * in-kernel progress flags.  Default 1 (fastest with one GPU per host; measured variants: csrc/env.cu, profiles/README.md).             */

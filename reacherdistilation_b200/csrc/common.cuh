@@ -31,6 +31,10 @@ struct rb_env {
     uint32_t* prog_flags_dev = nullptr;           // device alias of prog_flags_host
     uint32_t prog_epoch = 0;
     int prog_slab_len = 0;                        // > 0 only while the host call launches its kernel
+    uint64_t* done_mask_out = nullptr;            // set around a rollout launch: per-env bit mask of the steps that ended an episode (bit t = step t)
+    float* return_sum_out = nullptr;              // set around a rollout launch: per-env sum of the rewards of the launch's steps (in step order)
+    float* d_return_sum = nullptr;
+    uint64_t* d_done_mask = nullptr;              // device staging of that mask when the caller's buffer is not mapped
     int host_zerocopy = 1;                        // rb_env_set_host_transport: bit 0 reward, bit 1 done stored by the kernel into mapped host memory
     void* serve = nullptr;                        // resident env server of the small host-surface envs (serve.cu), NULL until first used
 };

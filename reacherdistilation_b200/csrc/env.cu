@@ -166,7 +166,8 @@ template <int NOUT>
 __global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, float4* qv, float4* tp, uint4* ctr, const float* __restrict__ params,
                                                                    int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
                                                                    float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf,
-                                                                   uint32_t k0, uint32_t k1, uint32_t offset) {
+                                                                   uint32_t k0, uint32_t k1, uint32_t offset, uint64_t* __restrict__ done_mask,
+                                                                   float* __restrict__ return_sum) {
     __shared__ PolicySmem S;
     __shared__ __align__(16) float strips[ENV_BLOCK / 32][32 * OBS];
     policy_load_smem(S, params, NOUT);
@@ -181,12 +182,16 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, fl
     EnvState e;
     if (valid) e = load_state(qv, tp, ctr, i);
     else e = zero_state();
+    uint64_t dmask = 0ull;
+    float rsum = 0.f;
     for (int t = 0; t < T; ++t) {
         float ob[OBS], pd[4];
         observe(e, ob);
         policy_fwd_simt<NOUT>(S, ob, pd);
         bool d;
         const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
+        dmask |= (uint64_t)(d ? 1u : 0u) << (t & 63);
+        rsum = __fadd_rn(rsum, rw);
         const int64_t row = (int64_t)t * n + i;
         if (valid) {
             if (pd_buf) pd_buf[row] = make_float4(pd[0], pd[1], pd[2], pd[3]);
@@ -195,7 +200,7 @@ __global__ void __launch_bounds__(ENV_BLOCK) k_rollout_policy_fp32(int64_t n, fl
         }
         if (obs_buf) warp_store_rows<OBS>(obs_buf, (int64_t)t * n + row0, nvalid, ob, strips[warp], lane);
     }
-    if (valid) store_state(qv, tp, ctr, i, e);
+    if (valid) { store_state(qv, tp, ctr, i, e); if (done_mask) done_mask[i] = dmask; if (return_sum) return_sum[i] = rsum; }
 }
 
 inline unsigned env_grid(int64_t n) { return (unsigned)((n + ENV_BLOCK - 1) / ENV_BLOCK); }
@@ -240,7 +245,7 @@ int rb_env_destroy(rb_env* e) {
     cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
-    cudaFree(e->prog_counters);
+    cudaFree(e->prog_counters); cudaFree(e->d_done_mask); cudaFree(e->d_return_sum);
     if (e->prog_flags_host) cudaFreeHost((void*)e->prog_flags_host);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -404,10 +409,10 @@ int rb_env_rollout_policy(rb_env* e, const float* params, int nout, int T, float
     const uint32_t k0 = (uint32_t)e->seed, k1 = (uint32_t)(e->seed >> 32);
     if (nout == 2)
         k_rollout_policy_fp32<2><<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf,
-                                                                                         (float4*)pd_buf, rew_buf, done_buf, k0, k1, e->offset);
+                                                                                         (float4*)pd_buf, rew_buf, done_buf, k0, k1, e->offset, e->done_mask_out, e->return_sum_out);
     else
         k_rollout_policy_fp32<4><<<env_grid(e->n), ENV_BLOCK, 0, (cudaStream_t)stream>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf,
-                                                                                         (float4*)pd_buf, rew_buf, done_buf, k0, k1, e->offset);
+                                                                                         (float4*)pd_buf, rew_buf, done_buf, k0, k1, e->offset, e->done_mask_out, e->return_sum_out);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
@@ -426,8 +431,37 @@ constexpr int HOST_SLAB_FIRST = 2;      // ... with a short first slab so that t
 constexpr int HOST_SLABS_SMALL = 1;     // ... and when only small fields are copied
 constexpr int HOST_PROGRESS_SLABS = 5;  // tensor-core mode: time slabs reported by the ONE launch through in-kernel progress flags
 
+static int rollout_policy_host_impl(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
+                                    uint8_t* done_host, int mode);
+
 int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
                                uint8_t* done_host, int mode) {
+    return rb_env_rollout_policy_host_ex(e, params_host, nout, T, obs_host, pd_host, rew_host, done_host, nullptr, nullptr, mode);
+}
+
+int rb_env_rollout_policy_host_ex(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
+                                  uint8_t* done_host, uint64_t* done_mask_host, float* return_sum_host, int mode) {
+    RB_REQUIRE(e != nullptr && params_host != nullptr && T > 0, "bad argument");
+    if (!done_mask_host && !return_sum_host) return rollout_policy_host_impl(e, params_host, nout, T, obs_host, pd_host, rew_host, done_host, mode);
+    RB_REQUIRE(!done_mask_host || T <= 64, "done_mask holds one bit per step: T <= 64");
+    // page-locked + mapped buffers: the kernel stores the per-env words straight into them; otherwise device staging + one copy behind the call
+    uint64_t* zm = (uint64_t*)mapped_alias(done_mask_host);
+    float* zr = (float*)mapped_alias(return_sum_host);
+    DeviceGuard guard(e->device);
+    if (done_mask_host && !zm && !e->d_done_mask) RB_CUDA(cudaMalloc(&e->d_done_mask, sizeof(uint64_t) * e->n));
+    if (return_sum_host && !zr && !e->d_return_sum) RB_CUDA(cudaMalloc(&e->d_return_sum, sizeof(float) * e->n));
+    e->done_mask_out = done_mask_host ? (zm ? zm : e->d_done_mask) : nullptr;
+    e->return_sum_out = return_sum_host ? (zr ? zr : e->d_return_sum) : nullptr;
+    const int rc = rollout_policy_host_impl(e, params_host, nout, T, obs_host, pd_host, rew_host, done_host, mode);
+    e->done_mask_out = nullptr; e->return_sum_out = nullptr;
+    if (rc) return rc;
+    if (done_mask_host && !zm) RB_CUDA(cudaMemcpy(done_mask_host, e->d_done_mask, sizeof(uint64_t) * e->n, cudaMemcpyDeviceToHost));
+    if (return_sum_host && !zr) RB_CUDA(cudaMemcpy(return_sum_host, e->d_return_sum, sizeof(float) * e->n, cudaMemcpyDeviceToHost));
+    return RB_OK;
+}
+
+static int rollout_policy_host_impl(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
+                                    uint8_t* done_host, int mode) {
     RB_REQUIRE(e != nullptr && params_host != nullptr && T > 0, "bad argument");
     RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
     int rc = ensure_host_staging(e);
@@ -505,7 +539,7 @@ int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, in
         return RB_OK;
     }
     int ends[16];                                                                    // cumulative slab ends
-    int nslab = !any_copy ? 1 : (bulk ? nslab_bulk : nslab_small);
+    int nslab = (!any_copy || e->done_mask_out || e->return_sum_out) ? 1 : (bulk ? nslab_bulk : nslab_small);      // the per-env done mask counts steps from the launch's first step: one launch
     if (nslab > T) nslab = T;
     if (bulk) {
         const int first = (nslab > 1 && first_steps < T / nslab) ? first_steps : 0;  // 0: equal slabs

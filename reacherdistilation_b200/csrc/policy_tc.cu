@@ -443,7 +443,8 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
                                                                     int T, float* __restrict__ obs_buf, float4* __restrict__ pd_buf,
                                                                     float* __restrict__ rew_buf, uint8_t* __restrict__ done_buf, uint32_t k0,
                                                                     uint32_t k1, uint32_t offset, uint32_t stagger_ns, uint32_t* prog_counters,
-                                                                    uint32_t* prog_flags, int prog_slab_len, uint32_t prog_epoch) {
+                                                                    uint32_t* prog_flags, int prog_slab_len, uint32_t prog_epoch,
+                                                                    uint64_t* __restrict__ done_mask, float* __restrict__ return_sum) {
     extern __shared__ __align__(128) uint8_t smem_raw[];
     TcShared& S = *reinterpret_cast<TcShared*>(smem_raw);
     TcTile* tiles = reinterpret_cast<TcTile*>(smem_raw + sizeof(TcShared));
@@ -469,6 +470,8 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
         // step period lets one tile's epilogue overlap another tile's physics.
         for (uint32_t w = 0; w < (uint32_t)tile * stagger_ns; w += 1000u) __nanosleep(1000u);
         int next_mark = prog_slab_len > 0 ? min(prog_slab_len, T) : -1;      // step count at which the next time slab is complete (-1: no reporting)
+        uint64_t dmask = 0ull;                                               // bit t = this env finished an episode at step t of the chunk
+        float rsum = 0.f;                                                    // sum of this env's rewards over the chunk, in step order
 #pragma unroll 1
         for (int t = 0; t < T; ++t) {
             float ob[OBS], pd[4];
@@ -478,6 +481,8 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
             policy_tc_eval<NOUT, tile_cols<NT>()>(S, Tl, tile, row, bar_threads, row < 32, ob, pd, phase);
             bool d;
             const float rw = step_env(e, pd[0], pd[1], k0, k1, gid, d);
+            dmask |= (uint64_t)(d ? 1u : 0u) << (t & 63);
+            rsum = __fadd_rn(rsum, rw);
             const int64_t r = (int64_t)t * n + i;
             if (valid) {
                 if (pd_buf) pd_buf[r] = make_float4(pd[0], pd[1], pd[2], pd[3]);
@@ -500,7 +505,11 @@ __global__ void __launch_bounds__(NT* TILE, 1) k_rollout_policy_tc(int64_t n, fl
                 }
             }
         }
-        if (valid) store_state(qv, tp, ctr, i, e);
+        if (valid) {
+            store_state(qv, tp, ctr, i, e);
+            if (done_mask) done_mask[i] = dmask;                              // 8 B per env per chunk instead of T bytes (256 contiguous bytes per warp)
+            if (return_sum) return_sum[i] = rsum;
+        }
     }
     policy_tc_teardown<NT>(S);
 }
@@ -584,7 +593,7 @@ static int launch_rollout_tc(rb_env* e, const float* params, int T, float* obs_b
     const int stagger = ROLLOUT_STAGGER_NS;
     k_rollout_policy_tc<NOUT, NT><<<grid, NT * TILE, smem, s>>>(e->n, e->qv, e->tp, e->ctr, params, T, obs_buf, (float4*)pd_buf, rew_buf, done_buf, k0, k1,
                                                                 e->offset, (uint32_t)stagger, e->prog_counters, e->prog_flags_dev,
-                                                                e->prog_counters ? e->prog_slab_len : 0, e->prog_epoch);
+                                                                e->prog_counters ? e->prog_slab_len : 0, e->prog_epoch, e->done_mask_out, e->return_sum_out);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }

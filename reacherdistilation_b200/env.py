@@ -168,6 +168,13 @@ class VecReacher:
         if out is None:
             out = dict(obs=torch.empty((T, n, 11)).pin_memory(), pdflat=torch.empty((T, n, 4)).pin_memory(),
                        rew=torch.empty((T, n)).pin_memory(), done=torch.empty((T, n), dtype=torch.uint8).pin_memory())
+        if out.get("done_mask") is not None or out.get("return_sum") is not None:
+            # done_mask [N] int64: bit t = the env finished an episode at step t of this call (T <= 64); return_sum [N] float32: sum of the call's rewards
+            assert out.get("done_mask") is None or (out["done_mask"].dtype == torch.int64 and out["done_mask"].numel() == n)
+            assert out.get("return_sum") is None or (out["return_sum"].dtype == torch.float32 and out["return_sum"].numel() == n)
+            check(lib().rb_env_rollout_policy_host_ex(self._h, ptr(params_host), nout, T, ptr(out.get("obs")), ptr(out.get("pdflat")), ptr(out.get("rew")),
+                                                      ptr(out.get("done")), ptr(out.get("done_mask")), ptr(out.get("return_sum")), mode))
+            return out
         check(lib().rb_env_rollout_policy_host(self._h, ptr(params_host), nout, T, ptr(out.get("obs")), ptr(out.get("pdflat")), ptr(out.get("rew")),
                                                ptr(out.get("done")), mode))                  # None entries: that field is not copied to the host
         return out

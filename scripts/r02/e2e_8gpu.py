@@ -33,7 +33,7 @@ bdf, node = gpu_numa(local)
 aff0 = sorted(os.sched_getaffinity(0))
 print("rank %d gpu %s numa %d, affinity %d cpus [%d..%d], nodes %s" % (rank, bdf, node, len(aff0), aff0[0], aff0[-1], sorted(glob.glob("/sys/devices/system/node/node*"))), flush=True)
 p_host = torch.from_numpy(init_policy_params(seed=0)).pin_memory()
-def run(label, bind, transport):
+def run(label, bind, transport, mask=False):
     if bind and node >= 0:
         cpus = [c for c in (node_cpus(node) or []) if c in aff0]
         if cpus:
@@ -44,6 +44,8 @@ def run(label, bind, transport):
     env.reset()
     _lib.check(_lib.lib().rb_env_set_host_transport(env._h, transport))
     out = dict(obs=None, pdflat=None, rew=rew, done=done)
+    if mask:
+        out = dict(obs=None, pdflat=None, rew=rew, done=None, done_mask=torch.zeros((n,), dtype=torch.int64).pin_memory())
     fn = lambda: env.rollout_policy_host(p_host, T, nout=2, mode=MODE_TC, out=out)
     for _ in range(5): fn()
     if world > 1: torch.distributed.barrier()
@@ -60,5 +62,5 @@ def run(label, bind, transport):
 run("default (kernel-stored reward)", False, 1)
 run("copy engine for reward and done", False, 0)
 run("kernel-stored reward + done", False, 3)
-run("NUMA-local buffers, kernel-stored reward", True, 1)
-run("NUMA-local buffers, copy engine", True, 0)
+run("kernel-stored reward + done MASK (8 B per env)", False, 1, True)
+run("copy-engine reward + kernel-stored done mask", False, 0, True)

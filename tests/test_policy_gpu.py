@@ -155,3 +155,40 @@ def test_rollout_host_result_only_keeps_buffer_on_device(pinned, mode_name):
     for k in d2:
         assert torch.equal(d2[k].cpu(), h2[k]), k
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("pinned", [True, False])
+@pytest.mark.parametrize("mode_name", ["fp32", "tc"])
+def test_rollout_host_done_mask_is_the_bit_packed_done(pinned, mode_name):
+    """rb_env_rollout_policy_host_ex: done_mask[N] (bit t = the env finished an episode at step t of the call) == the u8 done[T,N] of the
+    device entry point, bit for bit, with reward bit-identical and no u8 `done` transferred at all; also next to a u8 `done` in the same call."""
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.teacher import init_policy_params
+    mode = MODE_FP32 if mode_name == "fp32" else MODE_TC
+    p = init_policy_params(seed=0)
+    n, T = 333, 64
+    a, b = VecReacher(num_envs=n, seed=4), VecReacher(num_envs=n, seed=4)
+    a.reset(); b.reset()
+    a.rollout_policy(torch.from_numpy(p).cuda(), 17, mode=mode); b.rollout_policy(torch.from_numpy(p).cuda(), 17, mode=mode)   # episode boundary not at a multiple of the call
+    for with_u8 in (False, True):
+        d = a.rollout_policy(torch.from_numpy(p).cuda(), T, mode=mode)
+        rew, mask, ret = torch.full((T, n), -7.0), torch.full((n,), -1, dtype=torch.int64), torch.full((n,), 3.0)
+        done = torch.full((T, n), 9, dtype=torch.uint8) if with_u8 else None
+        if pinned:
+            rew, mask, ret = rew.pin_memory(), mask.pin_memory(), ret.pin_memory()
+            done = done.pin_memory() if done is not None else None
+        b.rollout_policy_host(torch.from_numpy(p), T, mode=mode, out=dict(obs=None, pdflat=None, rew=rew, done=done, done_mask=mask, return_sum=ret))
+        acc = np.zeros(n, np.float32)
+        for t in range(T):                                     # the kernel adds in step order, in fp32: bit-exact
+            acc = (acc + d["rew"][t].cpu().numpy()).astype(np.float32)
+        assert np.array_equal(ret.numpy(), acc)
+        want = np.zeros(n, np.uint64)
+        dd = d["done"].cpu().numpy()
+        for t in range(T):
+            want |= dd[t].astype(np.uint64) << np.uint64(t)
+        assert np.array_equal(mask.numpy().view(np.uint64), want) and dd.sum() > 0
+        assert torch.equal(d["rew"].cpu(), rew) and (done is None or torch.equal(d["done"].cpu(), done))
+    with pytest.raises(Exception):
+        b.rollout_policy_host(torch.from_numpy(p), 65, mode=mode, out=dict(obs=None, pdflat=None, rew=None, done=None, done_mask=mask))
+    a.close(); b.close()
