@@ -672,19 +672,32 @@ def main():
         ns = STEP_API_ENVS
         env2 = VecReacher(num_envs=ns, seed=0, device=local, env_offset=0)
         env2.reset()
-        act = (torch.rand((ns, 2), device=dev) * 2 - 1)
-        sfn = lambda: env2.step(act)
-        for _ in range(W):
+        # action model of BASELINE config 2: a fresh U(-1, 1) action for every env at every step (8 pre-generated tensors, cycled).  A CONSTANT action
+        # per env -- what this leg used before -- drives every arm into its joint limit within 0.3 s and keeps it there: the contact branch then runs
+        # in all 8 RK4 stages of nearly every warp; that worst case is still reported as `pinned_at_joint_limit`.
+        acts = [(torch.rand((ns, 2), device=dev) * 2 - 1) for _ in range(8)]
+        cnt = [0]
+        def sfn():
+            env2.step(acts[cnt[0] & 7]); cnt[0] += 1
+        for _ in range(W + 50):                              # past the first episode boundary: the envs are spread over their state space
             sfn()
         ssec, _ = timed(sfn, 50)
+        pin = lambda: env2.step(acts[0])
+        for _ in range(60):
+            pin()
+        psec, _ = timed(pin, 50)
         line["step_api"] = dict(metric="reacher_env_steps_per_sec", value=float(ns) * 50 * world / ssec, unit="env-steps/s", envs_per_gpu=ns,
                                 roofline=dict(bound="hbm", achieved=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9, peak=pk["hbm"], unit="GB/s",
                                               frac=ALG_BYTES_STEP * ns / (ssec / 50) / 1e9 / pk["hbm"],
                                               traffic=(lambda c: (c["dram__bytes_read.sum"] + c["dram__bytes_write.sum"]) if ("dram__bytes_read.sum" in c and ns == (1 << 22)) else None)(ncu_counters("step")),
                                               peak_source=pk["src"], kernel="k_step", kernel_ms=1e3 * ssec / 50,
                                               issue_active_pct=ncu_counters("step").get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
-                                              note="working set %.0f MB > L2, constant random action per env (most envs sit on the joint limit: the contact "
-                                                   "branch runs in nearly every RK4 stage); instruction issue bounds this kernel before HBM does" % (ns * 105 / 1e6)))
+                                              note="working set %.0f MB > L2; a fresh uniform action per env and step (BASELINE config 2's action model); instruction "
+                                                   "issue bounds this kernel before HBM does (real DRAM traffic: `traffic`, 96 B of it the two-float state round trip)" % (ns * 153 / 1e6)),
+                                pinned_at_joint_limit=dict(value=float(ns) * 50 * world / psec, kernel_ms=1e3 * psec / 50,
+                                                           frac=ALG_BYTES_STEP * ns / (psec / 50) / 1e9 / pk["hbm"],
+                                                           note="constant action per env: every arm sits on its joint limit, the contact branch runs in all 8 RK4 "
+                                                                "stages (the workload the round-1 line and the committed ncu capture used)"))
         env2.close()
         if rank == 0 and world == 1:
             line["cpu_baseline"] = cpu_reference_leg()

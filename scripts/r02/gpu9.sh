@@ -1,0 +1,18 @@
+#!/bin/bash
+# round 2, call 9: bench on the final code (step_api with fresh actions), reference arm, sweep on one GPU
+mkdir -p gpurun_out
+timeout 900 python bench.py --steps 20 --warmup 5 > gpurun_out/bench_full.log 2> gpurun_out/bench_full.err; echo "bench rc=$?"; tail -3 gpurun_out/bench_full.err
+timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/bench_ref.log 2>&1; echo "ref rc=$?"
+timeout 900 python bench.py --sweep > gpurun_out/bench_sweep.log 2>&1; echo "sweep rc=$?"
+python - <<'PY'
+import json
+for l in open('gpurun_out/bench_full.log'):
+    if l.startswith('{'):
+        d=json.loads(l)
+        print('value %.4g e2e %.4g u8 %.4g ret %.4g' % (d['value'], d['e2e']['value'], d['e2e']['done_as_u8']['value'], d['e2e_episode_returns']['value']))
+        print('step_api', d['step_api']['value'], d['step_api']['roofline']['frac'], d['step_api']['pinned_at_joint_limit'])
+        print('cpu', d['cpu_baseline'])
+for l in open('gpurun_out/bench_ref.log'):
+    if l.startswith('{'): print(l[:600])
+PY
+tail -c 1500 gpurun_out/bench_sweep.log
