@@ -658,8 +658,7 @@ def main():
                 t2 = torch.cat([torch.randn((20, Bw2, 2), device=dev) * 0.3, -1 + 0.2 * torch.randn((20, Bw2, 2), device=dev)], -1)
                 r2 = torch.randn((20, Bw2), device=dev) * 0.2
                 def l2step():
-                    n2.loss_grad(o2, a2, t2, r2, None, keep_prob=0.5, seed=0, iteration=n2.t)
-                    n2.adam_step()
+                    n2.step(o2, a2, t2, r2, None, keep_prob=0.5, seed=0)          # one CUDA-graph launch (rb_lstm2_step)
                 for _ in range(3):
                     l2step()
                 s2, _ = timed(l2step, 10)

@@ -309,6 +309,12 @@ int rb_lstm2_loss_grad(const int* spec, const float* params_dev, const float* ob
                        const float* reward_target_dev, const float* init_state_dev, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0,
                        uint32_t iteration, int loss_kind, float* s_pdflat_dev, float* reward_dev, float* final_state_dev /* may be NULL */,
                        float* gradloss_dev, void* workspace_dev, void* stream);
+/* rb_lstm2_loss_grad + TF-form Adam as ONE CUDA-graph launch (context and device-side clock of rb_lstm_step: rb_lstm_ctx_create /
+ * rb_lstm_ctx_set_clock); pass the same (static) tensors every step, the graph is re-captured when a pointer or scalar changes.      */
+int rb_lstm2_step(rb_lstm_ctx* ctx, const int* spec, float* params_dev, float* m_dev, float* v_dev, const float* ob_dev, const float* action_dev,
+                  const float* t_pdflat_dev, const float* reward_target_dev, const float* init_state_dev, int64_t B, float keep_prob, uint64_t seed,
+                  uint32_t sample_id0, int loss_kind, float* s_pdflat_dev, float* reward_dev, float* gradloss_dev, void* workspace_dev, float lr,
+                  float beta1, float beta2, float eps, float grad_scale, int use_graph, void* stream);
 /* The tensor-core GEMM the LSTM is built from: C[M,N] (+)= epilogue(A[M,K] B[K,N]), fp32 in/out, bf16x3 inside.
  * x_mn = 0: element (row, k) of the operand at X[row * ld + k]; 1: at X[k * ld + row].  epilogue: + bias[n], tanh (act = 1),
  * * (1 - H[m,n]^2).  workspace (optional, floats) enables deterministic split-K.                                              */

@@ -89,6 +89,8 @@ _SIGS = {
     "rb_lstm2_fwd": (C.c_int, [C.POINTER(C.c_int), _fp, _fp, _fp, _fp, C.c_int64, _fp, _fp, _fp, _vp, _vp]),
     "rb_lstm2_loss_grad": (C.c_int, [C.POINTER(C.c_int), _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int,
                                      _fp, _fp, _fp, _fp, _vp, _vp]),
+    "rb_lstm2_step": (C.c_int, [_vp, C.POINTER(C.c_int), _fp, _fp, _fp, _fp, _fp, _fp, _fp, _fp, C.c_int64, C.c_float, C.c_uint64, C.c_uint32, C.c_int, _fp, _fp,
+                                _fp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp]),
     "rb_gemm_bf16x3": (C.c_int, [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
                                  C.c_int, _fp, C.c_int64, _vp]),
     "rb_dense_param_count": (C.c_int64, [C.c_int, C.POINTER(C.c_int)]),

@@ -340,6 +340,12 @@ __global__ void k_adam_dev_lr(float* __restrict__ p, float* __restrict__ m, floa
     p[i] = pi; m[i] = mi; v[i] = vi;
 }
 
+// implemented in lstm2.cu
+int lstm2_loss_grad_clocked(const int* spec, const float* params, const float* ob, const float* action, const float* t_pd, const float* reward_target,
+                            const float* init_state, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0, int loss_kind, float* s_out,
+                            float* reward_out, float* gradloss, void* workspace, const uint32_t* clock, cudaStream_t st);
+int64_t lstm2_params(const int* spec);
+
 }  // namespace rb
 
 struct rb_lstm_ctx {
@@ -442,6 +448,53 @@ int rb_lstm_step(rb_lstm_ctx* ctx, float* params, float* m, float* v, const floa
     for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
     const float fl[] = {keep_prob, lr, b1, b2, eps, gscale};
     for (float f : fl) { uint32_t u; memcpy(&u, &f, 4); mix(u); }
+    mix((uint64_t)B); mix(seed); mix(sample_id0); mix((uint64_t)loss_kind);
+    if (!ctx->gexec || ctx->gkey != key) {
+        if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+        cudaGraph_t graph = nullptr;
+        RB_CUDA(cudaStreamSynchronize(st));
+        RB_CUDA(cudaStreamBeginCapture(ctx->cap_stream, cudaStreamCaptureModeRelaxed));
+        const int rc = issue(ctx->cap_stream);
+        const cudaError_t ce = cudaStreamEndCapture(ctx->cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (ce != cudaSuccess) return cuda_fail(ce, "cudaStreamEndCapture");
+        const cudaError_t ci = cudaGraphInstantiate(&ctx->gexec, graph, 0);
+        cudaGraphDestroy(graph);
+        if (ci != cudaSuccess) { ctx->gexec = nullptr; return cuda_fail(ci, "cudaGraphInstantiate"); }
+        ctx->gkey = key;
+    }
+    RB_CUDA(cudaGraphLaunch(ctx->gexec, st));
+    return RB_OK;
+}
+
+/* rb_lstm2_loss_grad + TF-form Adam of the two-headed LSTM student as ONE CUDA-graph launch (same context type and device-side clock as
+ * rb_lstm_step): at the reference's own sizes (100 windows x 20 steps, ~70 small launches) the step is launch-bound without it.      */
+int rb_lstm2_step(rb_lstm_ctx* ctx, const int* spec, float* params, float* m, float* v, const float* ob, const float* action, const float* t_pd,
+                  const float* reward_target, const float* init_state, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0, int loss_kind,
+                  float* s_out, float* reward_out, float* gradloss, void* workspace, float lr, float b1, float b2, float eps, float gscale, int use_graph,
+                  void* stream) {
+    RB_REQUIRE(ctx && spec && params && m && v && ob && action && t_pd && reward_target && s_out && reward_out && gradloss && workspace, "NULL argument");
+    const int64_t P = lstm2_params(spec);
+    RB_REQUIRE(P > 0, "bad spec");
+    cudaStream_t st = (cudaStream_t)stream;
+    auto issue = [&](cudaStream_t s) -> int {
+        k_lstm_clock_prep<<<1, 1, 0, s>>>(ctx->clock, lr, b1, b2, ctx->lr_t);
+        int rc = lstm2_loss_grad_clocked(spec, params, ob, action, t_pd, reward_target, init_state, B, keep_prob, seed, sample_id0, loss_kind, s_out, reward_out,
+                                         gradloss, workspace, ctx->clock, s);
+        if (rc) return rc;
+        k_adam_dev_lr<<<(unsigned)((P + 255) / 256), 256, 0, s>>>(params, m, v, gradloss, P, ctx->lr_t, b1, b2, eps, gscale);
+        k_lstm_clock_advance<<<1, 1, 0, s>>>(ctx->clock);
+        RB_CUDA(cudaGetLastError());
+        return RB_OK;
+    };
+    if (!use_graph) return issue(st);
+    uint64_t key = 1469598103934665603ull ^ 0x2ull;
+    auto mix = [&](uint64_t vv) { key = (key ^ vv) * 1099511628211ull; };
+    const void* ptrs[] = {params, m, v, ob, action, t_pd, reward_target, init_state, s_out, reward_out, gradloss, workspace};
+    for (const void* q : ptrs) mix((uint64_t)(uintptr_t)q);
+    const float fl[] = {keep_prob, lr, b1, b2, eps, gscale};
+    for (float f : fl) { uint32_t u; memcpy(&u, &f, 4); mix(u); }
+    for (int i = 0; i < RB_LSTM2_SPEC_LEN; ++i) mix((uint64_t)(uint32_t)spec[i]);
     mix((uint64_t)B); mix(seed); mix(sample_id0); mix((uint64_t)loss_kind);
     if (!ctx->gexec || ctx->gkey != key) {
         if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }

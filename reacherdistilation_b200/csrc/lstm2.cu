@@ -91,9 +91,10 @@ __device__ __forceinline__ float l2_sigmoid(float x) { return 1.f / (1.f + expf(
 
 // rows of [dropout(ob) | action | m_prev | 0-pad]; the initial (c, m): c -> c[0], m -> the m_prev columns of step 0 (carry) or of EVERY step
 __global__ void k_lstm2_inputs(int64_t R, int64_t B, int U, int LDX, int carry, const float* __restrict__ ob, const float* __restrict__ action,
-                               float keep_prob, uint32_t k0, uint32_t k1, uint32_t sample_id0, uint32_t iteration,
+                               float keep_prob, uint32_t k0, uint32_t k1, uint32_t sample_id0, uint32_t iteration, const uint32_t* __restrict__ clock,
                                const float* __restrict__ init_state, float* __restrict__ xh, float* __restrict__ c0) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (clock) iteration = clock[0];                 // device-side step clock (CUDA-graph replay, rb_lstm2_step)
     if (i < R) {
         float o[11];
 #pragma unroll
@@ -186,6 +187,7 @@ struct L2Call {
     float keep_prob; uint64_t seed; uint32_t sample_id0, iteration;
     int64_t B; int loss_kind, fwd_only;
     float *s_out, *rew_out, *final_state, *gradloss;
+    const uint32_t* clock;
 };
 
 #define RB_TRY(x) do { int rc__ = (x); if (rc__) return rc__; } while (0)
@@ -214,7 +216,7 @@ static int l2_run(const L2Spec& s, const L2Call& c, float* ws, cudaStream_t st) 
     const long long HS = s.head_sz;
     // ---- inputs --------------------------------------------------------------------------------------------------------------------
     k_lstm2_inputs<<<(unsigned)((max(R, (s.carry ? B : R) * U) + 255) / 256), 256, 0, st>>>(R, B, U, s.LDX, s.carry, c.ob, c.action, c.keep_prob, (uint32_t)c.seed,
-                                                                                            (uint32_t)(c.seed >> 32), c.sample_id0, c.iteration, c.init_state, w.xh, w.c);
+                                                                                            (uint32_t)(c.seed >> 32), c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c);
     RB_CUDA(cudaGetLastError());
     // ---- the cell over the window --------------------------------------------------------------------------------------------------
     if (s.carry) {
@@ -310,6 +312,20 @@ static int l2_run(const L2Spec& s, const L2Call& c, float* ws, cudaStream_t st) 
     RB_TRY(colsum(w.dz, G, R, G, 1, 0, Gr + s.o_bl, 0, w.colpart, st));
     return RB_OK;
 }
+
+// loss_grad with the dropout iteration taken from a device-side clock: the body of rb_lstm2_step (lstm.cu owns the clock / Adam kernels and the graph)
+int lstm2_loss_grad_clocked(const int* spec, const float* params, const float* ob, const float* action, const float* t_pd, const float* reward_target,
+                            const float* init_state, int64_t B, float keep_prob, uint64_t seed, uint32_t sample_id0, int loss_kind, float* s_out,
+                            float* reward_out, float* gradloss, void* workspace, const uint32_t* clock, cudaStream_t st) {
+    L2Spec s;
+    RB_TRY(l2_parse(spec, s));
+    RB_REQUIRE(B > 0 && B * s.T < ((int64_t)1 << 24) && keep_prob > 0.f && pd_loss_kind_ok(loss_kind), "bad batch / keep_prob / loss kind");
+    L2Call c{};
+    c.params = params; c.ob = ob; c.action = action; c.t_pd = t_pd; c.rew_target = reward_target; c.init_state = init_state; c.keep_prob = keep_prob;
+    c.seed = seed; c.sample_id0 = sample_id0; c.B = B; c.loss_kind = loss_kind; c.s_out = s_out; c.rew_out = reward_out; c.gradloss = gradloss; c.clock = clock;
+    return l2_run(s, c, (float*)workspace, st);
+}
+int64_t lstm2_params(const int* spec) { L2Spec s; return l2_parse(spec, s) ? -1 : s.P; }
 
 }  // namespace rb
 

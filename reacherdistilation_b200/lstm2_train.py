@@ -85,6 +85,9 @@ def lstm_train(train=True, keep=0.5, lstm_trained_data_path=None, restore=False,
     ret = torch.zeros(N, device=dev)
     timestep, it, loss = 0, 0, None
     ar = torch.arange(T, device=dev)
+    # static window buffers: one optimiser step = ONE CUDA-graph launch (rb_lstm2_step) whose captured pointers stay valid from step to step
+    bufs = (torch.empty((T, batch_size, 11), device=dev), torch.empty((T, batch_size, 2), device=dev), torch.empty((T, batch_size, 4), device=dev),
+            torch.empty((T, batch_size), device=dev))
     while it < max_it and n_ob < cap - 1:
         t_pd = teacher.pdflat(ob)
         h_t[n_ob - 1].copy_(t_pd)
@@ -94,11 +97,10 @@ def lstm_train(train=True, keep=0.5, lstm_trained_data_path=None, restore=False,
         e_ix = torch.randint(0, N, (batch_size,), generator=gen).to(dev)
         index = (ep * EPISODE_STEPS + start).to(dev)
         rows = index[None, :] + ar[:, None]                                              # [T, B]
-        ob_w, t_w, rew_w = h_ob[rows, e_ix[None, :]], h_t[rows, e_ix[None, :]], h_rew[rows, e_ix[None, :]]
-        ac_w = h_ac[rows - 1, e_ix[None, :]]
-        student.loss_grad(ob_w, ac_w, t_w, rew_w, None, keep_prob=keep, seed=seed, sample_id0=0, iteration=student.t)
+        bufs[0].copy_(h_ob[rows, e_ix[None, :]]); bufs[2].copy_(h_t[rows, e_ix[None, :]]); bufs[3].copy_(h_rew[rows, e_ix[None, :]])
+        bufs[1].copy_(h_ac[rows - 1, e_ix[None, :]])
+        student.step(bufs[0], bufs[1], bufs[2], bufs[3], None, keep_prob=keep, seed=seed, sample_id0=0)
         loss = student.gradloss[student.P]
-        student.adam_step()
         # ---- generate_test_set (:243-258) + acting (:527-535): every env's last T rows, from the carried state -------------------------------
         lo = n_ob - T
         ob_t = h_ob[lo:n_ob] if lo >= 0 else torch.cat([torch.zeros((-lo, N, 11), device=dev), h_ob[:n_ob]])

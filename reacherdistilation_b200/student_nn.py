@@ -367,6 +367,30 @@ class StudentLSTM2:
         check(lib().rb_adam_step(ptr(self.params), ptr(self.m), ptr(self.v), ptr(self.gradloss), self.P, self.t, self.lr, self.beta1, self.beta2,
                                  self.eps, grad_scale, stream_ptr()))
 
+    def step(self, ob, action, t_pdflat, reward_target, state=None, keep_prob=1.0, seed=0, sample_id0=0, loss_kind=LOSS_KL_ST, use_graph=True):
+        """loss_grad + Adam as one CUDA-graph launch (rb_lstm2_step).  Pass the same (static) input tensors every step -- the graph is re-captured
+        whenever a pointer or scalar changes; the dropout iteration and the Adam step count live in a device-side clock.  Returns (s_pdflat, reward)
+        in static output buffers."""
+        import ctypes as C
+        T, B = ob.shape[0], ob.shape[1]
+        assert T == self.T and ob.is_contiguous() and action.is_contiguous() and t_pdflat.is_contiguous() and reward_target.is_contiguous()
+        if getattr(self, "_ctx", None) is None:
+            h = C.c_void_p()
+            check(lib().rb_lstm_ctx_create(C.byref(h), self.device.index))
+            self._ctx, self._clock_t, self._out_static = h, None, {}
+        if self._clock_t != self.t:                       # (re)load the device clock after any non-graph update
+            check(lib().rb_lstm_ctx_set_clock(self._ctx, self.t, self.t, stream_ptr()))
+        if B not in self._out_static:
+            self._out_static[B] = (torch.empty((T, B, 4), dtype=torch.float32, device=self.device), torch.empty((T, B), dtype=torch.float32, device=self.device))
+        s_out, rew_out = self._out_static[B]
+        check(lib().rb_lstm2_step(self._ctx, self._spec_p, ptr(self.params), ptr(self.m), ptr(self.v), ptr(ob), ptr(action), ptr(t_pdflat), ptr(reward_target),
+                                  ptr(state.contiguous() if state is not None else None), B, float(keep_prob), int(seed), int(sample_id0), loss_kind,
+                                  ptr(s_out), ptr(rew_out), ptr(self.gradloss), ptr(self._workspace(B)), self.lr, self.beta1, self.beta2, self.eps, 1.0,
+                                  1 if use_graph else 0, stream_ptr()))
+        self.t += 1
+        self._clock_t = self.t
+        return s_out, rew_out
+
     def state_dict(self):
         return dict(kind="lstm2", spec=self.spec.tolist(), params=self.params.cpu(), m=self.m.cpu(), v=self.v.cpu(), t=self.t)
 

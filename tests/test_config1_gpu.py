@@ -118,7 +118,8 @@ def test_host_surface_small_batches_match_device_step(n):
     from reacherdistilation_b200.env import VecReacher
     from reacherdistilation_b200.teacher import TeacherAgent, init_policy_params
     host, dev = VecReacher(num_envs=n, seed=11, host=True), VecReacher(num_envs=n, seed=11)
-    teacher = TeacherAgent(host, params=init_policy_params(seed=2, final_std=0.3)) if n in (3, 32) else None
+    nout = 4 if n == 32 else 2                                       # 32 envs: the four-output policy (the 2x64 student acting), SIMT path of the server
+    teacher = TeacherAgent(host, params=init_policy_params(seed=2, final_std=0.3, nout=nout), nout=nout) if n in (3, 32) else None
     oh, od = host.reset(), dev.reset()
     assert np.array_equal(oh, od.cpu().numpy())
     rng = np.random.default_rng(n)
@@ -129,7 +130,7 @@ def test_host_surface_small_batches_match_device_step(n):
         assert np.array_equal(oh, od.cpu().numpy()) and np.array_equal(rh, rd.cpu().numpy()) and np.array_equal(dh, dd.cpu().numpy().astype(bool)), t
         if teacher is not None:
             from reacherdistilation_b200 import MODE_FP32
-            want = TeacherAgent(None, params=teacher.params_host, mode=MODE_FP32).pdflat(od).cpu().numpy()
+            want = TeacherAgent(None, params=teacher.params_host, mode=MODE_FP32, nout=nout).pdflat(od).cpu().numpy()
             assert np.array_equal(teacher.pdflat(oh), want), t
         if t == 60:                                                  # a device-side call on the served env: state handed back through HBM, exactly
             st = host.get_state()

@@ -147,3 +147,25 @@ def test_lstm_train_loop_learns_saves_and_restores(tmp_path):
     src = lstm2_train.lstm_train(True, 1.0, str(tmp_path / "src.pt"), False, num_envs=4, batch_size=2, units=1, steps=2, iterations=20, verbose=False)
     assert np.isfinite(src["last_loss"]) and src["student"].P == 34246                         # the source's shipped sizes (:48-50)
     src["env"].close()
+
+
+def test_graph_step_equals_loss_grad_plus_adam():
+    """rb_lstm2_step (one CUDA-graph launch, device-side clock for the dropout iteration and the Adam step) vs rb_lstm2_loss_grad + rb_adam_step:
+    bit-identical parameters and losses over 6 steps on changing data in static buffers."""
+    from reacherdistilation_b200.student_nn import StudentLSTM2
+    spec = SPECS["source_commented"]
+    L = L2.Layout(spec)
+    a, b = StudentLSTM2(spec=L.spec_array(), seed=7), StudentLSTM2(spec=L.spec_array(), seed=7)
+    B = 100
+    bufs = [torch.empty((L.T, B, 11), device="cuda"), torch.empty((L.T, B, 2), device="cuda"), torch.empty((L.T, B, 4), device="cuda"), torch.empty((L.T, B), device="cuda")]
+    for it in range(6):
+        ob, ac, tp, rt, _ = _data(L, B, 50 + it)
+        for dst, src in zip(bufs, (ob, ac, tp, rt)):
+            dst.copy_(torch.from_numpy(src))
+        a.loss_grad(bufs[0], bufs[1], bufs[2], bufs[3], None, keep_prob=0.5, seed=3, sample_id0=0, iteration=a.t)
+        la = float(a.gradloss[L.P])
+        a.adam_step()
+        b.step(bufs[0], bufs[1], bufs[2], bufs[3], None, keep_prob=0.5, seed=3, sample_id0=0)
+        assert float(b.gradloss[L.P]) == la, it
+        assert torch.equal(a.params, b.params) and torch.equal(a.m, b.m) and torch.equal(a.v, b.v), it
+    assert a.t == b.t == 6
