@@ -81,8 +81,8 @@ def test_config2_4096_envs_500_steps_random_actions():
     touch = q1max.reshape(T // 50, 50, n).max(axis=1).ravel() > 2.95
     grz = graze.reshape(T // 50, 50, n).min(axis=1).ravel() < GRAZE
     free, lim = E[~touch], E[touch & ~grz]
-    print("config2 parity: bit-identical to the host twin; vs float64 oracle: free-motion episodes max %.3g (tol %.1g), joint-limit episodes max %.3g "
-          "(tol %.1g), %d of %d episodes set aside (RK4 stage within %.0e rad of the limit's activation threshold)"
+    print("config2 parity: bit-identical to the host twin; vs float64 oracle: free-motion episodes max %.3g (tol %.2g), joint-limit episodes max %.3g "
+          "(tol %.2g), %d of %d episodes set aside (RK4 stage within %.0e rad of the limit's activation threshold)"
           % (free.max(), TOL_FREE, lim.max(), TOL, int(grz.sum()), E.size, GRAZE))
     assert free.max() <= TOL_FREE and lim.max() <= TOL and grz.sum() <= 2e-3 * E.size
     env.close()
