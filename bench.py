@@ -492,12 +492,31 @@ def main():
             fn()                                                       # synchronous call (copies + sync inside)
         barrier()
         return max_over_ranks(time.perf_counter() - t0, dev)
+    def e2e_time_pipelined(chunks):
+        # the split-phase form of the same call (rb_env_rollout_policy_host_begin / _wait), two calls in flight on alternating result buffers:
+        # every call still copies its parameters in and delivers its result to the host; the host-side work around call i overlaps kernel i + 1
+        outs = [hres, dict(rew=torch.empty((CHUNK_T, n)).pin_memory(), done_mask=torch.empty((n,), dtype=torch.int64).pin_memory())]
+        for o in outs:
+            env.rollout_policy_host_begin(tparams_host, CHUNK_T, nout=2, mode=mode, out=o); env.rollout_policy_host_wait()
+        barrier()
+        t0 = time.perf_counter()
+        total = Ke * chunks
+        for i in range(total):
+            env.rollout_policy_host_begin(tparams_host, CHUNK_T, nout=2, mode=mode, out=outs[i & 1])
+            if i >= 1:
+                env.rollout_policy_host_wait()
+        env.rollout_policy_host_wait()
+        barrier()
+        return max_over_ranks(time.perf_counter() - t0, dev)
     hret = torch.empty((n,), dtype=torch.float32).pin_memory()
     hres_ret = dict(obs=None, pdflat=None, rew=None, done=None, done_mask=hmask, return_sum=hret)   # per-episode returns reduced on the device
-    e2e_sec, e2e_u8_sec, e2e_ret_sec, e2e_full_sec = e2e_time(hres, R), e2e_time(hres_u8, R), e2e_time(hres_ret, R), e2e_time(hbuf, 1)
+    e2e_sync_sec, e2e_u8_sec, e2e_ret_sec, e2e_full_sec = e2e_time(hres, R), e2e_time(hres_u8, R), e2e_time(hres_ret, R), e2e_time(hbuf, 1)
+    e2e_sec = e2e_time_pipelined(R)
     e2e = dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4) * R,
                d2h_bytes_per_step=int(n * CHUNK_T * 4 + n * 8) * R, steps=Ke,
-               api="rb_env_rollout_policy_host_ex (VecReacher.rollout_policy_host), %d calls per step" % R,
+               api="rb_env_rollout_policy_host_begin / _wait (VecReacher.rollout_policy_host_begin / _wait), %d calls per step, two in flight" % R,
+               synchronous_call=dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_sync_sec, api="rb_env_rollout_policy_host_ex: one call at a time, "
+                                     "returns when the result is in host memory"),
                result="reward[T,N] f32 of every env-step + done_mask[N] u64 (bit t = the env finished an episode at step t of the chunk) of every chunk, "
                       "both written by the kernel into the caller's page-locked buffers (no copy-engine transfer); obs / pdflat are written to the "
                       "device-resident rollout buffer (rb_env_rollout_buffer) and stay there",

@@ -142,6 +142,13 @@ int rb_env_rollout_policy_host(rb_env* env, const float* params_host, int nout, 
  * Page-locked buffers are written by the kernel directly: {reward, done_mask} or {return_sum, done_mask} need no copy-engine transfer. */
 int rb_env_rollout_policy_host_ex(rb_env* env, const float* params_host, int nout, int T, float* obs_buf_host, float* pd_buf_host,
                                   float* rew_buf_host, uint8_t* done_buf_host, uint64_t* done_mask_host, float* return_sum_host, int mode);
+/* Split-phase form for callers that keep the GPU busy: _begin queues {H2D of the parameters, the rollout launch} and returns, _wait blocks until
+ * the OLDEST outstanding call has finished (its outputs are then complete in host memory).  Up to two calls may be in flight, so the host-side
+ * work around call i overlaps the kernel of call i + 1.  Outputs: the kernel-stored ones only (reward [T,N], done_mask [N], return_sum [N]),
+ * each NULL or a page-locked buffer that must stay untouched until its _wait.                                                          */
+int rb_env_rollout_policy_host_begin(rb_env* env, const float* params_host, int nout, int T, float* rew_buf_host, uint64_t* done_mask_host,
+                                     float* return_sum_host, int mode);
+int rb_env_rollout_policy_host_wait(rb_env* env);
 /* How rb_env_rollout_policy_host brings reward / done into PAGE-LOCKED host buffers: bit 0 set = the kernel stores reward straight into the
  * mapped buffer (posted PCIe writes under the rollout), bit 1 = done too; a clear bit = device buffer + copy engine, slab by slab behind the
  * in-kernel progress flags.  Default 1 (fastest with one GPU per host; measured variants: csrc/env.cu, profiles/README.md).             */

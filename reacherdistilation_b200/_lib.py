@@ -46,6 +46,8 @@ _SIGS = {
     "rb_env_rollout_policy": (C.c_int, [_vp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _u8p, C.c_int, _vp]),
     "rb_env_rollout_policy_host": (C.c_int, [_vp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _u8p, C.c_int]),
     "rb_env_rollout_policy_host_ex": (C.c_int, [_vp, _fp, C.c_int, C.c_int, _fp, _fp, _fp, _u8p, _vp, _fp, C.c_int]),
+    "rb_env_rollout_policy_host_begin": (C.c_int, [_vp, _fp, C.c_int, C.c_int, _fp, _vp, _fp, C.c_int]),
+    "rb_env_rollout_policy_host_wait": (C.c_int, [_vp]),
     "rb_env_set_host_transport": (C.c_int, [_vp, C.c_int]),
     "rb_env_rollout_buffer": (C.c_int, [_vp, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_void_p),
                               C.POINTER(C.c_int)]),

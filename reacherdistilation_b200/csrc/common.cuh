@@ -32,6 +32,10 @@ struct rb_env {
     uint32_t prog_epoch = 0;
     int prog_slab_len = 0;                        // > 0 only while the host call launches its kernel
     uint64_t* done_mask_out = nullptr;            // set around a rollout launch: per-env bit mask of the steps that ended an episode (bit t = step t)
+    // split-phase host rollout (rb_env_rollout_policy_host_begin / _wait): up to two calls in flight, parameters double-buffered
+    float* d_params2 = nullptr;
+    cudaEvent_t pipe_done[2] = {};
+    uint64_t pipe_issued = 0, pipe_waited = 0;
     float* return_sum_out = nullptr;              // set around a rollout launch: per-env sum of the rewards of the launch's steps (in step order)
     float* d_return_sum = nullptr;
     uint64_t* d_done_mask = nullptr;              // device staging of that mask when the caller's buffer is not mapped

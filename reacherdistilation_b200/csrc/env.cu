@@ -245,7 +245,8 @@ int rb_env_destroy(rb_env* e) {
     cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
-    cudaFree(e->prog_counters); cudaFree(e->d_done_mask); cudaFree(e->d_return_sum);
+    cudaFree(e->prog_counters); cudaFree(e->d_done_mask); cudaFree(e->d_return_sum); cudaFree(e->d_params2);
+    for (int i = 0; i < 2; ++i) if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
     if (e->prog_flags_host) cudaFreeHost((void*)e->prog_flags_host);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
     if (e->copy_stream) cudaStreamDestroy(e->copy_stream);
@@ -434,6 +435,65 @@ constexpr int HOST_PROGRESS_SLABS = 5;  // tensor-core mode: time slabs reported
 static int rollout_policy_host_impl(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
                                     uint8_t* done_host, int mode);
 
+// host staging + the device-resident rollout buffer for T steps
+static int ensure_rollout_buffer(rb_env* e, int T) {
+    int rc = ensure_host_staging(e);
+    if (rc) return rc;
+    if (e->buf_T < T) {
+        DeviceGuard guard(e->device);
+        cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
+        e->d_buf_obs = e->d_buf_pd = e->d_buf_rew = nullptr; e->d_buf_done = nullptr; e->buf_T = 0;
+        const int64_t rows = (int64_t)T * e->n;
+        RB_CUDA(cudaMalloc(&e->d_buf_obs, sizeof(float) * OBS * rows));
+        RB_CUDA(cudaMalloc(&e->d_buf_pd, sizeof(float) * 4 * rows));
+        RB_CUDA(cudaMalloc(&e->d_buf_rew, sizeof(float) * rows));
+        RB_CUDA(cudaMalloc(&e->d_buf_done, rows));
+        e->buf_T = T;
+    }
+    e->buf_last_T = T;
+    return RB_OK;
+}
+
+/* Split-phase form of the host rollout for callers that keep the GPU busy: _begin queues {H2D of the parameters, the rollout launch} and returns;
+ * _wait blocks until the OLDEST outstanding call has finished (its outputs are then complete in host memory).  Up to two calls may be in flight,
+ * so the host-side work around call i (parameter copy, launch, completion wait) overlaps the kernel of call i + 1.  Outputs are the kernel-stored
+ * ones only -- reward [T,N], done_mask [N], return_sum [N], each NULL or a page-locked (mapped) buffer that stays untouched until its _wait. */
+int rb_env_rollout_policy_host_begin(rb_env* e, const float* params_host, int nout, int T, float* rew_host, uint64_t* done_mask_host,
+                                     float* return_sum_host, int mode) {
+    RB_REQUIRE(e != nullptr && params_host != nullptr && T > 0, "bad argument");
+    RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
+    RB_REQUIRE(!done_mask_host || T <= 64, "done_mask holds one bit per step: T <= 64");
+    RB_REQUIRE(e->pipe_issued - e->pipe_waited < 2, "two rollouts are already in flight: call rb_env_rollout_policy_host_wait");
+    float* zr = (float*)mapped_alias(rew_host);
+    uint64_t* zm = (uint64_t*)mapped_alias(done_mask_host);
+    float* zs = (float*)mapped_alias(return_sum_host);
+    RB_REQUIRE((!rew_host || zr) && (!done_mask_host || zm) && (!return_sum_host || zs), "the split-phase rollout needs page-locked (mapped) output buffers");
+    int rc = ensure_rollout_buffer(e, T);
+    if (rc) return rc;
+    DeviceGuard guard(e->device);
+    const int slot = (int)(e->pipe_issued & 1);
+    if (!e->d_params2) RB_CUDA(cudaMalloc(&e->d_params2, sizeof(float) * rb_policy_param_count(4)));
+    if (!e->pipe_done[slot]) RB_CUDA(cudaEventCreateWithFlags(&e->pipe_done[slot], cudaEventDisableTiming));
+    float* dp = slot ? e->d_params2 : e->d_params;             // the call still in flight reads the other copy
+    cudaStream_t s = e->host_stream;
+    RB_CUDA(cudaMemcpyAsync(dp, params_host, sizeof(float) * rb_policy_param_count(nout), cudaMemcpyHostToDevice, s));
+    e->done_mask_out = zm; e->return_sum_out = zs;
+    rc = rb_env_rollout_policy(e, dp, nout, T, e->d_buf_obs, e->d_buf_pd, zr ? zr : e->d_buf_rew, nullptr, mode, s);
+    e->done_mask_out = nullptr; e->return_sum_out = nullptr;
+    if (rc) return rc;
+    RB_CUDA(cudaEventRecord(e->pipe_done[slot], s));
+    e->pipe_issued += 1;
+    return RB_OK;
+}
+
+int rb_env_rollout_policy_host_wait(rb_env* e) {
+    RB_REQUIRE(e != nullptr, "env is NULL");
+    RB_REQUIRE(e->pipe_waited < e->pipe_issued, "no split-phase rollout is in flight");
+    RB_CUDA(cudaEventSynchronize(e->pipe_done[e->pipe_waited & 1]));
+    e->pipe_waited += 1;
+    return RB_OK;
+}
+
 int rb_env_rollout_policy_host(rb_env* e, const float* params_host, int nout, int T, float* obs_host, float* pd_host, float* rew_host,
                                uint8_t* done_host, int mode) {
     return rb_env_rollout_policy_host_ex(e, params_host, nout, T, obs_host, pd_host, rew_host, done_host, nullptr, nullptr, mode);
@@ -464,19 +524,9 @@ static int rollout_policy_host_impl(rb_env* e, const float* params_host, int nou
                                     uint8_t* done_host, int mode) {
     RB_REQUIRE(e != nullptr && params_host != nullptr && T > 0, "bad argument");
     RB_REQUIRE(nout == 2 || nout == 4, "nout must be 2 or 4");
-    int rc = ensure_host_staging(e);
+    RB_REQUIRE(e->pipe_issued == e->pipe_waited, "a split-phase rollout (rb_env_rollout_policy_host_begin) is still in flight: wait for it first");
+    int rc = ensure_rollout_buffer(e, T);
     if (rc) return rc;
-    if (e->buf_T < T) {
-        cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
-        e->d_buf_obs = e->d_buf_pd = e->d_buf_rew = nullptr; e->d_buf_done = nullptr; e->buf_T = 0;
-        const int64_t rows = (int64_t)T * e->n;
-        RB_CUDA(cudaMalloc(&e->d_buf_obs, sizeof(float) * OBS * rows));
-        RB_CUDA(cudaMalloc(&e->d_buf_pd, sizeof(float) * 4 * rows));
-        RB_CUDA(cudaMalloc(&e->d_buf_rew, sizeof(float) * rows));
-        RB_CUDA(cudaMalloc(&e->d_buf_done, rows));
-        e->buf_T = T;
-    }
-    e->buf_last_T = T;
     cudaStream_t s = e->host_stream, sc = e->copy_stream;
     RB_CUDA(cudaMemcpyAsync(e->d_params, params_host, sizeof(float) * rb_policy_param_count(nout), cudaMemcpyHostToDevice, s));
     // The kernel ALWAYS fills the device-resident rollout buffer (obs, pdflat: rb_env_rollout_buffer() hands it to the distillation loop);

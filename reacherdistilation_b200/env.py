@@ -179,6 +179,17 @@ class VecReacher:
                                                ptr(out.get("done")), mode))                  # None entries: that field is not copied to the host
         return out
 
+    def rollout_policy_host_begin(self, params_host, T, nout=2, mode=_lib.MODE_FP32, out=None):
+        """Split-phase host rollout: queue {H2D of the parameters, the launch} and return; rollout_policy_host_wait() completes the OLDEST
+        outstanding call.  Up to two in flight.  out: dict of page-locked tensors rew [T,N] f32 / done_mask [N] int64 / return_sum [N] f32 (any
+        may be absent); they must not be touched until the matching wait."""
+        check(lib().rb_env_rollout_policy_host_begin(self._h, ptr(params_host), nout, T, ptr(out.get("rew")), ptr(out.get("done_mask")),
+                                                     ptr(out.get("return_sum")), mode))
+        return out
+
+    def rollout_policy_host_wait(self):
+        check(lib().rb_env_rollout_policy_host_wait(self._h))
+
     def rollout_buffer(self):
         """Device views (no copy) of the resident rollout buffer the last rollout_policy_host() filled: dict(obs [T,N,11], pdflat [T,N,4],
         rew [T,N], done [T,N]).  rew / done only hold data when that call's host buffers were pageable or absent (page-locked ones are

@@ -192,3 +192,47 @@ def test_rollout_host_done_mask_is_the_bit_packed_done(pinned, mode_name):
     with pytest.raises(Exception):
         b.rollout_policy_host(torch.from_numpy(p), 65, mode=mode, out=dict(obs=None, pdflat=None, rew=None, done=None, done_mask=mask))
     a.close(); b.close()
+
+
+@pytest.mark.parametrize("mode_name", ["fp32", "tc"])
+def test_split_phase_host_rollout_two_in_flight(mode_name):
+    """rb_env_rollout_policy_host_begin / _wait: two calls in flight, outputs of call i complete after its wait while call i + 1 runs; the
+    trajectories equal the synchronous entry point's bit for bit; a third begin without a wait is refused."""
+    from reacherdistilation_b200 import MODE_FP32, MODE_TC
+    from reacherdistilation_b200._lib import ReacherB200Error
+    from reacherdistilation_b200.env import VecReacher
+    from reacherdistilation_b200.teacher import init_policy_params
+    mode = MODE_FP32 if mode_name == "fp32" else MODE_TC
+    p = torch.from_numpy(init_policy_params(seed=0)).pin_memory()
+    n, T, calls = 4099, 50, 5
+    a, b = VecReacher(num_envs=n, seed=6), VecReacher(num_envs=n, seed=6)
+    a.reset(); b.reset()
+    want = [a.rollout_policy(p.cuda(), T, mode=mode) for _ in range(calls)]
+    want = [{k: v.clone() for k, v in w.items()} for w in want]
+    bufs = [dict(rew=torch.full((T, n), -7.0).pin_memory(), done_mask=torch.full((n,), -1, dtype=torch.int64).pin_memory(),
+                 return_sum=torch.full((n,), 3.0).pin_memory()) for _ in range(2)]
+    got = []
+    for i in range(calls):
+        b.rollout_policy_host_begin(p, T, mode=mode, out=bufs[i & 1])
+        if i == 1:
+            with pytest.raises(ReacherB200Error):
+                b.rollout_policy_host_begin(p, T, mode=mode, out=bufs[0])          # two are in flight
+        if i >= 1:
+            b.rollout_policy_host_wait()
+            got.append({k: v.clone() for k, v in bufs[(i - 1) & 1].items()})
+    b.rollout_policy_host_wait()
+    got.append({k: v.clone() for k, v in bufs[(calls - 1) & 1].items()})
+    with pytest.raises(ReacherB200Error):
+        b.rollout_policy_host_wait()
+    for w, g in zip(want, got):
+        assert torch.equal(w["rew"].cpu(), g["rew"])
+        dd = w["done"].cpu().numpy()
+        m = np.zeros(n, np.uint64)
+        for t in range(T):
+            m |= dd[t].astype(np.uint64) << np.uint64(t)
+        assert np.array_equal(g["done_mask"].numpy().view(np.uint64), m)
+        acc = np.zeros(n, np.float32)
+        for t in range(T):
+            acc = (acc + w["rew"][t].cpu().numpy()).astype(np.float32)
+        assert np.array_equal(g["return_sum"].numpy(), acc)
+    a.close(); b.close()
