@@ -34,6 +34,9 @@ struct rb_env {
     uint64_t* done_mask_out = nullptr;            // set around a rollout launch: per-env bit mask of the steps that ended an episode (bit t = step t)
     // split-phase host rollout (rb_env_rollout_policy_host_begin / _wait): up to two calls in flight, parameters double-buffered
     float* d_params2 = nullptr;
+    float* d_rew_pipe[2] = {};                    // reward staging of the two in-flight calls when the copy engine brings it to the host
+    int64_t rew_pipe_rows = 0;
+    cudaEvent_t pipe_kernel[2] = {};
     cudaEvent_t pipe_done[2] = {};
     uint64_t pipe_issued = 0, pipe_waited = 0;
     float* return_sum_out = nullptr;              // set around a rollout launch: per-env sum of the rewards of the launch's steps (in step order)

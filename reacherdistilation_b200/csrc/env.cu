@@ -245,7 +245,8 @@ int rb_env_destroy(rb_env* e) {
     cudaFree(e->qv); cudaFree(e->tp); cudaFree(e->ctr);
     cudaFree(e->d_act); cudaFree(e->d_obs); cudaFree(e->d_rew); cudaFree(e->d_done); cudaFree(e->d_params);
     cudaFree(e->d_buf_obs); cudaFree(e->d_buf_pd); cudaFree(e->d_buf_rew); cudaFree(e->d_buf_done);
-    cudaFree(e->prog_counters); cudaFree(e->d_done_mask); cudaFree(e->d_return_sum); cudaFree(e->d_params2);
+    cudaFree(e->prog_counters); cudaFree(e->d_done_mask); cudaFree(e->d_return_sum); cudaFree(e->d_params2); cudaFree(e->d_rew_pipe[0]); cudaFree(e->d_rew_pipe[1]);
+    for (int i = 0; i < 2; ++i) if (e->pipe_kernel[i]) cudaEventDestroy(e->pipe_kernel[i]);
     for (int i = 0; i < 2; ++i) if (e->pipe_done[i]) cudaEventDestroy(e->pipe_done[i]);
     if (e->prog_flags_host) cudaFreeHost((void*)e->prog_flags_host);
     if (e->host_stream) cudaStreamDestroy(e->host_stream);
@@ -475,13 +476,35 @@ int rb_env_rollout_policy_host_begin(rb_env* e, const float* params_host, int no
     if (!e->d_params2) RB_CUDA(cudaMalloc(&e->d_params2, sizeof(float) * rb_policy_param_count(4)));
     if (!e->pipe_done[slot]) RB_CUDA(cudaEventCreateWithFlags(&e->pipe_done[slot], cudaEventDisableTiming));
     float* dp = slot ? e->d_params2 : e->d_params;             // the call still in flight reads the other copy
-    cudaStream_t s = e->host_stream;
+    cudaStream_t s = e->host_stream, sc = e->copy_stream;
     RB_CUDA(cudaMemcpyAsync(dp, params_host, sizeof(float) * rb_policy_param_count(nout), cudaMemcpyHostToDevice, s));
+    // reward [T,N] (the bulk of the result): stored by the kernel straight into the host buffer (rb_env_set_host_transport bit 0, default), or
+    // -- bit 0 clear -- written to a per-slot device buffer and brought over by the copy engine WHILE THE NEXT CALL'S KERNEL RUNS: the posted
+    // PCIe stores slow the kernel by ~3 % (0.305 vs 0.295 ms at config 3), a copy of the previous chunk beside it does not.
+    const bool rew_copy = rew_host && !(e->host_zerocopy & 1);
+    float* rew_dst = zr ? zr : e->d_buf_rew;
+    if (rew_copy) {
+        const int64_t rows = (int64_t)T * e->n;
+        if (e->rew_pipe_rows < rows) {
+            RB_REQUIRE(e->pipe_issued == e->pipe_waited, "reward staging can only grow while no split-phase rollout is in flight");
+            for (int i = 0; i < 2; ++i) { cudaFree(e->d_rew_pipe[i]); e->d_rew_pipe[i] = nullptr; RB_CUDA(cudaMalloc(&e->d_rew_pipe[i], sizeof(float) * rows)); }
+            e->rew_pipe_rows = rows;
+        }
+        if (!e->pipe_kernel[slot]) RB_CUDA(cudaEventCreateWithFlags(&e->pipe_kernel[slot], cudaEventDisableTiming));
+        rew_dst = e->d_rew_pipe[slot];
+    }
     e->done_mask_out = zm; e->return_sum_out = zs;
-    rc = rb_env_rollout_policy(e, dp, nout, T, e->d_buf_obs, e->d_buf_pd, zr ? zr : e->d_buf_rew, nullptr, mode, s);
+    rc = rb_env_rollout_policy(e, dp, nout, T, e->d_buf_obs, e->d_buf_pd, rew_dst, nullptr, mode, s);
     e->done_mask_out = nullptr; e->return_sum_out = nullptr;
     if (rc) return rc;
-    RB_CUDA(cudaEventRecord(e->pipe_done[slot], s));
+    if (rew_copy) {
+        RB_CUDA(cudaEventRecord(e->pipe_kernel[slot], s));
+        RB_CUDA(cudaStreamWaitEvent(sc, e->pipe_kernel[slot], 0));
+        RB_CUDA(cudaMemcpyAsync(rew_host, rew_dst, sizeof(float) * (size_t)T * e->n, cudaMemcpyDeviceToHost, sc));
+        RB_CUDA(cudaEventRecord(e->pipe_done[slot], sc));      // the call is complete when its reward has landed (the mask / return words were stored by the kernel)
+    } else {
+        RB_CUDA(cudaEventRecord(e->pipe_done[slot], s));
+    }
     e->pipe_issued += 1;
     return RB_OK;
 }

@@ -194,8 +194,9 @@ def test_rollout_host_done_mask_is_the_bit_packed_done(pinned, mode_name):
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("transport", [1, 0])
 @pytest.mark.parametrize("mode_name", ["fp32", "tc"])
-def test_split_phase_host_rollout_two_in_flight(mode_name):
+def test_split_phase_host_rollout_two_in_flight(mode_name, transport):
     """rb_env_rollout_policy_host_begin / _wait: two calls in flight, outputs of call i complete after its wait while call i + 1 runs; the
     trajectories equal the synchronous entry point's bit for bit; a third begin without a wait is refused."""
     from reacherdistilation_b200 import MODE_FP32, MODE_TC
@@ -207,6 +208,8 @@ def test_split_phase_host_rollout_two_in_flight(mode_name):
     n, T, calls = 4099, 50, 5
     a, b = VecReacher(num_envs=n, seed=6), VecReacher(num_envs=n, seed=6)
     a.reset(); b.reset()
+    from reacherdistilation_b200 import _lib
+    _lib.check(_lib.lib().rb_env_set_host_transport(b._h, transport))        # 1: reward stored by the kernel; 0: copy engine beside the next kernel
     want = [a.rollout_policy(p.cuda(), T, mode=mode) for _ in range(calls)]
     want = [{k: v.clone() for k, v in w.items()} for w in want]
     bufs = [dict(rew=torch.full((T, n), -7.0).pin_memory(), done_mask=torch.full((n,), -1, dtype=torch.int64).pin_memory(),
