@@ -528,7 +528,7 @@ static int sm_count_current(int* sms) {
 
 constexpr int FWD_NT = 2;       // standalone forward: 2 tiles per CTA (97 KB) -> 2 CTAs per SM
 constexpr int ROLLOUT_NT = 4;   // fused rollout: 4 tiles = 16 warps per CTA, one CTA per SM
-constexpr int ROLLOUT_STAGGER_NS = 2000;   // start offset between consecutive tiles of a CTA (step period ~ 8 us)
+constexpr int ROLLOUT_STAGGER_NS = 1000;   // start offset between consecutive tiles of a CTA (step period 5.9 us; swept 0 .. 4000 ns in round 2: 1.115 / 1.120 / 1.112 / 1.093e10 env-steps/s at 0 / 1000 / 2000 / 4000)
 
 int policy_fwd_tc(const float* params, int nout, const float* obs, int64_t n, float* pd, cudaStream_t s) {
     int sms = 148;
