@@ -512,13 +512,18 @@ def main():
     hret = torch.empty((n,), dtype=torch.float32).pin_memory()
     hres_ret = dict(obs=None, pdflat=None, rew=None, done=None, done_mask=hmask, return_sum=hret)   # per-episode returns reduced on the device
     e2e_sync_sec, e2e_u8_sec, e2e_ret_sec, e2e_full_sec = e2e_time(hres, R), e2e_time(hres_u8, R), e2e_time(hres_ret, R), e2e_time(hbuf, 1)
-    e2e_sec = e2e_time_pipelined(R)                         # reward stored by the kernel into the host buffer (default transport)
+    e2e_ks_sec = e2e_time_pipelined(R)                      # reward stored by the kernel into the host buffer (default transport)
     check(L.rb_env_set_host_transport(env._h, 0))           # reward through a per-call device buffer + the copy engine, beside the next call's kernel
     e2e_ce_sec = e2e_time_pipelined(R)
     check(L.rb_env_set_host_transport(env._h, 1))
+    # transport rule (measured, profiles/README.md): one GPU per host link -> kernel-posted stores (1.05e10 vs 1.02e10); several ranks sharing the
+    # host's PCIe ingest -> copy engine (2 ranks: 1.71e10 vs 1.58e10; the posted 128-byte stores of several GPUs contend on the shared uplink)
+    e2e_sec = e2e_ks_sec if world == 1 else e2e_ce_sec
     e2e = dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_sec, unit="env-steps/s", h2d_bytes_per_step=int(tparams_host.numel() * 4) * R,
                d2h_bytes_per_step=int(n * CHUNK_T * 4 + n * 8) * R, steps=Ke,
                api="rb_env_rollout_policy_host_begin / _wait (VecReacher.rollout_policy_host_begin / _wait), %d calls per step, two in flight" % R,
+               transport="kernel-posted reward stores (rb_env_set_host_transport 1)" if world == 1 else "copy engine for the reward (rb_env_set_host_transport 0)",
+               split_phase_kernel_stored_reward=dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_ks_sec),
                split_phase_copy_engine_reward=dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_ce_sec,
                                                    note="rb_env_set_host_transport 0: the reward of call i goes through a device buffer and the copy engine while kernel i + 1 runs"),
                synchronous_call=dict(value=float(n) * CHUNK_T * R * Ke * world / e2e_sync_sec, api="rb_env_rollout_policy_host_ex: one call at a time, "
