@@ -76,3 +76,51 @@ def test_bptt_matches_finite_differences():
             q[k] -= 2 * e
             lm = total(q)
             assert abs((lp - lm) / (2 * e) - g[k]) <= 2e-6 * max(1.0, abs(g[k])), (spec, k)
+
+
+def _torch_total_loss(L, theta, ob, ac, tp, rt, st):
+    """The same graph written independently with torch float64 ops (no code shared with oracle/lstm2_np.py beyond the layout): autograd gives
+    the gradient of EVERY parameter, against which the oracle's hand-derived back-propagation is checked."""
+    import torch
+    U, T = L.U, L.T
+    Wl, bl = theta[L.o_Wl:L.o_bl].reshape(L.XH, L.G), theta[L.o_bl:L.head0]
+    c0, m0 = torch.as_tensor(st[0]), torch.as_tensor(st[1])
+    c, m = c0, m0
+    total = 0.0
+    for t in range(T):
+        c_prev, m_prev = (c, m) if L.carry else (c0, m0)
+        x = torch.cat([torch.as_tensor(ob[t]), torch.as_tensor(ac[t]), m_prev], -1)
+        z = x @ Wl + bl
+        i, j, f, o = torch.sigmoid(z[:, :U]), torch.tanh(z[:, U:2 * U]), torch.sigmoid(z[:, 2 * U:3 * U] + 1.0), torch.sigmoid(z[:, 3 * U:])
+        c = f * c_prev + i * j
+        m = o * torch.tanh(c)
+        base = L.head0 + t * L.head_sz
+        lay = {name: (theta[base + ow:base + ow + fi * fo].reshape(fi, fo), theta[base + ob_:base + ob_ + fo]) for name, ow, ob_, fi, fo in L.blocks}
+        trunk = torch.tanh(m @ lay["trunk"][0] + lay["trunk"][1])
+        a = trunk
+        for k in range(L.nR):
+            a = torch.tanh(a @ lay["reward%d" % k][0] + lay["reward%d" % k][1])
+        rew = (a @ lay["reward_out"][0] + lay["reward_out"][1])[:, 0]
+        s = torch.tanh(trunk @ lay["action"][0] + lay["action"][1]) @ lay["pd"][0] + lay["pd"][1]
+        ms, ls = s[:, :2], s[:, 2:]
+        mt, lt = torch.as_tensor(tp[t][:, :2]), torch.as_tensor(tp[t][:, 2:])
+        kl = (lt - ls + (torch.exp(2 * ls) + (ms - mt) ** 2) / (2 * torch.exp(2 * lt)) - 0.5).sum()      # lstm_loss, backup/student_rollout.py:196-200
+        total = total + kl + ((rew - torch.as_tensor(rt[t])) ** 2).sum()                                 # + reward term, :328
+    return total
+
+
+def test_bptt_matches_torch_autograd_on_every_parameter():
+    import torch
+    for spec in (L2.SOURCE_SPEC(units=7, steps=4), (7, 4, 1, 128, 64, 1, 64), L2.TFEVENTS_SPEC, (5, 3, 1, 24, 16, 3, 16, 8, 16)):
+        L = L2.Layout(spec)
+        rng = np.random.default_rng(3)
+        p = L2.init_params(spec, 2).astype(np.float64) + rng.standard_normal(L.P) * 0.02
+        ob, ac, tp, rt, st = _data(L, 5, 9)
+        _, _, (tot, _, _), g = L2.loss_grad(spec, p, ob, ac, tp, rt, st)
+        theta = torch.tensor(p, dtype=torch.float64, requires_grad=True)
+        loss = _torch_total_loss(L, theta, ob, ac, tp, rt, st)
+        loss.backward()
+        ga = theta.grad.numpy()
+        assert abs(loss.item() - tot) <= 1e-10 * max(1.0, abs(tot))
+        assert np.abs(ga - g).max() <= 1e-9 * max(1.0, np.abs(g).max()), spec
+        assert (np.abs(g) > 0).mean() > 0.5                                 # the comparison is not vacuous

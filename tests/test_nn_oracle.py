@@ -54,3 +54,37 @@ def test_dropout_mask_statistics_and_determinism():
     assert not np.array_equal(k1, NN.dropout_keep(5, ids, 4, 0.5))
     x = NN.student_input(np.ones((4, 11), np.float32), np.zeros((4, 4)), np.zeros(4), 0.5, 5, ids[:4], 3)
     assert set(np.unique(x[:, :11])) <= {0.0, 2.0} and x.shape == (4, 16)
+
+
+def test_student_mlp_gradient_matches_torch_autograd_for_every_loss():
+    """oracle/nn_np.py (student_nn.py:51-57 graph, loss.py:3-13 KL and the other loss kinds) against torch autograd in float64 on an independently
+    written graph: all 24 380 gradients, four loss kinds."""
+    import torch
+    rng = np.random.default_rng(5)
+    P = (rng.standard_normal(NN.mlp_param_count()) * 0.2).astype(np.float32)
+    x, t = rng.standard_normal((33, 16)), np.concatenate([rng.standard_normal((33, 2)) * 0.3, -1 + 0.2 * rng.standard_normal((33, 2))], -1)
+    dims, tanh = (16, 24, 128, 128, 32, 4), (True, True, False, True, False)        # the third layer is LINEAR (student_nn.py:55)
+    for kind in (0, 1, 2, 3):
+        s, hs = NN.mlp_fwd(x, P)
+        l, ds = NN.pd_loss(s, t, kind)
+        g = NN.mlp_bwd(hs, P, ds)
+        th = torch.tensor(P.astype(np.float64), requires_grad=True)
+        a, o = torch.as_tensor(x), 0
+        for i in range(5):
+            W = th[o:o + dims[i] * dims[i + 1]].reshape(dims[i], dims[i + 1]); o += dims[i] * dims[i + 1]
+            b = th[o:o + dims[i + 1]]; o += dims[i + 1]
+            a = a @ W + b
+            if tanh[i]:
+                a = torch.tanh(a)
+        ms, ls, mt, lt = a[:, :2], a[:, 2:], torch.as_tensor(t[:, :2]), torch.as_tensor(t[:, 2:])
+        if kind == 0:
+            loss = (lt - ls + (torch.exp(2 * ls) + (ms - mt) ** 2) / (2 * torch.exp(2 * lt)) - 0.5).sum()
+        elif kind == 1:
+            loss = (ls - lt + (torch.exp(2 * lt) + (ms - mt) ** 2) / (2 * torch.exp(2 * ls)) - 0.5).sum()
+        elif kind == 2:
+            loss = ((a - torch.as_tensor(t)) ** 2).sum()
+        else:
+            loss = ((ms - mt) ** 2).sum()
+        loss.backward()
+        assert abs(loss.item() - l) <= 1e-10 * max(1.0, abs(l)), kind
+        assert np.abs(th.grad.numpy() - g).max() <= 1e-9 * max(1.0, np.abs(g).max()), kind
