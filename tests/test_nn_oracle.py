@@ -88,3 +88,39 @@ def test_student_mlp_gradient_matches_torch_autograd_for_every_loss():
         loss.backward()
         assert abs(loss.item() - l) <= 1e-10 * max(1.0, abs(l)), kind
         assert np.abs(th.grad.numpy() - g).max() <= 1e-9 * max(1.0, np.abs(g).max()), kind
+
+
+def test_policy64_student_gradient_matches_torch_autograd():
+    """The 2x64 student of the backup experiment (backup/student_rollout.py:79-87: obfilter clip +-5, two tanh layers, 4 outputs) with both KL
+    directions (:639-642): oracle/nn_np.policy_bwd against torch float64 autograd, every trainable parameter; the obfilter and logstd slots of the
+    flat layout get no gradient."""
+    import torch
+    rng = np.random.default_rng(6)
+    P = (rng.standard_normal(NN.policy_param_count(4)) * 0.2).astype(np.float32)
+    P[:11] = rng.standard_normal(11) * 0.1
+    P[11:22] = 0.5 + rng.random(11)
+    x = rng.standard_normal((21, 11)) * 3.0                      # some inputs beyond the clip
+    t = np.concatenate([rng.standard_normal((21, 2)) * 0.3, -1 + 0.2 * rng.standard_normal((21, 2))], -1)
+    for kind, loss_fn in ((0, NN.kl_loss), (1, NN.kl_loss_rev)):
+        s = NN.policy_fwd(x, P, nout=4)
+        l, ds = loss_fn(s, t)
+        g = NN.policy_bwd(x, P, ds)
+        th = torch.tensor(P.astype(np.float64), requires_grad=True)
+        mu, sd = th[:11], th[11:22]
+        o = 22
+        W1 = th[o:o + 704].reshape(11, 64); o += 704
+        b1 = th[o:o + 64]; o += 64
+        W2 = th[o:o + 4096].reshape(64, 64); o += 4096
+        b2 = th[o:o + 64]; o += 64
+        W3 = th[o:o + 256].reshape(64, 4); o += 256
+        b3 = th[o:o + 4]
+        z = torch.clamp((torch.as_tensor(x) - mu.detach()) / sd.detach(), -5.0, 5.0)     # the filter statistics are not trained
+        a = torch.tanh(torch.tanh(z @ W1 + b1) @ W2 + b2) @ W3 + b3
+        ms, ls, mt, lt = a[:, :2], a[:, 2:], torch.as_tensor(t[:, :2]), torch.as_tensor(t[:, 2:])
+        loss = (lt - ls + (torch.exp(2 * ls) + (ms - mt) ** 2) / (2 * torch.exp(2 * lt)) - 0.5).sum() if kind == 0 else \
+            (ls - lt + (torch.exp(2 * lt) + (ms - mt) ** 2) / (2 * torch.exp(2 * ls)) - 0.5).sum()
+        loss.backward()
+        ga = th.grad.numpy()
+        assert abs(loss.item() - l) <= 1e-10 * max(1.0, abs(l))
+        assert np.abs(ga - g).max() <= 1e-9 * max(1.0, np.abs(g).max()) and (g[:22] == 0).all() and (g[-2:] == 0).all()
+        assert (np.abs(np.clip((x - P[:11]) / P[11:22], -5, 5)) == 5).any()              # the clip was exercised
