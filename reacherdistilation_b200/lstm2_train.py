@@ -41,7 +41,9 @@ def lstm_train(train=True, keep=0.5, lstm_trained_data_path=None, restore=False,
     teacher = TeacherAgent(env, params=tparams, mode=MODE_TC)
     student = StudentLSTM2(spec=lstm2_spec(units, T, carry_state, reward_hidden=tuple(reward_hidden)), seed=1, device=dev, lr=lr)
     ckpt = lstm_trained_data_path or os.path.join(base_path, "student_lstm2_b200.pt")
-    cap = EPISODE_STEPS * (int(total_episodes) + 4) + 8
+    cap = EPISODE_STEPS * (int(total_episodes) + 4) + 8                    # history rows: phase A (one episode) + one row per env step
+    if iterations is not None:
+        cap = max(cap, 2 * EPISODE_STEPS + int(iterations) + 8)
     h_ob, h_t = torch.zeros((cap, N, 11), device=dev), torch.zeros((cap, N, 4), device=dev)
     h_ac, h_rew = torch.zeros((cap, N, 2), device=dev), torch.zeros((cap, N), device=dev)
     n_ob = n_act = 0                       # len(ob_list), len(stepped_action_list) == len(reward_list)
@@ -52,6 +54,11 @@ def lstm_train(train=True, keep=0.5, lstm_trained_data_path=None, restore=False,
         student.load_state_dict(sd["student"])
         if train and "h_ob" in sd and sd["h_ob"].shape[1] == N:      # the reference reloads its lists too (:423-461)
             n_ob, n_act, episodes, losses, rets = int(sd["n_ob"]), int(sd["n_act"]), int(sd["episodes"]), list(sd["losses"]), list(sd["rets"])
+            if n_ob + (int(iterations) if iterations is not None else EPISODE_STEPS * (int(total_episodes) + 1)) + 8 > cap:      # room for the continued run
+                grow = n_ob + (int(iterations) if iterations is not None else EPISODE_STEPS * (int(total_episodes) + 1)) + 8
+                h_ob, h_t = torch.zeros((grow, N, 11), device=dev), torch.zeros((grow, N, 4), device=dev)
+                h_ac, h_rew = torch.zeros((grow, N, 2), device=dev), torch.zeros((grow, N), device=dev)
+                cap = grow
             for dst, key in ((h_ob, "h_ob"), (h_t, "h_t"), (h_ac, "h_ac"), (h_rew, "h_rew")):
                 dst[:sd[key].shape[0]].copy_(sd[key])
             gen.set_state(sd["gen"])
