@@ -328,6 +328,10 @@ int rb_lstm2_step(rb_lstm_ctx* ctx, const int* spec, float* params_dev, float* m
 int rb_gemm_bf16x3(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,
                    const float* bias, int act, int accumulate, const float* H, int ldh, float* workspace, int64_t workspace_floats,
                    void* stream);
+/* Pipeline shape of rb_gemm_bf16x3 (results are bit-identical either way): 0 = deep operand pipeline, one (128-wide tiles) or two CTAs per
+ * SM; 1 = packed, a two-stage pipeline at two / three CTAs per SM; -1 (default) = packed whenever the grid holds more CTAs than the GPU has
+ * SMs.  Process-wide tuning knob for measurements (scripts/r02/gemm_packing_ab.py); not part of any reference call path.              */
+int rb_gemm_set_cta_packing(int mode);
 
 /* ------------------------------------------------------------------------------------------------ dense stacks -
  * The auxiliary objectives of the reference's backup experiments, as a generic dense stack on rb_gemm_bf16x3:

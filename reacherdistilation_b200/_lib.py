@@ -95,6 +95,7 @@ _SIGS = {
                                 _fp, _vp, C.c_float, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int, _vp]),
     "rb_gemm_bf16x3": (C.c_int, [_fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp, C.c_int, C.c_int, C.c_int, C.c_int, _fp, C.c_int, C.c_int, _fp,
                                  C.c_int, _fp, C.c_int64, _vp]),
+    "rb_gemm_set_cta_packing": (C.c_int, [C.c_int]),
     "rb_dense_param_count": (C.c_int64, [C.c_int, C.POINTER(C.c_int)]),
     "rb_dense_workspace_bytes": (C.c_int64, [C.c_int, C.POINTER(C.c_int), C.c_int64]),
     "rb_dense_fwd": (C.c_int, [_fp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), _fp, C.c_int64, _fp, _vp, _vp]),

@@ -24,10 +24,10 @@ using namespace tc;
 constexpr int GM_THREADS = 256;
 constexpr int GM_BM = 128;
 constexpr int GM_BK = 32;
-constexpr int GM_BF_STAGES = 2;          // bf16 hi/lo operand stages (consumed by the MMAs)
+constexpr int GM_BF_STAGES_MAX = 2;      // bf16 hi/lo operand stages (consumed by the MMAs): see GemmCfg
 
 struct __align__(16) GemmCtl {
-    uint64_t stage_bar[GM_BF_STAGES];
+    uint64_t stage_bar[GM_BF_STAGES_MAX];
     uint64_t done_bar;
     uint32_t tmem_base;
 };
@@ -134,26 +134,38 @@ template <int R> struct OperandTile {
     }
 };
 
-// raw (fp32) stages in flight: the 128-wide tile runs one CTA per SM with a deep pipeline, the narrower ones two CTAs per SM
-template <int BN> struct GemmCfg {
-    static constexpr int RAW_STAGES = BN >= 128 ? 4 : (BN == 64 ? 2 : 3);       // BN <= 64: <= 113 KB so that two CTAs share an SM
+// Two pipeline shapes per tile width.  DEEP: 2 bf16 stages and 2-4 raw (fp32) stages, one CTA per SM for the 128-wide tile, two for the
+// narrower ones.  PACKED: 2 raw stages + 1 bf16 stage (97 / 73 / 61 KB) so that two 128-wide or three narrower CTAs share an SM.  The conversion
+// of a packed CTA's next k-tile waits for the MMAs of its previous one, but the other CTAs of the SM fill that time: the per-k-tile cost is the
+// latency of [copy landed -> convert -> barrier -> MMA], and 16-24 warps hide it better than 8-16; grids of 149 .. 296 wide tiles (the batched
+// LSTM heads: 160) also become one wave instead of two.  Measured (B200, scripts/r02/gemm_packing_ab.py and a sweep over every {2,3,4} x {1,2}
+// stage combination per width): LSTM step at 2048 windows 0.526 -> 0.487 ms, two-headed LSTM 0.620 -> 0.550 ms, 8192 x 4096 x 4096 product
+// 116 -> 152 TFLOP/s; grids of at most one CTA per SM (20 / 100 windows) are insensitive (all combinations within 1 %) and keep DEEP.
+template <int BN, bool PACKED = false> struct GemmCfg {
+    static constexpr int RAW_STAGES = PACKED ? 2 : (BN >= 128 ? 4 : (BN == 64 ? 2 : 3));
+    static constexpr int BF_STAGES = PACKED ? 1 : 2;
     static constexpr int BF_STAGE_BYTES = 2 * OperandTile<GM_BM>::BYTES + 2 * OperandTile<BN>::BYTES;
     static constexpr int RAW_STAGE_BYTES = OperandTile<GM_BM>::RAW_BYTES + OperandTile<BN>::RAW_BYTES;
-    static constexpr int PIPE_BYTES = GM_BF_STAGES * BF_STAGE_BYTES + RAW_STAGES * RAW_STAGE_BYTES;
+    static constexpr int PIPE_BYTES = BF_STAGES * BF_STAGE_BYTES + RAW_STAGES * RAW_STAGE_BYTES;
     static constexpr int CT_LD = BN + 4;                                 // fp32 C staging tile, padded rows (conflict-free 128-bit accesses)
     static constexpr int CT_BYTES = GM_BM * CT_LD * 4;
     static constexpr int SMEM = (PIPE_BYTES > CT_BYTES ? PIPE_BYTES : CT_BYTES) + (int)sizeof(GemmCtl);
+    // co-resident CTAs: what 228 KB of shared memory per SM holds (1 KB reserved per CTA), at most 3 (85 registers per thread)
+    static constexpr int FIT = 233472 / (SMEM + 1024);
+    static constexpr int MIN_CTAS = FIT < 1 ? 1 : (FIT > 3 ? 3 : FIT);
 };
+static_assert(GemmCfg<128, false>::MIN_CTAS == 1 && GemmCfg<64, false>::MIN_CTAS == 2 && GemmCfg<128, true>::MIN_CTAS == 2 &&
+              GemmCfg<64, true>::MIN_CTAS == 3 && GemmCfg<32, true>::MIN_CTAS == 3 && GemmCfg<16, true>::MIN_CTAS == 3, "CTAs per SM as documented");
 
-template <int BN>
-__global__ void __launch_bounds__(GM_THREADS, BN >= 128 ? 1 : 2) k_gemm_bf16x3(const GemmArgs g) {
+template <int BN, bool PACKED>
+__global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_gemm_bf16x3(const GemmArgs g) {
     using TA = OperandTile<GM_BM>;
     using TB = OperandTile<BN>;
-    using CF = GemmCfg<BN>;
-    constexpr int RS = CF::RAW_STAGES;
+    using CF = GemmCfg<BN, PACKED>;
+    constexpr int RS = CF::RAW_STAGES, BFS = CF::BF_STAGES;
     constexpr int TCOLS = BN < 32 ? 32 : BN;
     extern __shared__ __align__(128) uint8_t smem[];
-    uint8_t* raw_base = smem + GM_BF_STAGES * CF::BF_STAGE_BYTES;
+    uint8_t* raw_base = smem + BFS * CF::BF_STAGE_BYTES;
     GemmCtl& ctl = *reinterpret_cast<GemmCtl*>(smem + CF::SMEM - sizeof(GemmCtl));
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int m0 = blockIdx.x * GM_BM, n0 = blockIdx.y * BN;
@@ -166,7 +178,7 @@ __global__ void __launch_bounds__(GM_THREADS, BN >= 128 ? 1 : 2) k_gemm_bf16x3(c
     if (warp == 0) tmem_alloc<TCOLS>(&ctl.tmem_base);
     if (tid == 0) {
 #pragma unroll
-        for (int s = 0; s < GM_BF_STAGES; ++s) mbar_init(&ctl.stage_bar[s], 1);
+        for (int s = 0; s < BFS; ++s) mbar_init(&ctl.stage_bar[s], 1);
         mbar_init(&ctl.done_bar, 1);
         fence_mbar_init();
     }
@@ -203,12 +215,12 @@ __global__ void __launch_bounds__(GM_THREADS, BN >= 128 ? 1 : 2) k_gemm_bf16x3(c
         if (kt + RS - 1 < ktiles) issue_copies(kt + RS - 1);          // its raw stage was converted by this same thread in iteration kt - 1
         cp_async_commit();
         cp_async_wait<RS - 1>();                                      // this thread's copies of tile kt have landed
-        const int s = kt % GM_BF_STAGES;
+        const int s = kt % BFS;
         uint8_t* a_hi = smem + s * CF::BF_STAGE_BYTES;
         uint8_t* a_lo = a_hi + TA::BYTES;
         uint8_t* b_hi = a_lo + TA::BYTES;
         uint8_t* b_lo = b_hi + TB::BYTES;
-        if (kt >= GM_BF_STAGES) {                                     // the MMAs that read this bf16 stage (tile kt - 2) are done
+        if (kt >= BFS) {                                              // the MMAs that read this bf16 stage (tile kt - BFS) are done
             mbar_wait(&ctl.stage_bar[s], (stage_phase >> s) & 1u);
             stage_phase ^= 1u << s;
         }
@@ -341,14 +353,21 @@ __global__ void k_gemm_splitk_reduce(const GemmArgs g, int nsplit, int batch) {
     *c = x;
 }
 
-template <int BN> static int launch_gemm(const GemmArgs& g, dim3 grid, cudaStream_t st) {
-    constexpr size_t smem = GemmCfg<BN>::SMEM;
+template <int BN, bool PACKED> static int launch_gemm(const GemmArgs& g, dim3 grid, cudaStream_t st) {
+    constexpr size_t smem = GemmCfg<BN, PACKED>::SMEM;
     static bool seen[RB_MAX_DEVICES] = {};             // function attributes are per device
-    if (first_use_on_device(seen)) RB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_gemm_bf16x3<BN><<<grid, GM_THREADS, smem, st>>>(g);
+    if (first_use_on_device(seen)) RB_CUDA(cudaFuncSetAttribute(k_gemm_bf16x3<BN, PACKED>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_gemm_bf16x3<BN, PACKED><<<grid, GM_THREADS, smem, st>>>(g);
     RB_CUDA(cudaGetLastError());
     return RB_OK;
 }
+
+template <int BN> static int launch_gemm(bool packed, const GemmArgs& g, dim3 grid, cudaStream_t st) {
+    return packed ? launch_gemm<BN, true>(g, grid, st) : launch_gemm<BN, false>(g, grid, st);
+}
+
+// pipeline shape (GemmCfg): 0 = DEEP, 1 = PACKED, -1 = PACKED whenever the grid holds more CTAs than the GPU has SMs
+static int g_gemm_cta_packing = -1;
 
 int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, cudaStream_t st) {
     RB_REQUIRE(g.M > 0 && g.N > 0 && g.K >= 0, "bad GEMM shape");
@@ -370,11 +389,12 @@ int gemm_bf16x3(GemmArgs g, float* splitk_ws, size_t splitk_ws_floats, int sms, 
     g.ksplit = ks; g.nsplit = split; g.partial = splitk_ws;
     const dim3 grid((g.M + GM_BM - 1) / GM_BM, (g.N + bn - 1) / bn, split * g.batch);
     int rc;
+    const bool packed = g_gemm_cta_packing < 0 ? (int64_t)grid.x * grid.y * grid.z > sms : g_gemm_cta_packing != 0;
     switch (bn) {
-        case 128: rc = launch_gemm<128>(g, grid, st); break;
-        case 64: rc = launch_gemm<64>(g, grid, st); break;
-        case 32: rc = launch_gemm<32>(g, grid, st); break;
-        default: rc = launch_gemm<16>(g, grid, st); break;
+        case 128: rc = launch_gemm<128>(packed, g, grid, st); break;
+        case 64: rc = launch_gemm<64>(packed, g, grid, st); break;
+        case 32: rc = launch_gemm<32>(packed, g, grid, st); break;
+        default: rc = launch_gemm<16>(packed, g, grid, st); break;
     }
     if (rc) return rc;
     if (split > 1) {
@@ -437,6 +457,12 @@ int sum_serial(const float* x, int n, float* out, cudaStream_t st) {
 }  // namespace rb
 
 using namespace rb;
+
+extern "C" int rb_gemm_set_cta_packing(int mode) {
+    RB_REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (by grid size), 0 (deep pipeline) or 1 (packed CTAs)");
+    g_gemm_cta_packing = mode;
+    return RB_OK;
+}
 
 // C[M,N] (+)= epilogue(A * B); see the header of this file for the operand orientation flags.  workspace (optional) enables split-K.
 extern "C" int rb_gemm_bf16x3(const float* A, int lda, int a_mn, const float* B, int ldb, int b_mn, float* C, int ldc, int M, int N, int K,

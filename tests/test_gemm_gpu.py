@@ -44,3 +44,26 @@ def test_gemm_epilogues_and_accumulate():
     assert rel(_run(Am, 0, Bm, 1, M, N, K, C0=C0), ref + C0) <= 5e-5
     a = _run(Am, 0, Bm, 1, M, N, K, bias=bias)
     assert np.array_equal(a, _run(Am, 0, Bm, 1, M, N, K, bias=bias))                     # deterministic
+
+
+@pytest.mark.parametrize("M,N,K,ws", [(300, 128, 64, 0), (257, 200, 200, 0), (243, 800, 1000, 32 * 243 * 800), (1024, 64, 200, 0), (640, 32, 64, 0), (512, 4, 32, 0), (128, 65, 7, 0)])
+@pytest.mark.parametrize("a_mn,b_mn", [(0, 1), (1, 1), (0, 0)])
+def test_cta_packing_is_bit_identical(M, N, K, ws, a_mn, b_mn):
+    """Deep pipeline (2 bf16 + 2-4 raw stages) vs packed CTAs (1 + 2, two / three CTAs per SM): the same MMAs in the same order, every tile width."""
+    from reacherdistilation_b200._lib import check, lib
+    rng = np.random.default_rng(M + N + K)
+    sc = 0.1 / np.sqrt(max(K, 64) / 64.0)                              # pre-activations of order one (the bf16x3 error scales with them)
+    Am, Bm = (rng.standard_normal((M, K)) * sc).astype(np.float32), rng.standard_normal((K, N)).astype(np.float32)
+    A = np.ascontiguousarray(Am.T) if a_mn else Am
+    B = Bm if b_mn else np.ascontiguousarray(Bm.T)
+    bias = rng.standard_normal(N).astype(np.float32)
+    outs = []
+    try:
+        for mode in (0, 1):
+            check(lib().rb_gemm_set_cta_packing(mode))
+            outs.append(_run(A, a_mn, B, b_mn, M, N, K, bias=bias, act=1, ws_floats=ws))
+    finally:
+        check(lib().rb_gemm_set_cta_packing(-1))
+    ref = np.tanh(Am.astype(np.float64) @ Bm.astype(np.float64) + bias)
+    assert np.array_equal(outs[0], outs[1])
+    assert np.abs(outs[1] - ref).max() <= 5e-5
