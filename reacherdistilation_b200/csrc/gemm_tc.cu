@@ -157,6 +157,16 @@ template <int BN, bool PACKED = false> struct GemmCfg {
 static_assert(GemmCfg<128, false>::MIN_CTAS == 1 && GemmCfg<64, false>::MIN_CTAS == 2 && GemmCfg<128, true>::MIN_CTAS == 2 &&
               GemmCfg<64, true>::MIN_CTAS == 3 && GemmCfg<32, true>::MIN_CTAS == 3 && GemmCfg<16, true>::MIN_CTAS == 3, "CTAs per SM as documented");
 
+// phase timestamps (globaltimer, ns) of CTA 0 of the last launch: read back with rb_debug_gemm_stamps (scripts/r02/gemm_stamps.py)
+__device__ unsigned long long g_gemm_stamps[16];
+__device__ __forceinline__ void gm_stamp(int i) {
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0 && threadIdx.x == 0) {
+        unsigned long long v;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        g_gemm_stamps[i] = v;
+    }
+}
+
 template <int BN, bool PACKED>
 __global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_gemm_bf16x3(const GemmArgs g) {
     using TA = OperandTile<GM_BM>;
@@ -174,6 +184,7 @@ __global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_g
     const float* __restrict__ Bb = g.B + (size_t)bz * g.sB;
     const int kbeg = sz * g.ksplit, kend = min(g.K, kbeg + g.ksplit);
     const int ktiles = (kend - kbeg + GM_BK - 1) / GM_BK;
+    gm_stamp(0);
 
     if (warp == 0) tmem_alloc<TCOLS>(&ctl.tmem_base);
     if (tid == 0) {
@@ -207,6 +218,7 @@ __global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_g
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
+    gm_stamp(1);
     const uint32_t tmem = ctl.tmem_base;
     const uint32_t idesc = make_idesc_bf16(GM_BM, BN) | ((uint32_t)g.a_mn << 15) | ((uint32_t)g.b_mn << 16);
 
@@ -224,6 +236,7 @@ __global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_g
             mbar_wait(&ctl.stage_bar[s], (stage_phase >> s) & 1u);
             stage_phase ^= 1u << s;
         }
+        if (kt < 2) gm_stamp(2 + 2 * kt);
         const uint8_t* ra = raw_base + (kt % RS) * CF::RAW_STAGE_BYTES;
         const uint8_t* rb_ = ra + TA::RAW_BYTES;
 #pragma unroll
@@ -237,6 +250,7 @@ __global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_g
         fence_async_smem();
         fence_before_sync();
         __syncthreads();
+        if (kt < 2) gm_stamp(3 + 2 * kt);
         if (warp == 0 && elect_one_sync()) {
             fence_after_sync();
             const uint32_t ah = smem_u32(a_hi), al = smem_u32(a_lo), bh = smem_u32(b_hi), bl = smem_u32(b_lo);
@@ -258,82 +272,120 @@ __global__ void __launch_bounds__(GM_THREADS, GemmCfg<BN, PACKED>::MIN_CTAS) k_g
         mbar_wait(&ctl.done_bar, 0);
         fence_after_sync();
     }
+    gm_stamp(6);
     float* ct = reinterpret_cast<float*>(smem);
     {
         const int row = (warp & 3) * 32 + lane;                      // warps w and w + 4 share TMEM lane quadrant w & 3 and split the columns
         constexpr int CHUNKS8 = BN / 8, HALF = (CHUNKS8 + 1) / 2;
         const int c_beg = (warp >> 2) * HALF, c_end = min(CHUNKS8, c_beg + HALF);
         const uint32_t tacc = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-        for (int c = c_beg; c < c_end; ++c) {
-            float v[8];
-            if (ktiles > 0) { tmem_ld_x8(tacc + c * 8, v); tmem_ld_wait(); }
-            else {
+        constexpr int CB = HALF < 4 ? HALF : 4;                      // chunks per batch: all loads of a batch in flight, one wait
+        for (int c0 = c_beg; c0 < c_end; c0 += CB) {
+            float v[CB][8];
 #pragma unroll
-                for (int i = 0; i < 8; ++i) v[i] = 0.f;
+            for (int j = 0; j < CB; ++j) {
+                if (ktiles > 0 && c0 + j < c_end) tmem_ld_x8(tacc + (c0 + j) * 8, v[j]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 8; ++i) v[j][i] = 0.f;
+                }
             }
-            float4* d = reinterpret_cast<float4*>(ct + row * CF::CT_LD + c * 8);
-            d[0] = make_float4(v[0], v[1], v[2], v[3]);
-            d[1] = make_float4(v[4], v[5], v[6], v[7]);
+            if (ktiles > 0) tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < CB; ++j)
+                if (c0 + j < c_end) {
+                    float4* d = reinterpret_cast<float4*>(ct + row * CF::CT_LD + (c0 + j) * 8);
+                    d[0] = make_float4(v[j][0], v[j][1], v[j][2], v[j][3]);
+                    d[1] = make_float4(v[j][4], v[j][5], v[j][6], v[j][7]);
+                }
         }
     }
     fence_before_sync();
     __syncthreads();
+    gm_stamp(7);
     const bool split = g.nsplit > 1;
-    float* out = split ? g.partial + (size_t)blockIdx.z * g.M * g.N : g.C + (size_t)bz * g.sC;
+    float* __restrict__ out = split ? g.partial + (size_t)blockIdx.z * g.M * g.N : g.C + (size_t)bz * g.sC;
     const int ldo = split ? g.N : g.ldc;
-    const float* bias = (!split && g.bias) ? g.bias + (size_t)bz * g.sBias : nullptr;
-    const float* Hb = (!split && g.H) ? g.H + (size_t)bz * g.sH : nullptr;
+    const float* __restrict__ bias = (!split && g.bias) ? g.bias + (size_t)bz * g.sBias : nullptr;
+    const float* __restrict__ Hb = (!split && g.H) ? g.H + (size_t)bz * g.sH : nullptr;
     const int act = split ? 0 : g.act, accumulate = split ? 0 : g.accumulate;
-    constexpr int Q = BN / 4;                                        // float4 groups per tile row
-    // CTA-uniform: may rows of this output / bias / H be accessed as aligned float4 (n0 and the group offsets are multiples of 4)?
-    const bool vec_o = (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo & 3) == 0;
-    const bool vec_b = bias && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
-    const bool vec_h = Hb && (reinterpret_cast<uintptr_t>(Hb) & 15) == 0 && (g.ldh & 3) == 0;
-    for (int idx = tid; idx < GM_BM * Q; idx += GM_THREADS) {
-        const int r = idx / Q, q = idx - r * Q, m = m0 + r, n = n0 + q * 4;
-        if (m >= g.M || n >= g.N) continue;
-        const float4 cv = *reinterpret_cast<const float4*>(ct + r * CF::CT_LD + q * 4);
-        float x[4] = {cv.x, cv.y, cv.z, cv.w};
-        float* o = out + (size_t)m * ldo + n;
-        const float* hp = Hb ? Hb + (size_t)m * g.ldh + n : nullptr;
-        const int nv = min(4, g.N - n);
-        const bool full = nv == 4;
-        if (bias) {
-            float b[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full && vec_b) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n)); b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
-            else {
+    // A thread owns ONE float4 column group (GM_THREADS is a multiple of the groups per row) and every RPI-th row of it: its bias values are
+    // loaded once, and U rows are in flight together -- all shared / global loads of a batch are issued before the first dependent
+    // instruction (the one-row-at-a-time loop spent 4.7 of the 8.5 us a 128-wide CTA of the LSTM heads lives in this phase: one L2 round
+    // trip or one tanh chain per iteration, 2-4 warps per scheduler).
+    constexpr int Q = BN / 4, RPI = GM_THREADS / Q, ITER = GM_BM / RPI, U = ITER < 4 ? ITER : 4;
+    static_assert(GM_THREADS % Q == 0 && GM_BM % RPI == 0 && ITER % U == 0, "output mapping");
+    const int q = tid % Q, r0 = tid / Q, n = n0 + q * 4;
+    const int nv = min(4, g.N - n);                                  // <= 0: this thread's columns lie outside the matrix
+    const bool full = nv == 4;
+    // may rows of this output / bias / H be accessed as aligned float4 (n0 and the group offsets are multiples of 4)?
+    const bool vec_o = full && (reinterpret_cast<uintptr_t>(out) & 15) == 0 && (ldo & 3) == 0;
+    const bool vec_b = full && bias && (reinterpret_cast<uintptr_t>(bias) & 15) == 0;
+    const bool vec_h = full && Hb && (reinterpret_cast<uintptr_t>(Hb) & 15) == 0 && (g.ldh & 3) == 0;
+    float b[4] = {0.f, 0.f, 0.f, 0.f};
+    if (bias && nv > 0) {
+        if (vec_b) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + n)); b[0] = t.x; b[1] = t.y; b[2] = t.z; b[3] = t.w; }
+        else {
 #pragma unroll
-                for (int i = 0; i < 4; ++i) if (i < nv) b[i] = __ldg(bias + n + i);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] += b[i];
-        }
-        if (act == 1) {
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] = tanhf(x[i]);
-        }
-        if (hp) {
-            float h[4] = {0.f, 0.f, 0.f, 0.f};
-            if (full && vec_h) { const float4 t = __ldg(reinterpret_cast<const float4*>(hp)); h[0] = t.x; h[1] = t.y; h[2] = t.z; h[3] = t.w; }
-            else {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) if (i < nv) h[i] = __ldg(hp + i);
-            }
-#pragma unroll
-            for (int i = 0; i < 4; ++i) x[i] *= fmaf(-h[i], h[i], 1.f);
-        }
-        if (full && vec_o) {
-            if (accumulate) { const float4 t = *reinterpret_cast<const float4*>(o); x[0] += t.x; x[1] += t.y; x[2] += t.z; x[3] += t.w; }
-            *reinterpret_cast<float4*>(o) = make_float4(x[0], x[1], x[2], x[3]);
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (i < nv) o[i] = accumulate ? o[i] + x[i] : x[i];
+            for (int i = 0; i < 4; ++i) if (i < nv) b[i] = __ldg(bias + n + i);
         }
     }
+    if (nv > 0) {
+        for (int it0 = 0; it0 < ITER; it0 += U) {
+            float x[U][4], h[U][4], c[U][4];
+            bool ok[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                            // ---- loads of the batch
+                const int r = r0 + (it0 + u) * RPI, m = m0 + r;
+                ok[u] = m < g.M;
+                const float4 cv = *reinterpret_cast<const float4*>(ct + r * CF::CT_LD + q * 4);
+                x[u][0] = cv.x; x[u][1] = cv.y; x[u][2] = cv.z; x[u][3] = cv.w;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { h[u][i] = 0.f; c[u][i] = 0.f; }
+                if (!ok[u]) continue;
+                if (Hb) {
+                    const float* hp = Hb + (size_t)m * g.ldh + n;
+                    if (vec_h) { const float4 t = __ldg(reinterpret_cast<const float4*>(hp)); h[u][0] = t.x; h[u][1] = t.y; h[u][2] = t.z; h[u][3] = t.w; }
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (i < nv) h[u][i] = __ldg(hp + i);
+                    }
+                }
+                if (accumulate) {
+                    const float* o = out + (size_t)m * ldo + n;
+                    if (vec_o) { const float4 t = *reinterpret_cast<const float4*>(o); c[u][0] = t.x; c[u][1] = t.y; c[u][2] = t.z; c[u][3] = t.w; }
+                    else {
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) if (i < nv) c[u][i] = o[i];
+                    }
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {                            // ---- epilogue arithmetic and stores
+                if (!ok[u]) continue;
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    float v = x[u][i];
+                    if (bias) v += b[i];
+                    if (act == 1) v = tanh_mufu(v);        // ex2 + rcp, |error| ~3e-7: tanhf's ~25 instructions made this phase issue-bound
+                    if (Hb) v *= fmaf(-h[u][i], h[u][i], 1.f);
+                    if (accumulate) v = c[u][i] + v;
+                    x[u][i] = v;
+                }
+                float* o = out + (size_t)(m0 + r0 + (it0 + u) * RPI) * ldo + n;
+                if (vec_o) *reinterpret_cast<float4*>(o) = make_float4(x[u][0], x[u][1], x[u][2], x[u][3]);
+                else {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) if (i < nv) o[i] = x[u][i];
+                }
+            }
+        }
+    }
+    gm_stamp(8);
     fence_before_sync();
     __syncthreads();
     if (warp == 0) tmem_dealloc<TCOLS>(tmem);
+    gm_stamp(9);
 }
 
 // C (+)= epilogue(sum over the split-K partial tiles, in slice order), for every batch entry
@@ -346,7 +398,7 @@ __global__ void k_gemm_splitk_reduce(const GemmArgs g, int nsplit, int batch) {
     float x = 0.f;
     for (int z = 0; z < nsplit; ++z) x += g.partial[((size_t)bz * nsplit + z) * mn + r];
     if (g.bias) x += __ldg(g.bias + (size_t)bz * g.sBias + n);
-    if (g.act == 1) x = tanhf(x);
+    if (g.act == 1) x = tc::tanh_mufu(x);
     if (g.H) { const float h = __ldg(g.H + (size_t)bz * g.sH + (size_t)m * g.ldh + n); x *= fmaf(-h, h, 1.f); }
     float* c = g.C + (size_t)bz * g.sC + (size_t)m * g.ldc + n;
     if (g.accumulate) x += *c;
@@ -457,6 +509,14 @@ int sum_serial(const float* x, int n, float* out, cudaStream_t st) {
 }  // namespace rb
 
 using namespace rb;
+
+// debug: phase stamps (ns) of CTA 0 of the last k_gemm_bf16x3 launch: 0 start, 1 prologue done, 2 / 4 copies of k-tile 0 / 1 landed (and bf16 stage
+// free), 3 / 5 converted + CTA barrier, 6 all MMAs done, 7 accumulator staged in shared memory, 8 output written, 9 end
+extern "C" int rb_debug_gemm_stamps(unsigned long long* host_out) {
+    RB_REQUIRE(host_out != nullptr, "NULL argument");
+    RB_CUDA(cudaMemcpyFromSymbol(host_out, rb::g_gemm_stamps, sizeof(unsigned long long) * 16));
+    return RB_OK;
+}
 
 extern "C" int rb_gemm_set_cta_packing(int mode) {
     RB_REQUIRE(mode >= -1 && mode <= 1, "mode must be -1 (by grid size), 0 (deep pipeline) or 1 (packed CTAs)");
