@@ -8,10 +8,12 @@
 //     MN-contiguous (x_mn = 1): element (row, k) at X[k * ld + row]   -> UMMA MN-major tile (no transpose pass needed)
 // The loader threads read 8 contiguous floats (one 32 B sector), split them into bf16 hi / lo and write one 16-byte chunk into the
 // no-swizzle canonical layout of that orientation, so A^T B (wgrad), A B^T (dgrad) and A B (forward) all run at the same speed.
-// 128 x BN output tile per CTA, BK = 32 per k-tile.  Pipeline: cp.async (LDGSTS) streams the raw fp32 k-tiles into 3-4 shared-memory
-// stages (deep enough to cover the L2 / HBM latency without holding registers); each k-tile is then split into bf16 hi / lo
-// operand stages (2, reuse gated by tcgen05.commit -> mbarrier) and consumed by MMAs issued by one elected thread; accumulator in
-// TMEM; the epilogue goes through a padded shared-memory tile so every global access is a coalesced 128-bit one.
+// 128 x BN output tile per CTA, BK = 32 per k-tile.  Pipeline: cp.async (LDGSTS) streams the raw fp32 k-tiles into 2-4 shared-memory
+// stages; each k-tile is then split into bf16 hi / lo operand stages (1-2, reuse gated by tcgen05.commit -> mbarrier) and consumed by MMAs
+// issued by one elected thread; accumulator in TMEM; the epilogue goes through a padded shared-memory tile so every global access is a
+// coalesced 128-bit one.  Two pipeline shapes (GemmCfg): DEEP for grids of at most one CTA per SM, PACKED (two / three CTAs per SM) above.
+// Where a 128-wide CTA of the LSTM heads (K = 64) spends its 7 us (rb_debug_gemm_stamps, B200): set-up 0.9, first copies 0.7, 2 x [convert +
+// barrier] 0.4, MMA tail 0.3, TMEM -> shared 0.5, output 3.3 (10 MB of fp32 rows from 160 CTAs at once: store-bound), i.e. fixed costs, not MMAs.
 // Split-K (grid.z) writes partial tiles that a second kernel adds in a fixed order (deterministic).
 #include "common.cuh"
 #include "gemm_tc.cuh"
@@ -164,6 +166,11 @@ __device__ __forceinline__ void gm_stamp(int i) {
         unsigned long long v;
         asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
         g_gemm_stamps[i] = v;
+    }
+    if ((i == 0 || i == 9) && blockIdx.x == gridDim.x - 1 && blockIdx.y == gridDim.y - 1 && blockIdx.z == gridDim.z - 1 && threadIdx.x == 0) {
+        unsigned long long v;                      // start / end of the LAST CTA of the grid: tells one wave from two
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+        g_gemm_stamps[i == 0 ? 10 : 11] = v;
     }
 }
 

@@ -28,8 +28,9 @@ for (tag, M, N, K, a_mn, b_mn, act, useH, ws) in [("head fwd L2", 20480, 128, 64
         e1.record(); torch.cuda.synchronize()
         buf = (C.c_ulonglong * 16)()
         check(L.rb_debug_gemm_stamps(buf))
+        last = (buf[10] - buf[0]) / 1e3, (buf[11] - buf[0]) / 1e3
         st = np.array(list(buf)[:10], dtype=np.int64)
         d = np.diff(st) / 1e3
         print("%-14s %6d x %4d x %6d mode %d: %.1f us per launch, CTA 0 %.1f us: " % (tag, M, N, K, mode, 1e3 * e0.elapsed_time(e1) / 20, (st[9] - st[0]) / 1e3)
-              + ", ".join("%s %.2f" % (n, x) for n, x in zip(names, d)), flush=True)
+              + ", ".join("%s %.2f" % (n, x) for n, x in zip(names, d)) + "; last CTA of the grid: start +%.1f, end +%.1f us" % last, flush=True)
 check(L.rb_gemm_set_cta_packing(-1))
