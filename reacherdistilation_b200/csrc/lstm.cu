@@ -61,13 +61,24 @@ static void lstm_ws_carve(float* ws, int64_t R, int64_t B, LstmWs& w) {
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// x rows: dropout(ob) -> xh[:, 0:11]; initial m state -> xh rows of step 0, columns 43..242; initial c -> c[0]
+// x rows: dropout(ob) -> xh[:, 0:11]; e = prev_pdflat W_e + b_e -> xh[:, 11:43]; initial m state -> xh rows of step 0, columns 43..242;
+// initial c -> c[0].  The embedding is 4 fp32 FMAs per output (thread = one (row, column) pair: a warp reads one prev_pdflat row and one
+// 128-byte row of W_e and writes 128 contiguous bytes) -- as a K = 4 tensor-core GEMM it was one more launch on the critical path.
 __global__ void k_lstm_inputs(int64_t R, int64_t B, const float* __restrict__ ob, float keep_prob, uint32_t k0, uint32_t k1, uint32_t sample_id0,
                               uint32_t iteration, const uint32_t* __restrict__ clock, const float* __restrict__ init_state, float* __restrict__ xh,
                               float* __restrict__ c0, float* __restrict__ hh, float* __restrict__ a1, float* __restrict__ a2, float* __restrict__ a3,
-                              float* __restrict__ a4) {
+                              float* __restrict__ a4, const float* __restrict__ prev_pd, const float* __restrict__ W_e, const float* __restrict__ b_e) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (clock) iteration = clock[0];                 // device-side step clock (CUDA-graph replay)
+    if (i < R * LE) {
+        const int64_t r = i / LE;
+        const int n = (int)(i - r * LE);
+        const float* p = prev_pd + r * 4;
+        float e = __ldg(b_e + n);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) e = fmaf(__ldg(p + k), __ldg(W_e + k * LE + n), e);
+        xh[r * LDXH + 11 + n] = e;
+    }
     if (i < R) {
         float o[11];
 #pragma unroll
@@ -198,10 +209,11 @@ static int lstm_run(const LstmCall& c, float* ws, cudaStream_t st) {
         RB_CUDA(cudaEventRecord(side->ready[0], st));
         RB_CUDA(cudaStreamWaitEvent(side->s, side->ready[0], 0));
     }
-    k_lstm_inputs<<<(unsigned)((max(R, B * LU) + 255) / 256), 256, 0, st>>>(R, B, c.ob, c.keep_prob, (uint32_t)c.seed, (uint32_t)(c.seed >> 32),
-                                                                           c.sample_id0, c.iteration, c.clock, c.init_state, w.xh, w.c, w.hh, w.a[0], w.a[1], w.a[2], w.a[3]);
+    static_assert(LE * LT >= LU, "the embedding's R * LE threads cover the B * LU state elements");
+    k_lstm_inputs<<<(unsigned)((R * LE + 255) / 256), 256, 0, st>>>(R, B, c.ob, c.keep_prob, (uint32_t)c.seed, (uint32_t)(c.seed >> 32), c.sample_id0,
+                                                                   c.iteration, c.clock, c.init_state, w.xh, w.c, w.hh, w.a[0], w.a[1], w.a[2], w.a[3],
+                                                                   c.prev_pd, P + L_WE, P + L_BE);
     RB_CUDA(cudaGetLastError());
-    RB_TRY(gemm(c.prev_pd, 4, 0, P + L_WE, LE, 1, w.xh + 11, LDXH, Ri, LE, 4, P + L_BE, 0, 0, nullptr, 0, w, sms, st));
     // ---- recurrence: one persistent cluster launch (lstm_recur.cu); RB_LSTM_RECUR=0 keeps the GEMM + cell launch sequence ------------
     const int use_recur = c.per_step_gemm ? 0 : 1;     // persistent recurrence kernels (default) or the GEMM + cell launch per step
     LstmRecurArgs ra{};
