@@ -675,8 +675,9 @@ def main():
             lflop = 6.0 * (243 * 800 + 31400 + 128) * 10 * Bw                       # 3 x 2 x MAC per window row, T = 10
             line["lstm"] = dict(metric="lstm_window_rows_per_sec", value=10.0 * Bw * 10 / lsec2, unit="sample-steps/s", windows=Bw, steps_unrolled=10,
                                 ms_per_step=1e3 * lsec2 / 10, tensor_tflops=lflop / (lsec2 / 10) / 1e12, params=int(lnet.P),
-                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads: 34 launches (two persistent tcgen05 recurrence kernels, batched k_gemm_bf16x3 over the un-shared heads) captured once in a CUDA graph (rb_lstm_step, device-side step clock)"
-                                     "un-shared heads, element-wise kernels) captured once in a CUDA graph (rb_lstm_step, device-side step clock)")
+                                note="forward + KL + BPTT + Adam of the LSTM(200) student with per-step heads: 33 launches (two persistent tcgen05 recurrence kernels, "
+                                     "batched k_gemm_bf16x3 over the un-shared heads at two / three CTAs per SM, element-wise kernels) captured once in a CUDA graph "
+                                     "(rb_lstm_step, device-side step clock)")
             del lnet
             # ---- two-headed LSTM student of the backup experiment (backup/student_rollout.py:130-200,328) at the sizes the source comments
             # beside its debug values (NUM_UNITS 100, STEPS_UNROLLED 20, LSTM_BATCH_SIZE 100) and at 2048 windows: loss_grad + Adam ------------
