@@ -16,7 +16,7 @@ loop, device-resident rollout buffer; one bench "step" = 20 launches of the 50-s
 `distill` BASELINE.json config 4 shard (32 768 envs per GPU): DAgger iterations = env step + teacher label + student
           forward/backward + KL + [NCCL all-reduce of the flat gradient] + Adam; samples/s == env-steps/s of that loop.
 `step_api` the gym-style single-step kernel (HBM-bound) at 4 194 304 envs.
-`config1`  BASELINE.json config 1 (one env, 1000-step teacher rollout): host-thread restatement vs the gym surface at batch 1 vs one fused launch.
+`config1`  BASELINE.json config 1 (one env, 1000-step teacher rollout + one student epoch over those samples): host-thread restatement vs the gym surface at batch 1 vs one fused launch; student epoch in batches of 200.
 `cpu_baseline` / --impl reference: the float64 C restatement of the reference's CPU path (oracle/, OpenMP over host cores) on a
           bounded sample of the same workload.  The reference itself (TF-1.10 + gym + MuJoCo-1.50) is not installable here.
 """
@@ -233,8 +233,36 @@ def config1_leg(steps=1000):
         ret = float(out["rew"].sum())                      # device -> host read of the result
         fused = steps / (time.perf_counter() - t0)
     v.close()
-    return dict(workload="config1: 1 env, %d-step teacher rollout (20 episodes)" % steps, unit="env-steps/s", cpu_restatement_1_thread=cpu,
-                gpu_gym_loop_batch1=gym_loop, gpu_fused_one_launch=fused, teacher_return_per_episode=ret / (steps / 50.0))
+    # ---- the second half of config 1: one student epoch over those `steps` samples as flat batches of 200 (dataset.py:186-194's
+    # ratio), student_mlp_graph + KL + Adam per batch: numpy float64 restatement on one host thread vs rb_student_step (one launch per batch)
+    from reacherdistilation_b200 import MODE_TC, STUDENT_MLP
+    from reacherdistilation_b200.student_nn import StudentNet
+    rng = np.random.default_rng(0)
+    Bs, nb = 200, steps // 200
+    xs, ts = rng.standard_normal((nb, Bs, 16)).astype(np.float32), (rng.standard_normal((nb, Bs, 4)) * 0.3).astype(np.float32)
+    for rep in range(2):                                   # first pass = warm-up (BLAS start-up)
+        theta, opt = (np.random.default_rng(1).standard_normal(NN.mlp_param_count()) * 0.1), NN.AdamTF(NN.mlp_param_count())
+        t0 = time.perf_counter()
+        for b in range(nb):
+            s_, hs = NN.mlp_fwd(xs[b].astype(np.float64), theta.astype(np.float32)); _l, ds = NN.kl_loss(s_, ts[b].astype(np.float64))
+            theta = opt.update(theta, NN.mlp_bwd(hs, theta.astype(np.float32), ds))
+        cpu_epoch = nb * Bs / (time.perf_counter() - t0)
+    gpu_epoch = {}
+    for name, mode in (("tc", MODE_TC), ("fp32", MODE_FP32)):
+        net = StudentNet(kind=STUDENT_MLP, seed=1, mode=mode)
+        dx, dt_ = torch.from_numpy(xs).cuda(), torch.from_numpy(ts).cuda()
+        for rep in range(2):                               # first pass = warm-up
+            torch.cuda.synchronize(); t0 = time.perf_counter()
+            for b in range(nb):
+                net.step(dx[b], dt_[b])
+            loss = float(net.gradloss[net.P])              # device -> host read of the epoch's last loss
+            gpu_epoch[name] = nb * Bs / (time.perf_counter() - t0)
+    return dict(workload="config1: 1 env, %d-step teacher rollout (20 episodes) + one student epoch over those samples (batches of 200)" % steps,
+                unit="env-steps/s", cpu_restatement_1_thread=cpu, gpu_gym_loop_batch1=gym_loop, gpu_fused_one_launch=fused,
+                teacher_return_per_episode=ret / (steps / 50.0),
+                student_epoch=dict(unit="samples/s", batch=Bs, batches=nb, cpu_restatement_numpy=cpu_epoch, gpu_tc=gpu_epoch["tc"], gpu_fp32=gpu_epoch["fp32"],
+                                   note="gpu_tc = rb_student_step RB_MODE_TC (one cooperative tcgen05 launch per batch); gpu_fp32 = the fp32 CUDA-core "
+                                        "validation path (128-sample tiles: two CTAs at this batch, not built for it)"))
 
 
 REWARD_CHECK_ENVS = 1024      # both arms print the mean reward of the first 50-step chunk after reset over envs 0..1023 (cross-check)
